@@ -1,0 +1,147 @@
+/* mudpt_b200 -- C ABI of the B200-native MuDPT hot path (libmudpt_b200.so).
+ *
+ * The reference (YzM1a0/MuDPT) is pure Python/PyTorch and has no FFI of its own; the boundary
+ * below is what a maintainer binds (ctypes stub: INTEGRATION.md) to replace, with no other
+ * change, the bodies of
+ *
+ *   VisionTransformer_MuDPT.forward .......... clip/model.py:526-553
+ *   Transformer / ResidualAttentionBlock_MuDPT  clip/model.py:254-301, 404-440
+ *   TextEncoder.forward ...................... trainers/mudpt.py:142-156
+ *   CustomCLIP.forward (normalise + logits) .. trainers/mudpt.py:170-184
+ *   F.cross_entropy + loss.backward() ........ trainers/mudpt.py:249-251 (dgrad only: every
+ *                                              CLIP weight is frozen, :205-212)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; fp32 unless noted;
+ *   - the caller (PyTorch) owns every tensor it passes in or receives; the handle owns its
+ *     converted frozen weights and its activation workspace;
+ *   - calls are asynchronous on the `stream` argument (a cudaStream_t passed as void*), never
+ *     synchronise the device, and are CUDA-graph capturable after the first (allocating) call;
+ *   - return value 0 = ok, negative = error; mudpt_last_error() gives the message;
+ *   - one handle per process/GPU; a handle is not thread-safe;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Row layout of token matrices: row = sequence * L + token ("NLD"); the reference's LND is a
+ * permutation of the same data.
+ */
+#ifndef MUDPT_B200_H
+#define MUDPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUDPT_ABI_VERSION 1
+
+typedef struct mudpt_handle mudpt_handle;
+
+/* Architecture + prompt geometry. Mirrors the CLIP(...) constructor arguments
+ * (clip/model.py:667-681) and cfg.TRAINER.MUDPT.{N_CTX, DEEP_PROMPT_DEPTH} (train.py:114-119). */
+typedef struct mudpt_config {
+  int32_t embed_dim;
+  int32_t image_resolution;
+  int32_t vision_layers;
+  int32_t vision_width;
+  int32_t vision_patch_size;
+  int32_t context_length;
+  int32_t transformer_width;
+  int32_t transformer_heads;
+  int32_t transformer_layers;
+  int32_t n_ctx;        /* prompt tokens per tower */
+  int32_t prompt_depth; /* DEEP_PROMPT_DEPTH: layers 0..depth-1 see a fresh prompt */
+  int32_t device;       /* CUDA device ordinal */
+} mudpt_config;
+
+enum { MUDPT_TOWER_VISION = 0, MUDPT_TOWER_TEXT = 1 };
+
+int mudpt_abi_version(void);
+/* message of the last failing call on this thread that had no handle (create, unit kernels) */
+const char* mudpt_global_last_error(void);
+
+int mudpt_create(const mudpt_config* cfg, mudpt_handle** out);
+void mudpt_destroy(mudpt_handle* h);
+const char* mudpt_last_error(mudpt_handle* h);
+
+/* Frozen CLIP weights, one call per tensor, `name` = key of the reference CLIP.state_dict()
+ * ("visual.conv1.weight", "visual.transformer.resblocks.3.attn.in_proj_weight",
+ * "transformer.resblocks.0.mlp.c_fc.bias", "positional_embedding", "ln_final.weight",
+ * "text_projection", "logit_scale", ...; clip/model.py:499-524, 667-779).  The data is converted
+ * once (bf16, plus a transposed bf16 copy for the dgrad GEMMs) into handle-owned memory.
+ * Returns 1 for names the hot path does not use (token_embedding.weight, prompt parameters). */
+int mudpt_set_weight(mudpt_handle* h, const char* name, const float* data, int64_t numel, void* stream);
+/* 0 when every weight the two towers need has been set. */
+int mudpt_weights_complete(mudpt_handle* h);
+
+/* ---- vision tower: VisionTransformer_MuDPT.forward (clip/model.py:526-553) -------------------
+ * images   [B, 3, R, R]
+ * prompts  [depth, n_ctx, vision_width]: prompts[0] = ln_pre(visual_ctx + shared_ctx) (the layer-0
+ *          prompt rows after :541), prompts[i>=1] = t2v_visual_prompts[i-1] + visual_ctx_deep_prompts[i-1]
+ * f_img    [B, embed_dim] = ln_post(x[:, 0]) @ proj */
+int mudpt_vision_forward(mudpt_handle* h, const float* images, int32_t B, const float* prompts, float* f_img, void* stream);
+/* d_f_img [B, embed_dim] -> d_prompts [depth, n_ctx, vision_width] (summed over the batch).
+ * Must follow mudpt_vision_forward on the same handle (uses its saved activations). */
+int mudpt_vision_backward(mudpt_handle* h, const float* d_f_img, float* d_prompts, void* stream);
+
+/* ---- text tower: TextEncoder.forward (trainers/mudpt.py:142-156) -------------------------------
+ * Class set-up (once per class list): embeddings [C, src_len, width] are the token embeddings of the
+ * tokenised class prompts (prefix | placeholder ctx rows | suffix, trainers/mudpt.py:83-90),
+ * eot_host[C] = argmax of the token ids (:154).  seq_len <= src_len: tokens at positions >= seq_len
+ * are dropped; with seq_len = max(eot)+1 this is exact under the causal mask. */
+int mudpt_text_set_classes(mudpt_handle* h, const float* embeddings, int32_t C, int32_t src_len, int32_t seq_len,
+                           const int32_t* eot_host, void* stream);
+/* prompts [depth, n_ctx, width]: prompts[0] = ctx + positional_embedding[1:1+n_ctx],
+ *         prompts[i>=1] = deep_prompts[i-1] + v2t_text_prompts[i-1] (trainers/mudpt.py:175)
+ * splice_layer0 = 0 keeps rows 1..n_ctx of the embeddings as given (per-class ctx, dense API).
+ * f_txt [C, embed_dim] */
+int mudpt_text_forward(mudpt_handle* h, const float* prompts, int32_t splice_layer0, float* f_txt, void* stream);
+/* d_f_txt [C, embed_dim] -> d_prompts [depth, n_ctx, width]; d_x0 (optional, may be NULL)
+ * [C, seq_len, width] = gradient of the tower input (dense module-level API). */
+int mudpt_text_backward(mudpt_handle* h, const float* d_f_txt, float* d_prompts, float* d_x0, void* stream);
+
+/* ---- logits + loss head (trainers/mudpt.py:178-182, :250) ---------------------------------------
+ * labels int64 [B] or NULL (logits only).  loss (1 float) = sum_b CE_b * inv_global_batch,
+ * d_f_img [B,e] / d_f_txt [C,e] = gradients of that loss (NULL to skip). */
+int mudpt_logits_head(mudpt_handle* h, const float* f_img, const float* f_txt, const int64_t* labels, int32_t B,
+                      int32_t C, float inv_global_batch, float* logits, float* loss, float* d_f_img, float* d_f_txt,
+                      void* stream);
+/* backward of the logits for an external loss: dlogits [B, C] -> d_f_img, d_f_txt */
+int mudpt_logits_backward(mudpt_handle* h, const float* f_img, const float* f_txt, const float* dlogits, int32_t B,
+                          int32_t C, float* d_f_img, float* d_f_txt, void* stream);
+
+/* ---- unit-testable pieces (no handle) -----------------------------------------------------------
+ * bf16 buffers are passed as uint16_t*. */
+int mudpt_layernorm_forward(const float* x, const float* gamma, const float* beta, void* out, int32_t out_bf16,
+                            int32_t rows, int32_t width, void* stream);                     /* clip/model.py:164-170 */
+int mudpt_layernorm_backward(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
+                             uint16_t* dx_bf16, int32_t rows, int32_t width, void* stream);
+int mudpt_splice_forward(float* x, const float* prompt, int32_t S, int32_t L, int32_t row0, int32_t n, int32_t width,
+                         void* stream);                                                       /* clip/model.py:281-297 */
+int mudpt_splice_backward(float* dx, uint16_t* dx_bf16, float* d_prompt, int32_t S, int32_t L, int32_t row0, int32_t n,
+                          int32_t width, int32_t zero_rows, void* stream);
+/* qkv [S*L, 3*width] bf16 -> o [S*L, width] bf16, lse2 [S, H, L] (log2 domain) */
+int mudpt_attention_forward(const uint16_t* qkv, uint16_t* o, float* lse2, int32_t S, int32_t L, int32_t H,
+                            int32_t causal, void* stream);                                    /* clip/model.py:271-273 */
+int mudpt_attention_backward(const uint16_t* qkv, const uint16_t* o, const uint16_t* d_o, const float* lse2,
+                             float* dsum_scratch, uint16_t* dqkv, int32_t S, int32_t L, int32_t H, int32_t causal,
+                             void* stream);
+/* C = A[M,K] x B[N,K]^T (bf16, fp32 accumulate on tcgen05) with epilogue `mode`:
+ * 0 bf16 = acc+bias | 1 f32 = acc+bias | 2 f32 = acc+bias+resid | 3 out0 = h, out1 = QuickGELU(h)
+ * 4 bf16 = acc * QuickGELU'(aux) | 5 patch-embedding scatter (+pos) */
+int mudpt_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, int32_t K, int32_t mode, void* out0,
+                    void* out1, const float* bias, const float* resid, const void* aux, int32_t ldc, int32_t patch_np,
+                    int32_t patch_L, void* stream);
+int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream);
+int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream);
+
+/* ---- introspection for tests / profiling --------------------------------------------------------
+ * name in {"x_in","x_mid","qkv","o","h","lse","dx"}; layer ignored for "dx". */
+int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t layer, void** ptr, int64_t* numel);
+/* number of kernel launches issued by the library on this handle since creation */
+int64_t mudpt_launch_count(mudpt_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUDPT_B200_H */

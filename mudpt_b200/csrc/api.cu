@@ -1,0 +1,588 @@
+// C ABI of libmudpt_b200.so (include/mudpt_b200.h): handle, frozen-weight conversion, tower
+// forward / dgrad-only backward orchestration.  All launches go to the caller's stream; no
+// device synchronisation happens here (except the one-time read of logit_scale in set_weight).
+#include "../../include/mudpt_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "attention.h"
+#include "gemm.h"
+#include "head.h"
+#include "launch_count.h"
+#include "rowops.h"
+
+namespace mudpt {
+std::atomic<long long> g_launch_counter{0};
+}
+
+using namespace mudpt;
+typedef __nv_bfloat16 bf16;
+
+static thread_local std::string g_err;
+
+namespace {
+
+constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (clip/model.py:164)
+
+struct Layer {
+  // bf16 GEMM operands: forward uses the [out,in] weight as stored, dgrad the transposed copy
+  bf16 *w_in = nullptr, *w_in_t = nullptr, *w_out = nullptr, *w_out_t = nullptr;
+  bf16 *w_fc = nullptr, *w_fc_t = nullptr, *w_pr = nullptr, *w_pr_t = nullptr;
+  float *b_in = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_pr = nullptr;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  int have = 0;  // bit per tensor
+};
+
+struct Tower {
+  int d = 0, H = 0, layers = 0, n_ctx = 0, row0 = 0, depth = 0;
+  bool causal = false;
+  int L = 0;        // current tokens per sequence
+  int S = 0;        // current sequences
+  size_t cap_rows = 0;
+  std::vector<Layer> lw;
+  // saved activations, per layer
+  std::vector<float*> x_in, x_mid;
+  std::vector<bf16*> qkv, o, h;
+  std::vector<float*> lse;
+  // transients
+  bf16 *a_buf = nullptr, *g_buf = nullptr, *dh_buf = nullptr, *do_buf = nullptr, *dqkv_buf = nullptr, *dx_bf16 = nullptr;
+  float *dx = nullptr, *tmp_f32 = nullptr, *dsum = nullptr;
+  bool fwd_done = false;
+  int first_splice = 0;  // 0: layer 0 splices prompts[0]; 1: layer-0 rows kept as given
+};
+
+}  // namespace
+
+struct mudpt_handle {
+  mudpt_config cfg;
+  std::string err;
+  Tower vis, txt;
+  // vision stem / heads
+  bf16* w_conv = nullptr;  // [dv, Kp] bf16 (Kp = 3*p*p padded to a multiple of 8)
+  int Kp = 0;
+  float *cls = nullptr, *pos_v = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr,
+        *ln_post_b = nullptr, *proj_v = nullptr;
+  float *pos_t = nullptr, *ln_final_g = nullptr, *ln_final_b = nullptr, *proj_t = nullptr;
+  float logit_scale_exp = 0.f;
+  int stem_have = 0;
+  bf16* patches = nullptr;
+  size_t patches_cap = 0;
+  int* eot = nullptr;
+  size_t eot_cap = 0;
+  float* head_ws = nullptr;
+  size_t head_ws_cap = 0;
+  std::vector<void*> allocs;
+  long long launches_at_create = 0;
+};
+
+namespace {
+
+int fail(mudpt_handle* h, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  g_err = buf;
+  return -1;
+}
+
+#define CK(h, expr)                                   \
+  do {                                                \
+    const char* _e = (expr);                          \
+    if (_e) return fail((h), "%s (%s:%d)", _e, __FILE__, __LINE__); \
+  } while (0)
+
+#define CUDA_OK(h, expr)                                                                    \
+  do {                                                                                      \
+    cudaError_t _c = (expr);                                                                \
+    if (_c != cudaSuccess) return fail((h), "%s: %s (%s:%d)", #expr, cudaGetErrorString(_c), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(mudpt_handle* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t c = cudaMalloc(&q, n * sizeof(T) + 256);
+  if (c != cudaSuccess) return c;
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return cudaSuccess;
+}
+
+// (re)allocate the activation workspace of a tower for S sequences of L tokens
+int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
+  const size_t rows = static_cast<size_t>(S) * L;
+  t.S = S;
+  t.L = L;
+  if (rows <= t.cap_rows) return 0;
+  // grow: leak-free enough for a workspace that is sized once per configuration (old buffers stay
+  // registered in h->allocs and are released in mudpt_destroy)
+  gemm_clear_tensor_map_cache();
+  const size_t d = t.d;
+  t.x_in.assign(t.layers + 1, nullptr);
+  t.x_mid.assign(t.layers, nullptr);
+  t.qkv.assign(t.layers, nullptr);
+  t.o.assign(t.layers, nullptr);
+  t.h.assign(t.layers, nullptr);
+  t.lse.assign(t.layers, nullptr);
+  for (int i = 0; i <= t.layers; ++i) CUDA_OK(h, dev_alloc(h, &t.x_in[i], rows * d));
+  for (int i = 0; i < t.layers; ++i) {
+    CUDA_OK(h, dev_alloc(h, &t.x_mid[i], rows * d));
+    CUDA_OK(h, dev_alloc(h, &t.qkv[i], rows * 3 * d));
+    CUDA_OK(h, dev_alloc(h, &t.o[i], rows * d));
+    CUDA_OK(h, dev_alloc(h, &t.h[i], rows * 4 * d));
+    CUDA_OK(h, dev_alloc(h, &t.lse[i], rows * t.H));
+  }
+  CUDA_OK(h, dev_alloc(h, &t.a_buf, rows * d));
+  CUDA_OK(h, dev_alloc(h, &t.g_buf, rows * 4 * d));
+  CUDA_OK(h, dev_alloc(h, &t.dh_buf, rows * 4 * d));
+  CUDA_OK(h, dev_alloc(h, &t.do_buf, rows * d));
+  CUDA_OK(h, dev_alloc(h, &t.dqkv_buf, rows * 3 * d));
+  CUDA_OK(h, dev_alloc(h, &t.dx_bf16, rows * d));
+  CUDA_OK(h, dev_alloc(h, &t.dx, rows * d));
+  CUDA_OK(h, dev_alloc(h, &t.tmp_f32, rows * d));
+  CUDA_OK(h, dev_alloc(h, &t.dsum, rows * t.H));
+  t.cap_rows = rows;
+  t.fwd_done = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- weights
+int store_f32(mudpt_handle* h, float** dst, const float* src, int64_t numel, int64_t expect, const char* name,
+              cudaStream_t st) {
+  if (numel != expect) return fail(h, "weight %s: expected %lld elements, got %lld", name, (long long)expect, (long long)numel);
+  if (!*dst) CUDA_OK(h, dev_alloc(h, dst, static_cast<size_t>(numel)));
+  CUDA_OK(h, cudaMemcpyAsync(*dst, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+// [rows(out), cols(in)] fp32 -> bf16 as stored + bf16 transposed
+int store_gemm_weight(mudpt_handle* h, bf16** w, bf16** wt, const float* src, int64_t numel, int rows, int cols,
+                      const char* name, cudaStream_t st) {
+  if (numel != static_cast<int64_t>(rows) * cols)
+    return fail(h, "weight %s: expected %d x %d elements, got %lld", name, rows, cols, (long long)numel);
+  if (!*w) CUDA_OK(h, dev_alloc(h, w, static_cast<size_t>(numel)));
+  CK(h, cast_to_bf16(src, *w, static_cast<size_t>(numel), st));
+  if (wt) {
+    if (!*wt) CUDA_OK(h, dev_alloc(h, wt, static_cast<size_t>(numel)));
+    CK(h, transpose_cast_bf16(src, *wt, rows, cols, st));
+  }
+  return 0;
+}
+
+enum LayerBits {
+  LB_W_IN = 1 << 0, LB_B_IN = 1 << 1, LB_W_OUT = 1 << 2, LB_B_OUT = 1 << 3, LB_W_FC = 1 << 4, LB_B_FC = 1 << 5,
+  LB_W_PR = 1 << 6, LB_B_PR = 1 << 7, LB_LN1_G = 1 << 8, LB_LN1_B = 1 << 9, LB_LN2_G = 1 << 10, LB_LN2_B = 1 << 11,
+  LB_ALL = (1 << 12) - 1
+};
+enum StemBits {
+  SB_CONV = 1 << 0, SB_CLS = 1 << 1, SB_POS_V = 1 << 2, SB_LNPRE_G = 1 << 3, SB_LNPRE_B = 1 << 4, SB_LNPOST_G = 1 << 5,
+  SB_LNPOST_B = 1 << 6, SB_PROJ_V = 1 << 7, SB_POS_T = 1 << 8, SB_LNF_G = 1 << 9, SB_LNF_B = 1 << 10, SB_PROJ_T = 1 << 11,
+  SB_SCALE = 1 << 12, SB_ALL = (1 << 13) - 1
+};
+
+int set_block_weight(mudpt_handle* h, Tower& t, int layer, const char* sub, const float* data, int64_t numel,
+                     const char* full, cudaStream_t st) {
+  if (layer < 0 || layer >= t.layers) return fail(h, "weight %s: layer out of range", full);
+  Layer& l = t.lw[layer];
+  const int d = t.d;
+  int rc = 0;
+  if (!strcmp(sub, "attn.in_proj_weight")) { rc = store_gemm_weight(h, &l.w_in, &l.w_in_t, data, numel, 3 * d, d, full, st); l.have |= LB_W_IN; }
+  else if (!strcmp(sub, "attn.in_proj_bias")) { rc = store_f32(h, &l.b_in, data, numel, 3 * d, full, st); l.have |= LB_B_IN; }
+  else if (!strcmp(sub, "attn.out_proj.weight")) { rc = store_gemm_weight(h, &l.w_out, &l.w_out_t, data, numel, d, d, full, st); l.have |= LB_W_OUT; }
+  else if (!strcmp(sub, "attn.out_proj.bias")) { rc = store_f32(h, &l.b_out, data, numel, d, full, st); l.have |= LB_B_OUT; }
+  else if (!strcmp(sub, "mlp.c_fc.weight")) { rc = store_gemm_weight(h, &l.w_fc, &l.w_fc_t, data, numel, 4 * d, d, full, st); l.have |= LB_W_FC; }
+  else if (!strcmp(sub, "mlp.c_fc.bias")) { rc = store_f32(h, &l.b_fc, data, numel, 4 * d, full, st); l.have |= LB_B_FC; }
+  else if (!strcmp(sub, "mlp.c_proj.weight")) { rc = store_gemm_weight(h, &l.w_pr, &l.w_pr_t, data, numel, d, 4 * d, full, st); l.have |= LB_W_PR; }
+  else if (!strcmp(sub, "mlp.c_proj.bias")) { rc = store_f32(h, &l.b_pr, data, numel, d, full, st); l.have |= LB_B_PR; }
+  else if (!strcmp(sub, "ln_1.weight")) { rc = store_f32(h, &l.ln1_g, data, numel, d, full, st); l.have |= LB_LN1_G; }
+  else if (!strcmp(sub, "ln_1.bias")) { rc = store_f32(h, &l.ln1_b, data, numel, d, full, st); l.have |= LB_LN1_B; }
+  else if (!strcmp(sub, "ln_2.weight")) { rc = store_f32(h, &l.ln2_g, data, numel, d, full, st); l.have |= LB_LN2_G; }
+  else if (!strcmp(sub, "ln_2.bias")) { rc = store_f32(h, &l.ln2_b, data, numel, d, full, st); l.have |= LB_LN2_B; }
+  else return 1;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------- tower passes
+int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_splice_layer, cudaStream_t st) {
+  const int M = t.S * t.L, d = t.d;
+  for (int i = 0; i < t.layers; ++i) {
+    const Layer& w = t.lw[i];
+    if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
+      CK(h, splice_fwd(t.x_in[i], prompts + static_cast<size_t>(i) * t.n_ctx * d, t.S, t.L, t.row0, t.n_ctx, d, st));
+    // x + attn(ln_1(x))   (clip/model.py:299)
+    CK(h, layernorm_fwd(t.x_in[i], w.ln1_g, w.ln1_b, t.a_buf, true, M, d, kLnEps, st));
+    GemmEpilogue e1;
+    e1.mode = EPI_BF16; e1.out0 = t.qkv[i]; e1.bias = w.b_in; e1.ldc = 3 * d;
+    CK(h, gemm_bf16_tn(t.a_buf, d, w.w_in, d, e1, M, 3 * d, d, st));
+    CK(h, attention_fwd(t.qkv[i], t.o[i], t.lse[i], t.S, t.L, t.H, d, t.causal, st));
+    GemmEpilogue e2;
+    e2.mode = EPI_RESID_F32; e2.out0 = t.x_mid[i]; e2.bias = w.b_out; e2.resid = t.x_in[i]; e2.ldc = d;
+    CK(h, gemm_bf16_tn(t.o[i], d, w.w_out, d, e2, M, d, d, st));
+    // x + c_proj(QuickGELU(c_fc(ln_2(x))))   (clip/model.py:300)
+    CK(h, layernorm_fwd(t.x_mid[i], w.ln2_g, w.ln2_b, t.a_buf, true, M, d, kLnEps, st));
+    GemmEpilogue e3;
+    e3.mode = EPI_GELU; e3.out0 = t.h[i]; e3.out1 = t.g_buf; e3.bias = w.b_fc; e3.ldc = 4 * d;
+    CK(h, gemm_bf16_tn(t.a_buf, d, w.w_fc, d, e3, M, 4 * d, d, st));
+    GemmEpilogue e4;
+    e4.mode = EPI_RESID_F32; e4.out0 = t.x_in[i + 1]; e4.bias = w.b_pr; e4.resid = t.x_mid[i]; e4.ldc = d;
+    CK(h, gemm_bf16_tn(t.g_buf, 4 * d, w.w_pr, 4 * d, e4, M, d, 4 * d, st));
+  }
+  t.fwd_done = true;
+  return 0;
+}
+
+// Precondition: t.dx / t.dx_bf16 hold the gradient w.r.t. the tower output x_in[layers].
+int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice_layer, cudaStream_t st) {
+  const int M = t.S * t.L, d = t.d;
+  for (int i = t.layers - 1; i >= 0; --i) {
+    const Layer& w = t.lw[i];
+    // MLP branch: dg = dx W_pr ; dh = dg * GELU'(h) ; dm = dh W_fc ; dx += LN2_bwd(dm)
+    GemmEpilogue e1;
+    e1.mode = EPI_GELU_BWD; e1.out0 = t.dh_buf; e1.aux = t.h[i]; e1.ldc = 4 * d;
+    CK(h, gemm_bf16_tn(t.dx_bf16, d, w.w_pr_t, d, e1, M, 4 * d, d, st));
+    GemmEpilogue e2;
+    e2.mode = EPI_F32; e2.out0 = t.tmp_f32; e2.ldc = d;
+    CK(h, gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st));
+    CK(h, layernorm_bwd(t.tmp_f32, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    // attention branch: dO = dx W_out ; (dQ,dK,dV) ; da = dQKV W_in ; dx += LN1_bwd(da)
+    GemmEpilogue e3;
+    e3.mode = EPI_BF16; e3.out0 = t.do_buf; e3.ldc = d;
+    CK(h, gemm_bf16_tn(t.dx_bf16, d, w.w_out_t, d, e3, M, d, d, st));
+    CK(h, attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st));
+    GemmEpilogue e4;
+    e4.mode = EPI_F32; e4.out0 = t.tmp_f32; e4.ldc = d;
+    CK(h, gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st));
+    CK(h, layernorm_bwd(t.tmp_f32, t.x_in[i], w.ln1_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    // splice backward: the inserted prompt rows collect the batch-summed gradient; the rows
+    // they overwrote get none (clip/model.py:281-297)
+    if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
+      CK(h, splice_bwd(t.dx, t.dx_bf16, d_prompts + static_cast<size_t>(i) * t.n_ctx * d, t.S, t.L, t.row0, t.n_ctx, d,
+                       i > 0, st));
+  }
+  return 0;
+}
+
+bool tower_complete(const Tower& t) {
+  for (const Layer& l : t.lw)
+    if (l.have != LB_ALL) return false;
+  return true;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int mudpt_abi_version(void) { return MUDPT_ABI_VERSION; }
+const char* mudpt_global_last_error(void) { return g_err.c_str(); }
+const char* mudpt_last_error(mudpt_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int mudpt_create(const mudpt_config* cfg, mudpt_handle** out) {
+  if (!cfg || !out) return fail(nullptr, "mudpt_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, "mudpt_create: no CUDA device (there is no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "mudpt_create: bad device ordinal %d", cfg->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(nullptr, "mudpt_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  if (cfg->vision_width % 64 || cfg->transformer_width % 64 || cfg->transformer_width != cfg->transformer_heads * 64)
+    return fail(nullptr, "mudpt_create: tower widths must be heads * 64");
+  if (cfg->image_resolution % cfg->vision_patch_size) return fail(nullptr, "mudpt_create: resolution %% patch != 0");
+  if (cfg->prompt_depth < 1 || cfg->n_ctx < 0) return fail(nullptr, "mudpt_create: PROMPT_DEPTH should be > 0");
+  if (cfg->embed_dim != cfg->transformer_width)
+    return fail(nullptr, "mudpt_create: embed_dim must equal transformer_width (clip/model.py:519, trainers/mudpt.py:175)");
+  cudaSetDevice(cfg->device);
+  mudpt_handle* h = new mudpt_handle();
+  h->cfg = *cfg;
+  const int np = (cfg->image_resolution / cfg->vision_patch_size) * (cfg->image_resolution / cfg->vision_patch_size);
+  Tower& v = h->vis;
+  v.d = cfg->vision_width; v.H = cfg->vision_width / 64; v.layers = cfg->vision_layers; v.n_ctx = cfg->n_ctx;
+  v.L = np + 1 + cfg->n_ctx; v.row0 = np + 1; v.depth = cfg->prompt_depth; v.causal = false;
+  v.lw.resize(v.layers);
+  Tower& t = h->txt;
+  t.d = cfg->transformer_width; t.H = cfg->transformer_heads; t.layers = cfg->transformer_layers; t.n_ctx = cfg->n_ctx;
+  t.L = cfg->context_length; t.row0 = 1; t.depth = cfg->prompt_depth; t.causal = true;
+  t.lw.resize(t.layers);
+  h->Kp = (3 * cfg->vision_patch_size * cfg->vision_patch_size + 7) & ~7;
+  h->launches_at_create = g_launch_counter.load();
+  *out = h;
+  return 0;
+}
+
+void mudpt_destroy(mudpt_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (void* p : h->allocs) cudaFree(p);
+  gemm_clear_tensor_map_cache();
+  delete h;
+}
+
+int mudpt_set_weight(mudpt_handle* h, const char* name, const float* data, int64_t numel, void* stream) {
+  if (!h || !name || !data) return fail(h, "mudpt_set_weight: null argument");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mudpt_config& c = h->cfg;
+  const int dv = c.vision_width, dt = c.transformer_width, e = c.embed_dim;
+  const int np = (c.image_resolution / c.vision_patch_size) * (c.image_resolution / c.vision_patch_size);
+  int layer = -1, off = 0;
+  if (sscanf(name, "visual.transformer.resblocks.%d.%n", &layer, &off) == 1 && off > 0)
+    return set_block_weight(h, h->vis, layer, name + off, data, numel, name, st);
+  if (sscanf(name, "transformer.resblocks.%d.%n", &layer, &off) == 1 && off > 0)
+    return set_block_weight(h, h->txt, layer, name + off, data, numel, name, st);
+  int rc = 1;
+  if (!strcmp(name, "visual.conv1.weight")) {
+    const int k = 3 * c.vision_patch_size * c.vision_patch_size;
+    if (numel != static_cast<int64_t>(dv) * k) return fail(h, "weight %s: bad size", name);
+    if (!h->w_conv) CUDA_OK(h, dev_alloc(h, &h->w_conv, static_cast<size_t>(dv) * h->Kp));
+    CUDA_OK(h, cudaMemsetAsync(h->w_conv, 0, static_cast<size_t>(dv) * h->Kp * sizeof(bf16), st));
+    if (h->Kp == k) {
+      CK(h, cast_to_bf16(data, h->w_conv, static_cast<size_t>(numel), st));
+    } else {  // padded rows (ViT-L/14: 588 -> 592)
+      for (int r = 0; r < dv; ++r) CK(h, cast_to_bf16(data + static_cast<size_t>(r) * k, h->w_conv + static_cast<size_t>(r) * h->Kp, k, st));
+    }
+    h->stem_have |= SB_CONV; rc = 0;
+  } else if (!strcmp(name, "visual.class_embedding")) { rc = store_f32(h, &h->cls, data, numel, dv, name, st); h->stem_have |= SB_CLS; }
+  else if (!strcmp(name, "visual.positional_embedding")) { rc = store_f32(h, &h->pos_v, data, numel, static_cast<int64_t>(np + 1) * dv, name, st); h->stem_have |= SB_POS_V; }
+  else if (!strcmp(name, "visual.ln_pre.weight")) { rc = store_f32(h, &h->ln_pre_g, data, numel, dv, name, st); h->stem_have |= SB_LNPRE_G; }
+  else if (!strcmp(name, "visual.ln_pre.bias")) { rc = store_f32(h, &h->ln_pre_b, data, numel, dv, name, st); h->stem_have |= SB_LNPRE_B; }
+  else if (!strcmp(name, "visual.ln_post.weight")) { rc = store_f32(h, &h->ln_post_g, data, numel, dv, name, st); h->stem_have |= SB_LNPOST_G; }
+  else if (!strcmp(name, "visual.ln_post.bias")) { rc = store_f32(h, &h->ln_post_b, data, numel, dv, name, st); h->stem_have |= SB_LNPOST_B; }
+  else if (!strcmp(name, "visual.proj")) { rc = store_f32(h, &h->proj_v, data, numel, static_cast<int64_t>(dv) * e, name, st); h->stem_have |= SB_PROJ_V; }
+  else if (!strcmp(name, "positional_embedding")) { rc = store_f32(h, &h->pos_t, data, numel, static_cast<int64_t>(c.context_length) * dt, name, st); h->stem_have |= SB_POS_T; }
+  else if (!strcmp(name, "ln_final.weight")) { rc = store_f32(h, &h->ln_final_g, data, numel, dt, name, st); h->stem_have |= SB_LNF_G; }
+  else if (!strcmp(name, "ln_final.bias")) { rc = store_f32(h, &h->ln_final_b, data, numel, dt, name, st); h->stem_have |= SB_LNF_B; }
+  else if (!strcmp(name, "text_projection")) { rc = store_f32(h, &h->proj_t, data, numel, static_cast<int64_t>(dt) * e, name, st); h->stem_have |= SB_PROJ_T; }
+  else if (!strcmp(name, "logit_scale")) {
+    if (numel != 1) return fail(h, "weight logit_scale: expected 1 element");
+    float v = 0.f;
+    CUDA_OK(h, cudaMemcpyAsync(&v, data, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(h, cudaStreamSynchronize(st));
+    h->logit_scale_exp = expf(v);  // logit_scale.exp(), trainers/mudpt.py:181 (frozen)
+    h->stem_have |= SB_SCALE; rc = 0;
+  }
+  return rc;
+}
+
+int mudpt_weights_complete(mudpt_handle* h) {
+  if (!h) return fail(h, "null handle");
+  if (h->stem_have != SB_ALL) return fail(h, "stem/head weights missing (mask 0x%x of 0x%x)", h->stem_have, SB_ALL);
+  if (!tower_complete(h->vis)) return fail(h, "vision tower weights incomplete");
+  if (!tower_complete(h->txt)) return fail(h, "text tower weights incomplete");
+  return 0;
+}
+
+int mudpt_vision_forward(mudpt_handle* h, const float* images, int32_t B, const float* prompts, float* f_img, void* stream) {
+  if (!h || !images || !f_img || (!prompts && h->cfg.n_ctx > 0)) return fail(h, "mudpt_vision_forward: null argument");
+  if (B <= 0) return fail(h, "mudpt_vision_forward: empty batch");
+  if (mudpt_weights_complete(h)) return -1;
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mudpt_config& c = h->cfg;
+  Tower& t = h->vis;
+  const int np = t.row0 - 1;
+  if (ensure_tower(h, t, B, t.row0 + t.n_ctx)) return -1;
+  const size_t need = static_cast<size_t>(B) * np * h->Kp;
+  if (need > h->patches_cap) {
+    CUDA_OK(h, dev_alloc(h, &h->patches, need));
+    CUDA_OK(h, cudaMemsetAsync(h->patches, 0, need * sizeof(bf16), st));
+    h->patches_cap = need;
+  }
+  // conv1 as a GEMM over extracted patches, scattered to token rows 1..np with +pos (clip/model.py:527-531)
+  CK(h, im2col_bf16(images, h->patches, B, c.image_resolution, c.vision_patch_size, h->Kp, st));
+  GemmEpilogue ep;
+  ep.mode = EPI_PATCH; ep.out0 = t.x_in[0]; ep.resid = h->pos_v; ep.ldc = t.d; ep.patch_np = np; ep.patch_L = t.L;
+  CK(h, gemm_bf16_tn(h->patches, h->Kp, h->w_conv, h->Kp, ep, B * np, t.d, h->Kp, st));
+  CK(h, write_cls_rows(t.x_in[0], h->cls, h->pos_v, B, t.L, t.d, st));
+  // ln_pre in place (:541); the prompt rows are overwritten by the layer-0 splice with
+  // prompts[0] = ln_pre(visual_ctx + shared_ctx), which is identical for every image
+  CK(h, layernorm_fwd(t.x_in[0], h->ln_pre_g, h->ln_pre_b, t.x_in[0], false, B * t.L, t.d, kLnEps, st));
+  if (tower_forward(h, t, prompts, 0, st)) return -1;
+  CK(h, feature_head_fwd(t.x_in[t.layers], nullptr, h->ln_post_g, h->ln_post_b, h->proj_v, f_img, B, t.L, t.d, c.embed_dim, kLnEps, st));
+  return 0;
+}
+
+int mudpt_vision_backward(mudpt_handle* h, const float* d_f_img, float* d_prompts, void* stream) {
+  if (!h || !d_f_img || !d_prompts) return fail(h, "mudpt_vision_backward: null argument");
+  Tower& t = h->vis;
+  if (!t.fwd_done) return fail(h, "mudpt_vision_backward: no forward pass to differentiate");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(t.S) * t.L * t.d;
+  CUDA_OK(h, cudaMemsetAsync(t.dx, 0, n * sizeof(float), st));
+  CUDA_OK(h, cudaMemsetAsync(t.dx_bf16, 0, n * sizeof(bf16), st));
+  CK(h, feature_head_bwd(d_f_img, t.x_in[t.layers], nullptr, h->ln_post_g, h->proj_v, t.dx, t.dx_bf16, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  return tower_backward(h, t, d_prompts, 0, st);
+}
+
+int mudpt_text_set_classes(mudpt_handle* h, const float* embeddings, int32_t C, int32_t src_len, int32_t seq_len,
+                           const int32_t* eot_host, void* stream) {
+  if (!h || !embeddings || !eot_host) return fail(h, "mudpt_text_set_classes: null argument");
+  const mudpt_config& c = h->cfg;
+  if (C <= 0 || seq_len <= 0 || seq_len > src_len || src_len > c.context_length)
+    return fail(h, "mudpt_text_set_classes: bad lengths (C=%d src_len=%d seq_len=%d)", C, src_len, seq_len);
+  if (seq_len < 1 + c.n_ctx) return fail(h, "mudpt_text_set_classes: seq_len shorter than SOT + n_ctx");
+  for (int i = 0; i < C; ++i)
+    if (eot_host[i] < 0 || eot_host[i] >= seq_len) return fail(h, "mudpt_text_set_classes: eot[%d]=%d outside seq_len %d", i, eot_host[i], seq_len);
+  if (!(h->stem_have & SB_POS_T)) return fail(h, "mudpt_text_set_classes: positional_embedding not set");
+  cudaSetDevice(c.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Tower& t = h->txt;
+  if (ensure_tower(h, t, C, seq_len)) return -1;
+  if (static_cast<size_t>(C) > h->eot_cap) {
+    CUDA_OK(h, dev_alloc(h, &h->eot, static_cast<size_t>(C)));
+    h->eot_cap = C;
+  }
+  CUDA_OK(h, cudaMemcpyAsync(h->eot, eot_host, C * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_OK(h, cudaStreamSynchronize(st));  // eot_host may be freed by the caller after return
+  CK(h, add_positional(t.x_in[0], embeddings, h->pos_t, C, seq_len, src_len, t.d, st));
+  t.fwd_done = false;
+  return 0;
+}
+
+int mudpt_text_forward(mudpt_handle* h, const float* prompts, int32_t splice_layer0, float* f_txt, void* stream) {
+  if (!h || !f_txt || (!prompts && h->cfg.n_ctx > 0)) return fail(h, "mudpt_text_forward: null argument");
+  if (mudpt_weights_complete(h)) return -1;
+  Tower& t = h->txt;
+  if (t.cap_rows == 0 || t.S <= 0) return fail(h, "mudpt_text_forward: call mudpt_text_set_classes first");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tower_forward(h, t, prompts, splice_layer0 ? 0 : 1, st)) return -1;
+  CK(h, feature_head_fwd(t.x_in[t.layers], h->eot, h->ln_final_g, h->ln_final_b, h->proj_t, f_txt, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  t.first_splice = splice_layer0 ? 0 : 1;  // the backward must mirror the forward's splice set
+  return 0;
+}
+
+int mudpt_text_backward(mudpt_handle* h, const float* d_f_txt, float* d_prompts, float* d_x0, void* stream) {
+  if (!h || !d_f_txt || !d_prompts) return fail(h, "mudpt_text_backward: null argument");
+  Tower& t = h->txt;
+  if (!t.fwd_done) return fail(h, "mudpt_text_backward: no forward pass to differentiate");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(t.S) * t.L * t.d;
+  CUDA_OK(h, cudaMemsetAsync(t.dx, 0, n * sizeof(float), st));
+  CUDA_OK(h, cudaMemsetAsync(t.dx_bf16, 0, n * sizeof(bf16), st));
+  CK(h, feature_head_bwd(d_f_txt, t.x_in[t.layers], h->eot, h->ln_final_g, h->proj_t, t.dx, t.dx_bf16, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  if (tower_backward(h, t, d_prompts, t.first_splice, st)) return -1;
+  if (d_x0) CUDA_OK(h, cudaMemcpyAsync(d_x0, t.dx, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int mudpt_logits_head(mudpt_handle* h, const float* f_img, const float* f_txt, const int64_t* labels, int32_t B,
+                      int32_t C, float inv_global_batch, float* logits, float* loss, float* d_f_img, float* d_f_txt,
+                      void* stream) {
+  if (!h || !f_img || !f_txt || !logits) return fail(h, "mudpt_logits_head: null argument");
+  if (labels && !loss) return fail(h, "mudpt_logits_head: loss output required with labels");
+  if (!(h->stem_have & SB_SCALE)) return fail(h, "mudpt_logits_head: logit_scale not set");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t need = logits_head_workspace_floats(B, C, h->cfg.embed_dim);
+  if (need > h->head_ws_cap) {
+    CUDA_OK(h, dev_alloc(h, &h->head_ws, need));
+    h->head_ws_cap = need;
+  }
+  CK(h, logits_head(f_img, f_txt, reinterpret_cast<const long long*>(labels), h->logit_scale_exp, B, C, h->cfg.embed_dim,
+                    inv_global_batch, h->head_ws, logits, loss, d_f_img, d_f_txt, st));
+  return 0;
+}
+
+int mudpt_logits_backward(mudpt_handle* h, const float* f_img, const float* f_txt, const float* dlogits, int32_t B,
+                          int32_t C, float* d_f_img, float* d_f_txt, void* stream) {
+  if (!h || !f_img || !f_txt || !dlogits || !d_f_img || !d_f_txt) return fail(h, "mudpt_logits_backward: null argument");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t need = logits_head_workspace_floats(B, C, h->cfg.embed_dim);
+  if (need > h->head_ws_cap) {
+    CUDA_OK(h, dev_alloc(h, &h->head_ws, need));
+    h->head_ws_cap = need;
+  }
+  CK(h, logits_head_bwd(f_img, f_txt, dlogits, h->logit_scale_exp, B, C, h->cfg.embed_dim, h->head_ws, d_f_img, d_f_txt, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- unit pieces
+#define CKG(expr)                                       \
+  do {                                                  \
+    const char* _e = (expr);                            \
+    if (_e) return fail(nullptr, "%s", _e);             \
+  } while (0)
+
+int mudpt_layernorm_forward(const float* x, const float* gamma, const float* beta, void* out, int32_t out_bf16,
+                            int32_t rows, int32_t width, void* stream) {
+  CKG(layernorm_fwd(x, gamma, beta, out, out_bf16 != 0, rows, width, kLnEps, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_layernorm_backward(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
+                             uint16_t* dx_bf16, int32_t rows, int32_t width, void* stream) {
+  CKG(layernorm_bwd(dy, x, gamma, resid, dx, reinterpret_cast<bf16*>(dx_bf16), rows, width, kLnEps, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_splice_forward(float* x, const float* prompt, int32_t S, int32_t L, int32_t row0, int32_t n, int32_t width, void* stream) {
+  CKG(splice_fwd(x, prompt, S, L, row0, n, width, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_splice_backward(float* dx, uint16_t* dx_bf16, float* d_prompt, int32_t S, int32_t L, int32_t row0, int32_t n,
+                          int32_t width, int32_t zero_rows, void* stream) {
+  CKG(splice_bwd(dx, reinterpret_cast<bf16*>(dx_bf16), d_prompt, S, L, row0, n, width, zero_rows != 0, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_attention_forward(const uint16_t* qkv, uint16_t* o, float* lse2, int32_t S, int32_t L, int32_t H, int32_t causal, void* stream) {
+  CKG(attention_fwd(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(o), lse2, S, L, H, H * 64, causal != 0, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_attention_backward(const uint16_t* qkv, const uint16_t* o, const uint16_t* d_o, const float* lse2, float* dsum,
+                             uint16_t* dqkv, int32_t S, int32_t L, int32_t H, int32_t causal, void* stream) {
+  CKG(attention_bwd(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o),
+                    lse2, dsum, reinterpret_cast<bf16*>(dqkv), S, L, H, H * 64, causal != 0, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, int32_t K, int32_t mode, void* out0,
+                    void* out1, const float* bias, const float* resid, const void* aux, int32_t ldc, int32_t patch_np,
+                    int32_t patch_L, void* stream) {
+  GemmEpilogue ep;
+  ep.mode = mode; ep.out0 = out0; ep.out1 = out1; ep.bias = bias; ep.resid = resid; ep.aux = aux; ep.ldc = ldc;
+  ep.patch_np = patch_np > 0 ? patch_np : 1; ep.patch_L = patch_L > 0 ? patch_L : 1;
+  CKG(gemm_bf16_tn(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, ep, M, N, K, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream) {
+  CKG(im2col_bf16(images, reinterpret_cast<bf16*>(patches), B, R, patch, ld, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream) {
+  CKG(cast_to_bf16(in, reinterpret_cast<bf16*>(out), static_cast<size_t>(numel), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t layer, void** ptr, int64_t* numel) {
+  if (!h || !name || !ptr || !numel) return fail(h, "mudpt_debug_buffer: null argument");
+  Tower& t = tower == MUDPT_TOWER_VISION ? h->vis : h->txt;
+  if (t.cap_rows == 0) return fail(h, "mudpt_debug_buffer: tower has no workspace yet");
+  const int64_t rows = static_cast<int64_t>(t.S) * t.L;
+  if (!strcmp(name, "dx")) { *ptr = t.dx; *numel = rows * t.d; return 0; }
+  if (!strcmp(name, "x_in")) {
+    if (layer < 0 || layer > t.layers) return fail(h, "mudpt_debug_buffer: layer out of range");
+    *ptr = t.x_in[layer]; *numel = rows * t.d; return 0;
+  }
+  if (layer < 0 || layer >= t.layers) return fail(h, "mudpt_debug_buffer: layer out of range");
+  if (!strcmp(name, "x_mid")) { *ptr = t.x_mid[layer]; *numel = rows * t.d; return 0; }
+  if (!strcmp(name, "qkv")) { *ptr = t.qkv[layer]; *numel = rows * 3 * t.d; return 0; }
+  if (!strcmp(name, "o")) { *ptr = t.o[layer]; *numel = rows * t.d; return 0; }
+  if (!strcmp(name, "h")) { *ptr = t.h[layer]; *numel = rows * 4 * t.d; return 0; }
+  if (!strcmp(name, "lse")) { *ptr = t.lse[layer]; *numel = rows * t.H; return 0; }
+  return fail(h, "mudpt_debug_buffer: unknown buffer %s", name);
+}
+
+int64_t mudpt_launch_count(mudpt_handle* h) { return h ? g_launch_counter.load() - h->launches_at_create : 0; }
+
+#ifdef MUDPT_BRINGUP
+int mudpt_bringup_simt_gemm(int on) { gemm_set_bringup_simt(on != 0); return 0; }
+#endif
+
+}  // extern "C"

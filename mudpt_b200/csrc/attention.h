@@ -1,0 +1,14 @@
+// Internal interface of the attention kernels (see attention.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace mudpt {
+// qkv [S*L, 3d] bf16 (row = sequence*L + token; head h owns columns [64h, 64h+64) of each third),
+// o [S*L, d] bf16, lse2 [S, H, L] fp32 = log2-domain log-sum-exp of the scaled scores.
+const char* attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* o, float* lse2, int S, int L, int H, int d,
+                          bool causal, cudaStream_t stream);
+// dsum [S, H, L] fp32 scratch (rowsum(dO*O)), dqkv [S*L, 3d] bf16 out.
+const char* attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
+                          float* dsum, __nv_bfloat16* dqkv, int S, int L, int H, int d, bool causal, cudaStream_t stream);
+}  // namespace mudpt

@@ -1,0 +1,423 @@
+// tcgen05 / TMEM / TMA GEMM for the frozen-weight linear layers of the MuDPT towers.
+//
+//   C[M,N] = A[M,K] (bf16, row-major) x B[N,K]^T (bf16, row-major, i.e. nn.Linear's [out,in])
+//
+// Both operands are K-major, so forward GEMMs use the weight as stored and the dgrad GEMMs
+// use a pre-transposed copy made once at weight-load time (weights are frozen,
+// trainers/mudpt.py:205-212, so there is no wgrad and the transpose is free).
+//
+// Replaces the `addmm`/`mm` call sites of clip/model.py:273 (in-proj), :299 (out-proj),
+// :300 (c_fc, c_proj), :527 (conv1 as a GEMM) and their autograd dgrads.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles (128B swizzle) into a smem ring
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (128 x BN x 16), fp32
+//                                accumulators in TMEM, double-buffered (2 x BN columns)
+//   warps 2..5  epilogue       : tcgen05.ld the accumulator, apply the fused epilogue
+//                                (bias / QuickGELU / residual / GELU' / patch-embed scatter),
+//                                store to global
+// The epilogue of tile i overlaps the MMAs of tile i+1 through the second TMEM buffer.
+#include "gemm.h"
+
+#include <cstdio>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "launch_count.h"
+
+namespace mudpt {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+// ---------------------------------------------------------------------------------------
+// Fused epilogue on 8 consecutive columns of one row.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void store8_bf16(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16(v[0], v[1]);
+  u.y = pack_bf16(v[2], v[3]);
+  u.z = pack_bf16(v[4], v[5]);
+  u.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8_bf16(const bf16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = unpack_bf16(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16(u.w); v[6] = f.x; v[7] = f.y;
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue8(const GemmEpilogue& ep, int row, int col, float (&v)[8]) {
+  // row < M and col + 8 <= N are guaranteed by the caller (N % 8 == 0).
+  if (ep.bias != nullptr) {
+    float b[8];
+    load8_f32(ep.bias + col, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += b[i];
+  }
+  const size_t off = static_cast<size_t>(row) * ep.ldc + col;
+  if constexpr (MODE == EPI_BF16) {
+    store8_bf16(reinterpret_cast<bf16*>(ep.out0) + off, v);
+  } else if constexpr (MODE == EPI_F32) {
+    store8_f32(reinterpret_cast<float*>(ep.out0) + off, v);
+  } else if constexpr (MODE == EPI_RESID_F32) {
+    float r[8];
+    load8_f32(ep.resid + off, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+    store8_f32(reinterpret_cast<float*>(ep.out0) + off, v);
+  } else if constexpr (MODE == EPI_GELU) {
+    // out0 = pre-activation h (kept for the backward GELU'), out1 = QuickGELU(h)
+    if (ep.out0 != nullptr) store8_bf16(reinterpret_cast<bf16*>(ep.out0) + off, v);
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = quick_gelu(v[i]);
+    store8_bf16(reinterpret_cast<bf16*>(ep.out1) + off, g);
+  } else if constexpr (MODE == EPI_GELU_BWD) {
+    // out0 = acc * QuickGELU'(h), h = aux (bf16 pre-activation saved by the forward)
+    float h[8];
+    load8_bf16(reinterpret_cast<const bf16*>(ep.aux) + off, h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= quick_gelu_grad(h[i]);
+    store8_bf16(reinterpret_cast<bf16*>(ep.out0) + off, v);
+  } else if constexpr (MODE == EPI_PATCH) {
+    // patch-embedding scatter (clip/model.py:527-531): GEMM row r = image*np + p goes to token
+    // row image*L + 1 + p of the residual stream, plus positional_embedding[1 + p].
+    const int img = row / ep.patch_np;
+    const int p = row - img * ep.patch_np;
+    float pe[8];
+    load8_f32(ep.resid + static_cast<size_t>(1 + p) * ep.ldc + col, pe);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += pe[i];
+    const size_t o = (static_cast<size_t>(img) * ep.patch_L + 1 + p) * ep.ldc + col;
+    store8_f32(reinterpret_cast<float*>(ep.out0) + o, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------
+template <int BN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                       const GemmEpilogue ep, const int M, const int N, const int K) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024 B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B per K=16 step inside the 128 B swizzle row (start-address field is >>4)
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                      static_cast<uint32_t>((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (col0 + j * 8 < N) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+              epilogue8<MODE>(ep, row, col0 + j * 8, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+#ifdef MUDPT_BRINGUP
+// Bring-up diagnostic only (libmudpt_b200_bringup.so, never the shipped library): a plain
+// CUDA-core GEMM with the same epilogues, used to validate the rest of the pipeline
+// independently of the tcgen05 path.
+template <int MODE>
+__global__ void gemm_tn_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, const GemmEpilogue ep,
+                                    int M, int N, int K, int lda, int ldb) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const int row = blockIdx.y;
+  if (col >= N || row >= M) return;
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bf16* a = A + static_cast<size_t>(row) * lda;
+  for (int k = 0; k < K; ++k) {
+    const float av = __bfloat162float(a[k]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += av * __bfloat162float(B[static_cast<size_t>(col + i) * ldb + k]);
+  }
+  epilogue8<MODE>(ep, row, col, v);
+}
+static bool g_simt = false;
+void gemm_set_bringup_simt(bool on) { g_simt = on; }
+#endif
+
+// ---------------------------------------------------------------------------------------
+// Host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    // resolved through the runtime so the library has no link-time dependency on libcuda
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int rows, cols, ld, box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ static_cast<size_t>(k.rows);
+    h = h * 1000003u ^ static_cast<size_t>(k.cols);
+    h = h * 1000003u ^ static_cast<size_t>(k.ld);
+    h = h * 1000003u ^ static_cast<size_t>(k.box_rows);
+    return h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
+// 2D bf16 row-major [rows, cols] (leading dimension ld elements), box = [box_rows, 64], 128B swizzle.
+static const char* get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  MapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return nullptr; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return "cuTensorMapEncodeTiled not available (no CUDA driver?)";
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) return "TMA operand must be 16 B aligned with ld % 8 == 0";
+  CUtensorMap m;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return nullptr;
+}
+
+void gemm_clear_tensor_map_cache() {
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  g_maps.clear();
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int MODE>
+static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                              cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  auto kern = gemm_tn_tcgen05_kernel<BN, MODE>;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return "cudaFuncSetAttribute(max dynamic smem) failed";
+    attr_done = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, ep, M, N, K);
+  count_launch();
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "gemm kernel launch failed";
+}
+
+template <int MODE>
+static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, const GemmEpilogue& ep, int M, int N,
+                               int K, cudaStream_t stream) {
+#ifdef MUDPT_BRINGUP
+  if (g_simt) {
+    dim3 grid((N / 8 + 63) / 64, M);
+    gemm_tn_simt_kernel<MODE><<<grid, 64, 0, stream>>>(A, B, ep, M, N, K, lda, ldb);
+    count_launch();
+    return cudaPeekAtLastError() == cudaSuccess ? nullptr : "simt gemm launch failed";
+  }
+#endif
+  // Tile-shape choice: 128x256 tiles halve the A re-reads; use them when they still fill the
+  // machine (>= one full wave of 148 CTAs), otherwise 128x128 (thin N = d GEMMs).
+  const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
+  const bool wide = (N % 256 == 0 || N > 512) && tiles256 >= num_sms();
+  CUtensorMap ta, tb;
+  const char* e = get_tensor_map(A, M, K, lda, BM, &ta);
+  if (e) return e;
+  e = get_tensor_map(B, N, K, ldb, wide ? 256 : 128, &tb);
+  if (e) return e;
+  return wide ? launch_one<256, MODE>(ta, tb, ep, M, N, K, stream) : launch_one<128, MODE>(ta, tb, ep, M, N, K, stream);
+}
+
+const char* gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, const GemmEpilogue& ep, int M, int N, int K,
+                         cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return nullptr;
+  if (N % 8 != 0 || K % 8 != 0) return "gemm: N and K must be multiples of 8";
+  if (ep.ldc % 8 != 0) return "gemm: ldc must be a multiple of 8";
+  switch (ep.mode) {
+    case EPI_BF16: return launch_mode<EPI_BF16>(A, lda, B, ldb, ep, M, N, K, stream);
+    case EPI_F32: return launch_mode<EPI_F32>(A, lda, B, ldb, ep, M, N, K, stream);
+    case EPI_RESID_F32: return launch_mode<EPI_RESID_F32>(A, lda, B, ldb, ep, M, N, K, stream);
+    case EPI_GELU: return launch_mode<EPI_GELU>(A, lda, B, ldb, ep, M, N, K, stream);
+    case EPI_GELU_BWD: return launch_mode<EPI_GELU_BWD>(A, lda, B, ldb, ep, M, N, K, stream);
+    case EPI_PATCH: return launch_mode<EPI_PATCH>(A, lda, B, ldb, ep, M, N, K, stream);
+    default: return "gemm: unknown epilogue mode";
+  }
+}
+
+}  // namespace mudpt

@@ -1,0 +1,18 @@
+// Internal interface of the head kernels (see head.cu). All return nullptr on success.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace mudpt {
+const char* feature_head_fwd(const float* x, const int* rows, const float* gamma, const float* beta, const float* proj,
+                             float* f, int S, int L, int d, int e, float eps, cudaStream_t stream);
+const char* feature_head_bwd(const float* df, const float* x, const int* rows, const float* gamma, const float* proj,
+                             float* dx, __nv_bfloat16* dx_bf16, int S, int L, int d, int e, float eps, cudaStream_t stream);
+size_t logits_head_workspace_floats(int B, int C, int e);
+const char* logits_head(const float* f_img, const float* f_txt, const long long* labels, float scale, int B, int C, int e,
+                        float inv_global_batch, float* ws, float* logits, float* loss, float* d_f_img, float* d_f_txt,
+                        cudaStream_t stream);
+const char* logits_head_bwd(const float* f_img, const float* f_txt, const float* dlogits, float scale, int B, int C, int e,
+                            float* ws, float* d_f_img, float* d_f_txt, cudaStream_t stream);
+}  // namespace mudpt

@@ -1,0 +1,309 @@
+// HBM-bound row kernels of the MuDPT towers: LayerNorm forward / dgrad-only backward,
+// the deep-prompt splice (indexed row overwrite, bit-exact) and its backward (sum over
+// sequences + zeroing), patch extraction (im2col + bf16 cast) and weight re-layout.
+//
+//   LayerNorm ......... clip/model.py:164-170 (fp32 statistics, eps 1e-5, biased variance)
+//   splice ............ clip/model.py:281-297 (text rows 1..n, vision last n rows)
+//   patch extraction .. clip/model.py:527-529 (conv1 with stride == kernel == patch)
+#include "rowops.h"
+
+#include "common.cuh"
+#include "launch_count.h"
+
+namespace mudpt {
+
+static constexpr int LN_MAXV = 8;  // float4 per lane -> width <= 1024
+
+// ------------------------------------------------------------------ LayerNorm forward
+// One warp per row. OUT_BF16: normalized row as bf16 (GEMM A operand); else fp32 (may alias x).
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, void* __restrict__ out, int M, int d,
+                                                     float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<size_t>(row) * d;
+  float4 v[LN_MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      sq += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / d + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 b = *reinterpret_cast<const float4*>(beta + c);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (OUT_BF16) {
+        uint2 u;
+        u.x = pack_bf16(y.x, y.y);
+        u.y = pack_bf16(y.z, y.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + static_cast<size_t>(row) * d + c) = u;
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<size_t>(row) * d + c) = y;
+      }
+    }
+  }
+}
+
+const char* layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
+                          float eps, cudaStream_t stream) {
+  if (M <= 0) return nullptr;
+  if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
+  const int grid = (M + 7) / 8;
+  if (out_bf16) ln_fwd_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, out, M, d, eps);
+  else ln_fwd_kernel<false><<<grid, 256, 0, stream>>>(x, gamma, beta, out, M, d, eps);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "layernorm fwd launch failed";
+}
+
+// ------------------------------------------------------------------ LayerNorm backward (dgrad only)
+// dx = resid + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.
+// gamma/beta are frozen (trainers/mudpt.py:205-212): no dgamma/dbeta. Statistics are
+// recomputed from the saved fp32 input row. dx may alias resid. Also emits the bf16 copy of dx
+// that feeds the next dgrad GEMM.
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* resid, float* dx,
+                                                     bf16* __restrict__ dx_bf16, int M, int d, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const size_t off = static_cast<size_t>(row) * d;
+  float4 v[LN_MAXV], g[LN_MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      v[i] = *reinterpret_cast<const float4*>(x + off + c);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / d + eps);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float4 gy = *reinterpret_cast<const float4*>(dy + off + c);
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+      g[i].x = gy.x * gm.x; g[i].y = gy.y * gm.y; g[i].z = gy.z * gm.z; g[i].w = gy.w * gm.w;
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+    }
+  }
+  s1 = warp_sum(s1) / d;
+  s2 = warp_sum(s2) / d;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (resid != nullptr) r = *reinterpret_cast<const float4*>(resid + off + c);
+      float4 o;
+      o.x = r.x + rstd * (g[i].x - s1 - v[i].x * s2);
+      o.y = r.y + rstd * (g[i].y - s1 - v[i].y * s2);
+      o.z = r.z + rstd * (g[i].z - s1 - v[i].z * s2);
+      o.w = r.w + rstd * (g[i].w - s1 - v[i].w * s2);
+      *reinterpret_cast<float4*>(dx + off + c) = o;
+      if (dx_bf16 != nullptr) {
+        uint2 u;
+        u.x = pack_bf16(o.x, o.y);
+        u.y = pack_bf16(o.z, o.w);
+        *reinterpret_cast<uint2*>(dx_bf16 + off + c) = u;
+      }
+    }
+  }
+}
+
+const char* layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
+                          bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
+  if (M <= 0) return nullptr;
+  if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
+  ln_bwd_kernel<<<(M + 7) / 8, 256, 0, stream>>>(dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "layernorm bwd launch failed";
+}
+
+// ------------------------------------------------------------------ deep-prompt splice
+// x[s, row0 + r, :] = prompt[r, :] for every sequence s: the values are copied verbatim.
+__global__ void splice_fwd_kernel(float* __restrict__ x, const float* __restrict__ prompt, int L, int row0, int n, int d) {
+  const int s = blockIdx.x, r = blockIdx.y;
+  float4* dst = reinterpret_cast<float4*>(x + (static_cast<size_t>(s) * L + row0 + r) * d);
+  const float4* src = reinterpret_cast<const float4*>(prompt + static_cast<size_t>(r) * d);
+  for (int c = threadIdx.x; c < d / 4; c += blockDim.x) dst[c] = src[c];
+}
+
+const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, int n, int d, cudaStream_t stream) {
+  if (S <= 0 || n <= 0) return nullptr;
+  if (d % 4 != 0 || row0 < 0 || row0 + n > L) return "splice: bad geometry";
+  splice_fwd_kernel<<<dim3(S, n), 128, 0, stream>>>(x, prompt, L, row0, n, d);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "splice fwd launch failed";
+}
+
+// dprompt[r, :] = sum_s dx[s, row0 + r, :]; optionally the rows of dx (fp32 and bf16 copy) are
+// then zeroed (the overwritten activations receive no gradient).
+// Deterministic: fixed partition of s over the 8 warps, fixed-order smem reduction.
+__global__ void __launch_bounds__(256) splice_bwd_kernel(float* __restrict__ dx, bf16* __restrict__ dx_bf16,
+                                                         float* __restrict__ dprompt, int S, int L, int row0, int d,
+                                                         int zero_rows) {
+  __shared__ float4 part[8][32];
+  const int r = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < d) {
+    for (int s = warp; s < S; s += 8) {
+      const size_t off = (static_cast<size_t>(s) * L + row0 + r) * d + c;
+      const float4 v = *reinterpret_cast<const float4*>(dx + off);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      if (zero_rows) {
+        *reinterpret_cast<float4*>(dx + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dx_bf16 != nullptr) *reinterpret_cast<uint2*>(dx_bf16 + off) = make_uint2(0u, 0u);
+      }
+    }
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < d) {
+    float4 t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      t.x += part[w][lane].x; t.y += part[w][lane].y; t.z += part[w][lane].z; t.w += part[w][lane].w;
+    }
+    *reinterpret_cast<float4*>(dprompt + static_cast<size_t>(r) * d + c) = t;
+  }
+}
+
+const char* splice_bwd(float* dx, bf16* dx_bf16, float* dprompt, int S, int L, int row0, int n, int d, bool zero_rows,
+                       cudaStream_t stream) {
+  if (n <= 0) return nullptr;
+  if (d % 4 != 0 || row0 < 0 || row0 + n > L) return "splice: bad geometry";
+  splice_bwd_kernel<<<dim3(n, (d + 127) / 128), 256, 0, stream>>>(dx, dx_bf16, dprompt, S, L, row0, d, zero_rows ? 1 : 0);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "splice bwd launch failed";
+}
+
+// ------------------------------------------------------------------ patch extraction
+// patches[(b*gh + py)*gw + px, (c*p + iy)*p + ix] = image[b, c, py*p + iy, px*p + ix]  (bf16),
+// row stride ldo >= 3*p*p (padding columns, if any, are zeroed once at allocation).
+__global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int R, int p, int ldo, size_t total2) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total2) return;
+  const int gw = R / p;
+  const int kdim = 3 * p * p;
+  const size_t e = i * 2;  // 2 consecutive ix (p is even)
+  const int col = static_cast<int>(e % kdim);
+  const size_t row = e / kdim;
+  const int ix = col % p, iy = (col / p) % p, c = col / (p * p);
+  const int px = static_cast<int>(row % gw), py = static_cast<int>((row / gw) % gw);
+  const int b = static_cast<int>(row / (static_cast<size_t>(gw) * gw));
+  const float2 v = *reinterpret_cast<const float2*>(img + ((static_cast<size_t>(b) * 3 + c) * R + py * p + iy) * R + px * p + ix);
+  *reinterpret_cast<uint32_t*>(out + row * ldo + col) = pack_bf16(v.x, v.y);
+}
+
+const char* im2col_bf16(const float* img, bf16* out, int B, int R, int p, int ldo, cudaStream_t stream) {
+  if (B <= 0) return nullptr;
+  if (R % p != 0 || p % 2 != 0 || ldo < 3 * p * p || ldo % 2 != 0) return "im2col: bad geometry";
+  const size_t total2 = static_cast<size_t>(B) * 3 * R * R / 2;
+  im2col_kernel<<<static_cast<unsigned>((total2 + 255) / 256), 256, 0, stream>>>(img, out, R, p, ldo, total2);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "im2col launch failed";
+}
+
+// ------------------------------------------------------------------ small helpers
+// out[s, 0, :] = cls[:] + pos[0, :]  (class token row of every image)
+__global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int L, int d) {
+  float* dst = x + static_cast<size_t>(blockIdx.x) * L * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) dst[c] = cls[c] + pos[c];
+}
+const char* write_cls_rows(float* x, const float* cls, const float* pos, int S, int L, int d, cudaStream_t stream) {
+  if (S <= 0) return nullptr;
+  cls_rows_kernel<<<S, 256, 0, stream>>>(x, cls, pos, L, d);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "cls rows launch failed";
+}
+
+// x0[c, l, :] = emb[c, l, :] + pos[l, :] for l < L (L <= Lsrc): text-tower input, built once
+// per class set (trainers/mudpt.py:143); the ctx rows are overwritten by the splice each step.
+__global__ void add_pos_kernel(float* __restrict__ x0, const float* __restrict__ emb, const float* __restrict__ pos,
+                               int L, int Lsrc, int d) {
+  const int c = blockIdx.x, l = blockIdx.y;
+  const float* src = emb + (static_cast<size_t>(c) * Lsrc + l) * d;
+  float* dst = x0 + (static_cast<size_t>(c) * L + l) * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = src[i] + pos[static_cast<size_t>(l) * d + i];
+}
+const char* add_positional(float* x0, const float* emb, const float* pos, int S, int L, int Lsrc, int d, cudaStream_t stream) {
+  if (S <= 0) return nullptr;
+  add_pos_kernel<<<dim3(S, L), 128, 0, stream>>>(x0, emb, pos, L, Lsrc, d);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "add_pos launch failed";
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+const char* cast_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t stream) {
+  if (n == 0) return nullptr;
+  cast_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, out, n);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "cast launch failed";
+}
+
+// out[c, r] = bf16(in[r, c])  (in: [rows, cols] fp32) -- the K-major copy used by dgrad GEMMs
+__global__ void transpose_cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[static_cast<size_t>(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[static_cast<size_t>(c) * rows + r] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+const char* transpose_cast_bf16(const float* in, bf16* out, int rows, int cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return nullptr;
+  transpose_cast_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, stream>>>(in, out, rows, cols);
+  count_launch(1);
+  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "transpose launch failed";
+}
+
+}  // namespace mudpt

@@ -1,0 +1,111 @@
+"""Multi-GPU host logic: one process per GPU (torchrun), images data-parallel, class prompts
+sharded by class.  Replaces the reference's nn.DataParallel
+(trainers/mudpt.py:230-233), which replicates the whole module and recomputes the full text tower
+on every replica.
+
+Per step and rank: all-gather of the local text features [C/G, e] -> [C, e]; reduce-scatter (sum)
+of d text_features [C, e] -> [C/G, e]; all-reduce (sum) of the 1.2 M prompt gradients.  The
+functions work with any torch.distributed backend (NCCL on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def initialized() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def world_size() -> int:
+    return dist.get_world_size() if initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if initialized() else 0
+
+
+def shard_bounds(n: int, r: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of n rows: the first n % world ranks get one extra row."""
+    q, rem = divmod(n, world)
+    lo = r * q + min(r, rem)
+    return lo, lo + q + (1 if r < rem else 0)
+
+
+def _is_nccl() -> bool:
+    return initialized() and dist.get_backend() == "nccl"
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Concatenate the ranks' row shards (shard_bounds order) into [n_total, ...]."""
+    world = world_size()
+    if world == 1:
+        return local
+    if n_total % world == 0 and _is_nccl():
+        out = torch.empty((n_total,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+    q = -(-n_total // world)
+    pad = torch.zeros((q,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, r, world)
+        parts.append(bufs[r][:hi - lo])
+    return torch.cat(parts, dim=0)
+
+
+def reduce_scatter_rows(full: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Sum [n_total, ...] over ranks and return this rank's row shard."""
+    world = world_size()
+    if world == 1:
+        return full
+    lo, hi = shard_bounds(n_total, rank(), world)
+    if n_total % world == 0 and _is_nccl():
+        out = torch.empty((hi - lo,) + tuple(full.shape[1:]), device=full.device, dtype=full.dtype)
+        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM)
+        return out
+    buf = full.contiguous().clone()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf[lo:hi].contiguous()
+
+
+def all_reduce_sum(t: torch.Tensor) -> torch.Tensor:
+    if world_size() == 1:
+        return t
+    t = t.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def all_reduce_grads(params: List[torch.nn.Parameter]) -> None:
+    """Sum the .grad of the (small, replicated) trainable tensors across ranks in one flat bucket."""
+    if world_size() == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+class AllGatherRows(torch.autograd.Function):
+    """Differentiable all_gather_rows: backward = reduce_scatter_rows (used by CustomCLIP.forward)."""
+
+    @staticmethod
+    def forward(ctx, local, n_total):
+        ctx.n_total = n_total
+        return all_gather_rows(local, n_total)
+
+    @staticmethod
+    def backward(ctx, d_full):
+        return reduce_scatter_rows(d_full, ctx.n_total), None

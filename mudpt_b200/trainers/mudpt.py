@@ -1,0 +1,401 @@
+"""MuDPT method plugin on the native B200 path -- drop-in for the reference's trainers/mudpt.py.
+
+Same public classes, constructor signatures, parameter / buffer names and return shapes:
+
+  MuDPTPromptLearner(cfg, classnames, clip_model) ... trainers/mudpt.py:41-130
+  TextEncoder(clip_model) ........................... trainers/mudpt.py:133-156
+  CustomCLIP(cfg, classnames, clip_model) ........... trainers/mudpt.py:159-184
+  MuDPT (trainer: check_cfg / build_model / forward_backward / parse_batch_train / load_model)
+                                                      trainers/mudpt.py:187-302
+
+What changed underneath: both towers, the heads and (on the fused train path) the loss run in
+libmudpt_b200.so; the class prompts are never materialised as a [C, 77, d] tensor on the fused
+path (the reference's torch.cat at :106-113 is a pure copy); only the tiny [n_ctx, d] prompt
+algebra (the three trainable Linear layers, :127-128 and clip/model.py:534-539) stays in torch
+autograd, which is what delivers the gradients of the 10 trainable tensors.
+"""
+from __future__ import annotations
+
+import os
+import os.path as osp
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import clip
+from .. import dist as mdist
+from ..engine import LogitsFn, TextTowerDenseFn, TextTowerFn, VisionTowerFn
+
+try:  # the Dassl engine is not in the reference tree nor in this image
+    from dassl.engine import TRAINER_REGISTRY, TrainerX
+    from dassl.optim import build_optimizer, build_lr_scheduler
+    from dassl.utils import load_checkpoint, load_pretrained_weights
+    _HAVE_DASSL = True
+except Exception:  # pragma: no cover - exercised on boxes without dassl
+    _HAVE_DASSL = False
+
+    class _Registry:
+        def __init__(self):
+            self._m = {}
+
+        def register(self):
+            def deco(cls):
+                self._m[cls.__name__] = cls
+                return cls
+            return deco
+
+        def get(self, name):
+            return self._m[name]
+
+    TRAINER_REGISTRY = _Registry()
+
+    class TrainerX:
+        """Minimal stand-in for dassl.engine.TrainerX: just what `MuDPT` below touches."""
+
+        def __init__(self, cfg=None, classnames=None, device=None):
+            self.cfg = cfg
+            self.device = torch.device(device) if device is not None else (
+                torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu"))
+            self._models, self._optims, self._scheds = {}, {}, {}
+            self.batch_idx, self.num_batches = 0, 1
+            self._classnames = classnames
+            if cfg is not None:
+                self.check_cfg(cfg)
+                self.build_model()
+
+        def register_model(self, name, model, optim=None, sched=None):
+            self._models[name], self._optims[name], self._scheds[name] = model, optim, sched
+
+        def get_model_names(self):
+            return list(self._models)
+
+        def model_backward_and_update(self, loss):
+            for o in self._optims.values():
+                o.zero_grad()
+            if not torch.isfinite(loss).all():
+                raise FloatingPointError("Loss is infinite or NaN!")
+            loss.backward()
+            for o in self._optims.values():
+                o.step()
+
+        def update_lr(self):
+            for s in self._scheds.values():
+                if s is not None:
+                    s.step()
+
+    def build_optimizer(model, optim_cfg):
+        params = [p for p in model.parameters() if p.requires_grad]
+        return torch.optim.SGD(params, lr=getattr(optim_cfg, "LR", 0.0025), momentum=getattr(optim_cfg, "MOMENTUM", 0.9),
+                               weight_decay=getattr(optim_cfg, "WEIGHT_DECAY", 5e-4))
+
+    def build_lr_scheduler(optim, optim_cfg):
+        return torch.optim.lr_scheduler.CosineAnnealingLR(optim, float(getattr(optim_cfg, "MAX_EPOCH", 10)))
+
+    def load_checkpoint(path):
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+    def load_pretrained_weights(model, path):
+        model.load_state_dict(load_checkpoint(path)["state_dict"], strict=False)
+
+
+def load_clip_to_cpu(cfg):
+    """trainers/mudpt.py:20-38.  With a BACKBONE.PATH the checkpoint's state dict is used; without one
+    (no CLIP checkpoint exists on the build / GPU boxes) the model is random-initialised."""
+    path = getattr(cfg.MODEL.BACKBONE, "PATH", "")
+    if path:
+        print(f"Loading CLIP backbone: {cfg.MODEL.BACKBONE.NAME} from {path}")
+        try:
+            sd = torch.jit.load(path, map_location="cpu").state_dict()
+        except RuntimeError:
+            sd = torch.load(path, map_location="cpu")
+        return clip.build_model(sd, cfg=cfg)
+    from ..synthetic import ARCHS
+    print(f"No backbone path given: random-init {cfg.MODEL.BACKBONE.NAME}")
+    return clip.CLIP(*ARCHS[cfg.MODEL.BACKBONE.NAME].astuple(), cfg).float().eval()
+
+
+class MuDPTPromptLearner(nn.Module):
+    def __init__(self, cfg, classnames, clip_model, tokenizer=None):
+        super().__init__()
+        tokenize = tokenizer if tokenizer is not None else clip.tokenize
+        n_cls = len(classnames)
+        n_ctx = cfg.TRAINER.MUDPT.N_CTX
+        ctx_init = cfg.TRAINER.MUDPT.CTX_INIT
+        dtype = clip_model.dtype
+        ctx_dim = clip_model.ln_final.weight.shape[0]
+        clip_imsize = clip_model.visual.input_resolution
+        cfg_imsize = cfg.INPUT.SIZE[0]
+
+        assert cfg.TRAINER.MUDPT.DEEP_PROMPT_DEPTH > 0, "PROMPT_DEPTH should be > 0"
+        self.deep_prompts_depth = cfg.TRAINER.MUDPT.DEEP_PROMPT_DEPTH
+        assert cfg_imsize == clip_imsize, f"cfg_imsize ({cfg_imsize}) must equal to clip_imsize ({clip_imsize})"
+
+        if ctx_init:
+            ctx_init = ctx_init.replace("_", " ")
+            prompt = tokenize(ctx_init)
+            with torch.no_grad():
+                embedding = clip_model.token_embedding(prompt.to(clip_model.token_embedding.weight.device).long()).type(dtype)
+            ctx_vectors = embedding[0, 1: 1 + n_ctx, :].clone()
+            prompt_prefix = " ".join(ctx_init.split()[:n_ctx])
+        else:
+            ctx_vectors = torch.empty(n_ctx, ctx_dim, dtype=dtype)
+            nn.init.normal_(ctx_vectors, std=0.02)
+            prompt_prefix = " ".join(["X"] * n_ctx)
+        self.ctx = nn.Parameter(ctx_vectors)
+
+        self.embed_projection = nn.Linear(in_features=ctx_dim, out_features=clip_model.visual.positional_embedding.shape[1])
+        self.deep_prompts = nn.Parameter(torch.empty(self.deep_prompts_depth - 1, n_ctx, ctx_dim))
+        nn.init.normal_(self.deep_prompts, std=0.02)
+        self.deep_projections = nn.Linear(ctx_dim, clip_model.visual.proj.shape[0])
+
+        classnames = [name.replace("_", " ") for name in classnames]
+        prompts = [prompt_prefix + " " + name + "." for name in classnames]
+        tokenized_prompts = torch.cat([tokenize(p) for p in prompts], dim=0)  # (n_cls, 77)
+        with torch.no_grad():
+            embedding = clip_model.token_embedding(
+                tokenized_prompts.to(clip_model.token_embedding.weight.device).long()).type(dtype)
+
+        self.register_buffer("token_prefix", embedding[:, :1, :].clone())          # SOS
+        self.register_buffer("token_suffix", embedding[:, 1 + n_ctx:, :].clone())  # CLS . EOS ~
+
+        self.n_cls = n_cls
+        self.n_ctx = n_ctx
+        self.ctx_dim = ctx_dim
+        self.tokenized_prompts = tokenized_prompts  # plain attribute, as in the reference (:95)
+
+    def construct_prompts(self, ctx, prefix, suffix, label=None):
+        if label is not None:
+            prefix = prefix[label]
+            suffix = suffix[label]
+        return torch.cat([prefix, ctx, suffix], dim=1)
+
+    def forward(self):
+        """Reference API (trainers/mudpt.py:117-130): materialises the class prompts.  The fused
+        CustomCLIP path does not call this."""
+        ctx = self.ctx
+        if ctx.dim() == 2:
+            ctx = ctx.unsqueeze(0).expand(self.n_cls, self.n_ctx, self.ctx_dim)
+        prompts = self.construct_prompts(ctx, self.token_prefix, self.token_suffix)
+        visual_prompts = self.deep_projections(self.deep_prompts)
+        t2v_shared_ctx = self.embed_projection(self.ctx.unsqueeze(0))
+        return prompts, t2v_shared_ctx, self.deep_prompts, visual_prompts
+
+
+class TextEncoder(nn.Module):
+    def __init__(self, clip_model):
+        super().__init__()
+        self.transformer = clip_model.transformer
+        self.positional_embedding = clip_model.positional_embedding
+        self.ln_final = clip_model.ln_final
+        self.text_projection = clip_model.text_projection
+        self.dtype = clip_model.dtype
+        # strong reference that is NOT a registered submodule (state-dict keys must match the reference)
+        object.__setattr__(self, "_clip_ref", [clip_model])
+        self.truncate_to_eot = True
+
+    def forward(self, prompts, tokenized_prompts, deep_prompts):
+        """Reference API (trainers/mudpt.py:142-156): prompts [C, 77, d] -> text features [C, e]."""
+        engine = self._clip_ref[0].engine(prompts.device)
+        eot = tokenized_prompts.argmax(dim=-1).cpu()
+        seq_len = int(eot.max()) + 1 if self.truncate_to_eot else prompts.shape[1]
+        seq_len = max(seq_len, 1 + engine.n_ctx)
+        return TextTowerDenseFn.apply(engine, prompts.float(), eot, deep_prompts.float(), seq_len)
+
+
+class CustomCLIP(nn.Module):
+    def __init__(self, cfg, classnames, clip_model, tokenizer=None):
+        super().__init__()
+        self.mudpt_prompt_learner = MuDPTPromptLearner(cfg, classnames, clip_model, tokenizer=tokenizer)
+        self.tokenized_prompts = self.mudpt_prompt_learner.tokenized_prompts
+        self.text_encoder = TextEncoder(clip_model)
+        self.image_encoder = clip_model.visual
+        self.logit_scale = clip_model.logit_scale
+        self.dtype = clip_model.dtype
+        self.deep_prompts_depth = self.mudpt_prompt_learner.deep_prompts_depth
+        # strong reference that is NOT a registered submodule (state-dict keys must match the reference)
+        object.__setattr__(self, "_clip_ref", [clip_model])
+        # exact under the causal mask; set False to run all 77 positions
+        self.truncate_text_to_eot = os.environ.get("MUDPT_TEXT_FULL_LENGTH", "0") != "1"
+        self.shard_classes = True           # class-sharded text tower when torch.distributed is initialised
+        self._cached_text_features = None   # eval-time cache (parameters frozen under no_grad)
+
+    # ------------------------------------------------------------------ helpers
+    def _engine(self, device):
+        return self._clip_ref[0].engine(device)
+
+    def _class_range(self) -> Tuple[int, int]:
+        n = self.mudpt_prompt_learner.n_cls
+        if self.shard_classes and mdist.world_size() > 1:
+            return mdist.shard_bounds(n, mdist.rank(), mdist.world_size())
+        return 0, n
+
+    def _register_classes(self, device):
+        pl = self.mudpt_prompt_learner
+        lo, hi = self._class_range()
+        eot_all = self.tokenized_prompts.argmax(dim=-1)
+        # one global length so that every rank runs the same shapes
+        seq_len = int(eot_all.max()) + 1 if self.truncate_text_to_eot else self.tokenized_prompts.shape[1]
+        seq_len = max(seq_len, 1 + pl.n_ctx)
+        eng = self._engine(device)
+        key = (id(self), lo, hi, seq_len)
+        if eng.class_key == key:
+            return
+        prefix, suffix = pl.token_prefix[lo:hi], pl.token_suffix[lo:hi]
+        emb = torch.cat([prefix, torch.zeros(hi - lo, pl.n_ctx, pl.ctx_dim, device=prefix.device, dtype=prefix.dtype), suffix], dim=1)
+        eng.text_set_classes(emb.float(), eot_all[lo:hi], seq_len)
+        eng.class_key = key
+
+    def prompt_stacks(self):
+        """The two [depth, n_ctx, width] prompt stacks the towers splice in, as differentiable
+        functions of the 10 trainable tensors (trainers/mudpt.py:127-128, :175; clip/model.py:534-539)."""
+        pl, ve = self.mudpt_prompt_learner, self.image_encoder
+        visual_prompts = pl.deep_projections(pl.deep_prompts)                 # t2v deep
+        shared_ctx = pl.embed_projection(pl.ctx.unsqueeze(0))                 # t2v shallow
+        P_v = ve.prompt_stack(shared_ctx, visual_prompts)
+        v2t = ve.visual_ctx_deep_projections(ve.visual_ctx_deep_prompts)      # v2t deep
+        text_deep = pl.deep_prompts + v2t
+        pos = self.text_encoder.positional_embedding[1:1 + pl.n_ctx]
+        P_t = torch.cat([(pl.ctx + pos).unsqueeze(0), text_deep], dim=0).float()
+        return P_v, P_t
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, image):
+        """image [B, 3, H, W] -> logits [B, C] (trainers/mudpt.py:170-184), differentiable w.r.t. the prompts."""
+        device = image.device
+        eng = self._engine(device)
+        self._register_classes(device)
+        P_v, P_t = self.prompt_stacks()
+        image_features = VisionTowerFn.apply(eng, image.type(self.dtype), P_v)
+        text_features = TextTowerFn.apply(eng, P_t)
+        if self.shard_classes and mdist.world_size() > 1:
+            text_features = mdist.AllGatherRows.apply(text_features, self.mudpt_prompt_learner.n_cls)
+        return LogitsFn.apply(eng, image_features, text_features)
+
+    # ------------------------------------------------------------------ fused train / eval paths
+    def forward_backward(self, image, label):
+        """Fused train step: forward, mean cross-entropy over the GLOBAL batch (F.cross_entropy of
+        trainers/mudpt.py:250 under nn.DataParallel semantics) and backward into the .grad of the 10
+        trainable tensors.  Returns (loss, logits).  Gradients are all-reduced across ranks."""
+        device = image.device
+        eng = self._engine(device)
+        self._register_classes(device)
+        world = mdist.world_size() if self.shard_classes else 1
+        P_v, P_t = self.prompt_stacks()
+        f_img = eng.vision_forward(image.type(self.dtype), P_v.detach())
+        f_txt_loc = eng.text_forward(P_t.detach(), True)
+        n_cls = self.mudpt_prompt_learner.n_cls
+        f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
+        logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True)
+        d_t_loc = mdist.reduce_scatter_rows(d_t, n_cls) if world > 1 else d_t
+        dP_t, _ = eng.text_backward(d_t_loc)
+        dP_v = eng.vision_backward(d_i)
+        torch.autograd.backward([P_v, P_t], [dP_v, dP_t])
+        if world > 1:
+            mdist.all_reduce_grads([p for p in self.parameters() if p.requires_grad])
+            loss = mdist.all_reduce_sum(loss)
+        return loss, logits
+
+    @torch.no_grad()
+    def cache_text_features(self, device=None):
+        """Text features depend only on parameters: compute them once for evaluation (the reference
+        recomputes the text tower for every test batch)."""
+        device = device or self.logit_scale.device
+        eng = self._engine(device)
+        self._register_classes(device)
+        _, P_t = self.prompt_stacks()
+        f = eng.text_forward(P_t, True)
+        if self.shard_classes and mdist.world_size() > 1:
+            f = mdist.all_gather_rows(f, self.mudpt_prompt_learner.n_cls)
+        self._cached_text_features = f
+        return f
+
+    @torch.no_grad()
+    def inference(self, image):
+        """logits with cached text features (call cache_text_features() first / after each update)."""
+        if self._cached_text_features is None:
+            self.cache_text_features(image.device)
+        eng = self._engine(image.device)
+        P_v, _ = self.prompt_stacks()
+        f_img = eng.vision_forward(image.type(self.dtype), P_v)
+        logits, _, _, _ = eng.logits_head(f_img, self._cached_text_features, None, 1.0, False)
+        return logits
+
+
+@TRAINER_REGISTRY.register()
+class MuDPT(TrainerX):
+    def check_cfg(self, cfg):
+        assert cfg.TRAINER.MUDPT.PREC in ["fp16", "fp32", "amp"]
+
+    def build_model(self):
+        cfg = self.cfg
+        classnames = self.dm.dataset.classnames if hasattr(self, "dm") else self._classnames
+        print(f"Loading CLIP (backbone: {cfg.MODEL.BACKBONE.NAME})")
+        clip_model = load_clip_to_cpu(cfg)
+        clip_model.float()  # the reference's effective numerics are fp32 for every PREC
+
+        print("Building custom CLIP")
+        self.model = CustomCLIP(cfg, classnames, clip_model)
+
+        print("Turning off gradients in both the image and the text encoder")
+        name_to_optimize = "prompt_learner"
+        for name, param in self.model.named_parameters():
+            if name_to_optimize not in name:
+                param.requires_grad_("visual_ctx" in name)
+        enabled = {name for name, p in self.model.named_parameters() if p.requires_grad}
+        print(f"Parameters to be updated: {enabled}")
+
+        if getattr(cfg.MODEL, "INIT_WEIGHTS", ""):
+            load_pretrained_weights(self.model.mudpt_prompt_learner, cfg.MODEL.INIT_WEIGHTS)
+
+        self.model.to(self.device)
+        self.optim = build_optimizer(self.model, cfg.OPTIM)
+        self.sched = build_lr_scheduler(self.optim, cfg.OPTIM)
+        self.register_model("MultimodalDeepPromptTuning", self.model, self.optim, self.sched)
+        self.scaler = None  # "amp" needs no loss scaling here: bf16 operands, fp32 accumulation and master state
+
+    def forward_backward(self, batch):
+        image, label = self.parse_batch_train(batch)
+        if os.environ.get("MUDPT_FUSED_STEP", "1") == "1":
+            # fused loss + backward in the native head; same update as model_backward_and_update(loss)
+            self.optim.zero_grad()
+            loss, _ = self.model.forward_backward(image, label)
+            if not torch.isfinite(loss).all():
+                raise FloatingPointError("Loss is infinite or NaN!")
+            self.optim.step()
+        else:
+            output = self.model(image)
+            loss = F.cross_entropy(output, label)
+            self.model_backward_and_update(loss)
+        loss_summary = {"loss": loss.item()}
+        if (self.batch_idx + 1) == self.num_batches:
+            self.update_lr()
+        return loss_summary
+
+    def parse_batch_train(self, batch):
+        input = batch["img"].to(self.device)
+        label = batch["label"].to(self.device)
+        return input, label
+
+    def load_model(self, directory, epoch=None):
+        if not directory:
+            print("Note that load_model() is skipped as no pretrained model is given")
+            return
+        names = self.get_model_names()
+        model_file = "model-best.pth.tar"
+        if epoch is not None:
+            model_file = "model.pth.tar-" + str(epoch)
+        for name in names:
+            model_path = osp.join(directory, name, model_file)
+            if not osp.exists(model_path):
+                raise FileNotFoundError('Model not found at "{}"'.format(model_path))
+            checkpoint = load_checkpoint(model_path)
+            state_dict = checkpoint["state_dict"]
+            epoch = checkpoint["epoch"]
+            # class names may differ (base -> new): ignore the fixed token vectors
+            state_dict.pop("mudpt_prompt_learner.token_prefix", None)
+            state_dict.pop("mudpt_prompt_learner.token_suffix", None)
+            print('Loading weights to {} from "{}" (epoch = {})'.format(name, model_path, epoch))
+            self._models[name].load_state_dict(state_dict, strict=False)
+            self._models[name]._clip_ref[0].refresh_engine_weights()

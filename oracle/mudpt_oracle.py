@@ -236,3 +236,56 @@ def top1_agreement(logits: torch.Tensor, ref_logits: torch.Tensor, err: float):
     return {"raw": float(agree.float().mean()),
             "decidable_frac": float(dec.float().mean()),
             "margin_aware": float(agree[dec].float().mean()) if dec.any() else 1.0}
+
+
+# ---------------------------------------------------------------------------------------------
+# "Prompt stack" form of the towers: the exact decomposition the C ABI uses
+# (include/mudpt_b200.h): stack[0] = layer-0 prompt rows, stack[i>=1] = deep prompts of layer i.
+# Used by tests to emulate the native engine on CPU (tests/fake_engine.py).
+# ---------------------------------------------------------------------------------------------
+
+def tower_stack(x, stack, sd, pfx, n_layers, n_head, mask, row0, first_splice=0):
+    n_ctx = stack.shape[1]
+    for i in range(n_layers):
+        if first_splice <= i < stack.shape[0] and n_ctx > 0:
+            x = torch.cat([x[:, :row0], stack[i].unsqueeze(0).expand(x.shape[0], -1, -1), x[:, row0 + n_ctx:]], dim=1)
+        x = block(x, sd, f"{pfx}resblocks.{i}.", n_head, mask)
+    return x
+
+
+def vision_features_from_stack(sd, image, stack):
+    """mudpt_vision_forward: images + [depth, n, dv] stack (stack[0] already ln_pre'd) -> f_img."""
+    V = "image_encoder."
+    w = sd[V + "conv1.weight"]
+    width, patch = w.shape[0], w.shape[-1]
+    x = F.conv2d(image, w, stride=patch)
+    x = x.reshape(x.shape[0], width, -1).permute(0, 2, 1)
+    x = torch.cat([sd[V + "class_embedding"].expand(x.shape[0], 1, width), x], dim=1) + sd[V + "positional_embedding"]
+    x = layer_norm(x, sd[V + "ln_pre.weight"], sd[V + "ln_pre.bias"])
+    n = stack.shape[1]
+    x = torch.cat([x, torch.zeros(x.shape[0], n, width)], dim=1)
+    x = tower_stack(x, stack, sd, V + "transformer.", count_layers(sd, V + "transformer."), width // 64, None,
+                    x.shape[1] - n)
+    return layer_norm(x[:, 0, :], sd[V + "ln_post.weight"], sd[V + "ln_post.bias"]) @ sd[V + "proj"]
+
+
+def text_features_from_stack(sd, embeddings, eot, stack, seq_len, first_splice=0):
+    """mudpt_text_forward: token embeddings [C, >=seq_len, dt] (ctx rows ignored when
+    first_splice == 0) + [depth, n, dt] stack -> f_txt."""
+    T = "text_encoder."
+    d = embeddings.shape[-1]
+    x = embeddings[:, :seq_len] + sd[T + "positional_embedding"][:seq_len]
+    x = tower_stack(x, stack, sd, T + "transformer.", count_layers(sd, T + "transformer."), d // 64,
+                    causal_mask(seq_len), 1, first_splice)
+    x = layer_norm(x, sd[T + "ln_final.weight"], sd[T + "ln_final.bias"])
+    return x[torch.arange(x.shape[0]), eot] @ sd[T + "text_projection"]
+
+
+def logits_and_loss(f_img, f_txt, logit_scale, labels=None, inv_global_batch=None):
+    fi = f_img / f_img.norm(dim=-1, keepdim=True)
+    ft = f_txt / f_txt.norm(dim=-1, keepdim=True)
+    logits = logit_scale.exp() * fi @ ft.t()
+    if labels is None:
+        return logits, None
+    loss = F.cross_entropy(logits, labels, reduction="sum") * inv_global_batch
+    return logits, loss

@@ -29,3 +29,37 @@ def load(name):
                 labels=labels, golden=g, classnames=[str(c) for c in g["classnames"]])
     _cache[name] = case
     return case
+
+
+def make_cfg(n_ctx, depth, ctx_init, size, arch_name="ViT-B/16"):
+    """The subset of the yacs tree the hot path reads (train.py:114-119); plain attribute dicts."""
+    class N(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+    cfg = N()
+    cfg.TRAINER = N(NAME="MuDPT", MUDPT=N(N_CTX=n_ctx, CTX_INIT=ctx_init, DEEP_PROMPT_DEPTH=depth, PREC="fp32"))
+    cfg.INPUT = N(SIZE=(size, size))
+    cfg.MODEL = N(BACKBONE=N(NAME=arch_name, PATH=""), INIT_WEIGHTS="")
+    cfg.OPTIM = N(LR=0.0025, MAX_EPOCH=10)
+    return cfg
+
+
+def build_model(case, device="cuda"):
+    """mudpt_b200 CustomCLIP carrying exactly the golden case's weights (token ids from the fixture)."""
+    from mudpt_b200 import clip
+    from mudpt_b200.trainers.mudpt import CustomCLIP
+    g = case["golden"]
+    arch = case["arch"]
+    ctx_init = "a photo of a" if bool(g["has_ctx_init"]) else ""
+    cfg = make_cfg(case["n_ctx"], case["depth"], ctx_init, arch.image_resolution)
+    prefix = " ".join(ctx_init.split()[:case["n_ctx"]]) if ctx_init else " ".join(["X"] * case["n_ctx"])
+    table = {prefix + " " + n.replace("_", " ") + ".": case["tokenized"][i:i + 1] for i, n in enumerate(case["classnames"])}
+    if ctx_init:
+        table[ctx_init] = torch.from_numpy(g["ctx_init_tokens"]).view(1, -1)
+    clip_model = clip.CLIP(*arch.astuple(), cfg).float()
+    model = CustomCLIP(cfg, case["classnames"], clip_model, tokenizer=lambda s: table[s])
+    missing = model.load_state_dict(case["sd"], strict=True)
+    for n, p in model.named_parameters():
+        if "prompt_learner" not in n:
+            p.requires_grad_("visual_ctx" in n)
+    return model.to(device), cfg

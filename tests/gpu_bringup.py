@@ -1,0 +1,386 @@
+"""GPU bring-up / diagnostics driver (run on the B200 box through gpurun).
+
+    python tests/gpu_bringup.py [group ...]      # default: all groups
+
+Every group runs in its own subprocess under a timeout, so a trapping kernel cannot poison
+the other groups (a CUDA fault is sticky for its process).  Results go to stdout and to
+gpurun_out/bringup.json.  This is test infrastructure: it compares the native kernels with
+plain torch fp32 math on the same device and with the golden fixtures made from the reference.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+GROUPS = ["gemm", "rowops", "attention", "head", "model_tiny", "model_vitb16"]
+
+
+def _metrics(a, b):
+    import torch
+    a = a.double().flatten()
+    b = b.double().flatten()
+    d = (a - b)
+    return {"cos": float((a @ b) / (a.norm() * b.norm() + 1e-300)), "rel": float(d.norm() / (b.norm() + 1e-300)),
+            "max_abs": float(d.abs().max()), "ref_max": float(b.abs().max()), "nan": bool(torch.isnan(a).any())}
+
+
+# ------------------------------------------------------------------------------------------ gemm
+def group_gemm(res):
+    import torch
+    from mudpt_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    st = _lib.stream_ptr(dev)
+    torch.manual_seed(0)
+
+    def run(M, N, K, mode):
+        A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+        B = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+        bias = torch.randn(N, device=dev)
+        ref = A.float() @ B.float().t()
+        kw = dict(out1=None, resid=None, aux=None, np_=1, L=1)
+        if mode == 0:
+            out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16); exp = ref + bias
+        elif mode == 1:
+            out = torch.zeros(M, N, device=dev); exp = ref + bias
+        elif mode == 2:
+            resid = torch.randn(M, N, device=dev); kw["resid"] = resid
+            out = torch.zeros(M, N, device=dev); exp = ref + bias + resid
+        elif mode == 3:
+            out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            out1 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16); kw["out1"] = out1
+            h = ref + bias; exp = h
+        elif mode == 4:
+            aux = torch.randn(M, N, device=dev).bfloat16(); kw["aux"] = aux
+            out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            hf = aux.float(); s = torch.sigmoid(1.702 * hf)
+            exp = (ref + bias) * (s * (1 + 1.702 * hf * (1 - s)))
+        elif mode == 5:
+            np_, L = 4, 7
+            assert M % np_ == 0
+            pos = torch.randn(np_ + 1, N, device=dev); kw["resid"] = pos; kw["np_"] = np_; kw["L"] = L
+            out = torch.zeros(M // np_ * L, N, device=dev)
+            exp = torch.zeros_like(out)
+            r = torch.arange(M, device=dev)
+            exp[(r // np_) * L + 1 + r % np_] = ref + bias + pos[1 + r % np_]
+        rc = lib.mudpt_gemm_bf16(A.data_ptr(), B.data_ptr(), M, N, K, mode, out.data_ptr(),
+                                 kw["out1"].data_ptr() if kw["out1"] is not None else None, bias.data_ptr(),
+                                 kw["resid"].data_ptr() if kw["resid"] is not None else None,
+                                 kw["aux"].data_ptr() if kw["aux"] is not None else None, N, kw["np_"], kw["L"], st)
+        _lib.check(rc)
+        torch.cuda.synchronize()
+        m = _metrics(out.float(), exp)
+        if mode == 3:
+            m2 = _metrics(kw["out1"].float(), exp * torch.sigmoid(1.702 * exp))
+            m["gelu_rel"] = m2["rel"]
+        return m
+
+    shapes = [(128, 128, 64), (128, 128, 256), (128, 256, 64), (256, 512, 128), (6368, 2304, 768), (6368, 768, 3072),
+              (900, 1536, 512), (77, 64, 64), (300, 136, 200), (21, 384, 128), (784, 768, 592)]
+    for (M, N, K) in shapes:
+        for mode in ([0, 1, 2, 3, 4] if (M, N, K) in [(128, 128, 64), (6368, 2304, 768), (300, 136, 200)] else [0]):
+            key = f"gemm_{M}x{N}x{K}_m{mode}"
+            try:
+                res[key] = run(M, N, K, mode)
+            except Exception as e:  # noqa
+                res[key] = {"error": repr(e)}
+                raise
+            print(key, res[key], flush=True)
+    res["gemm_patch_m5"] = run(4 * 6, 128, 768, 5)
+    print("gemm_patch_m5", res["gemm_patch_m5"], flush=True)
+    # error pattern of the smallest case for debugging, if wrong
+    m = res["gemm_128x128x64_m0"]
+    res["gemm_ok"] = all(v.get("rel", 1) < 2e-2 for k, v in res.items() if k.startswith("gemm_") and isinstance(v, dict))
+    # timing of the big shapes
+    import torch
+    for (M, N, K) in [(6368, 2304, 768), (6368, 768, 768), (6368, 3072, 768), (6368, 768, 3072), (77000, 1536, 512)]:
+        A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            lib.mudpt_gemm_bf16(A.data_ptr(), B.data_ptr(), M, N, K, 0, out.data_ptr(), None, None, None, None, N, 1, 1, st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            lib.mudpt_gemm_bf16(A.data_ptr(), B.data_ptr(), M, N, K, 0, out.data_ptr(), None, None, None, None, N, 1, 1, st)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        c = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            torch.matmul(A, B.t(), out=c)
+        e0.record()
+        for _ in range(10):
+            torch.matmul(A, B.t(), out=c)
+        e1.record(); torch.cuda.synchronize()
+        ms_t = e0.elapsed_time(e1) / 10
+        res[f"gemm_time_{M}x{N}x{K}"] = {"ms": ms, "tflops": 2 * M * N * K / ms / 1e9, "cublas_ms": ms_t,
+                                        "cublas_tflops": 2 * M * N * K / ms_t / 1e9}
+        print(f"gemm_time_{M}x{N}x{K}", res[f"gemm_time_{M}x{N}x{K}"], flush=True)
+
+
+# ------------------------------------------------------------------------------------------ rowops
+def group_rowops(res):
+    import torch
+    import torch.nn.functional as F
+    from mudpt_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    st = _lib.stream_ptr(dev)
+    torch.manual_seed(1)
+    for (M, d) in [(37, 64), (1000, 512), (6368, 768), (513, 1024)]:
+        x = torch.randn(M, d, device=dev) * 2 + 0.5
+        g = torch.randn(d, device=dev); b = torch.randn(d, device=dev)
+        ref = F.layer_norm(x, (d,), g, b, 1e-5)
+        o16 = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.mudpt_layernorm_forward(x.data_ptr(), g.data_ptr(), b.data_ptr(), o16.data_ptr(), 1, M, d, st))
+        o32 = torch.empty(M, d, device=dev)
+        _lib.check(lib.mudpt_layernorm_forward(x.data_ptr(), g.data_ptr(), b.data_ptr(), o32.data_ptr(), 0, M, d, st))
+        torch.cuda.synchronize()
+        res[f"ln_fwd_{M}x{d}"] = {"f32": _metrics(o32, ref), "bf16": _metrics(o16.float(), ref)}
+        xr = x.clone().requires_grad_(True)
+        dy = torch.randn(M, d, device=dev)
+        resid = torch.randn(M, d, device=dev)
+        F.layer_norm(xr, (d,), g, b, 1e-5).backward(dy)
+        exp = resid + xr.grad
+        dx = resid.clone(); dx16 = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.mudpt_layernorm_backward(dy.data_ptr(), x.data_ptr(), g.data_ptr(), dx.data_ptr(), dx.data_ptr(),
+                                                dx16.data_ptr(), M, d, st))
+        torch.cuda.synchronize()
+        res[f"ln_bwd_{M}x{d}"] = {"f32": _metrics(dx, exp), "bf16": _metrics(dx16.float(), exp)}
+        print(f"ln_{M}x{d}", res[f"ln_fwd_{M}x{d}"], res[f"ln_bwd_{M}x{d}"], flush=True)
+    # splice
+    S, L, row0, n, d = 33, 21, 19, 2, 768
+    x = torch.randn(S, L, d, device=dev); p = torch.randn(n, d, device=dev)
+    exp = x.clone(); exp[:, row0:row0 + n] = p
+    _lib.check(lib.mudpt_splice_forward(x.data_ptr(), p.data_ptr(), S, L, row0, n, d, st))
+    torch.cuda.synchronize()
+    res["splice_fwd_bitexact"] = bool(torch.equal(x, exp))
+    dx = torch.randn(S, L, d, device=dev); dx16 = dx.bfloat16().contiguous()
+    exp_dp = dx[:, row0:row0 + n].double().sum(0).float()
+    exp_dx = dx.clone(); exp_dx[:, row0:row0 + n] = 0
+    dp = torch.empty(n, d, device=dev)
+    _lib.check(lib.mudpt_splice_backward(dx.data_ptr(), dx16.data_ptr(), dp.data_ptr(), S, L, row0, n, d, 1, st))
+    torch.cuda.synchronize()
+    res["splice_bwd"] = {"dp": _metrics(dp, exp_dp), "dx_zeroed": bool(torch.equal(dx, exp_dx)),
+                         "dx16_zeroed": bool((dx16[:, row0:row0 + n] == 0).all())}
+    print("splice", res["splice_fwd_bitexact"], res["splice_bwd"], flush=True)
+    # im2col
+    for (B, R, p_) in [(3, 224, 16), (2, 224, 14), (2, 32, 16)]:
+        img = torch.randn(B, 3, R, R, device=dev)
+        k = 3 * p_ * p_; ld = (k + 7) // 8 * 8
+        gw = R // p_
+        out = torch.zeros(B * gw * gw, ld, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.mudpt_im2col(img.data_ptr(), out.data_ptr(), B, R, p_, ld, st))
+        torch.cuda.synchronize()
+        exp = F.unfold(img, kernel_size=p_, stride=p_).transpose(1, 2).reshape(B * gw * gw, k).bfloat16()
+        res[f"im2col_{B}_{R}_{p_}"] = bool(torch.equal(out[:, :k], exp))
+        print(f"im2col_{B}_{R}_{p_}", res[f"im2col_{B}_{R}_{p_}"], flush=True)
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, S, L, H, causal):
+    import torch
+    d = H * 64
+    q, k, v = qkv.float().view(S, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device=qkv.device).triu_(1)
+    p = torch.softmax(s, -1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(S * L, d)
+    return o
+
+
+def group_attention(res):
+    import torch
+    from mudpt_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    st = _lib.stream_ptr(dev)
+    torch.manual_seed(2)
+    for (S, L, H, causal) in [(3, 199, 12, 0), (5, 77, 8, 1), (7, 9, 8, 1), (4, 16, 2, 1), (2, 64, 1, 0), (2, 259, 16, 0),
+                              (3, 7, 2, 0), (2, 130, 2, 1)]:
+        d = H * 64
+        qkv = torch.randn(S * L, 3 * d, device=dev).bfloat16()
+        o = torch.zeros(S * L, d, device=dev, dtype=torch.bfloat16)
+        lse = torch.zeros(S, H, L, device=dev)
+        _lib.check(lib.mudpt_attention_forward(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), S, L, H, causal, st))
+        torch.cuda.synchronize()
+        qr = qkv.float().clone().requires_grad_(True)
+        oref = _attn_ref(qr, S, L, H, causal)
+        do = torch.randn(S * L, d, device=dev).bfloat16()
+        oref.backward(do.float())
+        dqkv = torch.zeros(S * L, 3 * d, device=dev, dtype=torch.bfloat16)
+        dsum = torch.zeros(S, H, L, device=dev)
+        _lib.check(lib.mudpt_attention_backward(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
+                                                dqkv.data_ptr(), S, L, H, causal, st))
+        torch.cuda.synchronize()
+        g = qr.grad
+        key = f"attn_S{S}_L{L}_H{H}_c{causal}"
+        res[key] = {"o": _metrics(o.float(), oref.detach()), "dq": _metrics(dqkv[:, :d].float(), g[:, :d]),
+                    "dk": _metrics(dqkv[:, d:2 * d].float(), g[:, d:2 * d]), "dv": _metrics(dqkv[:, 2 * d:].float(), g[:, 2 * d:])}
+        print(key, res[key], flush=True)
+    # timing at the cfg-2 vision shape
+    S, L, H = 32, 199, 12
+    d = H * 64
+    qkv = torch.randn(S * L, 3 * d, device=dev).bfloat16()
+    o = torch.zeros(S * L, d, device=dev, dtype=torch.bfloat16); lse = torch.zeros(S, H, L, device=dev)
+    do = torch.randn(S * L, d, device=dev).bfloat16(); dqkv = torch.zeros(S * L, 3 * d, device=dev, dtype=torch.bfloat16)
+    dsum = torch.zeros(S, H, L, device=dev)
+    for name, fn in [("fwd", lambda: lib.mudpt_attention_forward(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), S, L, H, 0, st)),
+                     ("bwd", lambda: lib.mudpt_attention_backward(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                                                  dsum.data_ptr(), dqkv.data_ptr(), S, L, H, 0, st))]:
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        res[f"attn_time_vision_{name}_us"] = e0.elapsed_time(e1) / 20 * 1e3
+        print(f"attn_time_vision_{name}_us", res[f"attn_time_vision_{name}_us"], flush=True)
+
+
+# ------------------------------------------------------------------------------------------ head + model
+def _compare_model(name, res, fused=True):
+    import torch
+    import torch.nn.functional as F
+    from tests import golden_util as gu
+    from oracle import mudpt_oracle as orc
+    c = gu.load(name)
+    g = c["golden"]
+    model, _ = gu.build_model(c, "cuda")
+    image, labels = c["image"].cuda(), c["labels"].cuda()
+    out = {}
+    for mode in (["fused", "autograd"] if fused else ["autograd"]):
+        model.zero_grad(set_to_none=True)
+        if mode == "fused":
+            loss, logits = model.forward_backward(image, labels)
+        else:
+            logits = model(image)
+            loss = F.cross_entropy(logits, labels)
+            loss.backward()
+        torch.cuda.synchronize()
+        r = {"loss": float(loss), "loss_ref": float(g["loss"]),
+             "logits": _metrics(logits.detach().cpu(), torch.from_numpy(g["logits"]))}
+        ref_logits = torch.from_numpy(g["logits"])
+        r["top1"] = orc.top1_agreement(logits.detach().cpu(), ref_logits, r["logits"]["max_abs"])
+        for k in orc.TRAINABLE:
+            p = dict(model.named_parameters())[k]
+            ref = torch.from_numpy(g["grad/" + k])
+            if ref.numel() and float(ref.norm()) > 0:
+                r["grad/" + k] = _metrics(p.grad.detach().cpu(), ref)
+        out[mode] = r
+        print(name, mode, json.dumps(r), flush=True)
+    # features through the module-level API
+    with torch.no_grad():
+        prompts, shared, text_deep, t2v = model.mudpt_prompt_learner()
+        f_img, v2t = model.image_encoder(image, shared, t2v)
+        f_txt = model.text_encoder(prompts, model.tokenized_prompts, text_deep + v2t)
+    out["image_features"] = _metrics(f_img.cpu(), torch.from_numpy(g["image_features"]))
+    out["text_features"] = _metrics(f_txt.cpu(), torch.from_numpy(g["text_features"]))
+    print(name, "features", out["image_features"], out["text_features"], flush=True)
+    # truncated vs full-length text tower (exact under the causal mask)
+    model.truncate_text_to_eot = False
+    with torch.no_grad():
+        lf = model(image)
+    out["full_len_logits"] = _metrics(lf.cpu(), torch.from_numpy(g["logits"]))
+    print(name, "full-length logits", out["full_len_logits"], flush=True)
+    res[name] = out
+
+
+def group_head(res):
+    import torch
+    import torch.nn.functional as F
+    from mudpt_b200.engine import Engine
+    from mudpt_b200 import synthetic as syn, _lib
+    # logits head through a throw-away tiny engine
+    a = syn.ARCHS["tiny"]
+    arch = dict(zip(["embed_dim", "image_resolution", "vision_layers", "vision_width", "vision_patch_size", "context_length",
+                     "vocab_size", "transformer_width", "transformer_heads", "transformer_layers"], a.astuple()))
+    dev = torch.device("cuda")
+    eng = Engine(arch, 2, 2, dev)
+    ls = torch.tensor(math.log(1 / 0.07), device=dev)
+    _lib.check(eng.lib.mudpt_set_weight(eng.h, b"logit_scale", ls.data_ptr(), 1, _lib.stream_ptr(dev)), eng.h)
+    torch.manual_seed(3)
+    for (B, Cn, e) in [(4, 10, 64), (32, 1000, 64)]:
+        fi = torch.randn(B, e, device=dev, requires_grad=True); ft = torch.randn(Cn, e, device=dev, requires_grad=True)
+        y = torch.randint(0, Cn, (B,), device=dev)
+        logits_ref = ls.exp() * F.normalize(fi, dim=-1) @ F.normalize(ft, dim=-1).t()
+        loss_ref = F.cross_entropy(logits_ref, y)
+        loss_ref.backward()
+        logits, loss, di, dt = eng.logits_head(fi.detach(), ft.detach(), y, 1.0 / B, True)
+        torch.cuda.synchronize()
+        res[f"logits_head_{B}x{Cn}"] = {"logits": _metrics(logits, logits_ref.detach()), "loss": [float(loss), float(loss_ref)],
+                                       "d_img": _metrics(di, fi.grad), "d_txt": _metrics(dt, ft.grad)}
+        dl = torch.randn(B, Cn, device=dev)
+        fi.grad = None; ft.grad = None
+        logits_ref = ls.exp() * F.normalize(fi, dim=-1) @ F.normalize(ft, dim=-1).t()
+        logits_ref.backward(dl)
+        di2, dt2 = eng.logits_backward(fi.detach(), ft.detach(), dl)
+        res[f"logits_head_{B}x{Cn}"]["bwd_img"] = _metrics(di2, fi.grad)
+        res[f"logits_head_{B}x{Cn}"]["bwd_txt"] = _metrics(dt2, ft.grad)
+        print(f"logits_head_{B}x{Cn}", res[f"logits_head_{B}x{Cn}"], flush=True)
+
+
+def group_model_tiny(res):
+    for name in ["tiny_a", "tiny_b", "tiny_c", "tiny_d"]:
+        _compare_model(name, res)
+
+
+def group_model_vitb16(res):
+    _compare_model("vitb16_cfg1", res)
+
+
+def run_group(name):
+    res = {}
+    t0 = time.time()
+    try:
+        globals()["group_" + name](res)
+        res["_status"] = "ok"
+    except Exception:
+        res["_status"] = "exception"
+        res["_trace"] = traceback.format_exc()
+        print(res["_trace"], flush=True)
+    res["_seconds"] = time.time() - t0
+    return res
+
+
+def main():
+    args = sys.argv[1:]
+    if args and args[0] == "--child":
+        name = args[1]
+        res = run_group(name)
+        with open(args[2], "w") as f:
+            json.dump(res, f, indent=1)
+        return
+    groups = args or GROUPS
+    outdir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(outdir, exist_ok=True)
+    tag = os.environ.get("MUDPT_BRINGUP_TAG", "prod")
+    allres = {}
+    for gname in groups:
+        path = os.path.join(outdir, f"bringup_{tag}_{gname}.json")
+        print(f"===== group {gname} ({tag}) =====", flush=True)
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", gname, path], timeout=420)
+            rc = p.returncode
+        except subprocess.TimeoutExpired:
+            rc = "timeout"
+        if os.path.exists(path):
+            allres[gname] = json.load(open(path))
+        else:
+            allres[gname] = {"_status": f"died rc={rc}"}
+        print(f"===== group {gname}: {allres[gname].get('_status')} rc={rc} =====", flush=True)
+    with open(os.path.join(outdir, f"bringup_{tag}.json"), "w") as f:
+        json.dump(allres, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
