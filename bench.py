@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- MuDPT ViT-B/16 train step throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = one MuDPT train step of BASELINE config 2: forward + mean cross-entropy + dgrad-only
+backward into the 10 prompt tensors + SGD update, batch 32 images per GPU, 1000 classes
+(class-sharded over the ranks), ViT-B/16, n_ctx 2, prompt depth 9, synthetic data and random-init
+weights (no datasets / checkpoints exist on the box).
+
+One JSON line on stdout (rank 0):
+  value   whole-job imgs/s with the step's inputs already resident in HBM, full 77-token text tower
+          (the reference formulation, no work skipped)
+  e2e     the same metric through the reference-facing call MuDPT.forward_backward(batch) with HOST
+          batches: pinned-host -> device copies of images/labels and the loss.item() read inside the
+          timed region
+  eot_truncated   value / e2e with the text tower truncated to max(eot)+1 tokens -- exact under the
+          causal mask, the product default; reported beside, never instead of, the
+          full-length numbers
+  roofline        the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time, measured live
+          in an instrumented pass of the same step, against the measured sustained bf16 peak
+  cpu_baseline    the oracle (fp32 CPU port of the reference path) on a bounded 1/32 sample of the step
+`--impl reference` times that CPU path as the main line (the reference itself is pure PyTorch and
+cannot travel to the GPU box; oracle/ restates it and is pinned to it by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train imgs/s MuDPT ViT-B/16 1000-cls"
+UNIT = "imgs/s"
+BATCH_PER_GPU = 32
+N_CLASSES = 1000
+N_CTX, DEPTH = 2, 9
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_sustained": d.get("bf16_tflops_sustained", 1359.8), "bf16_burst": d.get("bf16_tflops", 1618.5),
+                "hbm": d.get("hbm_gbs", 6538.3), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference) -- cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+
+def cpu_sample_setup(frac_images: int = 1, frac_classes: int = 32):
+    """1/32 of the cfg-2 step: 1 image x 32 classes (vision cost is linear in images, text cost in
+    classes, so a full 32-image / 1000-class step costs 32 x (1 image + 31.25 classes))."""
+    import torch
+    from mudpt_b200 import synthetic as syn
+    from oracle import mudpt_oracle as orc  # the checker; executed here only as the CPU baseline
+    arch = syn.ARCHS["ViT-B/16"]
+    names = syn.synthetic_classnames(frac_classes)
+    tok = syn.synthetic_tokenize(["a photo " + n + "." for n in names])
+    ctx_tok = syn.synthetic_tokenize("a photo of a")[0]
+    sd = syn.assemble_state_dict(arch, tok, N_CTX, DEPTH, ctx_tok, seed=0)
+    image = syn.synthetic_images(frac_images, 224, seed=1)
+    labels = syn.synthetic_labels(frac_images, frac_classes, seed=1)
+    return orc, sd, image, tok, labels
+
+
+def cpu_time_steps(steps: int, warmup: int):
+    import torch
+    orc, sd, image, tok, labels = cpu_sample_setup()
+    threads = torch.get_num_threads()
+    for _ in range(warmup):
+        orc.forward_backward(sd, image, tok, labels)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.forward_backward(sd, image, tok, labels)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    # full step = 32 x sample  ->  imgs/s = 32 / (32 * dt) = 1 / dt
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"1/32 of the step per iteration (1 image x 32 classes, full 77-token text, fp32 torch CPU "
+                      f"oracle of the reference path, {threads} threads of {os.cpu_count()} cpus); "
+                      f"{steps} timed + {warmup} warm-up iterations, {dt:.2f} s each; imgs/s = 1 / t_iter",
+            "s_per_sample_step": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; use every host thread
+    # bound the run: each iteration is ~1-4 s on the box's host cores
+    steps = max(1, min(args.steps, 40))
+    warm = max(1, min(args.warmup, 3))
+    cb = cpu_time_steps(steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": cb["s_per_sample_step"] * 32 * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MuDPT ViT-B/16 train step, batch {BATCH_PER_GPU}/GPU, {N_CLASSES} classes, n_ctx 2, depth 9 "
+                               "(CPU fp32 path, one process; does not scale with --gpus)", "text_seq_len": 77},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU path
+# ------------------------------------------------------------------------------------------------
+
+def build_trainer(device, truncate: bool):
+    import torch
+    from mudpt_b200 import synthetic as syn
+    from mudpt_b200.trainers import mudpt as M
+    from tests.golden_util import make_cfg
+    cfg = make_cfg(N_CTX, DEPTH, "a photo of a", 224, "ViT-B/16")
+    arch = syn.ARCHS["ViT-B/16"]
+    clip_model = M.clip.CLIP(*arch.astuple(), cfg).float()
+    clip_model.load_state_dict(syn.synthetic_clip_state_dict(arch, 0), strict=False)
+    trainer = M.MuDPT.__new__(M.MuDPT)
+    M.TrainerX.__init__(trainer, None, None, device)
+    trainer.cfg = cfg
+    trainer.check_cfg(cfg)
+    model = M.CustomCLIP(cfg, syn.synthetic_classnames(N_CLASSES), clip_model)
+    for n, p in model.named_parameters():  # freeze rule, trainers/mudpt.py:205-212
+        if "prompt_learner" not in n:
+            p.requires_grad_("visual_ctx" in n)
+    model.truncate_text_to_eot = truncate
+    model.to(device)
+    trainer.model = model
+    trainer.optim = M.build_optimizer(model, cfg.OPTIM)
+    trainer.sched = M.build_lr_scheduler(trainer.optim, cfg.OPTIM)
+    trainer.register_model("MultimodalDeepPromptTuning", model, trainer.optim, trainer.sched)
+    trainer.batch_idx, trainer.num_batches = 0, 10 ** 9
+    return trainer
+
+
+def timed_loop(fn, steps, warmup, device, world):
+    """W warm-ups, then exactly K steps bracketed by barrier + synchronize, CUDA events on the
+    launching stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms, t0, t1
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mudpt_b200 import synthetic as syn
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    K, W = args.steps, max(args.warmup, 3)
+    B = BATCH_PER_GPU
+    NBUF = 8  # 8 distinct batches = 154 MB of inputs > 126 MB L2; the step's activations are GBs
+
+    imgs_host = [syn.synthetic_images(B, 224, seed=100 + rank * NBUF + i).pin_memory() for i in range(NBUF)]
+    labs_host = [syn.synthetic_labels(B, N_CLASSES, seed=100 + rank * NBUF + i).pin_memory() for i in range(NBUF)]
+    imgs_dev = [t.to(device) for t in imgs_host]
+    labs_dev = [t.to(device) for t in labs_host]
+
+    results = {}
+    sampler = ClockSampler(local)
+    clocks = None
+    if args.quick:
+        # profiling aid (ncu launch lists): the full-length variant's resident loop only, no JSON contract
+        trainer = build_trainer(device, False)
+
+        def step_q(i):
+            trainer.optim.zero_grad(set_to_none=False)
+            trainer.model.forward_backward(imgs_dev[i % NBUF], labs_dev[i % NBUF])
+            trainer.optim.step()
+
+        ms, _, _ = timed_loop(step_q, K, W, device, world)
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms / K, "value": B * world / (ms / K * 1e-3), "unit": UNIT}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    for variant, truncate in (("full", False), ("eot_truncated", True)):
+        trainer = build_trainer(device, truncate)
+        model = trainer.model
+        eng = model._clip_ref[0].engine(device)
+
+        def step_resident(i):
+            trainer.optim.zero_grad(set_to_none=False)
+            model.forward_backward(imgs_dev[i % NBUF], labs_dev[i % NBUF])
+            trainer.optim.step()
+
+        def step_e2e(i):
+            # the reference-facing call: host batch in, python float out (trainers/mudpt.py:235-261)
+            return trainer.forward_backward({"img": imgs_host[i % NBUF], "label": labs_host[i % NBUF]})
+
+        l0 = eng.launch_count()
+        if variant == "full":
+            sampler.start()
+        ms, t0, t1 = timed_loop(step_resident, K, W, device, world)
+        if variant == "full":
+            clocks = sampler.stop(t0, t1)
+        launches = (eng.launch_count() - l0) // (K + W)
+        ms_e2e, _, _ = timed_loop(step_e2e, K, W, device, world)
+        # instrumented pass of the same step: per-kernel-class CUDA-event times
+        eng.profile_begin()
+        torch.cuda.synchronize(device)
+        for i in range(min(K, 5)):
+            step_resident(i)
+        prof = eng.profile_end()
+        nprof = min(K, 5)
+        results[variant] = {"ms": ms / K, "ms_e2e": ms_e2e / K, "launches": launches, "prof": prof, "nprof": nprof,
+                            "text_len": eng.text_len, "loss": float(trainer.forward_backward(
+                                {"img": imgs_host[0], "label": labs_host[0]})["loss"])}
+        del trainer, model, eng
+        torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    full, tr = results["full"], results["eot_truncated"]
+    gB = B * world
+    g = full["prof"]["gemm"]
+    gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    step_prof_ms = sum(v["ms"] for v in full["prof"].values()) / full["nprof"]
+    shares = {k: round(v["ms"] / full["nprof"] / step_prof_ms, 4) for k, v in full["prof"].items() if v["ms"] > 0}
+
+    def cat_table(prof, nprof):
+        out = {}
+        for k, v in prof.items():
+            if v["launches"] == 0:
+                continue
+            us = v["ms"] * 1e3 / v["launches"]
+            e = {"launches_per_step": v["launches"] // nprof, "avg_us": round(us, 2), "ms_per_step": round(v["ms"] / nprof, 4)}
+            if v["flops"] > 0:
+                e["tflops"] = round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)
+            e["gbs_algorithmic"] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
+            out[k] = e
+        return out
+
+    h2d = B * 3 * 224 * 224 * 4 + B * 8
+    cb = cpu_time_steps(3, 1) if world == 1 else None  # rank 0 at N=1 only (torchrun pins OMP threads to 1)
+    line = {
+        "metric": METRIC, "value": gB / (full["ms"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": full["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"MuDPT ViT-B/16 16-shot-shaped train step (BASELINE configs[1]): batch {B}/GPU, "
+                               f"{N_CLASSES} classes sharded by class over {world} rank(s), n_ctx {N_CTX}, prompt depth {DEPTH}, "
+                               "fwd + CE + dgrad-only bwd + SGD step, random-init weights",
+                   "global_batch": gB, "classes_per_gpu": -(-N_CLASSES // world), "text_seq_len": full["text_len"],
+                   "parallelism": f"dp{world} images x class-sharded text",
+                   "l2": f"{NBUF} rotating input batches (154 MB > 126 MB L2); per-step activation working set is several GB",
+                   "operands": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LN / softmax / loss"},
+        "e2e": {"value": gB / (full["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": full["ms_e2e"],
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "api": "mudpt_b200.trainers.mudpt.MuDPT.forward_backward(batch) with pinned host batches, loss.item()"},
+        "gpu_launches": full["launches"] * K,
+        "gpu_launches_per_step": full["launches"],
+        "eot_truncated": {"value": gB / (tr["ms"] * 1e-3), "ms_per_step": tr["ms"], "text_seq_len": tr["text_len"],
+                          "e2e": {"value": gB / (tr["ms_e2e"] * 1e-3), "ms_per_step": tr["ms_e2e"]},
+                          "gpu_launches_per_step": tr["launches"], "kernels": cat_table(tr["prof"], tr["nprof"]),
+                          "note": "text tower run on max(eot)+1 tokens: exact under the causal mask (tests), product default"},
+        "roofline": {"bound": "tensor", "kernel": "gemm_tn_tcgen05_kernel (all GEMM launches of the step)",
+                     "achieved": round(gemm_tflops, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": round(gemm_tflops / peaks["bf16_sustained"], 4), "traffic": None,
+                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                     "launches_per_step": g["launches"] // full["nprof"],
+                     "avg_launch_us": round(g["ms"] * 1e3 / max(g["launches"], 1), 2),
+                     "flops_per_launch": g["flops"] / max(g["launches"], 1),
+                     "share_of_step": shares},
+        "kernels": cat_table(full["prof"], full["nprof"]),
+        "step_flops_reference_formulation_T": round((g["flops"] + full["prof"]["attn_fwd"]["flops"] +
+                                                     full["prof"]["attn_bwd"]["flops"]) / full["nprof"] / 1e12, 3),
+        "loss": full["loss"], "loss_eot_truncated": tr["loss"],
+        "clocks": clocks,
+        "cpu_baseline": cb,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="profiling aid: resident loop of the full-length variant only")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

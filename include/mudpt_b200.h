@@ -138,6 +138,12 @@ int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream)
 /* ---- introspection for tests / profiling --------------------------------------------------------
  * name in {"x_in","x_mid","qkv","o","h","lse","dx"}; layer ignored for "dx". */
 int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t layer, void** ptr, int64_t* numel);
+/* Per-kernel-class timing with CUDA events on the launch stream (bench.py's roofline leg).  Between
+ * begin and end every tower launch is bracketed by an event pair.  end() blocks until the recorded
+ * work has finished and fills out_host[cat*4 + {0,1,2,3}] = {total ms, launches, algorithmic FLOPs,
+ * algorithmic bytes} for cat = gemm, attn_fwd, attn_bwd, ln_fwd, ln_bwd, splice, head, stem. */
+int mudpt_profile_begin(mudpt_handle* h);
+int mudpt_profile_end(mudpt_handle* h, double* out_host, int32_t n_out);
 /* number of kernel launches issued by the library on this handle since creation */
 int64_t mudpt_launch_count(mudpt_handle* h);
 

@@ -58,9 +58,23 @@ struct Tower {
 
 }  // namespace
 
+// Optional per-kernel-class timing with CUDA events on the launch stream (bench.py's roofline leg).
+enum ProfCat { PC_GEMM = 0, PC_ATTN_FWD, PC_ATTN_BWD, PC_LN_FWD, PC_LN_BWD, PC_SPLICE, PC_HEAD, PC_STEM, PC_COUNT };
+struct ProfRec { int cat; cudaEvent_t e0, e1; double flops, bytes; };
+struct Prof {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+
 struct mudpt_handle {
   mudpt_config cfg;
   std::string err;
+  Prof prof;
   Tower vis, txt;
   // vision stem / heads
   bf16* w_conv = nullptr;  // [dv, Kp] bf16 (Kp = 3*p*p padded to a multiple of 8)
@@ -103,6 +117,16 @@ int fail(mudpt_handle* h, const char* fmt, ...) {
   do {                                                                                      \
     cudaError_t _c = (expr);                                                                \
     if (_c != cudaSuccess) return fail((h), "%s: %s (%s:%d)", #expr, cudaGetErrorString(_c), __FILE__, __LINE__); \
+  } while (0)
+
+// CK with optional event bracketing: category, algorithmic FLOPs and bytes of the launch
+#define CKP(h, st, cat, fl, by, expr)                                         \
+  do {                                                                        \
+    cudaEvent_t _e0 = nullptr, _e1 = nullptr;                                 \
+    if ((h)->prof.on) { _e0 = (h)->prof.get(); _e1 = (h)->prof.get(); cudaEventRecord(_e0, (st)); } \
+    const char* _e = (expr);                                                  \
+    if (_e) return fail((h), "%s (%s:%d)", _e, __FILE__, __LINE__);           \
+    if ((h)->prof.on) { cudaEventRecord(_e1, (st)); (h)->prof.recs.push_back(ProfRec{(cat), _e0, _e1, (double)(fl), (double)(by)}); } \
   } while (0)
 
 template <typename T>
@@ -211,27 +235,34 @@ int set_block_weight(mudpt_handle* h, Tower& t, int layer, const char* sub, cons
 // ---------------------------------------------------------------------------- tower passes
 int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_splice_layer, cudaStream_t st) {
   const int M = t.S * t.L, d = t.d;
+  const double Md = static_cast<double>(M), dd = d;
+  const double attn_fl = 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // QK^T + PV, dense count
   for (int i = 0; i < t.layers; ++i) {
     const Layer& w = t.lw[i];
     if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
-      CK(h, splice_fwd(t.x_in[i], prompts + static_cast<size_t>(i) * t.n_ctx * d, t.S, t.L, t.row0, t.n_ctx, d, st));
+      CKP(h, st, PC_SPLICE, 0, 2.0 * t.S * t.n_ctx * dd * 4,
+          splice_fwd(t.x_in[i], prompts + static_cast<size_t>(i) * t.n_ctx * d, t.S, t.L, t.row0, t.n_ctx, d, st));
     // x + attn(ln_1(x))   (clip/model.py:299)
-    CK(h, layernorm_fwd(t.x_in[i], w.ln1_g, w.ln1_b, t.a_buf, true, M, d, kLnEps, st));
+    CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_in[i], w.ln1_g, w.ln1_b, t.a_buf, true, M, d, kLnEps, st));
     GemmEpilogue e1;
     e1.mode = EPI_BF16; e1.out0 = t.qkv[i]; e1.bias = w.b_in; e1.ldc = 3 * d;
-    CK(h, gemm_bf16_tn(t.a_buf, d, w.w_in, d, e1, M, 3 * d, d, st));
-    CK(h, attention_fwd(t.qkv[i], t.o[i], t.lse[i], t.S, t.L, t.H, d, t.causal, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
+        gemm_bf16_tn(t.a_buf, d, w.w_in, d, e1, M, 3 * d, d, st));
+    CKP(h, st, PC_ATTN_FWD, attn_fl, Md * dd * 2 * 4, attention_fwd(t.qkv[i], t.o[i], t.lse[i], t.S, t.L, t.H, d, t.causal, st));
     GemmEpilogue e2;
     e2.mode = EPI_RESID_F32; e2.out0 = t.x_mid[i]; e2.bias = w.b_out; e2.resid = t.x_in[i]; e2.ldc = d;
-    CK(h, gemm_bf16_tn(t.o[i], d, w.w_out, d, e2, M, d, d, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (Md * dd + dd * dd) + 8 * Md * dd,
+        gemm_bf16_tn(t.o[i], d, w.w_out, d, e2, M, d, d, st));
     // x + c_proj(QuickGELU(c_fc(ln_2(x))))   (clip/model.py:300)
-    CK(h, layernorm_fwd(t.x_mid[i], w.ln2_g, w.ln2_b, t.a_buf, true, M, d, kLnEps, st));
+    CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_mid[i], w.ln2_g, w.ln2_b, t.a_buf, true, M, d, kLnEps, st));
     GemmEpilogue e3;
     e3.mode = EPI_GELU; e3.out0 = t.h[i]; e3.out1 = t.g_buf; e3.bias = w.b_fc; e3.ldc = 4 * d;
-    CK(h, gemm_bf16_tn(t.a_buf, d, w.w_fc, d, e3, M, 4 * d, d, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
+        gemm_bf16_tn(t.a_buf, d, w.w_fc, d, e3, M, 4 * d, d, st));
     GemmEpilogue e4;
     e4.mode = EPI_RESID_F32; e4.out0 = t.x_in[i + 1]; e4.bias = w.b_pr; e4.resid = t.x_mid[i]; e4.ldc = d;
-    CK(h, gemm_bf16_tn(t.g_buf, 4 * d, w.w_pr, 4 * d, e4, M, d, 4 * d, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 8 * Md * dd,
+        gemm_bf16_tn(t.g_buf, 4 * d, w.w_pr, 4 * d, e4, M, d, 4 * d, st));
   }
   t.fwd_done = true;
   return 0;
@@ -240,30 +271,36 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
 // Precondition: t.dx / t.dx_bf16 hold the gradient w.r.t. the tower output x_in[layers].
 int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice_layer, cudaStream_t st) {
   const int M = t.S * t.L, d = t.d;
+  const double Md = static_cast<double>(M), dd = d;
+  const double attn_fl = 2.5 * 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // 2.5x forward
   for (int i = t.layers - 1; i >= 0; --i) {
     const Layer& w = t.lw[i];
     // MLP branch: dg = dx W_pr ; dh = dg * GELU'(h) ; dm = dh W_fc ; dx += LN2_bwd(dm)
     GemmEpilogue e1;
     e1.mode = EPI_GELU_BWD; e1.out0 = t.dh_buf; e1.aux = t.h[i]; e1.ldc = 4 * d;
-    CK(h, gemm_bf16_tn(t.dx_bf16, d, w.w_pr_t, d, e1, M, 4 * d, d, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
+        gemm_bf16_tn(t.dx_bf16, d, w.w_pr_t, d, e1, M, 4 * d, d, st));
     GemmEpilogue e2;
     e2.mode = EPI_F32; e2.out0 = t.tmp_f32; e2.ldc = d;
-    CK(h, gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st));
-    CK(h, layernorm_bwd(t.tmp_f32, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 4 * Md * dd,
+        gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st));
+    CKP(h, st, PC_LN_BWD, 0, Md * dd * 18, layernorm_bwd(t.tmp_f32, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
     // attention branch: dO = dx W_out ; (dQ,dK,dV) ; da = dQKV W_in ; dx += LN1_bwd(da)
     GemmEpilogue e3;
     e3.mode = EPI_BF16; e3.out0 = t.do_buf; e3.ldc = d;
-    CK(h, gemm_bf16_tn(t.dx_bf16, d, w.w_out_t, d, e3, M, d, d, st));
-    CK(h, attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (2 * Md * dd + dd * dd), gemm_bf16_tn(t.dx_bf16, d, w.w_out_t, d, e3, M, d, d, st));
+    CKP(h, st, PC_ATTN_BWD, attn_fl, Md * dd * 2 * 8,
+        attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st));
     GemmEpilogue e4;
     e4.mode = EPI_F32; e4.out0 = t.tmp_f32; e4.ldc = d;
-    CK(h, gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st));
-    CK(h, layernorm_bwd(t.tmp_f32, t.x_in[i], w.ln1_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 4 * Md * dd,
+        gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st));
+    CKP(h, st, PC_LN_BWD, 0, Md * dd * 18, layernorm_bwd(t.tmp_f32, t.x_in[i], w.ln1_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
     // splice backward: the inserted prompt rows collect the batch-summed gradient; the rows
     // they overwrote get none (clip/model.py:281-297)
     if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
-      CK(h, splice_bwd(t.dx, t.dx_bf16, d_prompts + static_cast<size_t>(i) * t.n_ctx * d, t.S, t.L, t.row0, t.n_ctx, d,
-                       i > 0, st));
+      CKP(h, st, PC_SPLICE, 0, t.S * t.n_ctx * dd * 4,
+          splice_bwd(t.dx, t.dx_bf16, d_prompts + static_cast<size_t>(i) * t.n_ctx * d, t.S, t.L, t.row0, t.n_ctx, d, i > 0, st));
   }
   return 0;
 }
@@ -320,6 +357,8 @@ void mudpt_destroy(mudpt_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
+  for (ProfRec& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
   gemm_clear_tensor_map_cache();
   delete h;
 }
@@ -577,6 +616,36 @@ int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t
   if (!strcmp(name, "h")) { *ptr = t.h[layer]; *numel = rows * 4 * t.d; return 0; }
   if (!strcmp(name, "lse")) { *ptr = t.lse[layer]; *numel = rows * t.H; return 0; }
   return fail(h, "mudpt_debug_buffer: unknown buffer %s", name);
+}
+
+int mudpt_profile_begin(mudpt_handle* h) {
+  if (!h) return fail(h, "null handle");
+  for (ProfRec& r : h->prof.recs) { h->prof.pool.push_back(r.e0); h->prof.pool.push_back(r.e1); }
+  h->prof.recs.clear();
+  h->prof.on = true;
+  return 0;
+}
+
+// out[cat*4 + {0,1,2,3}] = {total ms, launches, algorithmic FLOPs, algorithmic bytes}; cat order:
+// gemm, attn_fwd, attn_bwd, ln_fwd, ln_bwd, splice, head, stem.  Blocks until the recorded work is done.
+int mudpt_profile_end(mudpt_handle* h, double* out_host, int32_t n_out) {
+  if (!h || !out_host) return fail(h, "mudpt_profile_end: null argument");
+  if (n_out < PC_COUNT * 4) return fail(h, "mudpt_profile_end: output too small");
+  h->prof.on = false;
+  for (int i = 0; i < PC_COUNT * 4; ++i) out_host[i] = 0.0;
+  for (ProfRec& r : h->prof.recs) {
+    CUDA_OK(h, cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CUDA_OK(h, cudaEventElapsedTime(&ms, r.e0, r.e1));
+    out_host[r.cat * 4 + 0] += ms;
+    out_host[r.cat * 4 + 1] += 1.0;
+    out_host[r.cat * 4 + 2] += r.flops;
+    out_host[r.cat * 4 + 3] += r.bytes;
+    h->prof.pool.push_back(r.e0);
+    h->prof.pool.push_back(r.e1);
+  }
+  h->prof.recs.clear();
+  return 0;
 }
 
 int64_t mudpt_launch_count(mudpt_handle* h) { return h ? g_launch_counter.load() - h->launches_at_create : 0; }

@@ -148,6 +148,18 @@ class Engine:
                                                   _lib.stream_ptr(self.device)), self.h)
         return d_i, d_t
 
+    PROFILE_CATEGORIES = ("gemm", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "splice", "head", "stem")
+
+    def profile_begin(self) -> None:
+        _lib.check(self.lib.mudpt_profile_begin(self.h), self.h)
+
+    def profile_end(self) -> dict:
+        n = len(self.PROFILE_CATEGORIES) * 4
+        buf = (C.c_double * n)()
+        _lib.check(self.lib.mudpt_profile_end(self.h, buf, n), self.h)
+        return {c: {"ms": buf[i * 4], "launches": int(buf[i * 4 + 1]), "flops": buf[i * 4 + 2], "bytes": buf[i * 4 + 3]}
+                for i, c in enumerate(self.PROFILE_CATEGORIES)}
+
     def launch_count(self) -> int:
         return int(self.lib.mudpt_launch_count(self.h))
 
