@@ -51,7 +51,7 @@ struct Tower {
   std::vector<float*> lse;
   // transients
   bf16 *a_buf = nullptr, *g_buf = nullptr, *dh_buf = nullptr, *do_buf = nullptr, *dqkv_buf = nullptr, *dx_bf16 = nullptr;
-  float *dx = nullptr, *tmp_f32 = nullptr, *dsum = nullptr;
+  float *dx = nullptr, *dsum = nullptr;
   bool fwd_done = false;
   int first_splice = 0;  // 0: layer 0 splices prompts[0]; 1: layer-0 rows kept as given
 };
@@ -170,7 +170,6 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
   CUDA_OK(h, dev_alloc(h, &t.dqkv_buf, rows * 3 * d));
   CUDA_OK(h, dev_alloc(h, &t.dx_bf16, rows * d));
   CUDA_OK(h, dev_alloc(h, &t.dx, rows * d));
-  CUDA_OK(h, dev_alloc(h, &t.tmp_f32, rows * d));
   CUDA_OK(h, dev_alloc(h, &t.dsum, rows * t.H));
   t.cap_rows = rows;
   t.fwd_done = false;
@@ -281,10 +280,10 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
     CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
         gemm_bf16_tn(t.dx_bf16, d, w.w_pr_t, d, e1, M, 4 * d, d, st));
     GemmEpilogue e2;
-    e2.mode = EPI_F32; e2.out0 = t.tmp_f32; e2.ldc = d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 4 * Md * dd,
+    e2.mode = EPI_BF16; e2.out0 = t.a_buf; e2.ldc = d;  // a_buf: forward transient, free during the backward
+    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 2 * Md * dd,
         gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st));
-    CKP(h, st, PC_LN_BWD, 0, Md * dd * 18, layernorm_bwd(t.tmp_f32, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
     // attention branch: dO = dx W_out ; (dQ,dK,dV) ; da = dQKV W_in ; dx += LN1_bwd(da)
     GemmEpilogue e3;
     e3.mode = EPI_BF16; e3.out0 = t.do_buf; e3.ldc = d;
@@ -292,10 +291,10 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
     CKP(h, st, PC_ATTN_BWD, attn_fl, Md * dd * 2 * 8,
         attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st));
     GemmEpilogue e4;
-    e4.mode = EPI_F32; e4.out0 = t.tmp_f32; e4.ldc = d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 4 * Md * dd,
+    e4.mode = EPI_BF16; e4.out0 = t.a_buf; e4.ldc = d;
+    CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 2 * Md * dd,
         gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st));
-    CKP(h, st, PC_LN_BWD, 0, Md * dd * 18, layernorm_bwd(t.tmp_f32, t.x_in[i], w.ln1_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_in[i], w.ln1_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
     // splice backward: the inserted prompt rows collect the batch-summed gradient; the rows
     // they overwrote get none (clip/model.py:281-297)
     if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
@@ -559,7 +558,7 @@ int mudpt_layernorm_forward(const float* x, const float* gamma, const float* bet
 }
 int mudpt_layernorm_backward(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
                              uint16_t* dx_bf16, int32_t rows, int32_t width, void* stream) {
-  CKG(layernorm_bwd(dy, x, gamma, resid, dx, reinterpret_cast<bf16*>(dx_bf16), rows, width, kLnEps, static_cast<cudaStream_t>(stream)));
+  CKG(layernorm_bwd(dy, false, x, gamma, resid, dx, reinterpret_cast<bf16*>(dx_bf16), rows, width, kLnEps, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 int mudpt_splice_forward(float* x, const float* prompt, int32_t S, int32_t L, int32_t row0, int32_t n, int32_t width, void* stream) {

@@ -11,7 +11,9 @@
 //   dKV pass: rows = keys.     P^T, dV = P^T dO, dP^T = V dO^T, dS^T, dK = dS^T Q
 // With L <= ~260 and head width 64 the kernel is bound by its Q/K/V/O traffic, not by MMA
 // rate (~100 FLOP/B vision, ~38 text), so the products run on warp-level
-// mma.sync (HMMA) tiles fed by ldmatrix from XOR-swizzled shared memory.
+// mma.sync (HMMA) tiles fed by ldmatrix from XOR-swizzled shared memory.  The backward passes
+// work on 32-column chunks and re-read their A fragments from shared memory instead of pinning
+// them in registers: that keeps them under ~128 registers so 4 CTAs fit per SM.
 #include "attention.h"
 
 #include "common.cuh"
@@ -37,36 +39,39 @@ __device__ __forceinline__ void load_tile(uint32_t tile, const bf16* g, int ld, 
   }
 }
 
-__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], uint32_t tile, int row0, int lane) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    ldsm_x4(tile + swz(row0 + (lane & 15), ks * 2 + (lane >> 4)), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], uint32_t tile, int row0, int ks, int lane) {
+  ldsm_x4(tile + swz(row0 + (lane & 15), ks * 2 + (lane >> 4)), a[0], a[1], a[2], a[3]);
 }
 
-// acc(16 x 64) = A(16 x 64dh) * T[c0 .. c0+64)^T  -- contraction over the head dimension;
-// only 16-column groups g in [g_lo, g_hi) are computed, the rest stay 0.
-__device__ __forceinline__ void mma_rows_x_cols(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int c0,
+// acc(16 x 16*NG) = A(16 rows of tileA at row0, 64 dh) * T[c0 .. c0+16*NG)^T -- contraction over the
+// head dimension.  Only 16-column groups g in [g_lo, g_hi) are computed, the rest stay 0.
+// k-step outermost: consecutive MMAs hit different accumulators (no back-to-back dependency).
+template <int NG>
+__device__ __forceinline__ void mma_rows_x_cols(float (&acc)[2 * NG][4], uint32_t tileA, int row0, uint32_t tile, int c0,
                                                 int g_lo, int g_hi, int lane) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (g >= g_lo && g < g_hi) {
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    load_a_frag(a, tileA, row0, ks, lane);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+    for (int g = 0; g < NG; ++g) {
+      if (g >= g_lo && g < g_hi) {
         uint32_t b0, b1, b2, b3;
         ldsm_x4(tile + swz(c0 + g * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
-        mma16816(acc[2 * g], a[ks], b0, b1);
-        mma16816(acc[2 * g + 1], a[ks], b2, b3);
+        mma16816(acc[2 * g], a, b0, b1);
+        mma16816(acc[2 * g + 1], a, b2, b3);
       }
     }
   }
 }
 
-// out(16 x 64dh) += P(16 x 64) * T[c0 .. c0+64)  -- contraction over the tile rows; P comes
+// out(16 x 64dh) += P(16 x 16*NG) * T[c0 .. c0+16*NG)  -- contraction over the tile rows; P comes
 // straight from accumulator registers (converted to bf16 A fragments).
-__device__ __forceinline__ void mma_p_x_tile(float (&out)[8][4], const float (&p)[8][4], uint32_t tile, int c0, int g_lo,
-                                             int g_hi, int lane) {
+template <int NG>
+__device__ __forceinline__ void mma_p_x_tile(float (&out)[8][4], const float (&p)[2 * NG][4], uint32_t tile, int c0,
+                                             int g_lo, int g_hi, int lane) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < NG; ++g) {
     if (g >= g_lo && g < g_hi) {
       uint32_t a[4];
       a[0] = pack_bf16(p[2 * g][0], p[2 * g][1]);
@@ -93,10 +98,9 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float 
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     const int r_lo = row0 + (lane >> 2), r_hi = r_lo + 8;
-    const int chunk = nt;                   // 8 bf16 columns per 16 B chunk
-    const int within = (lane & 3) * 4;      // byte offset of this thread's column pair
-    *reinterpret_cast<uint32_t*>(smem_gen + tile_off + swz(r_lo, chunk) + within) = pack_bf16(acc[nt][0] * scale0, acc[nt][1] * scale0);
-    *reinterpret_cast<uint32_t*>(smem_gen + tile_off + swz(r_hi, chunk) + within) = pack_bf16(acc[nt][2] * scale1, acc[nt][3] * scale1);
+    const int within = (lane & 3) * 4;  // byte offset of this thread's column pair inside the 16 B chunk nt
+    *reinterpret_cast<uint32_t*>(smem_gen + tile_off + swz(r_lo, nt) + within) = pack_bf16(acc[nt][0] * scale0, acc[nt][1] * scale0);
+    *reinterpret_cast<uint32_t*>(smem_gen + tile_off + swz(r_hi, nt) + within) = pack_bf16(acc[nt][2] * scale1, acc[nt][3] * scale1);
   }
   __syncwarp();
 #pragma unroll
@@ -111,12 +115,18 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float 
   }
 }
 
+template <int N>
+__device__ __forceinline__ void zero_acc(float (&a)[N][4]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
+}
+
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
 template <bool CAUSAL>
-__global__ void attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse2, int L,
-                                int H, int d, float scale_log2e) {
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+                                                       float* __restrict__ lse2, int L, int H, int d, float scale_log2e) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nwarps = blockDim.x >> 5, BQ = nwarps * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,11 +147,8 @@ __global__ void attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__
 
   const int row0 = warp * 16;
   if (q0 + row0 >= L) return;  // whole warp out of range (no further block-wide syncs below)
-  uint32_t qf[4][4];
-  load_a_frags(qf, sQ, row0, lane);
   float oacc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+  zero_acc(oacc);
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const int qrow[2] = {q0 + row0 + (lane >> 2), q0 + row0 + (lane >> 2) + 8};
   const int kv_warp = CAUSAL ? min(kv_len, q0 + row0 + 16) : kv_len;  // keys this warp can see
@@ -149,9 +156,8 @@ __global__ void attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__
   for (int c0 = 0; c0 < kv_warp; c0 += 64) {
     const int g_hi = min(4, (kv_warp - c0 + 15) >> 4);
     float sacc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
-    mma_rows_x_cols(sacc, qf, sK, c0, 0, g_hi, lane);
+    zero_acc(sacc);
+    mma_rows_x_cols<4>(sacc, sQ, row0, sK, c0, 0, g_hi, lane);
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -185,7 +191,7 @@ __global__ void attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__
         l_run[r] += p;
         oacc[nt][e] *= alpha[r];
       }
-    mma_p_x_tile(oacc, sacc, sV, c0, 0, g_hi, lane);
+    mma_p_x_tile<4>(oacc, sacc, sV, c0, 0, g_hi, lane);
   }
   float inv[2];
 #pragma unroll
@@ -203,9 +209,10 @@ __global__ void attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__
 // backward, dQ pass (rows = queries).  Also produces D = rowsum(dO * O) for the dKV pass.
 // ---------------------------------------------------------------------------------------
 template <bool CAUSAL>
-__global__ void attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
-                                   const float* __restrict__ lse2, float* __restrict__ dsum, bf16* __restrict__ dqkv,
-                                   int L, int H, int d, float scale, float scale_log2e) {
+__global__ void __launch_bounds__(128, 4) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+                                                             const bf16* __restrict__ d_o, const float* __restrict__ lse2,
+                                                             float* __restrict__ dsum, bf16* __restrict__ dqkv, int L,
+                                                             int H, int d, float scale, float scale_log2e) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nwarps = blockDim.x >> 5, BQ = nwarps * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,25 +268,18 @@ __global__ void attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __r
 #pragma unroll
   for (int r = 0; r < 2; ++r) lse[r] = qrow[r] < L ? lse2[stat_base + qrow[r]] : 0.f;
 
-  uint32_t qf[4][4], dof[4][4];
-  load_a_frags(qf, sQ, row0, lane);
-  load_a_frags(dof, sdO, row0, lane);
   float dq[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  zero_acc(dq);
   const int kv_warp = CAUSAL ? min(kv_len, q0 + row0 + 16) : kv_len;
-  for (int c0 = 0; c0 < kv_warp; c0 += 64) {
-    const int g_hi = min(4, (kv_warp - c0 + 15) >> 4);
-    float sacc[8][4], dp[8][4];
+  for (int c0 = 0; c0 < kv_warp; c0 += 32) {
+    const int g_hi = min(2, (kv_warp - c0 + 15) >> 4);
+    float sacc[4][4], dp[4][4];
+    zero_acc(sacc);
+    zero_acc(dp);
+    mma_rows_x_cols<2>(sacc, sQ, row0, sK, c0, 0, g_hi, lane);
+    mma_rows_x_cols<2>(dp, sdO, row0, sV, c0, 0, g_hi, lane);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
-      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
-    }
-    mma_rows_x_cols(sacc, qf, sK, c0, 0, g_hi, lane);
-    mma_rows_x_cols(dp, dof, sV, c0, 0, g_hi, lane);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);
@@ -288,7 +288,7 @@ __global__ void attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __r
         const float p = ok ? exp2f(sacc[nt][e] * scale_log2e - lse[r]) : 0.f;
         sacc[nt][e] = p * (dp[nt][e] - Dr[r]);  // dS (unscaled)
       }
-    mma_p_x_tile(dq, sacc, sK, c0, 0, g_hi, lane);
+    mma_p_x_tile<2>(dq, sacc, sK, c0, 0, g_hi, lane);
   }
   store_rows_bf16(dq, scale, scale, smem, 0, row0, dqkv + seq_row * ld + h * DH, ld, q0 + row0, L, lane);
 }
@@ -297,9 +297,10 @@ __global__ void attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __r
 // backward, dK/dV pass (rows = keys)
 // ---------------------------------------------------------------------------------------
 template <bool CAUSAL>
-__global__ void attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
-                                    const float* __restrict__ lse2, const float* __restrict__ dsum,
-                                    bf16* __restrict__ dqkv, int L, int H, int d, float scale, float scale_log2e) {
+__global__ void __launch_bounds__(128, 3) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                              const float* __restrict__ lse2, const float* __restrict__ dsum,
+                                                              bf16* __restrict__ dqkv, int L, int H, int d, float scale,
+                                                              float scale_log2e) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nwarps = blockDim.x >> 5, BKV = nwarps * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -312,10 +313,11 @@ __global__ void attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __
   const int ld = 3 * d;
   const size_t seq_row = static_cast<size_t>(s) * L;
   const bf16* base = qkv + seq_row * ld + h * DH;
+  const int q_blk = CAUSAL ? (k0 & ~15) : 0;  // queries below the block's first key never see it
   load_tile(sK, base + d, ld, k0, L, BKV);
   load_tile(sV, base + 2 * d, ld, k0, L, BKV);
-  load_tile(sQ, base, ld, 0, L, Lp);
-  load_tile(sdO, d_o + seq_row * d + h * DH, d, 0, L, Lp);
+  load_tile(sQ + q_blk * ROW_BYTES, base, ld, q_blk, L, Lp - q_blk);
+  load_tile(sdO + q_blk * ROW_BYTES, d_o + seq_row * d + h * DH, d, q_blk, L, Lp - q_blk);
   cp_async_commit();
   const size_t stat_base = (static_cast<size_t>(s) * H + h) * L;
   for (int i = threadIdx.x; i < Lp; i += blockDim.x) {
@@ -327,31 +329,21 @@ __global__ void attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __
 
   const int row0 = warp * 16;
   if (k0 + row0 >= L) return;
-  uint32_t kf[4][4], vf[4][4];
-  load_a_frags(kf, sK, row0, lane);
-  load_a_frags(vf, sV, row0, lane);
   float dk[8][4], dv[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
-    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
-  }
+  zero_acc(dk);
+  zero_acc(dv);
   const int krow[2] = {k0 + row0 + (lane >> 2), k0 + row0 + (lane >> 2) + 8};
   const int q_first = CAUSAL ? (k0 + row0) : 0;  // first query that can see any of this warp's keys
-  for (int c0 = q_first & ~63; c0 < L; c0 += 64) {
+  for (int c0 = q_first & ~31; c0 < L; c0 += 32) {
     const int g_lo = max(0, (q_first - c0) >> 4);
-    const int g_hi = min(4, (L - c0 + 15) >> 4);
-    float st[8][4], dpt[8][4];
+    const int g_hi = min(2, (L - c0 + 15) >> 4);
+    float st[4][4], dpt[4][4];
+    zero_acc(st);
+    zero_acc(dpt);
+    mma_rows_x_cols<2>(st, sK, row0, sQ, c0, g_lo, g_hi, lane);
+    mma_rows_x_cols<2>(dpt, sV, row0, sdO, c0, g_lo, g_hi, lane);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
-      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
-    }
-    mma_rows_x_cols(st, kf, sQ, c0, g_lo, g_hi, lane);
-    mma_rows_x_cols(dpt, vf, sdO, c0, g_lo, g_hi, lane);
-    float ds[8][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int qi = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);  // query index (column)
@@ -360,10 +352,10 @@ __global__ void attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __
         const int qc = min(qi, Lp - 1);
         const float p = ok ? exp2f(st[nt][e] * scale_log2e - sLse[qc]) : 0.f;
         st[nt][e] = p;                               // P^T
-        ds[nt][e] = p * (dpt[nt][e] - sD[qc]);       // dS^T (unscaled)
+        dpt[nt][e] = p * (dpt[nt][e] - sD[qc]);      // dS^T (unscaled), in place
       }
-    mma_p_x_tile(dv, st, sdO, c0, g_lo, g_hi, lane);
-    mma_p_x_tile(dk, ds, sQ, c0, g_lo, g_hi, lane);
+    mma_p_x_tile<2>(dv, st, sdO, c0, g_lo, g_hi, lane);
+    mma_p_x_tile<2>(dk, dpt, sQ, c0, g_lo, g_hi, lane);
   }
   bf16* out = dqkv + seq_row * ld + h * DH;
   store_rows_bf16(dk, scale, scale, smem, 0, row0, out + d, ld, k0 + row0, L, lane);

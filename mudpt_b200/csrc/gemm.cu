@@ -30,7 +30,8 @@ namespace mudpt {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
+static constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -38,85 +39,69 @@ struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = EPI_WARPS * 32 * 32 * 4;  // epilogue transpose buffers, 4 KB per warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;
 };
 
 // ---------------------------------------------------------------------------------------
-// Fused epilogue on 8 consecutive columns of one row.
+// Fused epilogue on 4 consecutive columns of one row (one lane of the coalesced phase).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void store8_bf16(bf16* p, const float (&v)[8]) {
-  uint4 u;
-  u.x = pack_bf16(v[0], v[1]);
-  u.y = pack_bf16(v[2], v[3]);
-  u.z = pack_bf16(v[4], v[5]);
-  u.w = pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = u;
+__device__ __forceinline__ uint2 pack4_bf16(const float4& v) {
+  uint2 u;
+  u.x = pack_bf16(v.x, v.y);
+  u.y = pack_bf16(v.z, v.w);
+  return u;
 }
-__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
-  float4 a = *reinterpret_cast<const float4*>(p);
-  float4 b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void load8_bf16(const bf16* p, float (&v)[8]) {
-  uint4 u = *reinterpret_cast<const uint4*>(p);
-  float2 f;
-  f = unpack_bf16(u.x); v[0] = f.x; v[1] = f.y;
-  f = unpack_bf16(u.y); v[2] = f.x; v[3] = f.y;
-  f = unpack_bf16(u.z); v[4] = f.x; v[5] = f.y;
-  f = unpack_bf16(u.w); v[6] = f.x; v[7] = f.y;
+
+// Extra per-element operand of the epilogue (residual / saved pre-activation / positional embedding),
+// fetched ahead of time so that its DRAM latency overlaps the TMEM drain instead of serialising
+// against the stores (out0 and the operand may alias as far as the compiler knows).
+template <int MODE>
+__device__ __forceinline__ float4 epilogue_prefetch(const GemmEpilogue& ep, int row, int col) {
+  if constexpr (MODE == EPI_RESID_F32) {
+    return *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(row) * ep.ldc + col);
+  } else if constexpr (MODE == EPI_GELU_BWD) {
+    const uint2 hu = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + static_cast<size_t>(row) * ep.ldc + col);
+    const float2 h0 = unpack_bf16(hu.x), h1 = unpack_bf16(hu.y);
+    return make_float4(h0.x, h0.y, h1.x, h1.y);
+  } else if constexpr (MODE == EPI_PATCH) {
+    const int p = row % ep.patch_np;
+    return *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(1 + p) * ep.ldc + col);
+  } else {
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 template <int MODE>
-__device__ __forceinline__ void epilogue8(const GemmEpilogue& ep, int row, int col, float (&v)[8]) {
-  // row < M and col + 8 <= N are guaranteed by the caller (N % 8 == 0).
-  if (ep.bias != nullptr) {
-    float b[8];
-    load8_f32(ep.bias + col, b);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += b[i];
-  }
+__device__ __forceinline__ void epilogue4(const GemmEpilogue& ep, int row, int col, float4 v, const float4& ex) {
+  // row < M and col + 4 <= N are guaranteed by the caller (N % 8 == 0); bias already added.
   const size_t off = static_cast<size_t>(row) * ep.ldc + col;
   if constexpr (MODE == EPI_BF16) {
-    store8_bf16(reinterpret_cast<bf16*>(ep.out0) + off, v);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + off) = pack4_bf16(v);
   } else if constexpr (MODE == EPI_F32) {
-    store8_f32(reinterpret_cast<float*>(ep.out0) + off, v);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + off) = v;
   } else if constexpr (MODE == EPI_RESID_F32) {
-    float r[8];
-    load8_f32(ep.resid + off, r);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += r[i];
-    store8_f32(reinterpret_cast<float*>(ep.out0) + off, v);
+    v.x += ex.x; v.y += ex.y; v.z += ex.z; v.w += ex.w;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + off) = v;
   } else if constexpr (MODE == EPI_GELU) {
     // out0 = pre-activation h (kept for the backward GELU'), out1 = QuickGELU(h)
-    if (ep.out0 != nullptr) store8_bf16(reinterpret_cast<bf16*>(ep.out0) + off, v);
-    float g[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = quick_gelu(v[i]);
-    store8_bf16(reinterpret_cast<bf16*>(ep.out1) + off, g);
+    if (ep.out0 != nullptr) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + off) = pack4_bf16(v);
+    const float4 g = make_float4(quick_gelu(v.x), quick_gelu(v.y), quick_gelu(v.z), quick_gelu(v.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out1) + off) = pack4_bf16(g);
   } else if constexpr (MODE == EPI_GELU_BWD) {
-    // out0 = acc * QuickGELU'(h), h = aux (bf16 pre-activation saved by the forward)
-    float h[8];
-    load8_bf16(reinterpret_cast<const bf16*>(ep.aux) + off, h);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= quick_gelu_grad(h[i]);
-    store8_bf16(reinterpret_cast<bf16*>(ep.out0) + off, v);
+    // out0 = acc * QuickGELU'(h), h = saved bf16 pre-activation (prefetched into ex)
+    v.x *= quick_gelu_grad(ex.x); v.y *= quick_gelu_grad(ex.y);
+    v.z *= quick_gelu_grad(ex.z); v.w *= quick_gelu_grad(ex.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + off) = pack4_bf16(v);
   } else if constexpr (MODE == EPI_PATCH) {
     // patch-embedding scatter (clip/model.py:527-531): GEMM row r = image*np + p goes to token
-    // row image*L + 1 + p of the residual stream, plus positional_embedding[1 + p].
+    // row image*L + 1 + p of the residual stream, plus positional_embedding[1 + p] (in ex).
     const int img = row / ep.patch_np;
     const int p = row - img * ep.patch_np;
-    float pe[8];
-    load8_f32(ep.resid + static_cast<size_t>(1 + p) * ep.ldc + col, pe);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += pe[i];
+    v.x += ex.x; v.y += ex.y; v.z += ex.z; v.w += ex.w;
     const size_t o = (static_cast<size_t>(img) * ep.patch_L + 1 + p) * ep.ldc + col;
-    store8_f32(reinterpret_cast<float*>(ep.out0) + o, v);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + o) = v;
   }
 }
 
@@ -133,7 +118,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
@@ -156,7 +142,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -216,34 +202,64 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quadrant (quad = warp % 4); the pair splits the 32-column chunks of the
+    // accumulator between them (even / odd), so every SM sub-partition has two epilogue warps to
+    // overlap TMEM / shared / global latencies.
+    //   Phase A: thread = accumulator row (TMEM lane): 32 fp32 columns -> this warp's staging buffer
+    //            (32 rows x 128 B, 16-byte chunks XOR-swizzled by row: conflict-free).
+    //   Phase B: 8 lanes per row, lane j owns columns 4j..4j+3, so every global load/store
+    //            instruction covers whole 128 B (fp32) / 64 B (bf16) row segments of 4 rows.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* stage = smem_stage + (warp - 2) * 4096;
+    const int rr0 = lane >> 3, j = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
+    constexpr int kChunks = BN / 32;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const int ncol = N - n_blk * BN;  // valid columns in this tile (may exceed BN)
+      uint32_t r[32];
+      int c = half;
+      if (c * 32 < ncol) tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), r);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), r);
-        tmem_ld_wait();
-        if (row < M) {
+      for (; c < kChunks && c * 32 < ncol; c += 2) {
+        const int col = n_blk * BN + c * 32 + 4 * j;  // this lane's 4 columns in phase B
+        constexpr bool kHasExtra = (MODE == EPI_RESID_F32 || MODE == EPI_GELU_BWD || MODE == EPI_PATCH);
+        float4 ex[kHasExtra ? 8 : 1];
+        if constexpr (kHasExtra) {
+          // issue the 8 operand loads of this chunk back to back, before waiting on TMEM
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (col0 + j * 8 < N) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
-              epilogue8<MODE>(ep, row, col0 + j * 8, v);
-            }
+          for (int it = 0; it < 8; ++it) {
+            const int row = m_blk * BM + quad * 32 + it * 4 + rr0;
+            ex[it] = (col < N && row < M) ? epilogue_prefetch<MODE>(ep, row, col) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        tmem_ld_wait_regs(r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(stage + lane * 128 + (((k ^ lane) & 7) << 4)) =
+              make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        __syncwarp();
+        // prefetch the next chunk's accumulator columns while phase B runs
+        if (c + 2 < kChunks && (c + 2) * 32 < ncol) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * 32), r);
+        if (col < N) {
+          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias != nullptr) bias = *reinterpret_cast<const float4*>(ep.bias + col);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rr0;
+            const int row = m_blk * BM + quad * 32 + rr;
+            float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + (((j ^ rr) & 7) << 4));
+            v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+            if (row < M) epilogue4<MODE>(ep, row, col, v, ex[kHasExtra ? it : 0]);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -277,7 +293,10 @@ __global__ void gemm_tn_simt_kernel(const bf16* __restrict__ A, const bf16* __re
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += av * __bfloat162float(B[static_cast<size_t>(col + i) * ldb + k]);
   }
-  epilogue8<MODE>(ep, row, col, v);
+  if (ep.bias != nullptr)
+    for (int i = 0; i < 8; ++i) v[i] += ep.bias[col + i];
+  epilogue4<MODE>(ep, row, col, make_float4(v[0], v[1], v[2], v[3]), epilogue_prefetch<MODE>(ep, row, col));
+  epilogue4<MODE>(ep, row, col + 4, make_float4(v[4], v[5], v[6], v[7]), epilogue_prefetch<MODE>(ep, row, col + 4));
 }
 static bool g_simt = false;
 void gemm_set_bringup_simt(bool on) { g_simt = on; }

@@ -15,8 +15,10 @@ namespace mudpt {
 static constexpr int LN_MAXV = 8;  // float4 per lane -> width <= 1024
 
 // ------------------------------------------------------------------ LayerNorm forward
-// One warp per row. OUT_BF16: normalized row as bf16 (GEMM A operand); else fp32 (may alias x).
-template <bool OUT_BF16>
+// One warp per row, NV float4 per lane (NV = ceil(width / 128), compile-time so that narrow towers
+// do not pay registers for wide ones). OUT_BF16: normalized row as bf16 (GEMM A operand); else fp32
+// (may alias x).
+template <int NV, bool OUT_BF16>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, void* __restrict__ out, int M, int d,
                                                      float eps) {
@@ -24,10 +26,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float* xr = x + static_cast<size_t>(row) * d;
-  float4 v[LN_MAXV];
+  float4 v[NV];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
       v[i] = *reinterpret_cast<const float4*>(xr + c);
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   const float mean = warp_sum(sum) / d;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
       const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   }
   const float rstd = rsqrtf(warp_sum(sq) / d + eps);
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
       const float4 g = *reinterpret_cast<const float4*>(gamma + c);
@@ -68,13 +70,30 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   }
 }
 
+static int pick_nv(int d) {
+  const int nv = (d + 127) / 128;
+  return nv <= 1 ? 1 : nv <= 2 ? 2 : nv <= 4 ? 4 : nv <= 6 ? 6 : 8;
+}
+
+template <int NV>
+static void launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
+                          float eps, cudaStream_t stream) {
+  const int grid = (M + 7) / 8;
+  if (out_bf16) ln_fwd_kernel<NV, true><<<grid, 256, 0, stream>>>(x, gamma, beta, out, M, d, eps);
+  else ln_fwd_kernel<NV, false><<<grid, 256, 0, stream>>>(x, gamma, beta, out, M, d, eps);
+}
+
 const char* layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
                           float eps, cudaStream_t stream) {
   if (M <= 0) return nullptr;
   if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
-  const int grid = (M + 7) / 8;
-  if (out_bf16) ln_fwd_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, out, M, d, eps);
-  else ln_fwd_kernel<false><<<grid, 256, 0, stream>>>(x, gamma, beta, out, M, d, eps);
+  switch (pick_nv(d)) {
+    case 1: launch_ln_fwd<1>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
+    case 2: launch_ln_fwd<2>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
+    case 4: launch_ln_fwd<4>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
+    case 6: launch_ln_fwd<6>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
+    default: launch_ln_fwd<8>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
+  }
   count_launch(1);
   return cudaPeekAtLastError() == cudaSuccess ? nullptr : "layernorm fwd launch failed";
 }
@@ -83,28 +102,37 @@ const char* layernorm_fwd(const float* x, const float* gamma, const float* beta,
 // dx = resid + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.
 // gamma/beta are frozen (trainers/mudpt.py:205-212): no dgamma/dbeta. Statistics are
 // recomputed from the saved fp32 input row. dx may alias resid. Also emits the bf16 copy of dx
-// that feeds the next dgrad GEMM.
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+// that feeds the next dgrad GEMM.  DY_BF16: dy comes from a bf16 GEMM epilogue.
+template <int NV, bool DY_BF16>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* resid, float* dx,
                                                      bf16* __restrict__ dx_bf16, int M, int d, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const size_t off = static_cast<size_t>(row) * d;
-  float4 v[LN_MAXV], g[LN_MAXV];
+  float4 v[NV], g[NV];
   float sum = 0.f;
+  // issue every load of the row up front (x, dy, residual gradient): 3 streams in flight per lane
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
       v[i] = *reinterpret_cast<const float4*>(x + off + c);
+      if constexpr (DY_BF16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy) + off + c);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        g[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        g[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + off + c);
+      }
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
   const float mean = warp_sum(sum) / d;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
       v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
@@ -114,13 +142,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   const float rstd = rsqrtf(warp_sum(sq) / d + eps);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
-      const float4 gy = *reinterpret_cast<const float4*>(dy + off + c);
       const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
       v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
-      g[i].x = gy.x * gm.x; g[i].y = gy.y * gm.y; g[i].z = gy.z * gm.z; g[i].w = gy.w * gm.w;
+      g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
       s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
       s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
     }
@@ -128,7 +155,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   s1 = warp_sum(s1) / d;
   s2 = warp_sum(s2) / d;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -149,11 +176,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   }
 }
 
-const char* layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
+template <int NV>
+static void launch_ln_bwd(const void* dy, bool dy_bf16, const float* x, const float* gamma, const float* resid, float* dx,
+                          bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
+  const int grid = (M + 7) / 8;
+  if (dy_bf16) ln_bwd_kernel<NV, true><<<grid, 256, 0, stream>>>(dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
+  else ln_bwd_kernel<NV, false><<<grid, 256, 0, stream>>>(dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
+}
+
+const char* layernorm_bwd(const void* dy, bool dy_bf16, const float* x, const float* gamma, const float* resid, float* dx,
                           bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
   if (M <= 0) return nullptr;
   if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
-  ln_bwd_kernel<<<(M + 7) / 8, 256, 0, stream>>>(dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
+  switch (pick_nv(d)) {
+    case 1: launch_ln_bwd<1>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    case 2: launch_ln_bwd<2>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    case 4: launch_ln_bwd<4>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    case 6: launch_ln_bwd<6>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    default: launch_ln_bwd<8>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+  }
   count_launch(1);
   return cudaPeekAtLastError() == cudaSuccess ? nullptr : "layernorm bwd launch failed";
 }

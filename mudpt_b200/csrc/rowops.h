@@ -7,7 +7,7 @@
 namespace mudpt {
 const char* layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
                           float eps, cudaStream_t stream);
-const char* layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
+const char* layernorm_bwd(const void* dy, bool dy_bf16, const float* x, const float* gamma, const float* resid, float* dx,
                           __nv_bfloat16* dx_bf16, int M, int d, float eps, cudaStream_t stream);
 const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, int n, int d, cudaStream_t stream);
 const char* splice_bwd(float* dx, __nv_bfloat16* dx_bf16, float* dprompt, int S, int L, int row0, int n, int d,

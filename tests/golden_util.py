@@ -34,7 +34,11 @@ def load(name):
 def make_cfg(n_ctx, depth, ctx_init, size, arch_name="ViT-B/16"):
     """The subset of the yacs tree the hot path reads (train.py:114-119); plain attribute dicts."""
     class N(dict):
-        __getattr__ = dict.__getitem__
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError as e:
+                raise AttributeError(k) from e
         __setattr__ = dict.__setitem__
     cfg = N()
     cfg.TRAINER = N(NAME="MuDPT", MUDPT=N(N_CTX=n_ctx, CTX_INIT=ctx_init, DEEP_PROMPT_DEPTH=depth, PREC="fp32"))

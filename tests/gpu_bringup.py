@@ -123,6 +123,35 @@ def group_gemm(res):
         res[f"gemm_time_{M}x{N}x{K}"] = {"ms": ms, "tflops": 2 * M * N * K / ms / 1e9, "cublas_ms": ms_t,
                                         "cublas_tflops": 2 * M * N * K / ms_t / 1e9}
         print(f"gemm_time_{M}x{N}x{K}", res[f"gemm_time_{M}x{N}x{K}"], flush=True)
+    # the text-tower shapes of BASELINE config 2 with their real epilogues
+    M = 77000
+    for (N, K, mode, tag) in [(1536, 512, 0, "qkv"), (512, 512, 2, "out_proj+resid"), (2048, 512, 3, "c_fc+gelu"),
+                              (512, 2048, 2, "c_proj+resid"), (2048, 512, 4, "d_c_proj*gelu'"), (512, 2048, 0, "d_c_fc")]:
+        A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
+        bias = torch.randn(N, device=dev)
+        f32 = mode in (1, 2)
+        out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+        out1 = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if mode == 3 else None
+        resid = torch.randn(M, N, device=dev) if mode == 2 else None
+        aux = torch.randn(M, N, device=dev).bfloat16() if mode == 4 else None
+
+        def call():
+            lib.mudpt_gemm_bf16(A.data_ptr(), B.data_ptr(), M, N, K, mode, out.data_ptr(),
+                                out1.data_ptr() if out1 is not None else None, bias.data_ptr(),
+                                resid.data_ptr() if resid is not None else None,
+                                aux.data_ptr() if aux is not None else None, N, 1, 1, st)
+        for _ in range(3):
+            call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        nbytes = 2 * (M * K + N * K) + M * N * ((4 if f32 else 2) + (2 if mode == 3 else 0) + (4 if mode == 2 else 0) + (2 if mode == 4 else 0))
+        res[f"gemm_text_{tag}"] = {"ms": ms, "tflops": 2 * M * N * K / ms / 1e9, "gbs": nbytes / ms / 1e6,
+                                   "hbm_bound_ms": nbytes / 6538.3e6, "mma_bound_ms": 2 * M * N * K / 1618.5e9}
+        print(f"gemm_text_{tag}", res[f"gemm_text_{tag}"], flush=True)
 
 
 # ------------------------------------------------------------------------------------------ rowops
