@@ -51,7 +51,7 @@ struct Tower {
   std::vector<float*> lse;
   // transients
   bf16 *a_buf = nullptr, *g_buf = nullptr, *dh_buf = nullptr, *do_buf = nullptr, *dqkv_buf = nullptr, *dx_bf16 = nullptr;
-  float *dx = nullptr, *dsum = nullptr;
+  float *dx = nullptr, *dsum = nullptr, *splice_ws = nullptr;
   bool fwd_done = false;
   int first_splice = 0;  // 0: layer 0 splices prompts[0]; 1: layer-0 rows kept as given
 };
@@ -171,6 +171,7 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
   CUDA_OK(h, dev_alloc(h, &t.dx_bf16, rows * d));
   CUDA_OK(h, dev_alloc(h, &t.dx, rows * d));
   CUDA_OK(h, dev_alloc(h, &t.dsum, rows * t.H));
+  if (!t.splice_ws) CUDA_OK(h, dev_alloc(h, &t.splice_ws, splice_bwd_workspace_floats(t.n_ctx > 0 ? t.n_ctx : 1, t.d)));
   t.cap_rows = rows;
   t.fwd_done = false;
   return 0;
@@ -299,7 +300,7 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
     // they overwrote get none (clip/model.py:281-297)
     if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
       CKP(h, st, PC_SPLICE, 0, t.S * t.n_ctx * dd * 4,
-          splice_bwd(t.dx, t.dx_bf16, d_prompts + static_cast<size_t>(i) * t.n_ctx * d, t.S, t.L, t.row0, t.n_ctx, d, i > 0, st));
+          splice_bwd(t.dx, t.dx_bf16, d_prompts + static_cast<size_t>(i) * t.n_ctx * d, t.splice_ws, t.S, t.L, t.row0, t.n_ctx, d, i > 0, st));
   }
   return 0;
 }
@@ -567,7 +568,13 @@ int mudpt_splice_forward(float* x, const float* prompt, int32_t S, int32_t L, in
 }
 int mudpt_splice_backward(float* dx, uint16_t* dx_bf16, float* d_prompt, int32_t S, int32_t L, int32_t row0, int32_t n,
                           int32_t width, int32_t zero_rows, void* stream) {
-  CKG(splice_bwd(dx, reinterpret_cast<bf16*>(dx_bf16), d_prompt, S, L, row0, n, width, zero_rows != 0, static_cast<cudaStream_t>(stream)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = nullptr;  // unit entry point: stream-ordered scratch (the towers own a persistent one)
+  if (cudaMallocAsync(reinterpret_cast<void**>(&ws), splice_bwd_workspace_floats(n, width) * sizeof(float), st) != cudaSuccess)
+    return fail(nullptr, "mudpt_splice_backward: scratch allocation failed");
+  const char* e = splice_bwd(dx, reinterpret_cast<bf16*>(dx_bf16), d_prompt, ws, S, L, row0, n, width, zero_rows != 0, st);
+  cudaFreeAsync(ws, st);
+  if (e) return fail(nullptr, "%s", e);
   return 0;
 }
 int mudpt_attention_forward(const uint16_t* qkv, uint16_t* o, float* lse2, int32_t S, int32_t L, int32_t H, int32_t causal, void* stream) {

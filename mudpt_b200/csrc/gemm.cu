@@ -57,24 +57,29 @@ __device__ __forceinline__ uint2 pack4_bf16(const float4& v) {
 // Extra per-element operand of the epilogue (residual / saved pre-activation / positional embedding),
 // fetched ahead of time so that its DRAM latency overlaps the TMEM drain instead of serialising
 // against the stores (out0 and the operand may alias as far as the compiler knows).
+template <int MODE> struct EpiExtra { typedef float4 type; };
+template <> struct EpiExtra<EPI_GELU_BWD> { typedef uint2 type; };  // 4 packed bf16: half the registers
+
+// `row`/`col` must be in range (the caller clamps them): the load is unconditional so that the
+// compiler can keep all prefetches of a chunk in flight (a predicated load + select forces a wait
+// on every single load).
 template <int MODE>
-__device__ __forceinline__ float4 epilogue_prefetch(const GemmEpilogue& ep, int row, int col) {
+__device__ __forceinline__ typename EpiExtra<MODE>::type epilogue_prefetch(const GemmEpilogue& ep, int row, int col) {
   if constexpr (MODE == EPI_RESID_F32) {
-    return *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(row) * ep.ldc + col);
+    return __ldg(reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(row) * ep.ldc + col));
   } else if constexpr (MODE == EPI_GELU_BWD) {
-    const uint2 hu = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + static_cast<size_t>(row) * ep.ldc + col);
-    const float2 h0 = unpack_bf16(hu.x), h1 = unpack_bf16(hu.y);
-    return make_float4(h0.x, h0.y, h1.x, h1.y);
+    return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + static_cast<size_t>(row) * ep.ldc + col));
   } else if constexpr (MODE == EPI_PATCH) {
     const int p = row % ep.patch_np;
-    return *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(1 + p) * ep.ldc + col);
+    return __ldg(reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(1 + p) * ep.ldc + col));
   } else {
     return make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
 template <int MODE>
-__device__ __forceinline__ void epilogue4(const GemmEpilogue& ep, int row, int col, float4 v, const float4& ex) {
+__device__ __forceinline__ void epilogue4(const GemmEpilogue& ep, int row, int col, float4 v,
+                                          const typename EpiExtra<MODE>::type& ex) {
   // row < M and col + 4 <= N are guaranteed by the caller (N % 8 == 0); bias already added.
   const size_t off = static_cast<size_t>(row) * ep.ldc + col;
   if constexpr (MODE == EPI_BF16) {
@@ -90,9 +95,10 @@ __device__ __forceinline__ void epilogue4(const GemmEpilogue& ep, int row, int c
     const float4 g = make_float4(quick_gelu(v.x), quick_gelu(v.y), quick_gelu(v.z), quick_gelu(v.w));
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out1) + off) = pack4_bf16(g);
   } else if constexpr (MODE == EPI_GELU_BWD) {
-    // out0 = acc * QuickGELU'(h), h = saved bf16 pre-activation (prefetched into ex)
-    v.x *= quick_gelu_grad(ex.x); v.y *= quick_gelu_grad(ex.y);
-    v.z *= quick_gelu_grad(ex.z); v.w *= quick_gelu_grad(ex.w);
+    // out0 = acc * QuickGELU'(h), h = saved bf16 pre-activation (prefetched, packed, in ex)
+    const float2 h0 = unpack_bf16(ex.x), h1 = unpack_bf16(ex.y);
+    v.x *= quick_gelu_grad(h0.x); v.y *= quick_gelu_grad(h0.y);
+    v.z *= quick_gelu_grad(h1.x); v.w *= quick_gelu_grad(h1.y);
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + off) = pack4_bf16(v);
   } else if constexpr (MODE == EPI_PATCH) {
     // patch-embedding scatter (clip/model.py:527-531): GEMM row r = image*np + p goes to token
@@ -115,7 +121,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // Pointer arithmetic on the __shared__ array (no integer round trip) keeps the shared address space
+  // visible to the compiler, so the epilogue staging accesses compile to STS/LDS, not generic ST/LD.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
   uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -219,26 +227,31 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     constexpr int kChunks = BN / 32;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      typedef typename EpiExtra<MODE>::type Ex;
+      constexpr bool kHasExtra = (MODE == EPI_RESID_F32 || MODE == EPI_GELU_BWD || MODE == EPI_PATCH);
+      constexpr bool kDouble = (MODE == EPI_GELU_BWD);  // packed operand: cheap enough to prefetch a chunk ahead
+      const int ncol = N - n_blk * BN;  // valid columns in this tile (may exceed BN)
+      const int row_base = m_blk * BM + quad * 32 + rr0;
+      int c = half;
+      Ex ex[kHasExtra ? 8 : 1], exn[kDouble ? 8 : 1];
+      auto load_extra = [&](Ex(&dst)[kHasExtra ? 8 : 1], int chunk) {
+        const int col = min(n_blk * BN + chunk * 32 + 4 * j, N - 4);  // clamped: out-of-range lanes never use it
+#pragma unroll
+        for (int it = 0; it < (kHasExtra ? 8 : 1); ++it)
+          dst[it] = epilogue_prefetch<MODE>(ep, min(row_base + it * 4, M - 1), col);
+      };
+      // the first chunk's operand loads are issued before waiting for the accumulator
+      if constexpr (kHasExtra) { if (c * 32 < ncol) load_extra(ex, c); }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      const int ncol = N - n_blk * BN;  // valid columns in this tile (may exceed BN)
       uint32_t r[32];
-      int c = half;
       if (c * 32 < ncol) tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), r);
 #pragma unroll 1
       for (; c < kChunks && c * 32 < ncol; c += 2) {
         const int col = n_blk * BN + c * 32 + 4 * j;  // this lane's 4 columns in phase B
-        constexpr bool kHasExtra = (MODE == EPI_RESID_F32 || MODE == EPI_GELU_BWD || MODE == EPI_PATCH);
-        float4 ex[kHasExtra ? 8 : 1];
-        if constexpr (kHasExtra) {
-          // issue the 8 operand loads of this chunk back to back, before waiting on TMEM
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = m_blk * BM + quad * 32 + it * 4 + rr0;
-            ex[it] = (col < N && row < M) ? epilogue_prefetch<MODE>(ep, row, col) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
+        const bool has_next = (c + 2 < kChunks) && ((c + 2) * 32 < ncol);
+        if constexpr (kDouble) { if (has_next) load_extra(exn, c + 2); }
         tmem_ld_wait_regs(r);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -246,7 +259,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
               make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
         __syncwarp();
         // prefetch the next chunk's accumulator columns while phase B runs
-        if (c + 2 < kChunks && (c + 2) * 32 < ncol) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * 32), r);
+        if (has_next) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * 32), r);
         if (col < N) {
           float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias != nullptr) bias = *reinterpret_cast<const float4*>(ep.bias + col);
@@ -260,6 +273,12 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
           }
         }
         __syncwarp();
+        if constexpr (kDouble) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) ex[it] = exn[it];
+        } else if constexpr (kHasExtra) {
+          if (has_next) load_extra(ex, c + 2);
+        }
       }
       tc_fence_before();
       __syncwarp();

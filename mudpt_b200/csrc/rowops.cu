@@ -218,17 +218,22 @@ const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, in
 
 // dprompt[r, :] = sum_s dx[s, row0 + r, :]; optionally the rows of dx (fp32 and bf16 copy) are
 // then zeroed (the overwritten activations receive no gradient).
-// Deterministic: fixed partition of s over the 8 warps, fixed-order smem reduction.
-__global__ void __launch_bounds__(256) splice_bwd_kernel(float* __restrict__ dx, bf16* __restrict__ dx_bf16,
-                                                         float* __restrict__ dprompt, int S, int L, int row0, int d,
-                                                         int zero_rows) {
+// Deterministic two-stage reduction: stage 1 sums a fixed slice of the sequences per block
+// (fixed partition over 8 warps, fixed-order smem reduction) into partial[slice][r][:],
+// stage 2 adds the slices in order.
+static constexpr int SPLICE_MAX_SLICES = 64;
+
+__global__ void __launch_bounds__(256) splice_bwd_partial_kernel(float* __restrict__ dx, bf16* __restrict__ dx_bf16,
+                                                                 float* __restrict__ partial, int S, int L, int row0,
+                                                                 int n, int d, int per_slice, int zero_rows) {
   __shared__ float4 part[8][32];
-  const int r = blockIdx.x;
+  const int r = blockIdx.x, slice = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = (blockIdx.y * 32 + lane) * 4;
+  const int s_end = min(S, (slice + 1) * per_slice);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < d) {
-    for (int s = warp; s < S; s += 8) {
+    for (int s = slice * per_slice + warp; s < s_end; s += 8) {
       const size_t off = (static_cast<size_t>(s) * L + row0 + r) * d + c;
       const float4 v = *reinterpret_cast<const float4*>(dx + off);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -246,16 +251,35 @@ __global__ void __launch_bounds__(256) splice_bwd_kernel(float* __restrict__ dx,
     for (int w = 1; w < 8; ++w) {
       t.x += part[w][lane].x; t.y += part[w][lane].y; t.z += part[w][lane].z; t.w += part[w][lane].w;
     }
-    *reinterpret_cast<float4*>(dprompt + static_cast<size_t>(r) * d + c) = t;
+    *reinterpret_cast<float4*>(partial + (static_cast<size_t>(slice) * n + r) * d + c) = t;
   }
 }
 
-const char* splice_bwd(float* dx, bf16* dx_bf16, float* dprompt, int S, int L, int row0, int n, int d, bool zero_rows,
-                       cudaStream_t stream) {
+__global__ void splice_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__ dprompt, int nslices, int nd) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= nd) return;
+  float4 t = *reinterpret_cast<const float4*>(partial + i);
+  for (int sl = 1; sl < nslices; ++sl) {
+    const float4 v = *reinterpret_cast<const float4*>(partial + static_cast<size_t>(sl) * nd + i);
+    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dprompt + i) = t;
+}
+
+size_t splice_bwd_workspace_floats(int n, int d) { return static_cast<size_t>(SPLICE_MAX_SLICES) * n * d; }
+
+const char* splice_bwd(float* dx, bf16* dx_bf16, float* dprompt, float* workspace, int S, int L, int row0, int n, int d,
+                       bool zero_rows, cudaStream_t stream) {
   if (n <= 0) return nullptr;
   if (d % 4 != 0 || row0 < 0 || row0 + n > L) return "splice: bad geometry";
-  splice_bwd_kernel<<<dim3(n, (d + 127) / 128), 256, 0, stream>>>(dx, dx_bf16, dprompt, S, L, row0, d, zero_rows ? 1 : 0);
-  count_launch(1);
+  int nslices = (S + 15) / 16;  // >= 16 sequences per block
+  if (nslices > SPLICE_MAX_SLICES) nslices = SPLICE_MAX_SLICES;
+  if (nslices < 1) nslices = 1;
+  const int per_slice = (S + nslices - 1) / nslices;
+  splice_bwd_partial_kernel<<<dim3(n, (d + 127) / 128, nslices), 256, 0, stream>>>(dx, dx_bf16, workspace, S, L, row0, n, d,
+                                                                                   per_slice, zero_rows ? 1 : 0);
+  splice_bwd_final_kernel<<<(n * d / 4 + 127) / 128, 128, 0, stream>>>(workspace, dprompt, nslices, n * d);
+  count_launch(2);
   return cudaPeekAtLastError() == cudaSuccess ? nullptr : "splice bwd launch failed";
 }
 
