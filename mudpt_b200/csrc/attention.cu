@@ -396,7 +396,7 @@ const char* attention_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L, i
     attn_fwd_kernel<false><<<grid, nw * 32, smem, stream>>>(qkv, o, lse2, L, H, d, sl2);
   }
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "attention fwd launch failed";
+  return launch_status("attention fwd launch failed");
 }
 
 const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv,
@@ -421,7 +421,7 @@ const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const
     attn_bwd_dkv_kernel<false><<<grid, nw * 32, smem_kv, stream>>>(qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
   }
   count_launch(2);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "attention bwd launch failed";
+  return launch_status("attention bwd launch failed");
 }
 
 }  // namespace mudpt

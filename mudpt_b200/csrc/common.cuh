@@ -162,6 +162,11 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr,
   int sz = valid ? 16 : 0;  // src-size 0 => zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void* gptr, bool valid) {
+  int sz = valid ? 4 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gptr), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 

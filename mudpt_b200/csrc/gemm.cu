@@ -416,7 +416,7 @@ static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, cons
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, ep, M, N, K);
   count_launch();
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "gemm kernel launch failed";
+  return launch_status("gemm kernel launch failed");
 }
 
 template <int MODE>
@@ -427,7 +427,7 @@ static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, c
     dim3 grid((N / 8 + 63) / 64, M);
     gemm_tn_simt_kernel<MODE><<<grid, 64, 0, stream>>>(A, B, ep, M, N, K, lda, ldb);
     count_launch();
-    return cudaPeekAtLastError() == cudaSuccess ? nullptr : "simt gemm launch failed";
+    return launch_status("simt gemm launch failed");
   }
 #endif
   // Tile-shape choice: 128x256 tiles halve the A re-reads; use them when they still fill the

@@ -67,7 +67,7 @@ const char* feature_head_fwd(const float* x, const int* rows, const float* gamma
   if (S <= 0) return nullptr;
   feature_head_fwd_kernel<<<S, 256, (d + 32) * sizeof(float), stream>>>(x, rows, gamma, beta, proj, f, L, d, e, eps);
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "feature head fwd launch failed";
+  return launch_status("feature head fwd launch failed");
 }
 
 // ------------------------------------------------------------------ feature head backward
@@ -121,7 +121,7 @@ const char* feature_head_bwd(const float* df, const float* x, const int* rows, c
   feature_head_bwd_kernel<<<S, 256, (e + 2 * d + 32) * sizeof(float), stream>>>(df, x, rows, gamma, proj, dx, dx_bf16, L,
                                                                                 d, e, eps);
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "feature head bwd launch failed";
+  return launch_status("feature head bwd launch failed");
 }
 
 // ------------------------------------------------------------------ logits / CE head
@@ -246,7 +246,7 @@ const char* logits_head(const float* f_img, const float* f_txt, const long long*
     }
   }
   count_launch(labels != nullptr ? 4 + (d_f_img ? 1 : 0) + (d_f_txt ? 1 : 0) : 3);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "logits head launch failed";
+  return launch_status("logits head launch failed");
 }
 
 size_t logits_head_workspace_floats(int B, int C, int e) {
@@ -272,7 +272,7 @@ const char* logits_head_bwd(const float* f_img, const float* f_txt, const float*
   if (s2 > 48 * 1024) return "logits head: batch too large";
   dfeat_kernel<true><<<C, 256, s2, stream>>>(dlogits, in_hat, tn_hat, inv_t, scale, d_f_txt, C, B, e);
   count_launch(4);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "logits head bwd launch failed";
+  return launch_status("logits head bwd launch failed");
 }
 
 }  // namespace mudpt

@@ -95,7 +95,7 @@ const char* layernorm_fwd(const float* x, const float* gamma, const float* beta,
     default: launch_ln_fwd<8>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
   }
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "layernorm fwd launch failed";
+  return launch_status("layernorm fwd launch failed");
 }
 
 // ------------------------------------------------------------------ LayerNorm backward (dgrad only)
@@ -196,7 +196,7 @@ const char* layernorm_bwd(const void* dy, bool dy_bf16, const float* x, const fl
     default: launch_ln_bwd<8>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
   }
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "layernorm bwd launch failed";
+  return launch_status("layernorm bwd launch failed");
 }
 
 // ------------------------------------------------------------------ deep-prompt splice
@@ -213,7 +213,7 @@ const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, in
   if (d % 4 != 0 || row0 < 0 || row0 + n > L) return "splice: bad geometry";
   splice_fwd_kernel<<<dim3(S, n), 128, 0, stream>>>(x, prompt, L, row0, n, d);
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "splice fwd launch failed";
+  return launch_status("splice fwd launch failed");
 }
 
 // dprompt[r, :] = sum_s dx[s, row0 + r, :]; optionally the rows of dx (fp32 and bf16 copy) are
@@ -280,7 +280,7 @@ const char* splice_bwd(float* dx, bf16* dx_bf16, float* dprompt, float* workspac
                                                                                    per_slice, zero_rows ? 1 : 0);
   splice_bwd_final_kernel<<<(n * d / 4 + 127) / 128, 128, 0, stream>>>(workspace, dprompt, nslices, n * d);
   count_launch(2);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "splice bwd launch failed";
+  return launch_status("splice bwd launch failed");
 }
 
 // ------------------------------------------------------------------ patch extraction
@@ -307,7 +307,7 @@ const char* im2col_bf16(const float* img, bf16* out, int B, int R, int p, int ld
   const size_t total2 = static_cast<size_t>(B) * 3 * R * R / 2;
   im2col_kernel<<<static_cast<unsigned>((total2 + 255) / 256), 256, 0, stream>>>(img, out, R, p, ldo, total2);
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "im2col launch failed";
+  return launch_status("im2col launch failed");
 }
 
 // ------------------------------------------------------------------ small helpers
@@ -320,7 +320,7 @@ const char* write_cls_rows(float* x, const float* cls, const float* pos, int S, 
   if (S <= 0) return nullptr;
   cls_rows_kernel<<<S, 256, 0, stream>>>(x, cls, pos, L, d);
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "cls rows launch failed";
+  return launch_status("cls rows launch failed");
 }
 
 // x0[c, l, :] = emb[c, l, :] + pos[l, :] for l < L (L <= Lsrc): text-tower input, built once
@@ -336,7 +336,7 @@ const char* add_positional(float* x0, const float* emb, const float* pos, int S,
   if (S <= 0) return nullptr;
   add_pos_kernel<<<dim3(S, L), 128, 0, stream>>>(x0, emb, pos, L, Lsrc, d);
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "add_pos launch failed";
+  return launch_status("add_pos launch failed");
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
@@ -347,7 +347,7 @@ const char* cast_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t stre
   if (n == 0) return nullptr;
   cast_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, out, n);
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "cast launch failed";
+  return launch_status("cast launch failed");
 }
 
 // out[c, r] = bf16(in[r, c])  (in: [rows, cols] fp32) -- the K-major copy used by dgrad GEMMs
@@ -368,7 +368,7 @@ const char* transpose_cast_bf16(const float* in, bf16* out, int rows, int cols, 
   if (rows <= 0 || cols <= 0) return nullptr;
   transpose_cast_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, stream>>>(in, out, rows, cols);
   count_launch(1);
-  return cudaPeekAtLastError() == cudaSuccess ? nullptr : "transpose launch failed";
+  return launch_status("transpose launch failed");
 }
 
 }  // namespace mudpt

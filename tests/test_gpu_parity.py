@@ -36,7 +36,7 @@ def test_gemm_tcgen05_all_epilogues(bring):
     res = {}
     bring.group_gemm(res)
     for k, v in res.items():
-        if not k.startswith("gemm_") or "time" in k or not isinstance(v, dict):
+        if not k.startswith("gemm_") or not isinstance(v, dict) or "rel" not in v:
             continue
         assert not v["nan"], k
         f32_out = k.endswith(("_m1", "_m2", "_m5"))
