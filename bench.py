@@ -174,6 +174,7 @@ def build_trainer(device, truncate: bool):
     from tests.golden_util import make_cfg
     cfg = make_cfg(N_CTX, DEPTH, "a photo of a", 224, "ViT-B/16")
     arch = syn.ARCHS["ViT-B/16"]
+    torch.manual_seed(0)  # prompt parameters are torch-initialised: identical replicas on every rank
     clip_model = M.clip.CLIP(*arch.astuple(), cfg).float()
     clip_model.load_state_dict(syn.synthetic_clip_state_dict(arch, 0), strict=False)
     trainer = M.MuDPT.__new__(M.MuDPT)

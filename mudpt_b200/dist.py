@@ -98,6 +98,20 @@ def all_reduce_grads(params: List[torch.nn.Parameter]) -> None:
         off += n
 
 
+def broadcast_params(params: List[torch.nn.Parameter], src: int = 0) -> None:
+    """Make the replicated trainable tensors identical on every rank (one flat bucket)."""
+    if world_size() == 1 or not params:
+        return
+    with torch.no_grad():
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        dist.broadcast(flat, src=src)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+
 class AllGatherRows(torch.autograd.Function):
     """Differentiable all_gather_rows: backward = reduce_scatter_rows (used by CustomCLIP.forward)."""
 

@@ -220,6 +220,7 @@ class CustomCLIP(nn.Module):
         self.truncate_text_to_eot = os.environ.get("MUDPT_TEXT_FULL_LENGTH", "0") != "1"
         self.shard_classes = True           # class-sharded text tower when torch.distributed is initialised
         self._cached_text_features = None   # eval-time cache (parameters frozen under no_grad)
+        self._replicas_synced = False       # trainable tensors broadcast from rank 0 once (replicated state)
 
     # ------------------------------------------------------------------ helpers
     def _engine(self, device):
@@ -233,6 +234,10 @@ class CustomCLIP(nn.Module):
 
     def _register_classes(self, device):
         pl = self.mudpt_prompt_learner
+        if self.shard_classes and mdist.world_size() > 1 and not self._replicas_synced:
+            # the prompt tensors are replicated: start every rank from rank 0's values (as DDP does)
+            mdist.broadcast_params([p for p in self.parameters() if p.requires_grad])
+            self._replicas_synced = True
         lo, hi = self._class_range()
         eot_all = self.tokenized_prompts.argmax(dim=-1)
         # one global length so that every rank runs the same shapes

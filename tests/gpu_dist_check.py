@@ -38,12 +38,33 @@ def main():
     gathered = [torch.empty_like(logits) for _ in range(world)]
     dist.all_gather(gathered, logits)
     out = {"world": world}
+    # diagnostics: sharded text features (gathered) and image features of this rank
+    with torch.no_grad():
+        eng = model._clip_ref[0].engine()
+        P_v, P_t = model.prompt_stacks()
+        ft_loc = eng.text_forward(P_t, True)
+        ft_all = [torch.empty_like(ft_loc) for _ in range(world)]
+        dist.all_gather(ft_all, ft_loc)
+        fi_loc = eng.vision_forward(images[rank * B:(rank + 1) * B].contiguous(), P_v)
     if rank == 0:
+        ref = _build_big(B * world, C).to(dev)  # fresh engine: unsharded reference
+        ref.shard_classes = False
+        with torch.no_grad():
+            reng = ref._clip_ref[0].engine()
+            ref._register_classes(dev)
+            rP_v, rP_t = ref.prompt_stacks()
+            out["text_feat_max_abs"] = float((torch.cat(ft_all) - reng.text_forward(rP_t, True)).abs().max())
+            out["img_feat_max_abs"] = float((fi_loc - reng.vision_forward(images, rP_v)[:B]).abs().max())
+        ref.zero_grad(set_to_none=True)
+        loss_f, logits_f = ref.forward_backward(images, labels)
+        out["loss_fresh_single"] = float(loss_f)
+        out["logits_vs_fresh_max_abs"] = float((torch.cat(gathered) - logits_f).abs().max())
         model.shard_classes = False
         model._clip_ref[0].engine().class_key = None
         model.zero_grad(set_to_none=True)
         loss1, logits1 = model.forward_backward(images, labels)
         torch.cuda.synchronize()
+        out["logits_reused_vs_fresh_max_abs"] = float((logits1 - logits_f).abs().max())
         out["loss_sharded"], out["loss_single"] = float(loss), float(loss1)
         out["logits_max_abs"] = float((torch.cat(gathered) - logits1).abs().max())
         worst = 1.0

@@ -30,6 +30,12 @@ def _worker(rank, world, port, name, nimg, mode, out):
     try:
         c = gu.load(name)
         model, _ = gu.build_model(c, "cpu")
+        if rank != 0:
+            # replicas that start from different prompt values must be re-synchronised from rank 0
+            with torch.no_grad():
+                for p in model.parameters():
+                    if p.requires_grad:
+                        p.add_(0.05 * torch.randn_like(p))
         fake_engine.attach(model, c)
         per = nimg // world
         img = c["image"][:nimg][rank * per:(rank + 1) * per]

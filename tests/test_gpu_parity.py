@@ -109,6 +109,7 @@ def _build_big(batch, n_cls, seed=0):
     from mudpt_b200.trainers.mudpt import CustomCLIP
     arch = syn.ARCHS["ViT-B/16"]
     cfg = gu.make_cfg(2, 9, "a photo of a", 224)
+    torch.manual_seed(seed)  # the prompt parameters are torch-initialised: same on every rank / rebuild
     clip_model = clip.CLIP(*arch.astuple(), cfg).float()
     clip_model.load_state_dict(syn.synthetic_clip_state_dict(arch, seed), strict=False)
     model = CustomCLIP(cfg, syn.synthetic_classnames(n_cls), clip_model)
