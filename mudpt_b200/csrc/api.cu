@@ -51,7 +51,7 @@ struct Tower {
   std::vector<float*> lse;
   // transients
   bf16 *a_buf = nullptr, *g_buf = nullptr, *dh_buf = nullptr, *do_buf = nullptr, *dqkv_buf = nullptr, *dx_bf16 = nullptr;
-  float *dx = nullptr, *dsum = nullptr, *splice_ws = nullptr;
+  float *dx = nullptr, *dsum = nullptr, *splice_ws = nullptr, *head_ws = nullptr;  // head_ws: [rows] floats >= S*d
   bool fwd_done = false;
   int first_splice = 0;  // 0: layer 0 splices prompts[0]; 1: layer-0 rows kept as given
 };
@@ -172,6 +172,7 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
   CUDA_OK(h, dev_alloc(h, &t.dx, rows * d));
   CUDA_OK(h, dev_alloc(h, &t.dsum, rows * t.H));
   if (!t.splice_ws) CUDA_OK(h, dev_alloc(h, &t.splice_ws, splice_bwd_workspace_floats(t.n_ctx > 0 ? t.n_ctx : 1, t.d)));
+  CUDA_OK(h, dev_alloc(h, &t.head_ws, static_cast<size_t>(S) * d));  // gathered CLS / EOT rows of the feature head
   t.cap_rows = rows;
   t.fwd_done = false;
   return 0;
@@ -443,7 +444,7 @@ int mudpt_vision_forward(mudpt_handle* h, const float* images, int32_t B, const 
   // prompts[0] = ln_pre(visual_ctx + shared_ctx), which is identical for every image
   CK(h, layernorm_fwd(t.x_in[0], h->ln_pre_g, h->ln_pre_b, t.x_in[0], false, B * t.L, t.d, kLnEps, st));
   if (tower_forward(h, t, prompts, 0, st)) return -1;
-  CK(h, feature_head_fwd(t.x_in[t.layers], nullptr, h->ln_post_g, h->ln_post_b, h->proj_v, f_img, B, t.L, t.d, c.embed_dim, kLnEps, st));
+  CK(h, feature_head_fwd(t.x_in[t.layers], nullptr, h->ln_post_g, h->ln_post_b, h->proj_v, f_img, t.head_ws, B, t.L, t.d, c.embed_dim, kLnEps, st));
   return 0;
 }
 
@@ -456,7 +457,7 @@ int mudpt_vision_backward(mudpt_handle* h, const float* d_f_img, float* d_prompt
   const size_t n = static_cast<size_t>(t.S) * t.L * t.d;
   CUDA_OK(h, cudaMemsetAsync(t.dx, 0, n * sizeof(float), st));
   CUDA_OK(h, cudaMemsetAsync(t.dx_bf16, 0, n * sizeof(bf16), st));
-  CK(h, feature_head_bwd(d_f_img, t.x_in[t.layers], nullptr, h->ln_post_g, h->proj_v, t.dx, t.dx_bf16, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  CK(h, feature_head_bwd(d_f_img, t.x_in[t.layers], nullptr, h->ln_post_g, h->proj_v, t.dx, t.dx_bf16, t.head_ws, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
   return tower_backward(h, t, d_prompts, 0, st);
 }
 
@@ -493,7 +494,7 @@ int mudpt_text_forward(mudpt_handle* h, const float* prompts, int32_t splice_lay
   cudaSetDevice(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tower_forward(h, t, prompts, splice_layer0 ? 0 : 1, st)) return -1;
-  CK(h, feature_head_fwd(t.x_in[t.layers], h->eot, h->ln_final_g, h->ln_final_b, h->proj_t, f_txt, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  CK(h, feature_head_fwd(t.x_in[t.layers], h->eot, h->ln_final_g, h->ln_final_b, h->proj_t, f_txt, t.head_ws, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
   t.first_splice = splice_layer0 ? 0 : 1;  // the backward must mirror the forward's splice set
   return 0;
 }
@@ -507,7 +508,7 @@ int mudpt_text_backward(mudpt_handle* h, const float* d_f_txt, float* d_prompts,
   const size_t n = static_cast<size_t>(t.S) * t.L * t.d;
   CUDA_OK(h, cudaMemsetAsync(t.dx, 0, n * sizeof(float), st));
   CUDA_OK(h, cudaMemsetAsync(t.dx_bf16, 0, n * sizeof(bf16), st));
-  CK(h, feature_head_bwd(d_f_txt, t.x_in[t.layers], h->eot, h->ln_final_g, h->proj_t, t.dx, t.dx_bf16, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  CK(h, feature_head_bwd(d_f_txt, t.x_in[t.layers], h->eot, h->ln_final_g, h->proj_t, t.dx, t.dx_bf16, t.head_ws, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
   if (tower_backward(h, t, d_prompts, t.first_splice, st)) return -1;
   if (d_x0) CUDA_OK(h, cudaMemcpyAsync(d_x0, t.dx, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;

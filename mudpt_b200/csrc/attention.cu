@@ -16,6 +16,8 @@
 // them in registers: that keeps them under ~128 registers so 4 CTAs fit per SM.
 #include "attention.h"
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch_count.h"
 
@@ -365,9 +367,20 @@ __global__ void __launch_bounds__(128, 3) attn_bwd_dkv_kernel(const bf16* __rest
 // ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
+// Warps (16-row tiles) per CTA.  The problems are tiny, so what matters is how many independent
+// load->compute->store chains an SM has in flight: short sequences (text) use 2-warp CTAs, which
+// doubles the resident CTAs per SM; long ones (vision) are limited by the K/V tile in shared memory
+// anyway and keep 4 warps per CTA to amortise it.  MUDPT_ATTN_WARPS overrides (tuning aid).
 static int pick_warps(int L) {
   const int tiles = (L + 15) / 16;
-  return tiles >= 4 ? 4 : tiles;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("MUDPT_ATTN_WARPS");
+    forced = e ? atoi(e) : 0;
+  }
+  int nw = forced > 0 ? forced : (L <= 128 ? 2 : 4);
+  if (nw > 4) nw = 4;
+  return tiles >= nw ? nw : tiles;
 }
 
 template <typename K>

@@ -5,10 +5,13 @@
 #include <stddef.h>
 
 namespace mudpt {
+size_t feature_head_workspace_floats(int S, int d);
+// ws: S*d floats of scratch (gathered + normalised rows / their gradient)
 const char* feature_head_fwd(const float* x, const int* rows, const float* gamma, const float* beta, const float* proj,
-                             float* f, int S, int L, int d, int e, float eps, cudaStream_t stream);
+                             float* f, float* ws, int S, int L, int d, int e, float eps, cudaStream_t stream);
 const char* feature_head_bwd(const float* df, const float* x, const int* rows, const float* gamma, const float* proj,
-                             float* dx, __nv_bfloat16* dx_bf16, int S, int L, int d, int e, float eps, cudaStream_t stream);
+                             float* dx, __nv_bfloat16* dx_bf16, float* ws, int S, int L, int d, int e, float eps,
+                             cudaStream_t stream);
 size_t logits_head_workspace_floats(int B, int C, int e);
 const char* logits_head(const float* f_img, const float* f_txt, const long long* labels, float scale, int B, int C, int e,
                         float inv_global_batch, float* ws, float* logits, float* loss, float* d_f_img, float* d_f_txt,

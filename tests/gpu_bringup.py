@@ -255,25 +255,33 @@ def group_attention(res):
         res[key] = {"o": _metrics(o.float(), oref.detach()), "dq": _metrics(dqkv[:, :d].float(), g[:, :d]),
                     "dk": _metrics(dqkv[:, d:2 * d].float(), g[:, d:2 * d]), "dv": _metrics(dqkv[:, 2 * d:].float(), g[:, 2 * d:])}
         print(key, res[key], flush=True)
-    # timing at the cfg-2 vision shape
-    S, L, H = 32, 199, 12
-    d = H * 64
-    qkv = torch.randn(S * L, 3 * d, device=dev).bfloat16()
-    o = torch.zeros(S * L, d, device=dev, dtype=torch.bfloat16); lse = torch.zeros(S, H, L, device=dev)
-    do = torch.randn(S * L, d, device=dev).bfloat16(); dqkv = torch.zeros(S * L, 3 * d, device=dev, dtype=torch.bfloat16)
-    dsum = torch.zeros(S, H, L, device=dev)
-    for name, fn in [("fwd", lambda: lib.mudpt_attention_forward(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), S, L, H, 0, st)),
-                     ("bwd", lambda: lib.mudpt_attention_backward(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
-                                                                  dsum.data_ptr(), dqkv.data_ptr(), S, L, H, 0, st))]:
-        for _ in range(3):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            fn()
-        e1.record(); torch.cuda.synchronize()
-        res[f"attn_time_vision_{name}_us"] = e0.elapsed_time(e1) / 20 * 1e3
-        print(f"attn_time_vision_{name}_us", res[f"attn_time_vision_{name}_us"], flush=True)
+    # timing at the cfg-2 shapes: vision, full-length text, EOT-truncated text
+    for (S, L, H, causal, tag) in [(32, 199, 12, 0, "vision"), (1000, 77, 8, 1, "text77"), (1000, 9, 8, 1, "text9")]:
+        _time_attention(res, lib, st, dev, S, L, H, causal, tag)
+
+
+def _time_attention(res, lib, st, dev, S, L, H, causal, tag):
+    import torch
+    if True:
+        d = H * 64
+        qkv = torch.randn(S * L, 3 * d, device=dev).bfloat16()
+        o = torch.zeros(S * L, d, device=dev, dtype=torch.bfloat16); lse = torch.zeros(S, H, L, device=dev)
+        do = torch.randn(S * L, d, device=dev).bfloat16(); dqkv = torch.zeros(S * L, 3 * d, device=dev, dtype=torch.bfloat16)
+        dsum = torch.zeros(S, H, L, device=dev)
+        for name, fn in [("fwd", lambda: lib.mudpt_attention_forward(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), S, L, H, causal, st)),
+                         ("bwd", lambda: lib.mudpt_attention_backward(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                                                      dsum.data_ptr(), dqkv.data_ptr(), S, L, H, causal, st))]:
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 20 * 1e3
+            nbytes = S * L * d * 2 * (4 if name == "fwd" else 8)
+            res[f"attn_time_{tag}_{name}_us"] = us
+            print(f"attn_time_{tag}_{name}_us", round(us, 1), "hbm-bound us", round(nbytes / 6538.3e3, 1), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ head + model
