@@ -170,3 +170,59 @@ def test_full_size_properties_cfg2():
             eng.text_set_classes(emb, eot[lo:hi], int(eot.max()) + 1)
             halves.append(eng.text_forward(P_t, True).clone())
     assert torch.equal(torch.cat(halves), full)
+
+
+def _model_and_oracle_sd(arch_name, classnames, n_ctx, depth, ctx_init, seed=0):
+    """mudpt_b200 CustomCLIP (synthetic tokenizer) carrying the deterministic synthetic weights, plus the
+    flat state dict the oracle runs on."""
+    from mudpt_b200 import clip, synthetic as syn
+    from mudpt_b200.trainers.mudpt import CustomCLIP
+    arch = syn.ARCHS[arch_name]
+    cfg = gu.make_cfg(n_ctx, depth, ctx_init, arch.image_resolution, arch_name)
+    torch.manual_seed(seed)
+    clip_model = clip.CLIP(*arch.astuple(), cfg).float()
+    model = CustomCLIP(cfg, classnames, clip_model)
+    ctx_tokens = syn.synthetic_tokenize(ctx_init)[0] if ctx_init else None
+    sd = syn.assemble_state_dict(arch, model.tokenized_prompts, n_ctx, depth, ctx_tokens, seed=seed)
+    model.load_state_dict(sd, strict=True)
+    for n, p in model.named_parameters():
+        if "prompt_learner" not in n:
+            p.requires_grad_("visual_ctx" in n)
+    return model, sd, arch
+
+
+def test_vit_l14_depth12_vs_oracle():
+    """BASELINE config 5 architecture (ViT-L/14, prompt depth 12; patch 14 -> padded K = 592, 24 vision
+    layers of width 1024, text width 768) at a size the CPU oracle finishes in seconds."""
+    from mudpt_b200 import synthetic as syn
+    from oracle import mudpt_oracle as orc
+    names = ["class 0", "class 11", "red small class 2", "dog", "class 345", "x"]
+    model, sd, arch = _model_and_oracle_sd("ViT-L/14", names, 2, 12, "a photo of a")
+    image = syn.synthetic_images(2, arch.image_resolution, seed=3)
+    labels = syn.synthetic_labels(2, len(names), seed=3)
+    ref = orc.forward_backward(sd, image, model.tokenized_prompts, labels)
+    model = model.cuda()
+    loss, logits = model.forward_backward(image.cuda(), labels.cuda())
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref["loss"])) <= 0.02
+    assert float((logits.cpu() - ref["logits"]).abs().max()) <= 0.05
+    params = dict(model.named_parameters())
+    for k in orc.TRAINABLE:
+        m = orc.metrics(params[k].grad.cpu(), ref["grads"][k])
+        assert m["cos"] >= 0.999 and m["rel_l2"] <= 0.05, (k, m)
+
+
+def test_inference_with_cached_text_features_gpu():
+    """BASELINE config 3 path: logits from cached text features equal the full forward (the text
+    features depend only on parameters)."""
+    c = gu.load("tiny_d")
+    model, _ = gu.build_model(c, "cuda")
+    image = c["image"].cuda()
+    with torch.no_grad():
+        full = model(image)
+        model.cache_text_features(image.device)
+        cached = model.inference(image)
+        again = model.inference(image)
+    assert torch.equal(cached, again)
+    assert float((cached - full).abs().max()) == 0.0
+    assert float((cached.cpu() - torch.from_numpy(c["golden"]["logits"])).abs().max()) <= 0.05
