@@ -20,6 +20,7 @@
 #include "gemm.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -33,12 +34,18 @@ static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 static constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 static constexpr int EPI_WARPS = 8;
 
-template <int BN>
+// TWO = CTA pair (cta_group::2): the pair computes a 256 x BN tile, each CTA holds 128 rows of A
+// and BN/2 rows of B per stage, so the B half that an SM reads from its shared memory feeds both
+// tensor cores: 1/3 less operand traffic through shared memory per FLOP than two independent
+// 128 x BN tiles (the 1-CTA mainloop is bound by exactly that traffic).
+template <int BN, bool TWO>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBRows = TWO ? BN / 2 : BN;
+  static constexpr int kStages = (BN == 256 && !TWO) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTxBytes = TWO ? 2 * kStageBytes : kStageBytes;  // credited to the leader's barrier
   static constexpr int kStagingBytes = EPI_WARPS * 32 * 32 * 4;  // epilogue transpose buffers, 4 KB per warp
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;
@@ -114,11 +121,16 @@ __device__ __forceinline__ void epilogue4(const GemmEpilogue& ep, int row, int c
 // ---------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------
-template <int BN, int MODE>
+template <int BN, int MODE, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                        const GemmEpilogue ep, const int M, const int N, const int K) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, TWO>;
+  // CTA pair: rank 0 is the leader (issues the MMAs, owns the "full" and "accumulator drained" barriers)
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  constexpr int TM = TWO ? 2 * BM : BM;  // rows of a tile (of the pair)
+  const int unit = TWO ? (blockIdx.x >> 1) : blockIdx.x;          // CTA (pair) index = first tile
+  const int unit_stride = TWO ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment
   // Pointer arithmetic on the __shared__ array (no integer round trip) keeps the shared address space
@@ -136,7 +148,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BM - 1) / BM;
+  const int num_m = (M + TM - 1) / TM;
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
@@ -150,16 +162,17 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], (TWO ? 2 : 1) * EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (TWO) { tmem_alloc_2sm(tmem_base_slot, Cfg::kTmemCols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_base_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -168,26 +181,35 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += unit_stride) {
         const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        const int a_row = m_blk * TM + static_cast<int>(rank) * BM;               // this CTA's 128 rows of A
+        const int b_row = n_blk * BN + static_cast<int>(rank) * Cfg::kBRows;     // this CTA's share of B
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if constexpr (TWO) {
+            // both CTAs' loads are credited to the leader's barrier; only the leader arms it
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], Cfg::kTxBytes);
+            tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], kb * BK, b_row);
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::kTxBytes);
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], kb * BK, b_row);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += unit_stride) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -199,13 +221,19 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (start-address field is >>4)
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                      static_cast<uint32_t>((kb | k) != 0));
+            if constexpr (TWO)
+              umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                            static_cast<uint32_t>((kb | k) != 0));
+            else
+              umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                        static_cast<uint32_t>((kb | k) != 0));
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if constexpr (TWO) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if constexpr (TWO) umma_commit_2sm(&tmem_full_bar[acc], 3); else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -225,13 +253,14 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int kChunks = BN / 32;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < num_tiles; tile += unit_stride) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      const int m_row0 = m_blk * TM + static_cast<int>(rank) * BM;  // first row of this CTA's accumulator
       typedef typename EpiExtra<MODE>::type Ex;
       constexpr bool kHasExtra = (MODE == EPI_RESID_F32 || MODE == EPI_GELU_BWD || MODE == EPI_PATCH);
       constexpr bool kDouble = (MODE == EPI_GELU_BWD);  // packed operand: cheap enough to prefetch a chunk ahead
       const int ncol = N - n_blk * BN;  // valid columns in this tile (may exceed BN)
-      const int row_base = m_blk * BM + quad * 32 + rr0;
+      const int row_base = m_row0 + quad * 32 + rr0;
       int c = half;
       Ex ex[kHasExtra ? 8 : 1], exn[kDouble ? 8 : 1];
       auto load_extra = [&](Ex(&dst)[kHasExtra ? 8 : 1], int chunk) {
@@ -266,7 +295,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rr0;
-            const int row = m_blk * BM + quad * 32 + rr;
+            const int row = m_row0 + quad * 32 + rr;
             float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + (((j ^ rr) & 7) << 4));
             v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
             if (row < M) epilogue4<MODE>(ep, row, col, v, ex[kHasExtra ? it : 0]);
@@ -282,16 +311,20 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);  // the leader's MMA thread waits on it
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still uses it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (TWO) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -390,6 +423,7 @@ void gemm_clear_tensor_map_cache() {
   g_maps.clear();
 }
 
+static bool g_enable_2cta = []{ const char* e = getenv("MUDPT_GEMM_2CTA"); return e ? atoi(e) != 0 : true; }();
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -401,20 +435,34 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool TWO>
 static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                               cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, TWO>;
   static bool attr_done = false;
-  auto kern = gemm_tn_tcgen05_kernel<BN, MODE>;
+  auto kern = gemm_tn_tcgen05_kernel<BN, MODE, TWO>;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return "cudaFuncSetAttribute(max dynamic smem) failed";
     attr_done = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, ep, M, N, K);
+  constexpr int TM = TWO ? 2 * BM : BM;
+  const int tiles = ((M + TM - 1) / TM) * ((N + BN - 1) / BN);
+  const int units = TWO ? num_sms() / 2 : num_sms();
+  const int grid = (tiles < units ? tiles : units) * (TWO ? 2 : 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TWO ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K) != cudaSuccess) return launch_status("gemm kernel launch failed");
   count_launch();
   return launch_status("gemm kernel launch failed");
 }
@@ -432,14 +480,28 @@ static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, c
 #endif
   // Tile-shape choice: 128x256 tiles halve the A re-reads; use them when they still fill the
   // machine (>= one full wave of 148 CTAs), otherwise 128x128 (thin N = d GEMMs).
-  const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
-  const bool wide = (N % 256 == 0 || N > 512) && tiles256 >= num_sms();
+  // The grid is persistent (one CTA per SM), so what counts is the number of tile "waves":
+  // e.g. M = 6368 (32 images x 199 tokens), N = 768 gives 150 tiles of 128x256 -- two waves with
+  // the second almost empty -- but 300 tiles of 128x128 in three half-cost waves.  Pick the shape
+  // with the smaller estimated makespan (a 128x128 tile costs ~0.7 of a 128x256 one: it moves
+  // 1/3 more operand bytes per FLOP through shared memory).
+  const int mb = (M + BM - 1) / BM, sms = num_sms();
+  const int t256 = mb * ((N + 255) / 256), t128 = mb * ((N + 127) / 128);
+  const float cost256 = static_cast<float>((t256 + sms - 1) / sms);          // padded tiles cost a full tile
+  const float cost128 = 0.72f * static_cast<float>((t128 + sms - 1) / sms);  // measured: a 128x128 wave costs ~0.7 of a 128x256 one
+  const bool wide = cost256 <= cost128 * 1.02f;
+  // CTA pairs (256 x 256 tiles) when the pair grid is still well filled: a pair tile is two 128 x 256
+  // tiles' worth of work done with ~2/3 of the shared-memory operand traffic (est. cost 0.8 per wave).
+  const int t2 = ((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256), pairs = sms / 2;
+  const float cost2 = 0.8f * static_cast<float>((t2 + pairs - 1) / pairs);
+  const bool two = g_enable_2cta && N >= 256 && cost2 < cost256 && cost2 < cost128;
   CUtensorMap ta, tb;
   const char* e = get_tensor_map(A, M, K, lda, BM, &ta);
   if (e) return e;
-  e = get_tensor_map(B, N, K, ldb, wide ? 256 : 128, &tb);
+  e = get_tensor_map(B, N, K, ldb, (two || !wide) ? 128 : 256, &tb);
   if (e) return e;
-  return wide ? launch_one<256, MODE>(ta, tb, ep, M, N, K, stream) : launch_one<128, MODE>(ta, tb, ep, M, N, K, stream);
+  if (two) return launch_one<256, MODE, true>(ta, tb, ep, M, N, K, stream);
+  return wide ? launch_one<256, MODE, false>(ta, tb, ep, M, N, K, stream) : launch_one<128, MODE, false>(ta, tb, ep, M, N, K, stream);
 }
 
 const char* gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, const GemmEpilogue& ep, int M, int N, int K,
