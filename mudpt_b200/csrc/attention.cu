@@ -33,11 +33,25 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) {
 // Load `nrows` rows x 64 bf16 columns into a swizzled smem tile; global row = row_begin + r,
 // rows >= row_limit are zero-filled.
 __device__ __forceinline__ void load_tile(uint32_t tile, const bf16* g, int ld, int row_begin, int row_limit, int nrows) {
-  for (int idx = threadIdx.x; idx < nrows * 8; idx += blockDim.x) {
-    const int r = idx >> 3, c = idx & 7;
-    const int gr = row_begin + r;
-    const bool ok = gr < row_limit;
-    cp_async16(tile + swz(r, c), g + static_cast<size_t>(ok ? gr : 0) * ld + c * 8, ok);
+  const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3, rstep = blockDim.x >> 3;
+  if ((rstep & 7) == 0) {
+    // CTAs of >= 64 threads: a thread's rows are 8k apart, so its swizzled 16 B slot is loop-invariant
+    // and both addresses advance by constants (the load loop was ~15 % of all issued instructions)
+    uint32_t dst = tile + static_cast<uint32_t>(r0 * ROW_BYTES + ((c ^ (r0 & 7)) << 4));
+    const bf16* src = g + static_cast<size_t>(row_begin + r0) * ld + c * 8;
+    const size_t sstep = static_cast<size_t>(rstep) * ld;
+    for (int r = r0; r < nrows; r += rstep) {
+      const bool ok = row_begin + r < row_limit;
+      cp_async16(dst, ok ? src : g, ok);
+      dst += rstep * ROW_BYTES;
+      src += sstep;
+    }
+  } else {
+    for (int r = r0; r < nrows; r += rstep) {
+      const int gr = row_begin + r;
+      const bool ok = gr < row_limit;
+      cp_async16(tile + swz(r, c), g + static_cast<size_t>(ok ? gr : 0) * ld + c * 8, ok);
+    }
   }
 }
 
@@ -161,17 +175,27 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
     zero_acc(sacc);
     mma_rows_x_cols<4>(sacc, sQ, row0, sK, c0, 0, g_hi, lane);
     float mx[2] = {-INFINITY, -INFINITY};
+    // the kernel is instruction-bound (ncu: 3 % of the issued instructions are MMAs), so the softmax
+    // touches only the 8-column tiles that were computed (nt < 2*g_hi, warp-uniform) and skips the
+    // mask arithmetic for chunks that lie entirely inside the valid / causal region
+    const bool need_mask = (c0 + 64 > L) || (CAUSAL && c0 + 63 > q0 + row0);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt < 2 * g_hi) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-        const int r = e >> 1;
-        const bool ok = col < L && (!CAUSAL || col <= qrow[r]);
-        const float v = ok ? sacc[nt][e] * scale_log2e : -INFINITY;
-        sacc[nt][e] = v;
-        mx[r] = fmaxf(mx[r], v);
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          float v = sacc[nt][e] * scale_log2e;
+          if (need_mask) {
+            const int col = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+            const bool ok = col < L && (!CAUSAL || col <= qrow[r]);
+            v = ok ? v : -INFINITY;
+          }
+          sacc[nt][e] = v;
+          mx[r] = fmaxf(mx[r], v);
+        }
       }
+    }
     float alpha[2], m_use[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -184,15 +208,19 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
       l_run[r] *= alpha[r];
     }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt < 2 * g_hi) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = e >> 1;
-        const float p = exp2f(sacc[nt][e] - m_use[r]);
-        sacc[nt][e] = p;
-        l_run[r] += p;
-        oacc[nt][e] *= alpha[r];
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          const float p = exp2f(sacc[nt][e] - m_use[r]);
+          sacc[nt][e] = p;
+          l_run[r] += p;
+        }
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[nt][e] *= alpha[e >> 1];
+    }
     mma_p_x_tile<4>(oacc, sacc, sV, c0, 0, g_hi, lane);
   }
   float inv[2];
@@ -280,16 +308,25 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_dq_kernel(const bf16* __restr
     zero_acc(dp);
     mma_rows_x_cols<2>(sacc, sQ, row0, sK, c0, 0, g_hi, lane);
     mma_rows_x_cols<2>(dp, sdO, row0, sV, c0, 0, g_hi, lane);
+    // rows >= L of the last tile carry lse = 0 and finite garbage: they are never stored, so only the
+    // column mask matters; chunks entirely inside the valid / causal region skip it
+    const bool need_mask = (c0 + 32 > L) || (CAUSAL && c0 + 31 > q0 + row0);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt < 2 * g_hi) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-        const int r = e >> 1;
-        const bool ok = col < L && qrow[r] < L && (!CAUSAL || col <= qrow[r]);
-        const float p = ok ? exp2f(sacc[nt][e] * scale_log2e - lse[r]) : 0.f;
-        sacc[nt][e] = p * (dp[nt][e] - Dr[r]);  // dS (unscaled)
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          float p = exp2f(sacc[nt][e] * scale_log2e - lse[r]);
+          if (need_mask) {
+            const int col = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+            const bool ok = col < L && (!CAUSAL || col <= qrow[r]);
+            p = ok ? p : 0.f;
+          }
+          sacc[nt][e] = p * (dp[nt][e] - Dr[r]);  // dS (unscaled)
+        }
       }
+    }
     mma_p_x_tile<2>(dq, sacc, sK, c0, 0, g_hi, lane);
   }
   store_rows_bf16(dq, scale, scale, smem, 0, row0, dqkv + seq_row * ld + h * DH, ld, q0 + row0, L, lane);
@@ -344,18 +381,26 @@ __global__ void __launch_bounds__(128, 3) attn_bwd_dkv_kernel(const bf16* __rest
     zero_acc(dpt);
     mma_rows_x_cols<2>(st, sK, row0, sQ, c0, g_lo, g_hi, lane);
     mma_rows_x_cols<2>(dpt, sV, row0, sdO, c0, g_lo, g_hi, lane);
+    // key rows >= L only pollute their own (never stored) dK/dV rows; the query (column) mask is
+    // needed only where the chunk crosses L or the causal diagonal of this warp's 16 keys
+    const bool need_mask = (c0 + 32 > L) || (CAUSAL && c0 < k0 + row0 + 15);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt >= 2 * g_lo && nt < 2 * g_hi) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int qi = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);  // query index (column)
-        const int r = e >> 1;
-        const bool ok = qi < L && krow[r] < L && (!CAUSAL || krow[r] <= qi);
-        const int qc = min(qi, Lp - 1);
-        const float p = ok ? exp2f(st[nt][e] * scale_log2e - sLse[qc]) : 0.f;
-        st[nt][e] = p;                               // P^T
-        dpt[nt][e] = p * (dpt[nt][e] - sD[qc]);      // dS^T (unscaled), in place
+        for (int e = 0; e < 4; ++e) {
+          const int qi = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);  // query index (column), < Lp here
+          const int r = e >> 1;
+          float p = exp2f(st[nt][e] * scale_log2e - sLse[qi]);
+          if (need_mask) {
+            const bool ok = qi < L && (!CAUSAL || krow[r] <= qi);
+            p = ok ? p : 0.f;
+          }
+          st[nt][e] = p;                               // P^T
+          dpt[nt][e] = p * (dpt[nt][e] - sD[qi]);      // dS^T (unscaled), in place
+        }
       }
+    }
     mma_p_x_tile<2>(dv, st, sdO, c0, g_lo, g_hi, lane);
     mma_p_x_tile<2>(dk, dpt, sQ, c0, g_lo, g_hi, lane);
   }
