@@ -54,6 +54,17 @@ def _peaks():
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
+def _gemm_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_gemm_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum averaged over the
+    captured text-tower GEMM launches); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    try:
+        return json.load(open(p))["avg_traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -348,7 +359,8 @@ def run_ours(args):
                           "note": "text tower run on max(eot)+1 tokens: exact under the causal mask (tests), product default"},
         "roofline": {"bound": "tensor", "kernel": "gemm_tn_tcgen05_kernel (all GEMM launches of the step)",
                      "achieved": round(gemm_tflops, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": round(gemm_tflops / peaks["bf16_sustained"], 4), "traffic": None,
+                     "frac": round(gemm_tflops / peaks["bf16_sustained"], 4), "traffic": _gemm_traffic(),
+                     "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1),
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                      "launches_per_step": g["launches"] // full["nprof"],
                      "avg_launch_us": round(g["ms"] * 1e3 / max(g["launches"], 1), 2),
