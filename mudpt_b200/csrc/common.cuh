@@ -70,6 +70,58 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 2D tiled store, shared -> global (bulk async group of the issuing thread). Out-of-range parts of
+// the box are clipped by the hardware, so M / N tails need no predicates.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ------------------------------------------------------------------ packed fp32 pairs (FADD2 / FMUL2 / FFMA2)
+// sm_100 executes two fp32 lanes per instruction on 64-bit register pairs: halves the instruction
+// count of the issue-bound GEMM epilogues.
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_pack_u(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
@@ -165,12 +217,16 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-// Arrive on the mbarrier at this smem offset in CTA `rank` of the cluster.
+// Arrive on the mbarrier at this smem offset in CTA `rank` of the cluster.  Default (CTA-scope)
+// semantics as in cutlass::arch::ClusterBarrier::arrive: what the barrier orders here is TMEM traffic,
+// which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already cover; `.release.cluster` compiles
+// to MEMBAR.ALL.GPU + ERRBAR, i.e. a wait for every outstanding global store of the thread (ncu: 29 %
+// of all stall samples of the c_fc GEMM sat there).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
 

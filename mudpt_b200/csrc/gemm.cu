@@ -38,16 +38,30 @@ static constexpr int EPI_WARPS = 8;
 // and BN/2 rows of B per stage, so the B half that an SM reads from its shared memory feeds both
 // tensor cores: 1/3 less operand traffic through shared memory per FLOP than two independent
 // 128 x BN tiles (the 1-CTA mainloop is bound by exactly that traffic).
-template <int BN, bool TWO>
+// Epilogue flavour per mode.  "Row" epilogues keep the TMEM layout (thread = accumulator row, 32
+// consecutive columns in registers), do the fused math on packed fp32 pairs and hand 32 x 32 bf16
+// boxes to the TMA (store; for GELU' also the load of the saved pre-activation) through 2 KB
+// 64B-swizzled staging units: ~1/3 of the instructions of the transposing epilogue below, which the
+// fp32-output modes still use (their boxes would be twice as large and they are HBM-bound anyway).
+template <int MODE> struct RowEpi { static constexpr bool value = (MODE == EPI_BF16 || MODE == EPI_GELU || MODE == EPI_GELU_BWD); };
+static constexpr int kUnitBytes = 32 * 64;  // 32 rows x 32 bf16, SWIZZLE_64B
+static constexpr int kMaxSmem = 227 * 1024;
+
+template <int BN, int MODE, bool TWO>
 struct GemmCfg {
   static constexpr int kBRows = TWO ? BN / 2 : BN;
-  static constexpr int kStages = (BN == 256 && !TWO) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTxBytes = TWO ? 2 * kStageBytes : kStageBytes;  // credited to the leader's barrier
-  static constexpr int kStagingBytes = EPI_WARPS * 32 * 32 * 4;  // epilogue transpose buffers, 4 KB per warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // staging per epilogue warp: one 4 KB transpose buffer, or 2 (4 for the two-output c_fc) TMA units
+  static constexpr int kUnitsPerWarp = (MODE == EPI_GELU) ? 4 : 2;
+  static constexpr int kWarpStaging = RowEpi<MODE>::value ? kUnitsPerWarp * kUnitBytes : 32 * 32 * 4;
+  static constexpr int kStagingBytes = EPI_WARPS * kWarpStaging;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kFit = (kMaxSmem - kStagingBytes - 1024 - kBarBytes) / kStageBytes;
+  static constexpr int kStages = kFit < 6 ? kFit : 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + kBarBytes;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -118,14 +132,234 @@ __device__ __forceinline__ void epilogue4(const GemmEpilogue& ep, int row, int c
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Row-layout epilogue (EPI_BF16 / EPI_GELU / EPI_GELU_BWD), one call per epilogue warp.
+//   quad = warp % 4 selects the 32 TMEM lanes (accumulator rows) the warp may read, half selects
+//   which contiguous half of the tile's BN columns it drains, in boxes of 32 columns:
+//     tcgen05.ld 32x32b.x32 (thread = row)  ->  bias / QuickGELU / GELU' on packed fp32 pairs
+//     ->  bf16, 4 x STS.128 into a 2 KB unit (64B swizzle: conflict-free)  ->  TMA store.
+//   The next box's accumulator columns are in flight (second register set) during the math.
+//   EPI_GELU_BWD additionally TMA-loads the saved pre-activation box into the unit one box ahead
+//   (also across tiles) and rewrites it in place.
+//   TMA clips stores / zero-fills loads at the M and N tails, so there are no per-element predicates.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t unit_slot(int lane, int j) {  // byte offset of 16 B chunk j of row `lane`
+  return static_cast<uint32_t>(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+}
+
+// QuickGELU'(h) = s (1 + 1.702 h (1 - s)), s = sigmoid(1.702 h); with u = 0.851 h, t = tanh(u):
+//   = 0.5 (1 + t + u (1 - t^2))   -- one MUFU and three packed FMAs per pair
+__device__ __forceinline__ f32x2 quick_gelu_grad2(f32x2 h) {
+  const f32x2 u = f2_mul(h, f2_pack(0.851f, 0.851f));
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  const f32x2 t = f2_pack(tanh_approx(u0), tanh_approx(u1));
+  const f32x2 w = f2_fma(f2_mul(t, f2_pack(-1.f, -1.f)), t, f2_pack(1.f, 1.f));  // 1 - t^2
+  const f32x2 p = f2_fma(u, w, t);
+  return f2_fma(p, f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));
+}
+// QuickGELU(v) = v sigmoid(1.702 v) = 0.5 v + 0.5 v tanh(0.851 v)
+__device__ __forceinline__ f32x2 quick_gelu2(f32x2 v) {
+  const f32x2 u = f2_mul(v, f2_pack(0.851f, 0.851f));
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  const f32x2 t = f2_pack(tanh_approx(u0), tanh_approx(u1));
+  const f32x2 hv = f2_mul(v, f2_pack(0.5f, 0.5f));
+  return f2_fma(hv, t, hv);
+}
+__device__ __forceinline__ uint32_t pack_bf16_2(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack_bf16(lo, hi);
+}
+
+template <int BN, int MODE, bool TWO>
+__device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const CUtensorMap* tma_o1, const CUtensorMap* tma_ex,
+                                              const GemmEpilogue& ep, const int M, const int N, const int num_n,
+                                              const int num_tiles, const int unit, const int unit_stride, const uint32_t rank,
+                                              const uint32_t tmem_base, uint8_t* units, uint64_t* ex_bar,
+                                              uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const int warp,
+                                              const int lane) {
+  constexpr int TM = TWO ? 2 * BM : BM;
+  constexpr int kCols = BN / 2;       // columns per warp
+  constexpr int kBoxes = kCols / 32;  // boxes per warp and tile
+  const int quad = warp & 3, half = (warp - 2) >> 2;
+  auto box_origin = [&](int tile, int& row, int& col0) {
+    const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+    row = m_blk * TM + static_cast<int>(rank) * BM + quad * 32;
+    col0 = n_blk * BN + half * kCols;
+  };
+  auto boxes_of = [&](int tile) {  // valid boxes of this warp in `tile` (warp-uniform)
+    int row, col0;
+    box_origin(tile, row, col0);
+    if (row >= M || col0 >= N) return 0;
+    const int nb = (N - col0 + 31) >> 5;
+    return nb < kBoxes ? nb : kBoxes;
+  };
+  // EPI_GELU_BWD: lane 0 walks one box ahead of the warp and issues the pre-activation loads
+  int pf_tile = unit, pf_b = -1;
+  uint32_t pf_k = 0;
+  auto prefetch_next = [&]() {
+    for (;;) {
+      ++pf_b;
+      while (pf_tile < num_tiles && pf_b >= boxes_of(pf_tile)) { pf_tile += unit_stride; pf_b = 0; }
+      if (pf_tile >= num_tiles) return;
+      int row, col0;
+      box_origin(pf_tile, row, col0);
+      uint64_t* bar = &ex_bar[pf_k & 1];
+      mbar_expect_tx(bar, kUnitBytes);
+      tma_load_2d(units + (pf_k & 1) * kUnitBytes, tma_ex, bar, col0 + pf_b * 32, row);
+      ++pf_k;
+      return;
+    }
+  };
+  if constexpr (MODE == EPI_GELU_BWD) {
+    if (lane == 0) prefetch_next();
+  }
+
+  uint32_t k = 0;  // boxes processed so far by this warp
+  const bool has_bias = ep.bias != nullptr;
+  // one box: r = 32 accumulator columns of this thread's row
+  auto process = [&](uint32_t (&r)[32], int row, int col) {
+    float4 bv[8];
+    if (has_bias && col + 32 <= N) {  // the common case: no per-load guards
+      const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias && col + 4 * i < N) bv[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i);
+      }
+    }
+    if constexpr (MODE == EPI_BF16) {
+      uint8_t* u = units + (k & 1) * kUnitBytes;
+      if (lane == 0) bulk_wait_read<1>();  // the store issued from this unit two boxes ago has read it
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = 8 * j + 2 * q;
+          const float4 b4 = bv[e >> 2];
+          const f32x2 bb = (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
+          o[q] = pack_bf16_2(f2_add(f2_pack_u(r[e], r[e + 1]), bb));
+        }
+        *reinterpret_cast<uint4*>(u + unit_slot(lane, j)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(tma_o0, u, col, row); bulk_commit(); }
+    } else if constexpr (MODE == EPI_GELU) {
+      // units {0,1} / {2,3} alternate per box: h and QuickGELU(h)
+      uint8_t* uh = units + (k & 1) * 2 * kUnitBytes;
+      uint8_t* ug = uh + kUnitBytes;
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t oh[4], og[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = 8 * j + 2 * q;
+          const float4 b4 = bv[e >> 2];
+          const f32x2 bb = (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
+          const f32x2 v = f2_add(f2_pack_u(r[e], r[e + 1]), bb);
+          oh[q] = pack_bf16_2(v);
+          og[q] = pack_bf16_2(quick_gelu2(v));
+        }
+        *reinterpret_cast<uint4*>(uh + unit_slot(lane, j)) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        *reinterpret_cast<uint4*>(ug + unit_slot(lane, j)) = make_uint4(og[0], og[1], og[2], og[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (ep.out0 != nullptr) tma_store_2d(tma_o0, uh, col, row);
+        tma_store_2d(tma_o1, ug, col, row);
+        bulk_commit();  // both stores of the box form one group
+      }
+    } else {  // EPI_GELU_BWD
+      uint8_t* u = units + (k & 1) * kUnitBytes;
+      if (lane == 0) {
+        bulk_wait_read<0>();  // the other unit's store (previous box) has been read: it may be refilled
+        prefetch_next();
+      }
+      mbar_wait(&ex_bar[k & 1], (k >> 1) & 1);  // this box's pre-activation has landed
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4* slot = reinterpret_cast<uint4*>(u + unit_slot(lane, j));
+        const uint4 hq = *slot;
+        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = 8 * j + 2 * q;
+          const float4 b4 = bv[e >> 2];
+          const f32x2 bb = (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
+          const f32x2 v = f2_add(f2_pack_u(r[e], r[e + 1]), bb);
+          const f32x2 h = f2_pack_u(hw[q] << 16, hw[q] & 0xffff0000u);  // bf16 pair -> fp32 pair
+          o[q] = pack_bf16_2(f2_mul(v, quick_gelu_grad2(h)));
+        }
+        *slot = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(tma_o0, u, col, row); bulk_commit(); }
+    }
+    ++k;
+  };
+
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int tile = unit; tile < num_tiles; tile += unit_stride) {
+    int row, col0;
+    box_origin(tile, row, col0);
+    const int nb = boxes_of(tile);
+    mbar_wait(&tmem_full_bar[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kCols);
+    auto release_acc = [&]() {  // every column this warp needs is in registers: the MMA warp may reuse the buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
+    };
+    uint32_t ra[32], rb[32];
+    if (nb > 0) tmem_ld_32x32(taddr, ra);
+    else release_acc();
+#pragma unroll 1
+    for (int b = 0; b < nb; b += 2) {
+      tmem_ld_wait_regs(ra);
+      if (b + 1 < nb) tmem_ld_32x32(taddr + static_cast<uint32_t>((b + 1) * 32), rb);
+      else release_acc();
+      process(ra, row, col0 + b * 32);
+      if (b + 1 < nb) {
+        tmem_ld_wait_regs(rb);
+        if (b + 2 < nb) tmem_ld_32x32(taddr + static_cast<uint32_t>((b + 2) * 32), ra);
+        else release_acc();
+        process(rb, row, col0 + (b + 1) * 32);
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+  if (lane == 0) bulk_wait<0>();  // shared memory must outlive the last store's read; writes complete before exit
+}
+
 // ---------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------
 template <int BN, int MODE, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                       const GemmEpilogue ep, const int M, const int N, const int K) {
-  using Cfg = GemmCfg<BN, TWO>;
+                       const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1,
+                       const __grid_constant__ CUtensorMap tma_ex, const GemmEpilogue ep, const int M, const int N,
+                       const int K) {
+  using Cfg = GemmCfg<BN, MODE, TWO>;
   // CTA pair: rank 0 is the leader (issues the MMAs, owns the "full" and "accumulator drained" barriers)
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;
   constexpr int TM = TWO ? 2 * BM : BM;  // rows of a tile (of the pair)
@@ -144,7 +378,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* extra_bar = tmem_empty_bar + 2;  // [EPI_WARPS][2]: pre-activation boxes of the GELU' epilogue
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(extra_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,6 +399,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], (TWO ? 2 : 1) * EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
+    for (int a = 0; a < 2 * EPI_WARPS; ++a) mbar_init(&extra_bar[a], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -237,8 +473,13 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if constexpr (RowEpi<MODE>::value) {
+    // ===================== epilogue (warps 2..9), row layout + TMA stores =====================
+    epilogue_rows<BN, MODE, TWO>(&tma_o0, &tma_o1, &tma_ex, ep, M, N, num_n, num_tiles, unit, unit_stride, rank, tmem_base,
+                                 smem_stage + (warp - 2) * Cfg::kWarpStaging, extra_bar + (warp - 2) * 2, tmem_full_bar,
+                                 tmem_empty_bar, warp, lane);
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..9), transposing =====================
     // Two warps per TMEM lane quadrant (quad = warp % 4); the pair splits the 32-column chunks of the
     // accumulator between them (even / odd), so every SM sub-partition has two epilogue warps to
     // overlap TMEM / shared / global latencies.
@@ -376,9 +617,9 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols, ld, box_rows;
+  const void* ptr; int rows, cols, ld, box_rows, box_cols;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
   }
 };
 struct MapKeyHash {
@@ -388,15 +629,17 @@ struct MapKeyHash {
     h = h * 1000003u ^ static_cast<size_t>(k.cols);
     h = h * 1000003u ^ static_cast<size_t>(k.ld);
     h = h * 1000003u ^ static_cast<size_t>(k.box_rows);
+    h = h * 1000003u ^ static_cast<size_t>(k.box_cols);
     return h;
   }
 };
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 static std::mutex g_maps_mu;
 
-// 2D bf16 row-major [rows, cols] (leading dimension ld elements), box = [box_rows, 64], 128B swizzle.
-static const char* get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
-  MapKey key{ptr, rows, cols, ld, box_rows};
+// 2D bf16 row-major [rows, cols] (leading dimension ld elements), box = [box_rows, box_cols]:
+// box_cols = 64 with 128B swizzle (MMA operand tiles) or 32 with 64B swizzle (epilogue boxes).
+static const char* get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMap* out) {
+  MapKey key{ptr, rows, cols, ld, box_rows, box_cols};
   std::lock_guard<std::mutex> lk(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return nullptr; }
@@ -406,11 +649,11 @@ static const char* get_tensor_map(const void* ptr, int rows, int cols, int ld, i
   CUtensorMap m;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
   if (g_maps.size() > 4096) g_maps.clear();
   g_maps.emplace(key, m);
@@ -436,9 +679,9 @@ static int num_sms() {
 }
 
 template <int BN, int MODE, bool TWO>
-static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                              cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, TWO>;
+static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap (&te)[3], const GemmEpilogue& ep,
+                              int M, int N, int K, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, MODE, TWO>;
   static bool attr_done = false;
   auto kern = gemm_tn_tcgen05_kernel<BN, MODE, TWO>;
   if (!attr_done) {
@@ -462,7 +705,7 @@ static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K) != cudaSuccess) return launch_status("gemm kernel launch failed");
+  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, te[0], te[1], te[2], ep, M, N, K) != cudaSuccess) return launch_status("gemm kernel launch failed");
   count_launch();
   return launch_status("gemm kernel launch failed");
 }
@@ -496,12 +739,20 @@ static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, c
   const float cost2 = 0.8f * static_cast<float>((t2 + pairs - 1) / pairs);
   const bool two = g_enable_2cta && N >= 256 && cost2 < cost256 && cost2 < cost128;
   CUtensorMap ta, tb;
-  const char* e = get_tensor_map(A, M, K, lda, BM, &ta);
+  const char* e = get_tensor_map(A, M, K, lda, BM, BK, &ta);
   if (e) return e;
-  e = get_tensor_map(B, N, K, ldb, (two || !wide) ? 128 : 256, &tb);
+  e = get_tensor_map(B, N, K, ldb, (two || !wide) ? 128 : 256, BK, &tb);
   if (e) return e;
-  if (two) return launch_one<256, MODE, true>(ta, tb, ep, M, N, K, stream);
-  return wide ? launch_one<256, MODE, false>(ta, tb, ep, M, N, K, stream) : launch_one<128, MODE, false>(ta, tb, ep, M, N, K, stream);
+  // epilogue boxes (row-layout modes): out0, out1, saved pre-activation; unused slots repeat the A map
+  CUtensorMap te[3] = {ta, ta, ta};
+  if constexpr (RowEpi<MODE>::value) {
+    if (ep.out0 != nullptr && (e = get_tensor_map(ep.out0, M, N, ep.ldc, 32, 32, &te[0]))) return e;
+    if (MODE == EPI_GELU && (e = get_tensor_map(ep.out1, M, N, ep.ldc, 32, 32, &te[1]))) return e;
+    if (MODE == EPI_GELU_BWD && (e = get_tensor_map(ep.aux, M, N, ep.ldc, 32, 32, &te[2]))) return e;
+  }
+  if (two) return launch_one<256, MODE, true>(ta, tb, te, ep, M, N, K, stream);
+  return wide ? launch_one<256, MODE, false>(ta, tb, te, ep, M, N, K, stream)
+              : launch_one<128, MODE, false>(ta, tb, te, ep, M, N, K, stream);
 }
 
 const char* gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, const GemmEpilogue& ep, int M, int N, int K,
