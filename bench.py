@@ -178,7 +178,7 @@ def run_reference(args):
 # GPU path
 # ------------------------------------------------------------------------------------------------
 
-def build_trainer(device, truncate: bool):
+def build_trainer(device, truncate: bool, n_classes: int = N_CLASSES):
     import torch
     from mudpt_b200 import synthetic as syn
     from mudpt_b200.trainers import mudpt as M
@@ -192,7 +192,7 @@ def build_trainer(device, truncate: bool):
     M.TrainerX.__init__(trainer, None, None, device)
     trainer.cfg = cfg
     trainer.check_cfg(cfg)
-    model = M.CustomCLIP(cfg, syn.synthetic_classnames(N_CLASSES), clip_model)
+    model = M.CustomCLIP(cfg, syn.synthetic_classnames(n_classes), clip_model)
     for n, p in model.named_parameters():  # freeze rule, trainers/mudpt.py:205-212
         if "prompt_learner" not in n:
             p.requires_grad_("visual_ctx" in n)
@@ -261,7 +261,11 @@ def run_ours(args):
     clocks = None
     if args.quick:
         # profiling aid (ncu launch lists): the full-length variant's resident loop only, no JSON contract
-        trainer = build_trainer(device, False)
+        # --classes emulates the per-GPU shapes of an N-rank run on one GPU (1000 / N classes), no NCCL
+        trainer = build_trainer(device, False, args.classes)
+        labs_dev = [t % args.classes for t in labs_dev]
+        if args.no_overlap:
+            trainer.model.overlap_towers = False
 
         def step_q(i):
             trainer.optim.zero_grad(set_to_none=False)
@@ -297,11 +301,15 @@ def run_ours(args):
         launches = (eng.launch_count() - l0) // (K + W)
         ms_e2e, _, _ = timed_loop(step_e2e, K, W, device, world)
         # instrumented pass of the same step: per-kernel-class CUDA-event times
+        # (single stream: with the towers overlapped an event pair would also time the other tower's kernels)
+        overlap = model.overlap_towers
+        model.overlap_towers = False
         eng.profile_begin()
         torch.cuda.synchronize(device)
         for i in range(min(K, 5)):
             step_resident(i)
         prof = eng.profile_end()
+        model.overlap_towers = overlap
         nprof = min(K, 5)
         results[variant] = {"ms": ms / K, "ms_e2e": ms_e2e / K, "launches": launches, "prof": prof, "nprof": nprof,
                             "text_len": eng.text_len, "loss": float(trainer.forward_backward(
@@ -386,6 +394,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="profiling aid: resident loop of the full-length variant only")
+    ap.add_argument("--classes", type=int, default=N_CLASSES, help="--quick only: classes on this GPU")
+    ap.add_argument("--no-overlap", action="store_true", help="--quick only: towers on one stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

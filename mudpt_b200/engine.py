@@ -39,6 +39,13 @@ class Engine:
         self.n_classes = 0
         self.text_len = 0
         self.class_key = None  # identifies the class set currently resident in the text tower
+        self._side = None
+
+    def side_stream(self) -> torch.cuda.Stream:
+        """Second stream of this engine's device (the two towers use disjoint workspaces of the handle)."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
 
     def __del__(self):
         try:

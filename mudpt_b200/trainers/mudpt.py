@@ -221,6 +221,8 @@ class CustomCLIP(nn.Module):
         self.shard_classes = True           # class-sharded text tower when torch.distributed is initialised
         self._cached_text_features = None   # eval-time cache (parameters frozen under no_grad)
         self._replicas_synced = False       # trainable tensors broadcast from rank 0 once (replicated state)
+        # fused train step: vision tower on a side stream next to the text tower (see forward_backward)
+        self.overlap_towers = os.environ.get("MUDPT_OVERLAP_TOWERS", "1") != "0"
 
     # ------------------------------------------------------------------ helpers
     def _engine(self, device):
@@ -288,14 +290,40 @@ class CustomCLIP(nn.Module):
         self._register_classes(device)
         world = mdist.world_size() if self.shard_classes else 1
         P_v, P_t = self.prompt_stacks()
-        f_img = eng.vision_forward(image.type(self.dtype), P_v.detach())
-        f_txt_loc = eng.text_forward(P_t.detach(), True)
         n_cls = self.mudpt_prompt_learner.n_cls
-        f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
-        logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True)
-        d_t_loc = mdist.reduce_scatter_rows(d_t, n_cls) if world > 1 else d_t
-        dP_t, _ = eng.text_backward(d_t_loc)
-        dP_v = eng.vision_backward(d_i)
+        image = image.type(self.dtype)
+        if not self.overlap_towers or device.type != "cuda":  # (CPU: only the gloo tests' stand-in engine)
+            f_img = eng.vision_forward(image, P_v.detach())
+            f_txt_loc = eng.text_forward(P_t.detach(), True)
+            f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
+            logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True)
+            d_t_loc = mdist.reduce_scatter_rows(d_t, n_cls) if world > 1 else d_t
+            dP_t, _ = eng.text_backward(d_t_loc)
+            dP_v = eng.vision_backward(d_i)
+        else:
+            # The two towers are independent between the prompt algebra and the logits head (and again
+            # after it), so the vision tower runs on a side stream next to the text tower: the tail
+            # wave of one tower's persistent GEMM (e.g. 75 pair tiles on 74 SM pairs) and its small
+            # latency-bound kernels are filled by the other tower's CTAs, and the text-feature
+            # all-gather / reduce-scatter hide behind the vision tower.
+            main = torch.cuda.current_stream(device)
+            side = eng.side_stream()
+            side.wait_stream(main)  # P_v, image are ready
+            with torch.cuda.stream(side):
+                f_img = eng.vision_forward(image, P_v.detach())
+            f_txt_loc = eng.text_forward(P_t.detach(), True)
+            f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
+            main.wait_stream(side)
+            f_img.record_stream(main)
+            logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True)
+            side.wait_stream(main)  # d_i
+            with torch.cuda.stream(side):
+                dP_v = eng.vision_backward(d_i)
+            d_i.record_stream(side)
+            d_t_loc = mdist.reduce_scatter_rows(d_t, n_cls) if world > 1 else d_t
+            dP_t, _ = eng.text_backward(d_t_loc)
+            main.wait_stream(side)
+            dP_v.record_stream(main)
         torch.autograd.backward([P_v, P_t], [dP_v, dP_t])
         if world > 1:
             mdist.all_reduce_grads([p for p in self.parameters() if p.requires_grad])
