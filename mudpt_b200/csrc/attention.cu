@@ -409,6 +409,335 @@ __global__ void __launch_bounds__(128, 3) attn_bwd_dkv_kernel(const bf16* __rest
   store_rows_bf16(dv, 1.f, 1.f, smem, BKV * ROW_BYTES, row0, out + 2 * d, ld, k0 + row0, L, lane);
 }
 
+// =======================================================================================
+// Short sequences (L <= 128: the text tower, 77 tokens or fewer after EOT truncation).
+//
+// One CTA per (sequence, head), one warp per 16-row tile, Q / K / V (and dO, O) loaded ONCE.
+// The whole score row block of a warp (16 x 16*T, T = visible 16-key groups) lives in registers,
+// so the softmax is a single pass (no running max / rescale) and the code is straight-line per T
+// (dispatch on T: no per-group guards -- the generic kernels above spend ~2/3 of their issue
+// slots on those).  The backward is ONE kernel: phase 1 (rows = queries) computes S, P, dP, dS
+// once, dQ = dS K, and parks P / dS as bf16 in shared memory (over the dead K / V / O tiles);
+// phase 2 (rows = keys) reads them transposed with ldmatrix.trans: dV = P^T dO, dK = dS^T Q.
+// 5 MMA products instead of 7, one exp per score instead of two, a third of the tile loads.
+// =======================================================================================
+static constexpr int SHORT_MAX_TILES = 8;
+
+__device__ __forceinline__ uint32_t ps_stride(int Lp) { return static_cast<uint32_t>(2 * Lp + 16); }  // bytes; odd multiple of 16: conflict-free ldmatrix
+
+template <bool CAUSAL, int T>
+__device__ __forceinline__ void short_fwd_body(uint8_t* smem, uint32_t sQ, uint32_t sK, uint32_t sV, int t, int L, int lane,
+                                               float scale_log2e, bf16* o_base, int d, float* lse_base) {
+  const int row0 = t * 16;
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) load_a_frag(qa[ks], sQ, row0, ks, lane);
+  float s[2 * T][4];
+  zero_acc(s);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int g = 0; g < T; ++g) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(sK + swz(g * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+      mma16816(s[2 * g], qa[ks], b0, b1);
+      mma16816(s[2 * g + 1], qa[ks], b2, b3);
+    }
+  }
+  const int qr = row0 + (lane >> 2);
+  // only the last visible group can hold invisible keys (the causal diagonal / columns >= L)
+#pragma unroll
+  for (int nt = 2 * T - 2; nt < 2 * T; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = nt * 8 + (lane & 3) * 2 + (e & 1);
+      const bool ok = col < L && (!CAUSAL || col <= qr + 8 * (e >> 1));
+      s[nt][e] = ok ? s[nt][e] : -INFINITY;
+    }
+  }
+  float m[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 2 * T; ++nt) {
+    m[0] = fmaxf(m[0], fmaxf(s[nt][0], s[nt][1]));
+    m[1] = fmaxf(m[1], fmaxf(s[nt][2], s[nt][3]));
+  }
+  f32x2 nm[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    m[r] = fmaxf(m[r], __shfl_xor_sync(0xffffffffu, m[r], 1));
+    m[r] = fmaxf(m[r], __shfl_xor_sync(0xffffffffu, m[r], 2));
+    m[r] = (m[r] == -INFINITY) ? 0.f : m[r] * scale_log2e;  // scaled max (log2 domain)
+    nm[r] = f2_pack(-m[r], -m[r]);
+  }
+  const f32x2 sc = f2_pack(scale_log2e, scale_log2e);
+  f32x2 lsum[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+  uint32_t pk[2 * T][2];  // P as bf16 A fragments
+#pragma unroll
+  for (int nt = 0; nt < 2 * T; ++nt) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float a, b;
+      f2_unpack(f2_fma(f2_pack(s[nt][2 * r], s[nt][2 * r + 1]), sc, nm[r]), a, b);
+      a = exp2f(a);
+      b = exp2f(b);
+      lsum[r] = f2_add(lsum[r], f2_pack(a, b));
+      pk[nt][r] = pack_bf16(a, b);
+    }
+  }
+  float oacc[8][4];
+  zero_acc(oacc);
+#pragma unroll
+  for (int g = 0; g < T; ++g) {
+    const uint32_t a[4] = {pk[2 * g][0], pk[2 * g][1], pk[2 * g + 1][0], pk[2 * g + 1][1]};
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(sV + swz(g * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma16816(oacc[2 * dp], a, b0, b1);
+      mma16816(oacc[2 * dp + 1], a, b2, b3);
+    }
+  }
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float a, b;
+    f2_unpack(lsum[r], a, b);
+    float l = a + b;
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    inv[r] = l > 0.f ? 1.f / l : 0.f;
+    const int row = qr + 8 * r;
+    if ((lane & 3) == 0 && row < L) lse_base[row] = m[r] + log2f(l);
+  }
+  store_rows_bf16(oacc, inv[0], inv[1], smem, 0, row0, o_base, d, row0, L, lane);
+}
+
+// MAXT = most 16-row tiles (warps) this instantiation handles: sizes the register budget, so that the
+// 77-token text tower (5 tiles) does not pay for 128-token sequences (8 tiles).
+constexpr int short_min_ctas(int maxt, bool bwd) { return maxt <= 2 ? 8 : maxt <= 5 ? (bwd ? 3 : 4) : (bwd ? 1 : 2); }
+
+template <bool CAUSAL, int MAXT>
+__global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, false)) attn_short_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+                                                                              float* __restrict__ lse2, int L, int H, int d,
+                                                                              float scale_log2e) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int nw = blockDim.x >> 5, Lp = nw * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sh = blockIdx.x, s = sh / H, h = sh - s * H;
+  const uint32_t sQ = smem_u32(smem), sK = sQ + Lp * ROW_BYTES, sV = sK + Lp * ROW_BYTES;
+  const int ld = 3 * d;
+  const bf16* base = qkv + static_cast<size_t>(s) * L * ld + h * DH;
+  load_tile(sQ, base, ld, 0, L, Lp);
+  load_tile(sK, base + d, ld, 0, L, Lp);
+  load_tile(sV, base + 2 * d, ld, 0, L, Lp);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  bf16* ob = o + static_cast<size_t>(s) * L * d + h * DH;
+  float* lb = lse2 + (static_cast<size_t>(s) * H + h) * L;
+  const int T = CAUSAL ? warp + 1 : nw;
+#define MUDPT_FWD_CASE(k) \
+  case k: if constexpr (MAXT >= k) short_fwd_body<CAUSAL, k>(smem, sQ, sK, sV, warp, L, lane, scale_log2e, ob, d, lb); break;
+  switch (T) {
+    MUDPT_FWD_CASE(1) MUDPT_FWD_CASE(2) MUDPT_FWD_CASE(3) MUDPT_FWD_CASE(4)
+    MUDPT_FWD_CASE(5) MUDPT_FWD_CASE(6) MUDPT_FWD_CASE(7) MUDPT_FWD_CASE(8)
+    default: break;
+  }
+#undef MUDPT_FWD_CASE
+}
+
+// Phase 1 of the fused backward for query tile t: returns dQ in `dq`, P / dS (bf16, accumulator
+// fragment layout) in pp / ds.
+template <bool CAUSAL, int T, int MAXT>
+__device__ __forceinline__ void short_bwd_phase1(uint32_t sQ, uint32_t sdO, uint32_t sK, uint32_t sV, int t, int L, int lane,
+                                                 float scale_log2e, float lse0, float lse1, float D0, float D1,
+                                                 float (&dq)[8][4], uint32_t (&pp)[2 * MAXT][2], uint32_t (&ds)[2 * MAXT][2]) {
+  const int row0 = t * 16;
+  float sc[2 * T][4], dp[2 * T][4];
+  zero_acc(sc);
+  zero_acc(dp);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t qa[4], da[4];
+    load_a_frag(qa, sQ, row0, ks, lane);
+    load_a_frag(da, sdO, row0, ks, lane);
+#pragma unroll
+    for (int g = 0; g < T; ++g) {
+      const uint32_t off = swz(g * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1));
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(sK + off, b0, b1, b2, b3);
+      mma16816(sc[2 * g], qa, b0, b1);
+      mma16816(sc[2 * g + 1], qa, b2, b3);
+      ldsm_x4(sV + off, b0, b1, b2, b3);
+      mma16816(dp[2 * g], da, b0, b1);
+      mma16816(dp[2 * g + 1], da, b2, b3);
+    }
+  }
+  const int qr = row0 + (lane >> 2);
+  const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
+  const f32x2 nl[2] = {f2_pack(-lse0, -lse0), f2_pack(-lse1, -lse1)};
+  const f32x2 nD[2] = {f2_pack(-D0, -D0), f2_pack(-D1, -D1)};
+#pragma unroll
+  for (int nt = 0; nt < 2 * T; ++nt) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float a, b;
+      f2_unpack(f2_fma(f2_pack(sc[nt][2 * r], sc[nt][2 * r + 1]), c2, nl[r]), a, b);
+      a = exp2f(a);
+      b = exp2f(b);
+      if (nt >= 2 * T - 2) {  // only the last visible group can hold invisible keys
+        const int col = nt * 8 + (lane & 3) * 2;
+        const int lim = CAUSAL ? min(L - 1, qr + 8 * r) : L - 1;
+        a = col <= lim ? a : 0.f;
+        b = col + 1 <= lim ? b : 0.f;
+      }
+      const f32x2 p2 = f2_pack(a, b);
+      float x, y;
+      f2_unpack(f2_mul(p2, f2_add(f2_pack(dp[nt][2 * r], dp[nt][2 * r + 1]), nD[r])), x, y);  // dS (unscaled)
+      pp[nt][r] = pack_bf16(a, b);
+      ds[nt][r] = pack_bf16(x, y);
+    }
+  }
+  zero_acc(dq);
+#pragma unroll
+  for (int g = 0; g < T; ++g) {
+    const uint32_t a[4] = {ds[2 * g][0], ds[2 * g][1], ds[2 * g + 1][0], ds[2 * g + 1][1]};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(sK + swz(g * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), q * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma16816(dq[2 * q], a, b0, b1);
+      mma16816(dq[2 * q + 1], a, b2, b3);
+    }
+  }
+}
+
+template <bool CAUSAL, int MAXT>
+__global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, true)) attn_short_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+                                                                              const bf16* __restrict__ d_o,
+                                                                              const float* __restrict__ lse2,
+                                                                              bf16* __restrict__ dqkv, int L, int H, int d,
+                                                                              float scale, float scale_log2e) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int nw = blockDim.x >> 5, Lp = nw * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sh = blockIdx.x, s = sh / H, h = sh - s * H;
+  // [Q | dO | K | V | O ...]; after phase 1 the K/V/O region is reused for P and dS
+  const uint32_t tile_bytes = Lp * ROW_BYTES;
+  const uint32_t sQ = smem_u32(smem), sdO = sQ + tile_bytes, sK = sdO + tile_bytes, sV = sK + tile_bytes, sO = sV + tile_bytes;
+  const int ld = 3 * d;
+  const size_t seq_row = static_cast<size_t>(s) * L;
+  const bf16* base = qkv + seq_row * ld + h * DH;
+  load_tile(sQ, base, ld, 0, L, Lp);
+  load_tile(sdO, d_o + seq_row * d + h * DH, d, 0, L, Lp);
+  load_tile(sK, base + d, ld, 0, L, Lp);
+  load_tile(sV, base + 2 * d, ld, 0, L, Lp);
+  load_tile(sO, o + seq_row * d + h * DH, d, 0, L, Lp);
+  cp_async_commit();
+  const int row0 = warp * 16;
+  const int qr = row0 + (lane >> 2);
+  const size_t stat_base = (static_cast<size_t>(s) * H + h) * L;
+  // rows >= L: lse = 0 with zero Q / dO rows gives finite p and dS = 0, dO = 0: no contribution to dK / dV
+  const float lse0 = qr < L ? lse2[stat_base + qr] : 0.f;
+  const float lse1 = qr + 8 < L ? lse2[stat_base + qr + 8] : 0.f;
+  cp_async_wait_all();
+  __syncthreads();
+
+  // D_i = sum_j dO_ij O_ij for the warp's 16 rows: lane -> (row = lane/2, half = lane%2)
+  float dpart = 0.f;
+  {
+    const int r = row0 + (lane >> 1);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int chunk = (lane & 1) * 4 + c;
+      const uint4 a = *reinterpret_cast<const uint4*>(smem + (sdO - sQ) + swz(r, chunk));
+      const uint4 b = *reinterpret_cast<const uint4*>(smem + (sO - sQ) + swz(r, chunk));
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_bf16(pa[i]), y = unpack_bf16(pb[i]);
+        dpart += x.x * y.x + x.y * y.y;
+      }
+    }
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 1);
+  }
+  const float D0 = __shfl_sync(0xffffffffu, dpart, (lane >> 2) * 2);
+  const float D1 = __shfl_sync(0xffffffffu, dpart, ((lane >> 2) + 8) * 2);
+
+  float dq[8][4];
+  uint32_t pp[2 * MAXT][2], ds[2 * MAXT][2];
+  const int T = CAUSAL ? warp + 1 : nw;
+#define MUDPT_BWD_CASE(k) \
+  case k: if constexpr (MAXT >= k) short_bwd_phase1<CAUSAL, k, MAXT>(sQ, sdO, sK, sV, warp, L, lane, scale_log2e, lse0, lse1, D0, D1, dq, pp, ds); break;
+  switch (T) {
+    MUDPT_BWD_CASE(1) MUDPT_BWD_CASE(2) MUDPT_BWD_CASE(3) MUDPT_BWD_CASE(4)
+    MUDPT_BWD_CASE(5) MUDPT_BWD_CASE(6) MUDPT_BWD_CASE(7) MUDPT_BWD_CASE(8)
+    default: break;
+  }
+#undef MUDPT_BWD_CASE
+  __syncthreads();  // every warp is done with K / V / O: the region becomes P | dS
+  const uint32_t stride = ps_stride(Lp);
+  uint8_t* gP = smem + 2 * tile_bytes;
+  uint8_t* gS = gP + Lp * stride;
+  {
+    // accumulator fragment layout: rows (lane/4, +8), column pair 2*(lane%4) of each 8-column tile
+    const uint32_t r_lo = static_cast<uint32_t>(row0 + (lane >> 2)) * stride + (lane & 3) * 4;
+    const uint32_t r_hi = r_lo + 8 * stride;
+#pragma unroll
+    for (int nt = 0; nt < 2 * MAXT; ++nt) {
+      if (nt < 2 * T) {
+        *reinterpret_cast<uint32_t*>(gP + r_lo + nt * 16) = pp[nt][0];
+        *reinterpret_cast<uint32_t*>(gP + r_hi + nt * 16) = pp[nt][1];
+        *reinterpret_cast<uint32_t*>(gS + r_lo + nt * 16) = ds[nt][0];
+        *reinterpret_cast<uint32_t*>(gS + r_hi + nt * 16) = ds[nt][1];
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase 2: rows = this warp's 16 keys; query groups g that can see them
+  float dk[8][4], dv[8][4];
+  zero_acc(dk);
+  zero_acc(dv);
+  const uint32_t aP = smem_u32(gP), aS = smem_u32(gS);
+  for (int g = CAUSAL ? warp : 0; g < nw; ++g) {
+    // A = (P^T)[keys row0.., queries 16g..]: 8x8 blocks of P (rows = queries) read transposed.
+    // a0..a3 = blocks (queries 0-7, keys 0-7), (q 0-7, keys 8-15), (q 8-15, keys 0-7), (q 8-15, keys 8-15):
+    // lanes 8i..8i+7 address the 8 query rows of block i
+    const uint32_t off = static_cast<uint32_t>(g * 16 + (lane & 7) + ((lane >> 4) << 3)) * stride +
+                         static_cast<uint32_t>(row0 + (((lane >> 3) & 1) << 3)) * 2;
+    uint32_t pa[4], sa[4];
+    ldsm_x4_t(aP + off, pa[0], pa[1], pa[2], pa[3]);
+    ldsm_x4_t(aS + off, sa[0], sa[1], sa[2], sa[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t boff = swz(g * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), q * 2 + (lane >> 4));
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(sdO + boff, b0, b1, b2, b3);
+      mma16816(dv[2 * q], pa, b0, b1);
+      mma16816(dv[2 * q + 1], pa, b2, b3);
+      ldsm_x4_t(sQ + boff, b0, b1, b2, b3);
+      mma16816(dk[2 * q], sa, b0, b1);
+      mma16816(dk[2 * q + 1], sa, b2, b3);
+    }
+  }
+  __syncthreads();  // all reads of Q / dO / P / dS are done: the Q and dO tiles become store staging
+  bf16* out = dqkv + seq_row * ld + h * DH;
+  if (row0 < L) {
+    store_rows_bf16(dq, scale, scale, smem, 0, row0, out, ld, row0, L, lane);
+    store_rows_bf16(dk, scale, scale, smem, tile_bytes, row0, out + d, ld, row0, L, lane);
+    __syncwarp();
+    store_rows_bf16(dv, 1.f, 1.f, smem, 0, row0, out + 2 * d, ld, row0, L, lane);
+  }
+}
+
+static size_t short_bwd_smem(int Lp) {
+  const size_t tiles = 5u * Lp * ROW_BYTES;                       // Q dO K V O
+  const size_t need = 2u * Lp * ROW_BYTES + 2u * Lp * (2 * Lp + 16);  // Q dO P dS
+  return tiles > need ? tiles : need;
+}
+
 // ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
@@ -428,6 +757,16 @@ static int pick_warps(int L) {
   return tiles >= nw ? nw : tiles;
 }
 
+// L <= 128: the single-pass kernels (MUDPT_ATTN_SHORT=0 forces the generic ones; tuning / A-B aid)
+static bool use_short(int L) {
+  static int en = -1;
+  if (en < 0) {
+    const char* e = getenv("MUDPT_ATTN_SHORT");
+    en = e ? (atoi(e) != 0) : 1;
+  }
+  return en && L <= 16 * SHORT_MAX_TILES;
+}
+
 template <typename K>
 static const char* set_smem(K kern, size_t bytes) {
   if (bytes > 227 * 1024) return "attention: sequence too long for the shared-memory resident kernel";
@@ -441,9 +780,24 @@ const char* attention_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L, i
                           cudaStream_t stream) {
   if (S <= 0 || L <= 0) return nullptr;
   if (d != H * DH) return "attention: head width must be 64";
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  if (use_short(L)) {
+    const int tiles = (L + 15) / 16;
+    const size_t sm = 3u * tiles * 16 * ROW_BYTES;
+    const char* es = nullptr;
+#define MUDPT_LAUNCH_FWD(C, MT)                                                                        \
+  do {                                                                                                 \
+    if ((es = set_smem(attn_short_fwd_kernel<C, MT>, sm))) return es;                                  \
+    attn_short_fwd_kernel<C, MT><<<S * H, tiles * 32, sm, stream>>>(qkv, o, lse2, L, H, d, sl2);       \
+  } while (0)
+    if (causal) { if (tiles <= 2) MUDPT_LAUNCH_FWD(true, 2); else if (tiles <= 5) MUDPT_LAUNCH_FWD(true, 5); else MUDPT_LAUNCH_FWD(true, 8); }
+    else { if (tiles <= 2) MUDPT_LAUNCH_FWD(false, 2); else if (tiles <= 5) MUDPT_LAUNCH_FWD(false, 5); else MUDPT_LAUNCH_FWD(false, 8); }
+#undef MUDPT_LAUNCH_FWD
+    count_launch(1);
+    return launch_status("attention fwd (short) launch failed");
+  }
   const int nw = pick_warps(L), BQ = nw * 16, Lp = (L + 15) & ~15;
   const size_t smem = static_cast<size_t>(BQ + 2 * Lp) * ROW_BYTES;
-  const float sl2 = 0.125f * 1.4426950408889634f;
   dim3 grid((L + BQ - 1) / BQ, S * H);
   const char* e;
   if (causal) {
@@ -461,6 +815,22 @@ const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const
                           int S, int L, int H, int d, bool causal, cudaStream_t stream) {
   if (S <= 0 || L <= 0) return nullptr;
   if (d != H * DH) return "attention: head width must be 64";
+  if (use_short(L)) {
+    const int tiles = (L + 15) / 16;
+    const size_t sm = short_bwd_smem(tiles * 16);
+    const char* es = nullptr;
+    const float sc = 0.125f, sl2s = 0.125f * 1.4426950408889634f;
+#define MUDPT_LAUNCH_BWD(C, MT)                                                                                  \
+  do {                                                                                                           \
+    if ((es = set_smem(attn_short_bwd_kernel<C, MT>, sm))) return es;                                            \
+    attn_short_bwd_kernel<C, MT><<<S * H, tiles * 32, sm, stream>>>(qkv, o, d_o, lse2, dqkv, L, H, d, sc, sl2s); \
+  } while (0)
+    if (causal) { if (tiles <= 2) MUDPT_LAUNCH_BWD(true, 2); else if (tiles <= 5) MUDPT_LAUNCH_BWD(true, 5); else MUDPT_LAUNCH_BWD(true, 8); }
+    else { if (tiles <= 2) MUDPT_LAUNCH_BWD(false, 2); else if (tiles <= 5) MUDPT_LAUNCH_BWD(false, 5); else MUDPT_LAUNCH_BWD(false, 8); }
+#undef MUDPT_LAUNCH_BWD
+    count_launch(1);
+    return launch_status("attention bwd (short) launch failed");
+  }
   const int nw = pick_warps(L), BQ = nw * 16, Lp = (L + 15) & ~15;
   const size_t smem_q = static_cast<size_t>(3 * BQ + 2 * Lp) * ROW_BYTES;
   const size_t smem_kv = static_cast<size_t>(2 * BQ + 2 * Lp) * ROW_BYTES + 2 * Lp * sizeof(float);
