@@ -17,6 +17,7 @@
 #include "attention.h"
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "launch_count.h"
@@ -137,11 +138,82 @@ __device__ __forceinline__ void zero_acc(float (&a)[N][4]) {
   for (int i = 0; i < N; ++i) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
 }
 
+// One 64-key chunk of the online-softmax forward for a warp's 16 query rows.
+// FULL: all four 16-key groups are visible to every row (no guards, no mask).
+template <bool CAUSAL, bool FULL>
+__device__ __forceinline__ void fwd_chunk(float (&oacc)[8][4], float (&m_run)[2], float (&l_run)[2], uint32_t sQ, uint32_t sK,
+                                          uint32_t sV, int row0, int c0, int g_hi, int L, const int (&qrow)[2],
+                                          float scale_log2e, int lane) {
+  float sacc[8][4];
+  zero_acc(sacc);
+  mma_rows_x_cols<4>(sacc, sQ, row0, sK, c0, 0, FULL ? 4 : g_hi, lane);
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (FULL || nt < 2 * g_hi) {
+      if constexpr (!FULL) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+          const bool ok = col < L && (!CAUSAL || col <= qrow[e >> 1]);
+          sacc[nt][e] = ok ? sacc[nt][e] : -INFINITY;
+        }
+      }
+      mx[0] = fmaxf(mx[0], fmaxf(sacc[nt][0], sacc[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+  }
+  f32x2 alpha2[2], nm2[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    const float m_new = fmaxf(m_run[r], mx[r] * scale_log2e);  // running max of the scaled scores (log2 domain)
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = exp2f(m_run[r] - m_use);  // m_run = -inf -> 0
+    m_run[r] = m_new;
+    l_run[r] *= alpha;
+    alpha2[r] = f2_pack(alpha, alpha);
+    nm2[r] = f2_pack(-m_use, -m_use);
+  }
+  const f32x2 sc2 = f2_pack(scale_log2e, scale_log2e);
+  f32x2 ls[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (FULL || nt < 2 * g_hi) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float a, b;
+        f2_unpack(f2_fma(f2_pack(sacc[nt][2 * r], sacc[nt][2 * r + 1]), sc2, nm2[r]), a, b);
+        a = exp2f(a);
+        b = exp2f(b);
+        sacc[nt][2 * r] = a;
+        sacc[nt][2 * r + 1] = b;
+        ls[r] = f2_add(ls[r], f2_pack(a, b));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float a, b;
+      f2_unpack(f2_mul(f2_pack(oacc[nt][2 * r], oacc[nt][2 * r + 1]), alpha2[r]), a, b);
+      oacc[nt][2 * r] = a;
+      oacc[nt][2 * r + 1] = b;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float a, b;
+    f2_unpack(ls[r], a, b);
+    l_run[r] += a + b;
+  }
+  mma_p_x_tile<4>(oacc, sacc, sV, c0, 0, FULL ? 4 : g_hi, lane);
+}
+
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
 template <bool CAUSAL>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
                                                        float* __restrict__ lse2, int L, int H, int d, float scale_log2e) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nwarps = blockDim.x >> 5, BQ = nwarps * 16;
@@ -171,57 +243,12 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
 
   for (int c0 = 0; c0 < kv_warp; c0 += 64) {
     const int g_hi = min(4, (kv_warp - c0 + 15) >> 4);
-    float sacc[8][4];
-    zero_acc(sacc);
-    mma_rows_x_cols<4>(sacc, sQ, row0, sK, c0, 0, g_hi, lane);
-    float mx[2] = {-INFINITY, -INFINITY};
-    // the kernel is instruction-bound (ncu: 3 % of the issued instructions are MMAs), so the softmax
-    // touches only the 8-column tiles that were computed (nt < 2*g_hi, warp-uniform) and skips the
-    // mask arithmetic for chunks that lie entirely inside the valid / causal region
+    // the kernel is instruction-bound (ncu: 3 % of the issued instructions are MMAs): chunks that lie
+    // entirely inside the valid / causal region take a straight-line path without per-group guards or
+    // mask arithmetic (3 of the 4 chunks of a 199-token vision sequence)
     const bool need_mask = (c0 + 64 > L) || (CAUSAL && c0 + 63 > q0 + row0);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      if (nt < 2 * g_hi) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = e >> 1;
-          float v = sacc[nt][e] * scale_log2e;
-          if (need_mask) {
-            const int col = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-            const bool ok = col < L && (!CAUSAL || col <= qrow[r]);
-            v = ok ? v : -INFINITY;
-          }
-          sacc[nt][e] = v;
-          mx[r] = fmaxf(mx[r], v);
-        }
-      }
-    }
-    float alpha[2], m_use[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float m_new = fmaxf(m_run[r], mx[r]);
-      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
-      alpha[r] = exp2f(m_run[r] - m_use[r]);  // m_run = -inf -> 0
-      m_run[r] = m_new;
-      l_run[r] *= alpha[r];
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      if (nt < 2 * g_hi) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = e >> 1;
-          const float p = exp2f(sacc[nt][e] - m_use[r]);
-          sacc[nt][e] = p;
-          l_run[r] += p;
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) oacc[nt][e] *= alpha[e >> 1];
-    }
-    mma_p_x_tile<4>(oacc, sacc, sV, c0, 0, g_hi, lane);
+    if (g_hi == 4 && !need_mask) fwd_chunk<CAUSAL, true>(oacc, m_run, l_run, sQ, sK, sV, row0, c0, 4, L, qrow, scale_log2e, lane);
+    else fwd_chunk<CAUSAL, false>(oacc, m_run, l_run, sQ, sK, sV, row0, c0, g_hi, L, qrow, scale_log2e, lane);
   }
   float inv[2];
 #pragma unroll
@@ -239,7 +266,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
 // backward, dQ pass (rows = queries).  Also produces D = rowsum(dO * O) for the dKV pass.
 // ---------------------------------------------------------------------------------------
 template <bool CAUSAL>
-__global__ void __launch_bounds__(128, 4) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(256, 2) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
                                                              const bf16* __restrict__ d_o, const float* __restrict__ lse2,
                                                              float* __restrict__ dsum, bf16* __restrict__ dqkv, int L,
                                                              int H, int d, float scale, float scale_log2e) {
@@ -301,33 +328,46 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_dq_kernel(const bf16* __restr
   float dq[8][4];
   zero_acc(dq);
   const int kv_warp = CAUSAL ? min(kv_len, q0 + row0 + 16) : kv_len;
-  for (int c0 = 0; c0 < kv_warp; c0 += 32) {
-    const int g_hi = min(2, (kv_warp - c0 + 15) >> 4);
+  const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
+  const f32x2 nl2[2] = {f2_pack(-lse[0], -lse[0]), f2_pack(-lse[1], -lse[1])};
+  const f32x2 nD2[2] = {f2_pack(-Dr[0], -Dr[0]), f2_pack(-Dr[1], -Dr[1])};
+  // one 32-key chunk; FULL: both 16-key groups visible to every row (no guards / mask)
+  auto chunk = [&](auto full_tag, int c0, int g_hi) {
+    constexpr bool FULL = decltype(full_tag)::value;
     float sacc[4][4], dp[4][4];
     zero_acc(sacc);
     zero_acc(dp);
-    mma_rows_x_cols<2>(sacc, sQ, row0, sK, c0, 0, g_hi, lane);
-    mma_rows_x_cols<2>(dp, sdO, row0, sV, c0, 0, g_hi, lane);
+    mma_rows_x_cols<2>(sacc, sQ, row0, sK, c0, 0, FULL ? 2 : g_hi, lane);
+    mma_rows_x_cols<2>(dp, sdO, row0, sV, c0, 0, FULL ? 2 : g_hi, lane);
     // rows >= L of the last tile carry lse = 0 and finite garbage: they are never stored, so only the
-    // column mask matters; chunks entirely inside the valid / causal region skip it
-    const bool need_mask = (c0 + 32 > L) || (CAUSAL && c0 + 31 > q0 + row0);
+    // column mask matters
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      if (nt < 2 * g_hi) {
+      if (FULL || nt < 2 * g_hi) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = e >> 1;
-          float p = exp2f(sacc[nt][e] * scale_log2e - lse[r]);
-          if (need_mask) {
-            const int col = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-            const bool ok = col < L && (!CAUSAL || col <= qrow[r]);
-            p = ok ? p : 0.f;
+        for (int r = 0; r < 2; ++r) {
+          float a, b;
+          f2_unpack(f2_fma(f2_pack(sacc[nt][2 * r], sacc[nt][2 * r + 1]), c2, nl2[r]), a, b);
+          a = exp2f(a);
+          b = exp2f(b);
+          if constexpr (!FULL) {
+            const int col = c0 + nt * 8 + (lane & 3) * 2;
+            const int lim = CAUSAL ? min(L - 1, qrow[r]) : L - 1;
+            a = col <= lim ? a : 0.f;
+            b = col + 1 <= lim ? b : 0.f;
           }
-          sacc[nt][e] = p * (dp[nt][e] - Dr[r]);  // dS (unscaled)
+          f2_unpack(f2_mul(f2_pack(a, b), f2_add(f2_pack(dp[nt][2 * r], dp[nt][2 * r + 1]), nD2[r])), sacc[nt][2 * r],
+                    sacc[nt][2 * r + 1]);  // dS (unscaled)
         }
       }
     }
-    mma_p_x_tile<2>(dq, sacc, sK, c0, 0, g_hi, lane);
+    mma_p_x_tile<2>(dq, sacc, sK, c0, 0, FULL ? 2 : g_hi, lane);
+  };
+  for (int c0 = 0; c0 < kv_warp; c0 += 32) {
+    const int g_hi = min(2, (kv_warp - c0 + 15) >> 4);
+    const bool need_mask = (c0 + 32 > L) || (CAUSAL && c0 + 31 > q0 + row0);
+    if (g_hi == 2 && !need_mask) chunk(std::true_type{}, c0, 2);
+    else chunk(std::false_type{}, c0, g_hi);
   }
   store_rows_bf16(dq, scale, scale, smem, 0, row0, dqkv + seq_row * ld + h * DH, ld, q0 + row0, L, lane);
 }
@@ -336,7 +376,7 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_dq_kernel(const bf16* __restr
 // backward, dK/dV pass (rows = keys)
 // ---------------------------------------------------------------------------------------
 template <bool CAUSAL>
-__global__ void __launch_bounds__(128, 3) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+__global__ void __launch_bounds__(256, 2) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
                                                               const float* __restrict__ lse2, const float* __restrict__ dsum,
                                                               bf16* __restrict__ dqkv, int L, int H, int d, float scale,
                                                               float scale_log2e) {
@@ -373,36 +413,50 @@ __global__ void __launch_bounds__(128, 3) attn_bwd_dkv_kernel(const bf16* __rest
   zero_acc(dv);
   const int krow[2] = {k0 + row0 + (lane >> 2), k0 + row0 + (lane >> 2) + 8};
   const int q_first = CAUSAL ? (k0 + row0) : 0;  // first query that can see any of this warp's keys
-  for (int c0 = q_first & ~31; c0 < L; c0 += 32) {
-    const int g_lo = max(0, (q_first - c0) >> 4);
-    const int g_hi = min(2, (L - c0 + 15) >> 4);
+  const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
+  // one chunk of 32 queries (columns); FULL: both 16-query groups see all of this warp's keys
+  auto chunk = [&](auto full_tag, int c0, int g_lo, int g_hi) {
+    constexpr bool FULL = decltype(full_tag)::value;
     float st[4][4], dpt[4][4];
     zero_acc(st);
     zero_acc(dpt);
-    mma_rows_x_cols<2>(st, sK, row0, sQ, c0, g_lo, g_hi, lane);
-    mma_rows_x_cols<2>(dpt, sV, row0, sdO, c0, g_lo, g_hi, lane);
+    mma_rows_x_cols<2>(st, sK, row0, sQ, c0, FULL ? 0 : g_lo, FULL ? 2 : g_hi, lane);
+    mma_rows_x_cols<2>(dpt, sV, row0, sdO, c0, FULL ? 0 : g_lo, FULL ? 2 : g_hi, lane);
     // key rows >= L only pollute their own (never stored) dK/dV rows; the query (column) mask is
     // needed only where the chunk crosses L or the causal diagonal of this warp's 16 keys
-    const bool need_mask = (c0 + 32 > L) || (CAUSAL && c0 < k0 + row0 + 15);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      if (nt >= 2 * g_lo && nt < 2 * g_hi) {
+      if (FULL || (nt >= 2 * g_lo && nt < 2 * g_hi)) {
+        const int qi = c0 + nt * 8 + (lane & 3) * 2;  // query index (column), < Lp here
+        const float2 l2 = *reinterpret_cast<const float2*>(sLse + qi);
+        const float2 d2 = *reinterpret_cast<const float2*>(sD + qi);
+        const f32x2 nl = f2_pack(-l2.x, -l2.y), nd = f2_pack(-d2.x, -d2.y);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int qi = c0 + nt * 8 + (lane & 3) * 2 + (e & 1);  // query index (column), < Lp here
-          const int r = e >> 1;
-          float p = exp2f(st[nt][e] * scale_log2e - sLse[qi]);
-          if (need_mask) {
-            const bool ok = qi < L && (!CAUSAL || krow[r] <= qi);
-            p = ok ? p : 0.f;
+        for (int r = 0; r < 2; ++r) {
+          float a, b;
+          f2_unpack(f2_fma(f2_pack(st[nt][2 * r], st[nt][2 * r + 1]), c2, nl), a, b);
+          a = exp2f(a);
+          b = exp2f(b);
+          if constexpr (!FULL) {
+            a = (qi < L && (!CAUSAL || krow[r] <= qi)) ? a : 0.f;
+            b = (qi + 1 < L && (!CAUSAL || krow[r] <= qi + 1)) ? b : 0.f;
           }
-          st[nt][e] = p;                               // P^T
-          dpt[nt][e] = p * (dpt[nt][e] - sD[qi]);      // dS^T (unscaled), in place
+          st[nt][2 * r] = a;  // P^T
+          st[nt][2 * r + 1] = b;
+          f2_unpack(f2_mul(f2_pack(a, b), f2_add(f2_pack(dpt[nt][2 * r], dpt[nt][2 * r + 1]), nd)), dpt[nt][2 * r],
+                    dpt[nt][2 * r + 1]);  // dS^T (unscaled), in place
         }
       }
     }
-    mma_p_x_tile<2>(dv, st, sdO, c0, g_lo, g_hi, lane);
-    mma_p_x_tile<2>(dk, dpt, sQ, c0, g_lo, g_hi, lane);
+    mma_p_x_tile<2>(dv, st, sdO, c0, FULL ? 0 : g_lo, FULL ? 2 : g_hi, lane);
+    mma_p_x_tile<2>(dk, dpt, sQ, c0, FULL ? 0 : g_lo, FULL ? 2 : g_hi, lane);
+  };
+  for (int c0 = q_first & ~31; c0 < L; c0 += 32) {
+    const int g_lo = max(0, (q_first - c0) >> 4);
+    const int g_hi = min(2, (L - c0 + 15) >> 4);
+    const bool need_mask = (c0 + 32 > L) || (CAUSAL && c0 < k0 + row0 + 15);
+    if (g_lo == 0 && g_hi == 2 && !need_mask) chunk(std::true_type{}, c0, 0, 2);
+    else chunk(std::false_type{}, c0, g_lo, g_hi);
   }
   bf16* out = dqkv + seq_row * ld + h * DH;
   store_rows_bf16(dk, scale, scale, smem, 0, row0, out + d, ld, k0 + row0, L, lane);
@@ -752,9 +806,11 @@ static int pick_warps(int L) {
     const char* e = getenv("MUDPT_ATTN_WARPS");
     forced = e ? atoi(e) : 0;
   }
-  int nw = forced > 0 ? forced : (L <= 128 ? 2 : 4);
-  if (nw > 4) nw = 4;
-  return tiles >= nw ? nw : tiles;
+  if (forced > 0) return forced > 8 ? 8 : (tiles >= forced ? forced : tiles);
+  // as few CTAs per (sequence, head) as 8-warp CTAs allow, rows spread evenly: 199 tokens = 13 tiles ->
+  // 2 CTAs of 7 warps (each K/V tile is then loaded twice instead of four times)
+  const int ctas = (tiles + 7) / 8;
+  return (tiles + ctas - 1) / ctas;
 }
 
 // L <= 128: the single-pass kernels (MUDPT_ATTN_SHORT=0 forces the generic ones; tuning / A-B aid)
