@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ 
   const uint32_t sQ = smem_u32(smem), sK = sQ + BQ * ROW_BYTES, sV = sK + Lp * ROW_BYTES;
   const int ld = 3 * d;
   const bf16* base = qkv + static_cast<size_t>(s) * L * ld + h * DH;
+  pdl_wait();
+  pdl_trigger();
   load_tile(sQ, base, ld, q0, L, BQ);
   load_tile(sK, base + d, ld, 0, L, kv_rows);
   load_tile(sV, base + 2 * d, ld, 0, L, kv_rows);
@@ -283,6 +285,8 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_dq_kernel(const bf16* __restr
   const int ld = 3 * d;
   const size_t seq_row = static_cast<size_t>(s) * L;
   const bf16* base = qkv + seq_row * ld + h * DH;
+  pdl_wait();
+  pdl_trigger();
   load_tile(sQ, base, ld, q0, L, BQ);
   load_tile(sdO, d_o + seq_row * d + h * DH, d, q0, L, BQ);
   load_tile(sO, o + seq_row * d + h * DH, d, q0, L, BQ);
@@ -393,6 +397,8 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_dkv_kernel(const bf16* __rest
   const size_t seq_row = static_cast<size_t>(s) * L;
   const bf16* base = qkv + seq_row * ld + h * DH;
   const int q_blk = CAUSAL ? (k0 & ~15) : 0;  // queries below the block's first key never see it
+  pdl_wait();
+  pdl_trigger();
   load_tile(sK, base + d, ld, k0, L, BKV);
   load_tile(sV, base + 2 * d, ld, k0, L, BKV);
   load_tile(sQ + q_blk * ROW_BYTES, base, ld, q_blk, L, Lp - q_blk);
@@ -581,6 +587,8 @@ __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, false)) attn_s
   const uint32_t sQ = smem_u32(smem), sK = sQ + Lp * ROW_BYTES, sV = sK + Lp * ROW_BYTES;
   const int ld = 3 * d;
   const bf16* base = qkv + static_cast<size_t>(s) * L * ld + h * DH;
+  pdl_wait();
+  pdl_trigger();
   load_tile(sQ, base, ld, 0, L, Lp);
   load_tile(sK, base + d, ld, 0, L, Lp);
   load_tile(sV, base + 2 * d, ld, 0, L, Lp);
@@ -682,6 +690,8 @@ __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, true)) attn_sh
   const int ld = 3 * d;
   const size_t seq_row = static_cast<size_t>(s) * L;
   const bf16* base = qkv + seq_row * ld + h * DH;
+  pdl_wait();
+  pdl_trigger();
   load_tile(sQ, base, ld, 0, L, Lp);
   load_tile(sdO, d_o + seq_row * d + h * DH, d, 0, L, Lp);
   load_tile(sK, base + d, ld, 0, L, Lp);
@@ -844,7 +854,7 @@ const char* attention_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L, i
 #define MUDPT_LAUNCH_FWD(C, MT)                                                                        \
   do {                                                                                                 \
     if ((es = set_smem(attn_short_fwd_kernel<C, MT>, sm))) return es;                                  \
-    attn_short_fwd_kernel<C, MT><<<S * H, tiles * 32, sm, stream>>>(qkv, o, lse2, L, H, d, sl2);       \
+    launch_pdl(attn_short_fwd_kernel<C, MT>, dim3(S * H), dim3(tiles * 32), sm, stream, qkv, o, lse2, L, H, d, sl2); \
   } while (0)
     if (causal) { if (tiles <= 2) MUDPT_LAUNCH_FWD(true, 2); else if (tiles <= 5) MUDPT_LAUNCH_FWD(true, 5); else MUDPT_LAUNCH_FWD(true, 8); }
     else { if (tiles <= 2) MUDPT_LAUNCH_FWD(false, 2); else if (tiles <= 5) MUDPT_LAUNCH_FWD(false, 5); else MUDPT_LAUNCH_FWD(false, 8); }
@@ -858,10 +868,10 @@ const char* attention_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L, i
   const char* e;
   if (causal) {
     if ((e = set_smem(attn_fwd_kernel<true>, smem))) return e;
-    attn_fwd_kernel<true><<<grid, nw * 32, smem, stream>>>(qkv, o, lse2, L, H, d, sl2);
+    launch_pdl(attn_fwd_kernel<true>, grid, dim3(nw * 32), smem, stream, qkv, o, lse2, L, H, d, sl2);
   } else {
     if ((e = set_smem(attn_fwd_kernel<false>, smem))) return e;
-    attn_fwd_kernel<false><<<grid, nw * 32, smem, stream>>>(qkv, o, lse2, L, H, d, sl2);
+    launch_pdl(attn_fwd_kernel<false>, grid, dim3(nw * 32), smem, stream, qkv, o, lse2, L, H, d, sl2);
   }
   count_launch(1);
   return launch_status("attention fwd launch failed");
@@ -879,7 +889,7 @@ const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const
 #define MUDPT_LAUNCH_BWD(C, MT)                                                                                  \
   do {                                                                                                           \
     if ((es = set_smem(attn_short_bwd_kernel<C, MT>, sm))) return es;                                            \
-    attn_short_bwd_kernel<C, MT><<<S * H, tiles * 32, sm, stream>>>(qkv, o, d_o, lse2, dqkv, L, H, d, sc, sl2s); \
+    launch_pdl(attn_short_bwd_kernel<C, MT>, dim3(S * H), dim3(tiles * 32), sm, stream, qkv, o, d_o, lse2, dqkv, L, H, d, sc, sl2s); \
   } while (0)
     if (causal) { if (tiles <= 2) MUDPT_LAUNCH_BWD(true, 2); else if (tiles <= 5) MUDPT_LAUNCH_BWD(true, 5); else MUDPT_LAUNCH_BWD(true, 8); }
     else { if (tiles <= 2) MUDPT_LAUNCH_BWD(false, 2); else if (tiles <= 5) MUDPT_LAUNCH_BWD(false, 5); else MUDPT_LAUNCH_BWD(false, 8); }
@@ -896,13 +906,13 @@ const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const
   if (causal) {
     if ((e = set_smem(attn_bwd_dq_kernel<true>, smem_q))) return e;
     if ((e = set_smem(attn_bwd_dkv_kernel<true>, smem_kv))) return e;
-    attn_bwd_dq_kernel<true><<<grid, nw * 32, smem_q, stream>>>(qkv, o, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
-    attn_bwd_dkv_kernel<true><<<grid, nw * 32, smem_kv, stream>>>(qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
+    launch_pdl(attn_bwd_dq_kernel<true>, grid, dim3(nw * 32), smem_q, stream, qkv, o, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
+    launch_pdl(attn_bwd_dkv_kernel<true>, grid, dim3(nw * 32), smem_kv, stream, qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
   } else {
     if ((e = set_smem(attn_bwd_dq_kernel<false>, smem_q))) return e;
     if ((e = set_smem(attn_bwd_dkv_kernel<false>, smem_kv))) return e;
-    attn_bwd_dq_kernel<false><<<grid, nw * 32, smem_q, stream>>>(qkv, o, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
-    attn_bwd_dkv_kernel<false><<<grid, nw * 32, smem_kv, stream>>>(qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
+    launch_pdl(attn_bwd_dq_kernel<false>, grid, dim3(nw * 32), smem_q, stream, qkv, o, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
+    launch_pdl(attn_bwd_dkv_kernel<false>, grid, dim3(nw * 32), smem_kv, stream, qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
   }
   count_launch(2);
   return launch_status("attention bwd launch failed");

@@ -21,6 +21,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Kernels launched with launch_pdl() (launch_count.h) may be scheduled while the previous kernel of
+// the stream is still draining: everything before pdl_wait() (barrier init, TMEM allocation, tensor-map
+// prefetch, index math) overlaps that tail and the launch latency; pdl_wait() returns once the previous
+// grid has completed and its writes are visible, so no global memory may be touched before it.
+// pdl_trigger() then lets the NEXT kernel of the stream start being scheduled (it blocks in its own
+// pdl_wait() until this grid is done).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -411,6 +411,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   if constexpr (TWO) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -698,13 +701,15 @@ static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, cons
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = TWO ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // the kernel calls pdl_wait() after its prologue
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   if (cudaLaunchKernelEx(&cfg, kern, ta, tb, te[0], te[1], te[2], ep, M, N, K) != cudaSuccess) return launch_status("gemm kernel launch failed");
   count_launch();
   return launch_status("gemm kernel launch failed");

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (row >= M) return;
   const float* xr = x + static_cast<size_t>(row) * d;
   float4 v[NV];
@@ -79,8 +81,8 @@ template <int NV>
 static void launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
                           float eps, cudaStream_t stream) {
   const int grid = (M + 7) / 8;
-  if (out_bf16) ln_fwd_kernel<NV, true><<<grid, 256, 0, stream>>>(x, gamma, beta, out, M, d, eps);
-  else ln_fwd_kernel<NV, false><<<grid, 256, 0, stream>>>(x, gamma, beta, out, M, d, eps);
+  if (out_bf16) launch_pdl(ln_fwd_kernel<NV, true>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, out, M, d, eps);
+  else launch_pdl(ln_fwd_kernel<NV, false>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, out, M, d, eps);
 }
 
 const char* layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                                                      bf16* __restrict__ dx_bf16, int M, int d, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (row >= M) return;
   const size_t off = static_cast<size_t>(row) * d;
   float4 v[NV], g[NV];
@@ -180,8 +184,8 @@ template <int NV>
 static void launch_ln_bwd(const void* dy, bool dy_bf16, const float* x, const float* gamma, const float* resid, float* dx,
                           bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
   const int grid = (M + 7) / 8;
-  if (dy_bf16) ln_bwd_kernel<NV, true><<<grid, 256, 0, stream>>>(dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
-  else ln_bwd_kernel<NV, false><<<grid, 256, 0, stream>>>(dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
+  if (dy_bf16) launch_pdl(ln_bwd_kernel<NV, true>, dim3(grid), dim3(256), 0, stream, dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
+  else launch_pdl(ln_bwd_kernel<NV, false>, dim3(grid), dim3(256), 0, stream, dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
 }
 
 const char* layernorm_bwd(const void* dy, bool dy_bf16, const float* x, const float* gamma, const float* resid, float* dx,
@@ -203,6 +207,8 @@ const char* layernorm_bwd(const void* dy, bool dy_bf16, const float* x, const fl
 // x[s, row0 + r, :] = prompt[r, :] for every sequence s: the values are copied verbatim.
 __global__ void splice_fwd_kernel(float* __restrict__ x, const float* __restrict__ prompt, int L, int row0, int n, int d) {
   const int s = blockIdx.x, r = blockIdx.y;
+  pdl_wait();
+  pdl_trigger();
   float4* dst = reinterpret_cast<float4*>(x + (static_cast<size_t>(s) * L + row0 + r) * d);
   const float4* src = reinterpret_cast<const float4*>(prompt + static_cast<size_t>(r) * d);
   for (int c = threadIdx.x; c < d / 4; c += blockDim.x) dst[c] = src[c];
@@ -211,7 +217,7 @@ __global__ void splice_fwd_kernel(float* __restrict__ x, const float* __restrict
 const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, int n, int d, cudaStream_t stream) {
   if (S <= 0 || n <= 0) return nullptr;
   if (d % 4 != 0 || row0 < 0 || row0 + n > L) return "splice: bad geometry";
-  splice_fwd_kernel<<<dim3(S, n), 128, 0, stream>>>(x, prompt, L, row0, n, d);
+  launch_pdl(splice_fwd_kernel, dim3(S, n), dim3(128), 0, stream, x, prompt, L, row0, n, d);
   count_launch(1);
   return launch_status("splice fwd launch failed");
 }
@@ -232,6 +238,8 @@ __global__ void __launch_bounds__(256) splice_bwd_partial_kernel(float* __restri
   const int c = (blockIdx.y * 32 + lane) * 4;
   const int s_end = min(S, (slice + 1) * per_slice);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();
+  pdl_trigger();
   if (c < d) {
     for (int s = slice * per_slice + warp; s < s_end; s += 8) {
       const size_t off = (static_cast<size_t>(s) * L + row0 + r) * d + c;
@@ -257,6 +265,8 @@ __global__ void __launch_bounds__(256) splice_bwd_partial_kernel(float* __restri
 
 __global__ void splice_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__ dprompt, int nslices, int nd) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  pdl_wait();
+  pdl_trigger();
   if (i >= nd) return;
   float4 t = *reinterpret_cast<const float4*>(partial + i);
   for (int sl = 1; sl < nslices; ++sl) {
@@ -276,9 +286,9 @@ const char* splice_bwd(float* dx, bf16* dx_bf16, float* dprompt, float* workspac
   if (nslices > SPLICE_MAX_SLICES) nslices = SPLICE_MAX_SLICES;
   if (nslices < 1) nslices = 1;
   const int per_slice = (S + nslices - 1) / nslices;
-  splice_bwd_partial_kernel<<<dim3(n, (d + 127) / 128, nslices), 256, 0, stream>>>(dx, dx_bf16, workspace, S, L, row0, n, d,
-                                                                                   per_slice, zero_rows ? 1 : 0);
-  splice_bwd_final_kernel<<<(n * d / 4 + 127) / 128, 128, 0, stream>>>(workspace, dprompt, nslices, n * d);
+  launch_pdl(splice_bwd_partial_kernel, dim3(n, (d + 127) / 128, nslices), dim3(256), 0, stream, dx, dx_bf16, workspace, S, L,
+             row0, n, d, per_slice, zero_rows ? 1 : 0);
+  launch_pdl(splice_bwd_final_kernel, dim3((n * d / 4 + 127) / 128), dim3(128), 0, stream, workspace, dprompt, nslices, n * d);
   count_launch(2);
   return launch_status("splice bwd launch failed");
 }
