@@ -148,16 +148,19 @@ __device__ __forceinline__ uint32_t unit_slot(int lane, int j) {  // byte offset
   return static_cast<uint32_t>(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
 }
 
-// QuickGELU'(h) = s (1 + 1.702 h (1 - s)), s = sigmoid(1.702 h); with u = 0.851 h, t = tanh(u):
-//   = 0.5 (1 + t + u (1 - t^2))   -- one MUFU and three packed FMAs per pair
-__device__ __forceinline__ f32x2 quick_gelu_grad2(f32x2 h) {
-  const f32x2 u = f2_mul(h, f2_pack(0.851f, 0.851f));
-  float u0, u1;
-  f2_unpack(u, u0, u1);
-  const f32x2 t = f2_pack(tanh_approx(u0), tanh_approx(u1));
-  const f32x2 w = f2_fma(f2_mul(t, f2_pack(-1.f, -1.f)), t, f2_pack(1.f, 1.f));  // 1 - t^2
-  const f32x2 p = f2_fma(u, w, t);
-  return f2_fma(p, f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));
+// v * QuickGELU'(h), QuickGELU'(h) = s (1 + 1.702 h (1 - s)), s = sigmoid(1.702 h); with a = 0.851 h, t = tanh(a):
+//   QuickGELU'(h) = 0.5 (1 + t + a (1 - t^2)) = 0.5 + 0.5 p,  p = t + (-a)(t^2 - 1)
+// one MUFU and six packed fp32 ops per pair
+__device__ __forceinline__ f32x2 mul_quick_gelu_grad2(f32x2 v, f32x2 h) {
+  const f32x2 a = f2_mul(h, f2_pack(0.851f, 0.851f));
+  const f32x2 na = f2_mul(h, f2_pack(-0.851f, -0.851f));
+  float a0, a1;
+  f2_unpack(a, a0, a1);
+  const f32x2 t = f2_pack(tanh_approx(a0), tanh_approx(a1));
+  const f32x2 w = f2_fma(t, t, f2_pack(-1.f, -1.f));  // t^2 - 1
+  const f32x2 p = f2_fma(na, w, t);
+  const f32x2 vh = f2_mul(v, f2_pack(0.5f, 0.5f));
+  return f2_fma(vh, p, vh);
 }
 // QuickGELU(v) = v sigmoid(1.702 v) = 0.5 v + 0.5 v tanh(0.851 v)
 __device__ __forceinline__ f32x2 quick_gelu2(f32x2 v) {
@@ -244,9 +247,12 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = 8 * j + 2 * q;
-          const float4 b4 = bv[e >> 2];
-          const f32x2 bb = (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
-          o[q] = pack_bf16_2(f2_add(f2_pack_u(r[e], r[e + 1]), bb));
+          f32x2 v = f2_pack_u(r[e], r[e + 1]);
+          if (has_bias) {  // (dgrad GEMMs have none: warp-uniform)
+            const float4 b4 = bv[e >> 2];
+            v = f2_add(v, (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y));
+          }
+          o[q] = pack_bf16_2(v);
         }
         *reinterpret_cast<uint4*>(u + unit_slot(lane, j)) = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -297,11 +303,13 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = 8 * j + 2 * q;
-          const float4 b4 = bv[e >> 2];
-          const f32x2 bb = (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
-          const f32x2 v = f2_add(f2_pack_u(r[e], r[e + 1]), bb);
+          f32x2 v = f2_pack_u(r[e], r[e + 1]);
+          if (has_bias) {  // (dgrad GEMMs have none: warp-uniform)
+            const float4 b4 = bv[e >> 2];
+            v = f2_add(v, (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y));
+          }
           const f32x2 h = f2_pack_u(hw[q] << 16, hw[q] & 0xffff0000u);  // bf16 pair -> fp32 pair
-          o[q] = pack_bf16_2(f2_mul(v, quick_gelu_grad2(h)));
+          o[q] = pack_bf16_2(mul_quick_gelu_grad2(v, h));
         }
         *slot = make_uint4(o[0], o[1], o[2], o[3]);
       }
