@@ -66,12 +66,34 @@ class ResidualAttentionBlock_MuDPT(nn.Module):
         raise NotImplementedError("blocks run fused inside the native tower (mudpt_vision_forward / mudpt_text_forward)")
 
 
+class ResidualAttentionBlock(nn.Module):
+    """Plain block (clip/model.py:178-199): the cfg=None CLIP that CoCoOp builds on (trainers/cocoop.py:34)."""
+
+    def __init__(self, d_model: int, n_head: int, attn_mask: torch.Tensor = None):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, d_model * 4)),
+            ("gelu", QuickGELU()),
+            ("c_proj", nn.Linear(d_model * 4, d_model)),
+        ]))
+        self.ln_2 = LayerNorm(d_model)
+        self.attn_mask = attn_mask
+
+    def forward(self, x):  # pragma: no cover
+        raise NotImplementedError("blocks run fused inside the native tower (mudpt_vision_forward / mudpt_text_forward)")
+
+
 class Transformer(nn.Module):
     def __init__(self, width: int, layers: int, heads: int, attn_mask: torch.Tensor = None, prompt_depth: int = 0,
                  is_text_layer: bool = False, cfg=None):
         super().__init__()
         self.width, self.layers, self.heads = width, layers, heads
-        if cfg is None or cfg.TRAINER.NAME != "MuDPT":
+        if cfg is None:  # clip/model.py:436-437
+            self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
+            return
+        if cfg.TRAINER.NAME != "MuDPT":
             raise NotImplementedError(f"{getattr(getattr(cfg, 'TRAINER', None), 'NAME', None)} is not implemented")
         self.resblocks = nn.Sequential(*[
             ResidualAttentionBlock_MuDPT(width, heads, attn_mask, i, is_text_layer, cfg=cfg) for i in range(layers)])
@@ -116,6 +138,32 @@ class VisionTransformer_MuDPT(nn.Module):
         return feats, text_prompts
 
 
+class VisionTransformer(nn.Module):
+    """Plain ViT tower without image prompts (clip/model.py:443-496, cfg=None): same parameter names;
+    forward(x) -> image features through the native tower (no trainable tensor inside: forward only)."""
+
+    def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int, output_dim: int, cfg=None):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.output_dim = output_dim
+        self.conv1 = nn.Conv2d(in_channels=3, out_channels=width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.img_prompt_depth, self.img_prompt = 0, False
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads, cfg=None)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._owner = None
+
+    def forward(self, x: torch.Tensor):
+        engine = self._owner().engine(x.device)
+        empty = torch.zeros(engine.depth, 0, self.conv1.weight.shape[0], device=x.device, dtype=torch.float32)
+        with torch.no_grad():  # the tower is frozen and carries no prompts: nothing to differentiate
+            return engine.vision_forward(x, empty)
+
+
 class CLIP(nn.Module):
     def __init__(self, embed_dim: int, image_resolution: int, vision_layers: int, vision_width: int,
                  vision_patch_size: int, context_length: int, vocab_size: int, transformer_width: int,
@@ -123,18 +171,19 @@ class CLIP(nn.Module):
         super().__init__()
         if isinstance(vision_layers, (tuple, list)):
             raise NotImplementedError("ModifiedResNet towers are outside the MuDPT ViT hot path")
-        if cfg is None or cfg.TRAINER.NAME != "MuDPT":
-            raise NotImplementedError("only cfg.TRAINER.NAME == 'MuDPT' is implemented")
+        if cfg is not None and cfg.TRAINER.NAME != "MuDPT":
+            raise NotImplementedError("only cfg.TRAINER.NAME == 'MuDPT' and the plain cfg=None model are implemented")
         self.context_length = context_length
         self.arch = dict(embed_dim=embed_dim, image_resolution=image_resolution, vision_layers=vision_layers,
                          vision_width=vision_width, vision_patch_size=vision_patch_size, context_length=context_length,
                          vocab_size=vocab_size, transformer_width=transformer_width, transformer_heads=transformer_heads,
                          transformer_layers=transformer_layers)
-        self.n_ctx = _cfg_get(cfg, "N_CTX")
-        self.depth = _cfg_get(cfg, "DEEP_PROMPT_DEPTH")
-        self.visual = VisionTransformer_MuDPT(input_resolution=image_resolution, patch_size=vision_patch_size,
-                                              width=vision_width, layers=vision_layers, heads=vision_width // 64,
-                                              output_dim=embed_dim, cfg=cfg)
+        # cfg=None: plain towers (clip/model.py:742-750) -> a native handle without spliced prompts
+        self.n_ctx = _cfg_get(cfg, "N_CTX") if cfg is not None else 0
+        self.depth = _cfg_get(cfg, "DEEP_PROMPT_DEPTH") if cfg is not None else 1
+        vit = VisionTransformer_MuDPT if cfg is not None else VisionTransformer
+        self.visual = vit(input_resolution=image_resolution, patch_size=vision_patch_size, width=vision_width,
+                          layers=vision_layers, heads=vision_width // 64, output_dim=embed_dim, cfg=cfg)
         self.transformer = Transformer(width=transformer_width, layers=transformer_layers, heads=transformer_heads,
                                        attn_mask=None, is_text_layer=True, cfg=cfg)
         self.vocab_size = vocab_size

@@ -500,7 +500,7 @@ int mudpt_text_forward(mudpt_handle* h, const float* prompts, int32_t splice_lay
 }
 
 int mudpt_text_backward(mudpt_handle* h, const float* d_f_txt, float* d_prompts, float* d_x0, void* stream) {
-  if (!h || !d_f_txt || !d_prompts) return fail(h, "mudpt_text_backward: null argument");
+  if (!h || !d_f_txt || (!d_prompts && h->cfg.n_ctx > 0)) return fail(h, "mudpt_text_backward: null argument");
   Tower& t = h->txt;
   if (!t.fwd_done) return fail(h, "mudpt_text_backward: no forward pass to differentiate");
   cudaSetDevice(h->cfg.device);

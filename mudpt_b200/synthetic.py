@@ -239,3 +239,50 @@ def assemble_state_dict(arch: Arch, tokenized_prompts: torch.Tensor, n_ctx: int,
     sd["mudpt_prompt_learner.token_prefix"] = e[:, :1, :].clone()
     sd["mudpt_prompt_learner.token_suffix"] = e[:, 1 + n_ctx:, :].clone()
     return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# CoCoOp (BASELINE config 4, trainers/cocoop.py): plain CLIP towers + an instance-conditioned prompt learner
+# ------------------------------------------------------------------------------------------------
+
+def synthetic_cocoop_params(arch: Arch, n_ctx: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """ctx (random branch, trainers/cocoop.py:90-93) and the meta-net Linear(vis_dim, vis_dim // 16) ->
+    ReLU -> Linear(vis_dim // 16, ctx_dim) (:99-103), torch default init ranges."""
+    r = _Rng(seed + 15485863)
+    dt, e = arch.transformer_width, arch.embed_dim
+    hid = e // 16
+    return {
+        "ctx_random": r.normal((n_ctx, dt), 0.02),
+        "meta_net.linear1.weight": r.uniform((hid, e), e ** -0.5), "meta_net.linear1.bias": r.uniform((hid,), e ** -0.5),
+        "meta_net.linear2.weight": r.uniform((dt, hid), hid ** -0.5), "meta_net.linear2.bias": r.uniform((dt,), hid ** -0.5),
+    }
+
+
+def assemble_cocoop_state_dict(arch: Arch, tokenized_prompts: torch.Tensor, n_ctx: int, ctx_init_tokens=None,
+                               seed: int = 0, clip_sd=None) -> Dict[str, torch.Tensor]:
+    """Flat fp32 state dict under the reference CoCoOp `CustomCLIP.state_dict()` names
+    (`image_encoder.*`, `text_encoder.*`, `prompt_learner.*`, `logit_scale`; trainers/cocoop.py:166-174)."""
+    clip_sd = clip_sd if clip_sd is not None else synthetic_clip_state_dict(arch, seed)
+    pp = synthetic_cocoop_params(arch, n_ctx, seed)
+    emb = clip_sd["token_embedding.weight"]
+    sd: Dict[str, torch.Tensor] = {}
+    for k, v in clip_sd.items():
+        if k.startswith("visual."):
+            sd["image_encoder." + k[len("visual."):]] = v
+        elif k.startswith("transformer.") or k in ("positional_embedding", "ln_final.weight", "ln_final.bias",
+                                                   "text_projection"):
+            sd["text_encoder." + k] = v
+        elif k == "logit_scale":
+            sd[k] = v
+    for k, v in pp.items():
+        if k != "ctx_random":
+            sd["prompt_learner." + k] = v
+    if ctx_init_tokens is not None:
+        ids = torch.as_tensor(ctx_init_tokens).long().flatten()
+        sd["prompt_learner.ctx"] = emb[ids[1:1 + n_ctx]].clone()
+    else:
+        sd["prompt_learner.ctx"] = pp["ctx_random"]
+    e = emb[tokenized_prompts.long()]
+    sd["prompt_learner.token_prefix"] = e[:, :1, :].clone()
+    sd["prompt_learner.token_suffix"] = e[:, 1 + n_ctx:, :].clone()
+    return sd

@@ -116,12 +116,80 @@ def run_case(name: str, spec: dict, out_dir: str) -> None:
           f"({os.path.getsize(path)/1e6:.2f} MB, {time.time()-t0:.1f}s)")
 
 
+COCOOP_CASES = {
+    # BASELINE config 4 (CoCoOp-style instance-conditioned prompts), small shapes
+    "cocoop_tiny_a": dict(arch="tiny", n_ctx=4, ctx_init="a photo of a",
+                          classnames=["cat", "airplane model", "class 12", "x", "very long bird name here"], batch=3, kind="noise"),
+    "cocoop_tiny_b": dict(arch="tiny2", n_ctx=2, ctx_init="",
+                          classnames=["class 0", "class 1", "dog", "sun flower"], batch=2, kind="colour"),
+}
+
+
+def run_cocoop_case(name: str, spec: dict, out_dir: str) -> None:
+    """Unmodified reference trainers/cocoop.py CustomCLIP on the plain (cfg=None) reference CLIP."""
+    clip_pkg, clip_model_mod, _ = ref_shims.import_reference()
+    ref_cocoop = ref_shims.import_reference_cocoop()
+    arch = syn.ARCHS[spec["arch"]]
+    cfg = ref_shims.make_cfg(n_ctx=spec["n_ctx"], depth=1, ctx_init=spec["ctx_init"], size=arch.image_resolution, name="CoCoOp")
+    t0 = time.time()
+    clip_model = clip_model_mod.CLIP(*arch.astuple(), None).float()
+    clip_sd = syn.synthetic_clip_state_dict(arch, seed=0)
+    clip_model.load_state_dict(clip_sd, strict=True)
+    model = ref_cocoop.CustomCLIP(cfg, spec["classnames"], clip_model)
+    pp = syn.synthetic_cocoop_params(arch, spec["n_ctx"], seed=0)
+    pl = model.prompt_learner
+    with torch.no_grad():
+        for k in ("linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"):
+            getattr(getattr(pl.meta_net, k.split(".")[0]), k.split(".")[1]).copy_(pp["meta_net." + k])
+        if not spec["ctx_init"]:
+            pl.ctx.copy_(pp["ctx_random"])
+    for n, p in model.named_parameters():   # freeze rule, trainers/cocoop.py:221-225
+        if "prompt_learner" not in n:
+            p.requires_grad_(False)
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert len(trainable) == 5, trainable
+    tokenized = model.tokenized_prompts.clone()
+    ctx_tokens = clip_pkg.tokenize(spec["ctx_init"].replace("_", " "))[0] if spec["ctx_init"] else None
+    mine = syn.assemble_cocoop_state_dict(arch, tokenized, pl.n_ctx, ctx_tokens, seed=0, clip_sd=clip_sd)
+    ref_sd = model.state_dict()
+    assert set(mine) == set(ref_sd), (set(mine) ^ set(ref_sd))
+    for k in ref_sd:
+        assert torch.equal(mine[k], ref_sd[k]), k
+    image = syn.synthetic_images(spec["batch"], arch.image_resolution, seed=1, kind=spec["kind"])
+    labels = syn.synthetic_labels(spec["batch"], len(spec["classnames"]), seed=1)
+    model.train()
+    model.zero_grad()
+    loss = model(image, labels)     # trainers/cocoop.py:262 (training branch returns the cross-entropy, :195-196)
+    loss.backward()
+    model.eval()
+    with torch.no_grad():
+        logits = model(image)
+    out = {
+        "arch": np.array(spec["arch"]), "n_ctx": np.array(pl.n_ctx), "batch": np.array(spec["batch"]), "kind": np.array(spec["kind"]),
+        "classnames": np.array(spec["classnames"]), "has_ctx_init": np.array(bool(spec["ctx_init"])),
+        "ctx_init": np.array(spec["ctx_init"]),
+        "ctx_init_tokens": (ctx_tokens.numpy() if ctx_tokens is not None else np.zeros(0, np.int32)),
+        "tokenized_prompts": tokenized.numpy().astype(np.int32), "labels": labels.numpy(),
+        "logits": logits.numpy(), "loss": loss.detach().numpy(),
+    }
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            out["grad/" + n] = p.grad.numpy()
+    path = os.path.join(out_dir, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: loss={float(loss.detach()):.6f} logits{tuple(logits.shape)} -> {path} "
+          f"({os.path.getsize(path)/1e6:.2f} MB, {time.time()-t0:.1f}s)")
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    which = sys.argv[1:] or list(CASES)
+    which = sys.argv[1:] or (list(CASES) + list(COCOOP_CASES))
     for name in which:
-        run_case(name, CASES[name], out_dir)
+        if name in COCOOP_CASES:
+            run_cocoop_case(name, COCOOP_CASES[name], out_dir)
+        else:
+            run_case(name, CASES[name], out_dir)
 
 
 if __name__ == "__main__":

@@ -67,3 +67,51 @@ def build_model(case, device="cuda"):
         if "prompt_learner" not in n:
             p.requires_grad_("visual_ctx" in n)
     return model.to(device), cfg
+
+
+COCOOP = ["cocoop_tiny_a", "cocoop_tiny_b"]
+
+
+def load_cocoop(name):
+    """CoCoOp fixture (BASELINE config 4) made from the reference's trainers/cocoop.py."""
+    if name in _cache:
+        return _cache[name]
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    arch = syn.ARCHS[str(g["arch"])]
+    n_ctx, batch = int(g["n_ctx"]), int(g["batch"])
+    tok = torch.from_numpy(g["tokenized_prompts"])
+    ctx_tokens = torch.from_numpy(g["ctx_init_tokens"]) if bool(g["has_ctx_init"]) else None
+    sd = syn.assemble_cocoop_state_dict(arch, tok, n_ctx, ctx_tokens, seed=0)
+    image = syn.synthetic_images(batch, arch.image_resolution, seed=1, kind=str(g["kind"]))
+    case = dict(arch=arch, n_ctx=n_ctx, batch=batch, sd=sd, tokenized=tok, image=image, labels=torch.from_numpy(g["labels"]),
+                golden=g, classnames=[str(c) for c in g["classnames"]], ctx_init=str(g["ctx_init"]))
+    _cache[name] = case
+    return case
+
+
+def make_cocoop_cfg(n_ctx, ctx_init, size, arch_name="ViT-B/16"):
+    cfg = make_cfg(n_ctx, 1, ctx_init, size, arch_name)
+    cfg.TRAINER["NAME"] = "CoCoOp"
+    cfg.TRAINER["COCOOP"] = type(cfg)(N_CTX=n_ctx, CTX_INIT=ctx_init, PREC="fp32")
+    return cfg
+
+
+def build_cocoop_model(case, device="cuda"):
+    """mudpt_b200 CoCoOp CustomCLIP carrying exactly the golden case's weights (token ids from the fixture)."""
+    from mudpt_b200 import clip
+    from mudpt_b200.trainers.cocoop import CustomCLIP
+    g, arch = case["golden"], case["arch"]
+    ctx_init = case["ctx_init"]
+    cfg = make_cocoop_cfg(case["n_ctx"], ctx_init, arch.image_resolution)
+    prefix = ctx_init if ctx_init else " ".join(["X"] * case["n_ctx"])
+    table = {prefix + " " + n.replace("_", " ") + ".": case["tokenized"][i:i + 1] for i, n in enumerate(case["classnames"])}
+    if ctx_init:
+        table[ctx_init] = torch.from_numpy(g["ctx_init_tokens"]).view(1, -1)
+    clip_model = clip.CLIP(*arch.astuple(), None).float()
+    model = CustomCLIP(cfg, case["classnames"], clip_model, tokenizer=lambda s: table[s])
+    model.load_state_dict(case["sd"], strict=True)
+    for n, p in model.named_parameters():
+        if "prompt_learner" not in n:
+            p.requires_grad_(False)
+    return model.to(device), cfg

@@ -226,3 +226,74 @@ def test_inference_with_cached_text_features_gpu():
     assert torch.equal(cached, again)
     assert float((cached - full).abs().max()) == 0.0
     assert float((cached.cpu() - torch.from_numpy(c["golden"]["logits"])).abs().max()) <= 0.05
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4: CoCoOp (instance-conditioned prompts, B x C text sequences) on the shared kernels
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", gu.COCOOP)
+def test_cocoop_vs_reference_golden(name):
+    """mudpt_b200.trainers.cocoop.CustomCLIP against the output of the reference's trainers/cocoop.py:
+    loss, logits and the gradients of the 5 trainable tensors (ctx + meta-net)."""
+    from oracle import mudpt_oracle as orc
+    c = gu.load_cocoop(name)
+    g = c["golden"]
+    model, _ = gu.build_cocoop_model(c, "cuda")
+    image, labels = c["image"].cuda(), c["labels"].cuda()
+    model.train()
+    model.zero_grad(set_to_none=True)
+    loss = model(image, labels)
+    loss.backward()
+    model.eval()
+    with torch.no_grad():
+        logits = model(image)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(g["loss"])) <= 0.02
+    assert float((logits.cpu() - torch.from_numpy(g["logits"])).abs().max()) <= 0.05
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            m = orc.metrics(p.grad.cpu(), torch.from_numpy(g["grad/" + n]))
+            assert m["cos"] >= 0.999 and m["rel_l2"] <= 0.05, (n, m)
+
+
+def test_cocoop_cfg4_shape_properties():
+    """Config-4-shaped run (ViT-B/16, B = 2 images x C = 1000 classes = 2000 text sequences in one native
+    text-tower pass) through size-independent properties: the batched pass equals per-image passes (the
+    reference's loop, trainers/cocoop.py:187-192), the step is deterministic, gradients are finite."""
+    from mudpt_b200 import clip, synthetic as syn
+    from mudpt_b200.trainers.cocoop import CustomCLIP
+    arch = syn.ARCHS["ViT-B/16"]
+    cfg = gu.make_cocoop_cfg(4, "a photo of a", 224)
+    torch.manual_seed(0)
+    clip_model = clip.CLIP(*arch.astuple(), None).float()
+    clip_model.load_state_dict(syn.synthetic_clip_state_dict(arch, 0), strict=False)
+    model = CustomCLIP(cfg, syn.synthetic_classnames(1000), clip_model, tokenizer=syn.synthetic_tokenize)
+    for n, p in model.named_parameters():
+        if "prompt_learner" not in n:
+            p.requires_grad_(False)
+    model = model.cuda()
+    image = syn.synthetic_images(2, 224, seed=1).cuda()
+    label = syn.synthetic_labels(2, 1000, seed=1).cuda()
+    model.train()
+    model.zero_grad(set_to_none=True)
+    loss1 = model(image, label)
+    loss1.backward()
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
+    model.zero_grad(set_to_none=True)
+    loss2 = model(image, label)
+    loss2.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss1) and abs(float(loss1) - math.log(1000)) < 1.0
+    assert float(loss1) == float(loss2)
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            assert torch.equal(g1[n], p.grad), n
+            assert torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0, n
+    model.eval()
+    with torch.no_grad():
+        both = model(image)
+        one = torch.cat([model(image[i:i + 1]) for i in range(2)])
+    # not bitwise: the meta-net Linear (torch, fp32) picks a different library algorithm for 1 and 2 rows,
+    # and 1e-7 differences in the shifted ctx flip bf16 roundings inside the tower (logit tolerance as above)
+    assert float((both - one).abs().max()) <= 0.02

@@ -73,3 +73,45 @@ def test_oracle_matches_live_reference():
         if p.requires_grad:
             m = orc.metrics(res["grads"][n], p.grad)
             assert m["cos"] > 0.99999, (n, m)
+
+
+# ---------------------------------------------------------------------------------------------
+# CoCoOp (BASELINE config 4): oracle/cocoop_oracle.py against the reference's trainers/cocoop.py
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", gu.COCOOP)
+def test_cocoop_oracle_matches_reference_golden(name):
+    from oracle import cocoop_oracle as co
+    c = gu.load_cocoop(name)
+    g = c["golden"]
+    res = co.forward_backward(c["sd"], c["image"], c["tokenized"], c["labels"])
+    np.testing.assert_allclose(res["logits"].numpy(), g["logits"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(float(res["loss"]), float(g["loss"]), rtol=1e-5, atol=1e-5)
+    for k in co.TRAINABLE:
+        m = orc.metrics(res["grads"][k], torch.from_numpy(g["grad/" + k]))
+        assert m["cos"] > 0.99999 and m["rel_l2"] < 2e-3, (k, m)
+
+
+@pytest.mark.needs_reference
+def test_cocoop_oracle_matches_live_reference():
+    from oracle import cocoop_oracle as co, ref_shims
+    from mudpt_b200 import synthetic as syn
+    _, clip_model_mod, _ = ref_shims.import_reference()
+    ref_cocoop = ref_shims.import_reference_cocoop()
+    arch = syn.ARCHS["tiny"]
+    cfg = ref_shims.make_cfg(n_ctx=3, depth=1, ctx_init="", size=arch.image_resolution, name="CoCoOp")
+    torch.manual_seed(11)
+    clip_model = clip_model_mod.CLIP(*arch.astuple(), None).float()
+    model = ref_cocoop.CustomCLIP(cfg, ["dog", "class 7", "small red bird"], clip_model)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    image = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    labels = torch.tensor([2, 0])
+    model.train()
+    loss = model(image, labels)
+    loss.backward()
+    res = co.forward_backward(sd, image, model.tokenized_prompts, labels)
+    np.testing.assert_allclose(float(res["loss"]), float(loss.detach()), rtol=1e-5, atol=1e-5)
+    for k in co.TRAINABLE:
+        p = dict(model.named_parameters())[k]
+        m = orc.metrics(res["grads"][k], p.grad)
+        assert m["cos"] > 0.99999, (k, m)
