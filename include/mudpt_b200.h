@@ -135,6 +135,17 @@ int mudpt_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, 
 int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream);
 int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream);
 
+/* ---- fused SGD step over the (small) trainable tensors -----------------------------------------
+ * One launch for all tensors, torch.optim.SGD semantics (what Dassl's build_optimizer creates for
+ * the yaml's OPTIM.NAME = "sgd", configs/trainers/MuDPT/*.yaml:15-22; called from
+ * model_backward_and_update, trainers/mudpt.py:251):
+ *   d = g + weight_decay * p;  buf = first_step ? d : momentum * buf + (1 - dampening) * d;
+ *   d = nesterov ? d + momentum * buf : buf;  p -= lr * d          (momentum == 0: p -= lr * d, buf unused)
+ * params / grads / bufs: host arrays of n device pointers (fp32, contiguous), numel: host array. n <= 32. */
+int mudpt_sgd_step(void* const* params, const void* const* grads, void* const* bufs, const int64_t* numel, int32_t n,
+                   float lr, float momentum, float dampening, float weight_decay, int32_t nesterov, int32_t first_step,
+                   void* stream);
+
 /* ---- introspection for tests / profiling --------------------------------------------------------
  * name in {"x_in","x_mid","qkv","o","h","lse","dx"}; layer ignored for "dx". */
 int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t layer, void** ptr, int64_t* numel);

@@ -47,6 +47,8 @@ SIGNATURES = {
                                   C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_im2col": (C.c_int, [c_f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_cast_bf16": (C.c_int, [c_f32p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mudpt_sgd_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                 C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_debug_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mudpt_profile_begin": (C.c_int, [C.c_void_p]),
     "mudpt_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),

@@ -606,6 +606,15 @@ int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream)
   return 0;
 }
 
+int mudpt_sgd_step(void* const* params, const void* const* grads, void* const* bufs, const int64_t* numel, int32_t n,
+                   float lr, float momentum, float dampening, float weight_decay, int32_t nesterov, int32_t first_step,
+                   void* stream) {
+  if (!params || !grads || !numel || (momentum != 0.f && !bufs)) return fail(nullptr, "mudpt_sgd_step: null argument");
+  CKG(sgd_step(params, grads, bufs, reinterpret_cast<const long long*>(numel), n, lr, momentum, dampening, weight_decay,
+               nesterov != 0, first_step != 0, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t layer, void** ptr, int64_t* numel) {
   if (!h || !name || !ptr || !numel) return fail(h, "mudpt_debug_buffer: null argument");
   Tower& t = tower == MUDPT_TOWER_VISION ? h->vis : h->txt;

@@ -266,4 +266,61 @@ const char* logits_head_bwd(const float* f_img, const float* f_txt, const float*
   return launch_status("logits head bwd launch failed");
 }
 
+
+// ------------------------------------------------------------------ fused SGD step
+struct SgdTable {
+  float* p[SGD_MAX_TENSORS];
+  const float* g[SGD_MAX_TENSORS];
+  float* b[SGD_MAX_TENSORS];
+  long long n[SGD_MAX_TENSORS];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) sgd_step_kernel(const SgdTable t, float lr, float momentum, float dampening, float wd,
+                                                       int nesterov, int first_step) {
+  for (int k = blockIdx.y; k < t.count; k += gridDim.y) {
+    float* __restrict__ p = t.p[k];
+    const float* __restrict__ g = t.g[k];
+    float* __restrict__ b = t.b[k];
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < t.n[k];
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const float pv = p[i];
+      float d = g[i];
+      if (wd != 0.f) d = d + wd * pv;  // torch: d_p.add(p, alpha=wd)
+      if (momentum != 0.f) {
+        float bv;
+        if (first_step) bv = d;  // buf = clone(d_p)
+        else bv = b[i] * momentum + (1.f - dampening) * d;  // buf.mul_(momentum).add_(d_p, alpha=1-dampening)
+        b[i] = bv;
+        d = nesterov ? d + momentum * bv : bv;
+      }
+      p[i] = pv + (-lr) * d;  // p.add_(d_p, alpha=-lr)
+    }
+  }
+}
+
+const char* sgd_step(void* const* params, const void* const* grads, void* const* bufs, const long long* numel, int n, float lr,
+                     float momentum, float dampening, float weight_decay, bool nesterov, bool first_step, cudaStream_t stream) {
+  if (n <= 0) return nullptr;
+  if (n > SGD_MAX_TENSORS) return "sgd_step: too many tensors";
+  SgdTable t;
+  long long mx = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!params[i] || !grads[i] || (momentum != 0.f && !bufs[i])) return "sgd_step: null tensor";
+    t.p[i] = static_cast<float*>(params[i]);
+    t.g[i] = static_cast<const float*>(grads[i]);
+    t.b[i] = static_cast<float*>(bufs ? bufs[i] : nullptr);
+    t.n[i] = numel[i];
+    if (numel[i] > mx) mx = numel[i];
+  }
+  t.count = n;
+  long long bx = (mx + 255) / 256;
+  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx < 1) bx = 1;
+  sgd_step_kernel<<<dim3(static_cast<unsigned>(bx), n), 256, 0, stream>>>(t, lr, momentum, dampening, weight_decay, nesterov ? 1 : 0,
+                                                                         first_step ? 1 : 0);
+  count_launch(1);
+  return launch_status("sgd step launch failed");
+}
+
 }  // namespace mudpt

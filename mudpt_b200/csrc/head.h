@@ -18,4 +18,10 @@ const char* logits_head(const float* f_img, const float* f_txt, const long long*
                         cudaStream_t stream);
 const char* logits_head_bwd(const float* f_img, const float* f_txt, const float* dlogits, float scale, int B, int C, int e,
                             float* ws, float* d_f_img, float* d_f_txt, cudaStream_t stream);
+
+// fused multi-tensor SGD (torch.optim.SGD semantics); pointer arrays live on the host
+static constexpr int SGD_MAX_TENSORS = 32;
+const char* sgd_step(void* const* params, const void* const* grads, void* const* bufs, const long long* numel, int n, float lr,
+                     float momentum, float dampening, float weight_decay, bool nesterov, bool first_step, cudaStream_t stream);
+
 }  // namespace mudpt

@@ -86,9 +86,15 @@ except Exception:  # pragma: no cover - exercised on boxes without dassl
                     s.step()
 
     def build_optimizer(model, optim_cfg):
+        """Dassl's SGD defaults (momentum 0.9, weight decay 5e-4); on a CUDA model the update runs as one
+        native multi-tensor launch (mudpt_b200.optim.FusedSGD, same torch.optim.SGD semantics and state)."""
         params = [p for p in model.parameters() if p.requires_grad]
-        return torch.optim.SGD(params, lr=getattr(optim_cfg, "LR", 0.0025), momentum=getattr(optim_cfg, "MOMENTUM", 0.9),
-                               weight_decay=getattr(optim_cfg, "WEIGHT_DECAY", 5e-4))
+        kw = dict(lr=getattr(optim_cfg, "LR", 0.0025), momentum=getattr(optim_cfg, "MOMENTUM", 0.9),
+                  weight_decay=getattr(optim_cfg, "WEIGHT_DECAY", 5e-4))
+        if params and all(p.is_cuda for p in params) and os.environ.get("MUDPT_FUSED_SGD", "1") == "1":
+            from ..optim import FusedSGD
+            return FusedSGD(params, **kw)
+        return torch.optim.SGD(params, **kw)
 
     def build_lr_scheduler(optim, optim_cfg):
         return torch.optim.lr_scheduler.CosineAnnealingLR(optim, float(getattr(optim_cfg, "MAX_EPOCH", 10)))

@@ -297,3 +297,29 @@ def test_cocoop_cfg4_shape_properties():
     # not bitwise: the meta-net Linear (torch, fp32) picks a different library algorithm for 1 and 2 rows,
     # and 1e-7 differences in the shifted ctx flip bf16 roundings inside the tower (logit tolerance as above)
     assert float((both - one).abs().max()) <= 0.02
+
+
+def test_fused_sgd_matches_torch_sgd():
+    """mudpt_sgd_step (one launch for all trainable tensors) against torch.optim.SGD with Dassl's
+    defaults and with nesterov / dampening variants, over several steps (momentum buffer carried in state)."""
+    from mudpt_b200.optim import FusedSGD
+    torch.manual_seed(0)
+    shapes = [(2, 512), (8, 2, 512), (768, 512), (768,), (2, 768), (8, 2, 768), (512, 768), (512,), (33,), (5, 7)]
+    for kw in (dict(lr=0.0025, momentum=0.9, weight_decay=5e-4), dict(lr=0.01, momentum=0.8, weight_decay=0.0, nesterov=True),
+               dict(lr=0.02, momentum=0.0, weight_decay=1e-3), dict(lr=0.01, momentum=0.5, dampening=0.3, weight_decay=1e-4)):
+        ref = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+        mine = [p.detach().clone().requires_grad_(True) for p in ref]
+        o_ref, o_mine = torch.optim.SGD(ref, **kw), FusedSGD(mine, **kw)
+        for step in range(4):
+            for a, b in zip(ref, mine):
+                g = torch.randn_like(a)
+                a.grad, b.grad = g.clone(), g.clone()
+            o_ref.step()
+            o_mine.step()
+        torch.cuda.synchronize()
+        for a, b in zip(ref, mine):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), (kw, float((a - b).abs().max()))
+            if kw["momentum"]:
+                assert torch.allclose(o_ref.state[a]["momentum_buffer"], o_mine.state[b]["momentum_buffer"], rtol=1e-6, atol=1e-7)
+        if kw["momentum"]:
+            assert set(o_mine.state_dict()["state"][0]) == set(o_ref.state_dict()["state"][0])
