@@ -16,6 +16,7 @@ autograd, which is what delivers the gradients of the 10 trainable tensors.
 """
 from __future__ import annotations
 
+import math
 import os
 import os.path as osp
 from typing import List, Optional, Tuple
@@ -229,6 +230,7 @@ class CustomCLIP(nn.Module):
         self._replicas_synced = False       # trainable tensors broadcast from rank 0 once (replicated state)
         # fused train step: vision tower on a side stream next to the text tower (see forward_backward)
         self.overlap_towers = os.environ.get("MUDPT_OVERLAP_TOWERS", "1") != "0"
+        self._loss_host, self._loss_event, self._loss_pending = None, None, False
 
     # ------------------------------------------------------------------ helpers
     def _engine(self, device):
@@ -291,18 +293,24 @@ class CustomCLIP(nn.Module):
         """Fused train step: forward, mean cross-entropy over the GLOBAL batch (F.cross_entropy of
         trainers/mudpt.py:250 under nn.DataParallel semantics) and backward into the .grad of the 10
         trainable tensors.  Returns (loss, logits).  Gradients are all-reduced across ranks."""
-        device = image.device
+        host_batch = image.device.type == "cpu" and self.logit_scale.device.type == "cuda"
+        device = self.logit_scale.device if host_batch else image.device
         eng = self._engine(device)
         self._register_classes(device)
         world = mdist.world_size() if self.shard_classes else 1
         P_v, P_t = self.prompt_stacks()
         n_cls = self.mudpt_prompt_learner.n_cls
-        image = image.type(self.dtype)
+        if host_batch and not self.overlap_towers:
+            image, label = image.to(device), label.to(device)
+            host_batch = False
+        if not host_batch:
+            image = image.type(self.dtype)
         if not self.overlap_towers or device.type != "cuda":  # (CPU: only the gloo tests' stand-in engine)
             f_img = eng.vision_forward(image, P_v.detach())
             f_txt_loc = eng.text_forward(P_t.detach(), True)
             f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
             logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True)
+            loss = self._publish_loss(loss, world)
             d_t_loc = mdist.reduce_scatter_rows(d_t, n_cls) if world > 1 else d_t
             dP_t, _ = eng.text_backward(d_t_loc)
             dP_v = eng.vision_backward(d_i)
@@ -316,12 +324,20 @@ class CustomCLIP(nn.Module):
             side = eng.side_stream()
             side.wait_stream(main)  # P_v, image are ready
             with torch.cuda.stream(side):
+                if host_batch:
+                    # host (pinned) batch: the upload runs on the vision stream, so the text tower -- which does
+                    # not need the images -- starts at once and hides the PCIe copy (19 MB, ~0.8 ms)
+                    image = image.to(device, non_blocking=True).type(self.dtype)
+                    label = label.to(device, non_blocking=True)
                 f_img = eng.vision_forward(image, P_v.detach())
             f_txt_loc = eng.text_forward(P_t.detach(), True)
             f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
             main.wait_stream(side)
             f_img.record_stream(main)
+            if host_batch:
+                label.record_stream(main)
             logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True)
+            loss = self._publish_loss(loss, world)
             side.wait_stream(main)  # d_i
             with torch.cuda.stream(side):
                 dP_v = eng.vision_backward(d_i)
@@ -333,8 +349,29 @@ class CustomCLIP(nn.Module):
         torch.autograd.backward([P_v, P_t], [dP_v, dP_t])
         if world > 1:
             mdist.all_reduce_grads([p for p in self.parameters() if p.requires_grad])
-            loss = mdist.all_reduce_sum(loss)
         return loss, logits
+
+    def _publish_loss(self, loss, world):
+        """Global loss right after the head: all-reduce across ranks, then an asynchronous copy into pinned host
+        memory + an event, so that the trainer can read the value (loss_value()) while the backward is still
+        running instead of draining the stream with loss.item()."""
+        if world > 1:
+            loss = mdist.all_reduce_sum(loss)
+        if loss.is_cuda:
+            if self._loss_host is None:
+                self._loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+                self._loss_event = torch.cuda.Event()
+            self._loss_host.copy_(loss, non_blocking=True)
+            self._loss_event.record(torch.cuda.current_stream(loss.device))
+            self._loss_pending = True
+        return loss
+
+    def loss_value(self) -> float:
+        """Python float of the last fused step's loss; waits only for the head, not for the backward."""
+        if not self._loss_pending:
+            raise RuntimeError("loss_value(): no fused step has been run")
+        self._loss_event.synchronize()
+        return float(self._loss_host)
 
     @torch.no_grad()
     def cache_text_features(self, device=None):
@@ -395,15 +432,26 @@ class MuDPT(TrainerX):
         self.scaler = None  # "amp" needs no loss scaling here: bf16 operands, fp32 accumulation and master state
 
     def forward_backward(self, batch):
-        image, label = self.parse_batch_train(batch)
         if os.environ.get("MUDPT_FUSED_STEP", "1") == "1":
-            # fused loss + backward in the native head; same update as model_backward_and_update(loss)
+            # fused loss + backward in the native head; same update as model_backward_and_update(loss).
+            # Host batches go in as they are: the fused step uploads them on its vision stream
+            # (parse_batch_train's blocking .to(device) would put the PCIe copy on the critical path).
+            image, label = batch["img"], batch["label"]
+            if not (image.device.type == "cpu" and self.device.type == "cuda"):
+                image, label = self.parse_batch_train(batch)
             self.optim.zero_grad()
             loss, _ = self.model.forward_backward(image, label)
-            if not torch.isfinite(loss).all():
+            # the loss value is on the host as soon as the head has run (the backward is still in flight):
+            # same check-before-update order as model_backward_and_update, without draining the stream
+            loss_value = self.model.loss_value() if loss.is_cuda else float(loss)
+            if not math.isfinite(loss_value):
                 raise FloatingPointError("Loss is infinite or NaN!")
             self.optim.step()
+            if (self.batch_idx + 1) == self.num_batches:
+                self.update_lr()
+            return {"loss": loss_value}
         else:
+            image, label = self.parse_batch_train(batch)
             output = self.model(image)
             loss = F.cross_entropy(output, label)
             self.model_backward_and_update(loss)
