@@ -236,8 +236,12 @@ def group_attention(res):
     dev = torch.device("cuda")
     st = _lib.stream_ptr(dev)
     torch.manual_seed(2)
-    for (S, L, H, causal) in [(3, 199, 12, 0), (5, 77, 8, 1), (7, 9, 8, 1), (4, 16, 2, 1), (2, 64, 1, 0), (2, 259, 16, 0),
-                              (3, 7, 2, 0), (2, 130, 2, 1)]:
+    shapes = [(3, 199, 12, 0), (5, 77, 8, 1), (7, 9, 8, 1), (4, 16, 2, 1), (2, 64, 1, 0), (2, 259, 16, 0),
+              (3, 7, 2, 0), (2, 130, 2, 1)]
+    # tile-boundary lengths of the short-sequence kernels (1 / 2 / 5 / 8 tiles, both masks) and the first
+    # lengths that fall back to the generic ones
+    shapes += [(2, L, 2, c) for L in (2, 15, 17, 31, 32, 33, 48, 79, 80, 81, 96, 127, 128, 129, 144) for c in (0, 1)]
+    for (S, L, H, causal) in shapes:
         d = H * 64
         qkv = torch.randn(S * L, 3 * d, device=dev).bfloat16()
         o = torch.zeros(S * L, d, device=dev, dtype=torch.bfloat16)

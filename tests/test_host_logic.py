@@ -100,3 +100,34 @@ def test_error_conventions():
     bad.TRAINER.NAME = "VPT"
     with pytest.raises(NotImplementedError):  # clip/model.py:433-434
         clip.CLIP(*a.astuple(), bad)
+
+
+def test_cocoop_containers_match_reference_names():
+    """BASELINE config 4: the plain (cfg=None) CLIP containers and the CoCoOp CustomCLIP expose the reference's
+    parameter / buffer names (trainers/cocoop.py:166-174; freeze rule :221-225 -> 5 trainable tensors)."""
+    from tests import golden_util as gu
+    c = gu.load_cocoop("cocoop_tiny_b")
+    model, _ = gu.build_cocoop_model(c, "cpu")
+    assert set(model.state_dict()) == set(c["sd"])
+    trainable = sorted(n for n, p in model.named_parameters() if p.requires_grad)
+    assert trainable == sorted(["prompt_learner.ctx", "prompt_learner.meta_net.linear1.weight", "prompt_learner.meta_net.linear1.bias",
+                                "prompt_learner.meta_net.linear2.weight", "prompt_learner.meta_net.linear2.bias"])
+    import torch
+    prompts = model.prompt_learner(torch.randn(3, c["arch"].embed_dim))
+    assert tuple(prompts.shape) == (3, len(c["classnames"]), 77, c["arch"].transformer_width)
+    # same prompts as the reference's per-image construct_prompts loop (trainers/cocoop.py:156-162)
+    pl = model.prompt_learner
+    bias = pl.meta_net(torch.zeros(1, c["arch"].embed_dim))
+    ctx_i = (pl.ctx.unsqueeze(0) + bias.unsqueeze(1)).expand(pl.n_cls, -1, -1)
+    ref0 = pl.construct_prompts(ctx_i, pl.token_prefix, pl.token_suffix)
+    assert torch.equal(model.prompt_learner(torch.zeros(1, c["arch"].embed_dim))[0], ref0)
+
+
+def test_fused_sgd_has_no_cpu_fallback():
+    import pytest
+    import torch
+    from mudpt_b200.optim import FusedSGD
+    p = torch.nn.Parameter(torch.randn(4))
+    p.grad = torch.randn(4)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        FusedSGD([p], lr=0.1, momentum=0.9).step()
