@@ -43,7 +43,13 @@ static constexpr int EPI_WARPS = 8;
 // boxes to the TMA (store; for GELU' also the load of the saved pre-activation) through 2 KB
 // 64B-swizzled staging units: ~1/3 of the instructions of the transposing epilogue below, which the
 // fp32-output modes still use (their boxes would be twice as large and they are HBM-bound anyway).
-template <int MODE> struct RowEpi { static constexpr bool value = (MODE == EPI_BF16 || MODE == EPI_GELU || MODE == EPI_GELU_BWD); };
+template <int MODE> struct RowEpi { static constexpr bool value = (MODE != EPI_PATCH && MODE != 6 /*EPI_RESID_DEEP*/); };
+// internal variant of EPI_RESID_F32 for long-K GEMMs (c_proj, K >= 1024): these keep the transposing epilogue
+// (coalesced residual loads straight from global memory, 6 operand stages) -- measured 134 us against 139 us for
+// the row-layout / TMA version, whose gain is the short-K out-proj (93 -> 78 us)
+static constexpr int EPI_RESID_DEEP = 6;
+template <int MODE> struct F32Epi { static constexpr bool value = (MODE == EPI_F32 || MODE == EPI_RESID_F32 || MODE == EPI_RESID_DEEP); };
+template <int MODE> struct ResidEpi { static constexpr bool value = (MODE == EPI_RESID_F32 || MODE == EPI_RESID_DEEP); };
 static constexpr int kUnitBytes = 32 * 64;  // 32 rows x 32 bf16, SWIZZLE_64B
 static constexpr int kMaxSmem = 227 * 1024;
 
@@ -55,7 +61,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTxBytes = TWO ? 2 * kStageBytes : kStageBytes;  // credited to the leader's barrier
   // staging per epilogue warp: one 4 KB transpose buffer, or 2 (4 for the two-output c_fc) TMA units
-  static constexpr int kUnitsPerWarp = (MODE == EPI_GELU) ? 4 : 2;
+  // fp32 outputs: a 32-column box is 4 KB (two units), double-buffered
+  static constexpr int kUnitsPerWarp = (MODE == EPI_GELU || (F32Epi<MODE>::value && MODE != EPI_RESID_DEEP)) ? 4 : 2;
   static constexpr int kWarpStaging = RowEpi<MODE>::value ? kUnitsPerWarp * kUnitBytes : 32 * 32 * 4;
   static constexpr int kStagingBytes = EPI_WARPS * kWarpStaging;
   static constexpr int kBarBytes = 512;
@@ -211,13 +218,20 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
       int row, col0;
       box_origin(pf_tile, row, col0);
       uint64_t* bar = &ex_bar[pf_k & 1];
-      mbar_expect_tx(bar, kUnitBytes);
-      tma_load_2d(units + (pf_k & 1) * kUnitBytes, tma_ex, bar, col0 + pf_b * 32, row);
+      if constexpr (ResidEpi<MODE>::value) {  // fp32 residual: one 32 x 32 fp32 box (128 B rows, 4 KB = two units)
+        constexpr uint32_t kBufMask = MODE == EPI_RESID_DEEP ? 0u : 1u;
+        bar = &ex_bar[pf_k & kBufMask];
+        mbar_expect_tx(bar, 2 * kUnitBytes);
+        tma_load_2d(units + (pf_k & kBufMask) * 2 * kUnitBytes, tma_ex, bar, col0 + pf_b * 32, row);
+      } else {
+        mbar_expect_tx(bar, kUnitBytes);
+        tma_load_2d(units + (pf_k & 1) * kUnitBytes, tma_ex, bar, col0 + pf_b * 32, row);
+      }
       ++pf_k;
       return;
     }
   };
-  if constexpr (MODE == EPI_GELU_BWD) {
+  if constexpr (MODE == EPI_GELU_BWD || MODE == EPI_RESID_F32) {
     if (lane == 0) prefetch_next();
   }
 
@@ -287,6 +301,44 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
         tma_store_2d(tma_o1, ug, col, row);
         bulk_commit();  // both stores of the box form one group
       }
+    } else if constexpr (F32Epi<MODE>::value) {
+      // out0 (fp32) = acc + bias (+ residual): the box is 32 rows x 128 B (two units, 128B TMA swizzle); the residual
+      // is TMA-loaded into it one box ahead and rewritten in place (out-proj / c_proj, clip/model.py:299-300)
+      constexpr uint32_t kBufMask = MODE == EPI_RESID_DEEP ? 0u : 1u;
+      uint8_t* u = units + (k & kBufMask) * 2 * kUnitBytes;
+      if constexpr (ResidEpi<MODE>::value) {
+        if (lane == 0) {
+          // double-buffered: the other buffer's stores (previous box) have been read, it is refilled for the next
+          // box; single-buffered (DEEP): this box's own residual is requested now
+          bulk_wait_read<0>();
+          prefetch_next();
+        }
+        mbar_wait(&ex_bar[k & kBufMask], (MODE == EPI_RESID_DEEP ? k : (k >> 1)) & 1);  // this box's residual has landed
+      } else {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4* slot = reinterpret_cast<uint4*>(u + lane * 128 + ((j ^ (lane & 7)) << 4));  // 128B swizzle
+        f32x2 v0 = f2_pack_u(r[4 * j], r[4 * j + 1]), v1 = f2_pack_u(r[4 * j + 2], r[4 * j + 3]);
+        if (has_bias) {
+          v0 = f2_add(v0, f2_pack(bv[j].x, bv[j].y));
+          v1 = f2_add(v1, f2_pack(bv[j].z, bv[j].w));
+        }
+        if constexpr (ResidEpi<MODE>::value) {
+          const uint4 rq = *slot;
+          v0 = f2_add(v0, f2_pack_u(rq.x, rq.y));
+          v1 = f2_add(v1, f2_pack_u(rq.z, rq.w));
+        }
+        uint4 o;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(o.x), "=r"(o.y) : "l"(v0));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(o.z), "=r"(o.w) : "l"(v1));
+        *slot = o;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(tma_o0, u, col, row); bulk_commit(); }
     } else {  // EPI_GELU_BWD
       uint8_t* u = units + (k & 1) * kUnitBytes;
       if (lane == 0) {
@@ -500,7 +552,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     //            instruction covers whole 128 B (fp32) / 64 B (bf16) row segments of 4 rows.
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    uint8_t* stage = smem_stage + (warp - 2) * 4096;
+    uint8_t* stage = smem_stage + (warp - 2) * Cfg::kWarpStaging;
     const int rr0 = lane >> 3, j = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -508,8 +560,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     for (int tile = unit; tile < num_tiles; tile += unit_stride) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       const int m_row0 = m_blk * TM + static_cast<int>(rank) * BM;  // first row of this CTA's accumulator
-      typedef typename EpiExtra<MODE>::type Ex;
-      constexpr bool kHasExtra = (MODE == EPI_RESID_F32 || MODE == EPI_GELU_BWD || MODE == EPI_PATCH);
+      constexpr int OM = (MODE == EPI_RESID_DEEP) ? EPI_RESID_F32 : MODE;  // epilogue math of the transposing path
+      typedef typename EpiExtra<OM>::type Ex;
+      constexpr bool kHasExtra = (OM == EPI_RESID_F32 || OM == EPI_GELU_BWD || OM == EPI_PATCH);
       constexpr bool kDouble = (MODE == EPI_GELU_BWD);  // packed operand: cheap enough to prefetch a chunk ahead
       const int ncol = N - n_blk * BN;  // valid columns in this tile (may exceed BN)
       const int row_base = m_row0 + quad * 32 + rr0;
@@ -519,7 +572,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         const int col = min(n_blk * BN + chunk * 32 + 4 * j, N - 4);  // clamped: out-of-range lanes never use it
 #pragma unroll
         for (int it = 0; it < (kHasExtra ? 8 : 1); ++it)
-          dst[it] = epilogue_prefetch<MODE>(ep, min(row_base + it * 4, M - 1), col);
+          dst[it] = epilogue_prefetch<OM>(ep, min(row_base + it * 4, M - 1), col);
       };
       // the first chunk's operand loads are issued before waiting for the accumulator
       if constexpr (kHasExtra) { if (c * 32 < ncol) load_extra(ex, c); }
@@ -550,7 +603,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             const int row = m_row0 + quad * 32 + rr;
             float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + (((j ^ rr) & 7) << 4));
             v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-            if (row < M) epilogue4<MODE>(ep, row, col, v, ex[kHasExtra ? it : 0]);
+            if (row < M) epilogue4<OM>(ep, row, col, v, ex[kHasExtra ? it : 0]);
           }
         }
         __syncwarp();
@@ -628,9 +681,10 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols, ld, box_rows, box_cols;
+  const void* ptr; int rows, cols, ld, box_rows, box_cols, esize;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols &&
+           esize == o.esize;
   }
 };
 struct MapKeyHash {
@@ -641,16 +695,19 @@ struct MapKeyHash {
     h = h * 1000003u ^ static_cast<size_t>(k.ld);
     h = h * 1000003u ^ static_cast<size_t>(k.box_rows);
     h = h * 1000003u ^ static_cast<size_t>(k.box_cols);
+    h = h * 1000003u ^ static_cast<size_t>(k.esize);
     return h;
   }
 };
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 static std::mutex g_maps_mu;
 
-// 2D bf16 row-major [rows, cols] (leading dimension ld elements), box = [box_rows, box_cols]:
-// box_cols = 64 with 128B swizzle (MMA operand tiles) or 32 with 64B swizzle (epilogue boxes).
-static const char* get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMap* out) {
-  MapKey key{ptr, rows, cols, ld, box_rows, box_cols};
+// 2D row-major [rows, cols] (leading dimension ld elements), box = [box_rows, box_cols]: bf16 with box_cols = 64
+// and 128B swizzle (MMA operand tiles) or 32 and 64B swizzle (bf16 epilogue boxes); fp32 (esize 4) with box_cols = 32
+// and 128B swizzle (fp32 epilogue boxes).
+static const char* get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMap* out,
+                                  int esize = 2) {
+  MapKey key{ptr, rows, cols, ld, box_rows, box_cols, esize};
   std::lock_guard<std::mutex> lk(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return nullptr; }
@@ -659,11 +716,12 @@ static const char* get_tensor_map(const void* ptr, int rows, int cols, int ld, i
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) return "TMA operand must be 16 B aligned with ld % 8 == 0";
   CUtensorMap m;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const bool f32 = esize == 4;  // fp32 epilogue boxes (32 columns = 128 B rows); everything else is bf16
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = enc(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols * esize == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
   if (g_maps.size() > 4096) g_maps.clear();
@@ -729,7 +787,7 @@ static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, c
 #ifdef MUDPT_BRINGUP
   if (g_simt) {
     dim3 grid((N / 8 + 63) / 64, M);
-    gemm_tn_simt_kernel<MODE><<<grid, 64, 0, stream>>>(A, B, ep, M, N, K, lda, ldb);
+    gemm_tn_simt_kernel<(MODE == EPI_RESID_DEEP ? EPI_RESID_F32 : MODE)><<<grid, 64, 0, stream>>>(A, B, ep, M, N, K, lda, ldb);
     count_launch();
     return launch_status("simt gemm launch failed");
   }
@@ -758,7 +816,10 @@ static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, c
   if (e) return e;
   // epilogue boxes (row-layout modes): out0, out1, saved pre-activation; unused slots repeat the A map
   CUtensorMap te[3] = {ta, ta, ta};
-  if constexpr (RowEpi<MODE>::value) {
+  if constexpr (F32Epi<MODE>::value) {
+    if ((e = get_tensor_map(ep.out0, M, N, ep.ldc, 32, 32, &te[0], 4))) return e;
+    if (ResidEpi<MODE>::value && (e = get_tensor_map(ep.resid, M, N, ep.ldc, 32, 32, &te[2], 4))) return e;
+  } else if constexpr (RowEpi<MODE>::value) {
     if (ep.out0 != nullptr && (e = get_tensor_map(ep.out0, M, N, ep.ldc, 32, 32, &te[0]))) return e;
     if (MODE == EPI_GELU && (e = get_tensor_map(ep.out1, M, N, ep.ldc, 32, 32, &te[1]))) return e;
     if (MODE == EPI_GELU_BWD && (e = get_tensor_map(ep.aux, M, N, ep.ldc, 32, 32, &te[2]))) return e;
@@ -776,7 +837,9 @@ const char* gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, const G
   switch (ep.mode) {
     case EPI_BF16: return launch_mode<EPI_BF16>(A, lda, B, ldb, ep, M, N, K, stream);
     case EPI_F32: return launch_mode<EPI_F32>(A, lda, B, ldb, ep, M, N, K, stream);
-    case EPI_RESID_F32: return launch_mode<EPI_RESID_F32>(A, lda, B, ldb, ep, M, N, K, stream);
+    case EPI_RESID_F32:
+      return K >= 1024 ? launch_mode<EPI_RESID_DEEP>(A, lda, B, ldb, ep, M, N, K, stream)
+                       : launch_mode<EPI_RESID_F32>(A, lda, B, ldb, ep, M, N, K, stream);
     case EPI_GELU: return launch_mode<EPI_GELU>(A, lda, B, ldb, ep, M, N, K, stream);
     case EPI_GELU_BWD: return launch_mode<EPI_GELU_BWD>(A, lda, B, ldb, ep, M, N, K, stream);
     case EPI_PATCH: return launch_mode<EPI_PATCH>(A, lda, B, ldb, ep, M, N, K, stream);
