@@ -9,14 +9,17 @@
 // Replaces the `addmm`/`mm` call sites of clip/model.py:273 (in-proj), :299 (out-proj),
 // :300 (c_fc, c_proj), :527 (conv1 as a GEMM) and their autograd dgrads.
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads; CTA pairs in cta_group::2 mode):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles (128B swizzle) into a smem ring
-//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (128 x BN x 16), fp32
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (128|256 x BN x 16), fp32
 //                                accumulators in TMEM, double-buffered (2 x BN columns)
-//   warps 2..5  epilogue       : tcgen05.ld the accumulator, apply the fused epilogue
+//   warps 2..9  epilogue       : tcgen05.ld the accumulator, apply the fused epilogue
 //                                (bias / QuickGELU / residual / GELU' / patch-embed scatter),
-//                                store to global
-// The epilogue of tile i overlaps the MMAs of tile i+1 through the second TMEM buffer.
+//                                hand 32 x 32 boxes to the TMA (UTMASTG; residual / saved
+//                                pre-activation boxes arrive by UTMALDG one box ahead)
+// The epilogue of tile i overlaps the MMAs of tile i+1 through the second TMEM buffer.  The kernel
+// is launched with programmatic stream serialization: its prologue (barriers, TMEM allocation,
+// descriptor prefetch) overlaps the tail of the previous kernel (pdl_wait() in common.cuh).
 #include "gemm.h"
 
 #include <cstdio>
