@@ -321,6 +321,11 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
       }
+      uint4 rq8[ResidEpi<MODE>::value ? 8 : 1];
+      if constexpr (ResidEpi<MODE>::value) {  // read the whole residual row first (see the GELU' branch)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rq8[j] = *reinterpret_cast<const uint4*>(u + lane * 128 + ((j ^ (lane & 7)) << 4));
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint4* slot = reinterpret_cast<uint4*>(u + lane * 128 + ((j ^ (lane & 7)) << 4));  // 128B swizzle
@@ -330,7 +335,7 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
           v1 = f2_add(v1, f2_pack(bv[j].z, bv[j].w));
         }
         if constexpr (ResidEpi<MODE>::value) {
-          const uint4 rq = *slot;
+          const uint4 rq = rq8[j];
           v0 = f2_add(v0, f2_pack_u(rq.x, rq.y));
           v1 = f2_add(v1, f2_pack_u(rq.z, rq.w));
         }
@@ -349,11 +354,16 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
         prefetch_next();
       }
       mbar_wait(&ex_bar[k & 1], (k >> 1) & 1);  // this box's pre-activation has landed
+      // all four 16 B groups of the row are read before anything is written back: with a load per group the
+      // in-place store of group j would order the load of group j + 1 behind it (the compiler cannot prove the
+      // slots distinct) and serialise the four dependent chains
+      uint4 hq4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hq4[j] = *reinterpret_cast<const uint4*>(u + unit_slot(lane, j));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4* slot = reinterpret_cast<uint4*>(u + unit_slot(lane, j));
-        const uint4 hq = *slot;
-        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+        const uint32_t hw[4] = {hq4[j].x, hq4[j].y, hq4[j].z, hq4[j].w};
         uint32_t o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
