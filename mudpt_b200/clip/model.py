@@ -93,8 +93,9 @@ class Transformer(nn.Module):
         if cfg is None:  # clip/model.py:436-437
             self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
             return
-        if cfg.TRAINER.NAME != "MuDPT":
+        if cfg.TRAINER.NAME not in ("MuDPT", "UMuDPT", "UUMuDPT"):
             raise NotImplementedError(f"{getattr(getattr(cfg, 'TRAINER', None), 'NAME', None)} is not implemented")
+        # the UMuDPT / UUMuDPT blocks (clip/model.py:302-400) splice exactly like the MuDPT block (:275-301)
         self.resblocks = nn.Sequential(*[
             ResidualAttentionBlock_MuDPT(width, heads, attn_mask, i, is_text_layer, cfg=cfg) for i in range(layers)])
 
@@ -138,6 +139,103 @@ class VisionTransformer_MuDPT(nn.Module):
         return feats, text_prompts
 
 
+class LightTransformer(nn.Module):
+    """One plain block over the handful of prompt tokens (trainers/umudpt.py:56-79, clip/model.py:203-226): the only
+    part of the UMuDPT / UUMuDPT variants that is not a frozen tower.  [n_ctx x depth] tokens -- real torch modules
+    under autograd (this is trainable prompt algebra, like the three Linear layers of MuDPT)."""
+
+    def __init__(self, d_model: int, n_head: int, attn_mask: torch.Tensor = None):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = nn.LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, d_model * 4)),
+            ("gelu", _QuickGELUTorch()),
+            ("c_proj", nn.Linear(d_model * 4, d_model)),
+        ]))
+        self.ln_2 = nn.LayerNorm(d_model)
+        self.attn_mask = attn_mask
+
+    def forward(self, x: torch.Tensor):
+        a = self.ln_1(x)
+        x = x + self.attn(a, a, a, need_weights=False, attn_mask=self.attn_mask)[0]
+        return x + self.mlp(self.ln_2(x))
+
+
+class _QuickGELUTorch(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(1.702 * x)
+
+
+def _stack_with_ln_pre(vit, shared_ctx, deeper_prompts):
+    """[depth, n_ctx, width]: row block 0 = ln_pre(shared ctx) (the ctx rows are appended before ln_pre,
+    clip/model.py:578-581), blocks 1.. = the deep visual prompts."""
+    p0 = F.layer_norm(shared_ctx.float(), (shared_ctx.shape[-1],), vit.ln_pre.weight.float(), vit.ln_pre.bias.float(),
+                      vit.ln_pre.eps)
+    return torch.cat([p0, deeper_prompts.float()], dim=0)
+
+
+class VisionTransformer_UMuDPT(nn.Module):
+    """clip/model.py:556-597: no trainable tensor of its own; forward(x, shared_ctx [1,n,w], deeper [D-1,n,w])."""
+
+    def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int, output_dim: int, cfg=None):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.output_dim = output_dim
+        self.conv1 = nn.Conv2d(in_channels=3, out_channels=width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.deep_prompts_depth = _cfg_get(cfg, "DEEP_PROMPT_DEPTH")
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads, cfg=cfg)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._owner = None
+
+    def forward(self, x: torch.Tensor, shared_ctx, deeper_prompts):
+        engine = self._owner().engine(x.device)
+        return VisionTowerFn.apply(engine, x, _stack_with_ln_pre(self, shared_ctx, deeper_prompts))
+
+
+class VisionTransformer_UUMuDPT(nn.Module):
+    """clip/model.py:600-664: UMuDPT plus vision-side prompts and their LightTransformer -> text prompts."""
+
+    def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int, output_dim: int, cfg=None):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.output_dim = output_dim
+        self.conv1 = nn.Conv2d(in_channels=3, out_channels=width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.deep_prompts_depth = _cfg_get(cfg, "DEEP_PROMPT_DEPTH")
+        n_ctx = _cfg_get(cfg, "N_CTX")
+        self.visual_ctx = nn.Parameter(torch.empty(n_ctx, width).normal_(std=0.02))
+        self.visual_ctx_deep_prompts = nn.Parameter(torch.empty(self.deep_prompts_depth - 1, n_ctx, width).normal_(std=0.02))
+        self.visual_ctx_ln_intra_pre = nn.LayerNorm(width)
+        self.visual_ctx_self_attn = LightTransformer(d_model=width, n_head=width // 64)
+        self.visual_ctx_ln_intra_post = nn.LayerNorm(width)
+        self.visual_ctx_text_proj = nn.Linear(in_features=width, out_features=output_dim)
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads, cfg=cfg)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._owner = None
+
+    def textual_prompts(self):
+        t = self.visual_ctx_ln_intra_pre(self.visual_ctx_deep_prompts)
+        t = self.visual_ctx_self_attn(t.permute(1, 0, 2)).permute(1, 0, 2)
+        return self.visual_ctx_text_proj(self.visual_ctx_ln_intra_post(t))
+
+    def forward(self, x: torch.Tensor, shared_ctx, deeper_prompts):
+        engine = self._owner().engine(x.device)
+        shared = shared_ctx + self.visual_ctx.unsqueeze(0)
+        deeper = deeper_prompts + self.visual_ctx_deep_prompts
+        feats = VisionTowerFn.apply(engine, x, _stack_with_ln_pre(self, shared, deeper))
+        return feats, self.textual_prompts()
+
+
 class VisionTransformer(nn.Module):
     """Plain ViT tower without image prompts (clip/model.py:443-496, cfg=None): same parameter names;
     forward(x) -> image features through the native tower (no trainable tensor inside: forward only)."""
@@ -171,8 +269,8 @@ class CLIP(nn.Module):
         super().__init__()
         if isinstance(vision_layers, (tuple, list)):
             raise NotImplementedError("ModifiedResNet towers are outside the MuDPT ViT hot path")
-        if cfg is not None and cfg.TRAINER.NAME != "MuDPT":
-            raise NotImplementedError("only cfg.TRAINER.NAME == 'MuDPT' and the plain cfg=None model are implemented")
+        if cfg is not None and cfg.TRAINER.NAME not in ("MuDPT", "UMuDPT", "UUMuDPT"):
+            raise NotImplementedError("implemented: cfg.TRAINER.NAME in MuDPT / UMuDPT / UUMuDPT and the plain cfg=None model")
         self.context_length = context_length
         self.arch = dict(embed_dim=embed_dim, image_resolution=image_resolution, vision_layers=vision_layers,
                          vision_width=vision_width, vision_patch_size=vision_patch_size, context_length=context_length,
@@ -181,7 +279,8 @@ class CLIP(nn.Module):
         # cfg=None: plain towers (clip/model.py:742-750) -> a native handle without spliced prompts
         self.n_ctx = _cfg_get(cfg, "N_CTX") if cfg is not None else 0
         self.depth = _cfg_get(cfg, "DEEP_PROMPT_DEPTH") if cfg is not None else 1
-        vit = VisionTransformer_MuDPT if cfg is not None else VisionTransformer
+        vit = VisionTransformer if cfg is None else {"MuDPT": VisionTransformer_MuDPT, "UMuDPT": VisionTransformer_UMuDPT,
+                                                     "UUMuDPT": VisionTransformer_UUMuDPT}[cfg.TRAINER.NAME]
         self.visual = vit(input_resolution=image_resolution, patch_size=vision_patch_size, width=vision_width,
                           layers=vision_layers, heads=vision_width // 64, output_dim=embed_dim, cfg=cfg)
         self.transformer = Transformer(width=transformer_width, layers=transformer_layers, heads=transformer_heads,

@@ -286,3 +286,24 @@ def assemble_cocoop_state_dict(arch: Arch, tokenized_prompts: torch.Tensor, n_ct
     sd["prompt_learner.token_prefix"] = e[:, :1, :].clone()
     sd["prompt_learner.token_suffix"] = e[:, 1 + n_ctx:, :].clone()
     return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# UMuDPT / UUMuDPT: the trainable tensors are many small modules (LightTransformer, LayerNorms,
+# projections), so they are generated per NAME: both the reference model (oracle/make_golden.py) and the model
+# under test load `param_by_name(name, shape)` into every trainable tensor.
+# ------------------------------------------------------------------------------------------------
+
+def param_by_name(name: str, shape, seed: int = 0) -> torch.Tensor:
+    import zlib
+    r = _Rng((zlib.crc32(name.encode()) + 7919 * seed) % (2 ** 31))
+    shape = tuple(shape)
+    leaf = name.split(".")[-1]
+    is_ln = any(part.startswith("ln_") or "_ln_" in part for part in name.split(".")[:-1])
+    if len(shape) == 1:
+        if is_ln and leaf == "weight":
+            return 1.0 + r.normal(shape, 0.1)
+        return r.normal(shape, 0.05)
+    if "ctx" in leaf or "prompts" in leaf:
+        return r.normal(shape, 0.02)
+    return r.normal(shape, float(shape[-1]) ** -0.5)

@@ -181,12 +181,68 @@ def run_cocoop_case(name: str, spec: dict, out_dir: str) -> None:
           f"({os.path.getsize(path)/1e6:.2f} MB, {time.time()-t0:.1f}s)")
 
 
+VARIANT_CASES = {
+    # UMuDPT / UUMuDPT (LightTransformer-mixed prompts on the same towers)
+    "umudpt_tiny": dict(trainer="UMuDPT", arch="tiny", n_ctx=2, depth=3, ctx_init="a photo of a",
+                        classnames=["cat", "airplane model", "class 12", "x"], batch=3, kind="noise"),
+    "uumudpt_tiny": dict(trainer="UUMuDPT", arch="tiny", n_ctx=3, depth=2, ctx_init="",
+                         classnames=["class 0", "class 1", "dog", "sun flower", "y"], batch=2, kind="noise"),
+}
+
+
+def run_variant_case(name: str, spec: dict, out_dir: str) -> None:
+    """Unmodified reference trainers/{umudpt,uumudpt}.py CustomCLIP; every trainable tensor = syn.param_by_name."""
+    clip_pkg, clip_model_mod, _ = ref_shims.import_reference()
+    ref_mod = ref_shims.import_reference_variant(spec["trainer"])
+    arch = syn.ARCHS[spec["arch"]]
+    cfg = ref_shims.make_cfg(n_ctx=spec["n_ctx"], depth=spec["depth"], ctx_init=spec["ctx_init"], size=arch.image_resolution,
+                             name=spec["trainer"])
+    t0 = time.time()
+    clip_model = clip_model_mod.CLIP(*arch.astuple(), cfg).float()
+    clip_model.load_state_dict(syn.synthetic_clip_state_dict(arch, seed=0), strict=False)
+    model = ref_mod.CustomCLIP(cfg, spec["classnames"], clip_model)
+    keep_vis = spec["trainer"] == "UUMuDPT"
+    for n, p in model.named_parameters():   # trainers/umudpt.py:250-253, uumudpt.py:252-261
+        if "prompt_learner" not in n:
+            p.requires_grad_(keep_vis and "visual_ctx" in n)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.requires_grad and not (n.endswith("prompt_learner.ctx") and spec["ctx_init"]):
+                p.copy_(syn.param_by_name(n, p.shape, seed=0))
+    tokenized = model.tokenized_prompts.clone()
+    ctx_tokens = clip_pkg.tokenize(spec["ctx_init"].replace("_", " "))[0] if spec["ctx_init"] else None
+    image = syn.synthetic_images(spec["batch"], arch.image_resolution, seed=1, kind=spec["kind"])
+    labels = syn.synthetic_labels(spec["batch"], len(spec["classnames"]), seed=1)
+    model.zero_grad()
+    logits = model(image)
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+    out = {
+        "trainer": np.array(spec["trainer"]), "arch": np.array(spec["arch"]), "n_ctx": np.array(spec["n_ctx"]),
+        "depth": np.array(spec["depth"]), "batch": np.array(spec["batch"]), "kind": np.array(spec["kind"]),
+        "classnames": np.array(spec["classnames"]), "ctx_init": np.array(spec["ctx_init"]),
+        "ctx_init_tokens": (ctx_tokens.numpy() if ctx_tokens is not None else np.zeros(0, np.int32)),
+        "tokenized_prompts": tokenized.numpy().astype(np.int32), "labels": labels.numpy(),
+        "logits": logits.detach().numpy(), "loss": loss.detach().numpy(),
+        "state_keys": np.array(sorted(model.state_dict().keys())),
+    }
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            out["grad/" + n] = p.grad.numpy()
+    path = os.path.join(out_dir, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: loss={float(loss.detach()):.6f} logits{tuple(logits.shape)} trainable={sum(1 for k in out if k.startswith('grad/'))} "
+          f"-> {path} ({os.path.getsize(path)/1e6:.2f} MB, {time.time()-t0:.1f}s)")
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    which = sys.argv[1:] or (list(CASES) + list(COCOOP_CASES))
+    which = sys.argv[1:] or (list(CASES) + list(COCOOP_CASES) + list(VARIANT_CASES))
     for name in which:
-        if name in COCOOP_CASES:
+        if name in VARIANT_CASES:
+            run_variant_case(name, VARIANT_CASES[name], out_dir)
+        elif name in COCOOP_CASES:
             run_cocoop_case(name, COCOOP_CASES[name], out_dir)
         else:
             run_case(name, CASES[name], out_dir)

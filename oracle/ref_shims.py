@@ -48,6 +48,8 @@ def make_cfg(n_ctx: int = 2, depth: int = 9, ctx_init: str = "a photo of a",
     cfg.TRAINER.NAME = name
     cfg.TRAINER.MUDPT = CfgNode(N_CTX=n_ctx, CTX_INIT=ctx_init, DEEP_PROMPT_DEPTH=depth, PREC=prec)
     cfg.TRAINER.COCOOP = CfgNode(N_CTX=n_ctx, CTX_INIT=ctx_init, PREC=prec)  # trainers/cocoop.py:69-70
+    cfg.TRAINER.UMUDPT = CfgNode(N_CTX=n_ctx, CTX_INIT=ctx_init, DEEP_PROMPT_DEPTH=depth, PREC=prec)
+    cfg.TRAINER.UUMUDPT = CfgNode(N_CTX=n_ctx, CTX_INIT=ctx_init, DEEP_PROMPT_DEPTH=depth, PREC=prec)
     cfg.INPUT = CfgNode(SIZE=(size, size))
     cfg.MODEL = CfgNode(BACKBONE=CfgNode(NAME="ViT-B/16", PATH=""), INIT_WEIGHTS="")
     return cfg
@@ -107,6 +109,13 @@ def import_reference():
     clip_model = importlib.import_module("clip.model")
     ref_mudpt = importlib.import_module("trainers.mudpt")
     return clip_pkg, clip_model, ref_mudpt
+
+
+def import_reference_variant(name: str):
+    """The reference's trainers/umudpt.py or trainers/uumudpt.py, under the same shims."""
+    import importlib
+    import_reference()
+    return importlib.import_module("trainers." + name.lower())
 
 
 def import_reference_cocoop():

@@ -131,3 +131,45 @@ def test_fused_sgd_has_no_cpu_fallback():
     p.grad = torch.randn(4)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         FusedSGD([p], lr=0.1, momentum=0.9).step()
+
+
+def test_umudpt_uumudpt_containers_match_reference_names():
+    """same state-dict keys and trainable sets as the reference's UMuDPT / UUMuDPT CustomCLIP
+    (key lists recorded in the fixtures by oracle/make_golden.py from the reference itself)."""
+    from tests import golden_util as gu
+    for name in gu.VARIANTS:
+        c = gu.load_variant(name)
+        model, _ = gu.build_variant_model(c, "cpu")
+        assert sorted(model.state_dict().keys()) == [str(k) for k in c["golden"]["state_keys"]], name
+        trainable = sorted("grad/" + n for n, p in model.named_parameters() if p.requires_grad)
+        assert trainable == sorted(k for k in c["golden"] if k.startswith("grad/")), name
+
+
+def test_variant_prompt_algebra_matches_reference():
+    """The host-side prompt algebra of UMuDPT / UUMuDPT (LightTransformer mixing -> the two prompt stacks of the C ABI)
+    fed through the fp32 oracle towers reproduces the REFERENCE logits of the fixtures to fp32 round-off: whatever
+    the GPU tests then differ by is kernel numerics, not semantics."""
+    import torch
+    from mudpt_b200 import synthetic as syn
+    from oracle import mudpt_oracle as orc
+    from tests import golden_util as gu
+    for name in gu.VARIANTS:
+        c = gu.load_variant(name)
+        model, _ = gu.build_variant_model(c, "cpu")
+        with torch.no_grad():
+            P_v, P_t = model.prompt_stacks()
+        sd = {}
+        for k, v in syn.synthetic_clip_state_dict(c["arch"], 0).items():
+            if k.startswith("visual."):
+                sd["image_encoder." + k[len("visual."):]] = v
+            elif k.startswith("transformer.") or k in ("positional_embedding", "ln_final.weight", "ln_final.bias", "text_projection"):
+                sd["text_encoder." + k] = v
+            elif k == "logit_scale":
+                sd[k] = v
+        pl = model.mudpt_prompt_learner
+        emb = torch.cat([pl.token_prefix, torch.zeros(pl.n_cls, pl.n_ctx, pl.ctx_dim), pl.token_suffix], dim=1)
+        eot = c["tokenized"].argmax(-1).long()
+        f_img = orc.vision_features_from_stack(sd, c["image"], P_v)
+        f_txt = orc.text_features_from_stack(sd, emb, eot, P_t, 77, 0)
+        logits, _ = orc.logits_and_loss(f_img, f_txt, sd["logit_scale"])
+        assert float((logits - torch.from_numpy(c["golden"]["logits"])).abs().max()) <= 1e-4, name
