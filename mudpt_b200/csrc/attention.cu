@@ -574,7 +574,7 @@ __device__ __forceinline__ void short_fwd_body(uint8_t* smem, uint32_t sQ, uint3
 
 // MAXT = most 16-row tiles (warps) this instantiation handles: sizes the register budget, so that the
 // 77-token text tower (5 tiles) does not pay for 128-token sequences (8 tiles).
-constexpr int short_min_ctas(int maxt, bool bwd) { return maxt <= 2 ? 8 : maxt <= 5 ? (bwd ? 3 : 4) : (bwd ? 1 : 2); }
+constexpr int short_min_ctas(int maxt, bool bwd) { return maxt <= 2 ? 8 : maxt <= 5 ? (bwd ? 3 : 5) : (bwd ? 1 : 2); }
 
 template <bool CAUSAL, int MAXT>
 __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, false)) attn_short_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
