@@ -34,8 +34,12 @@ namespace mudpt {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
-static constexpr int EPI_WARPS = 8;
+// Epilogue warps per CTA (TMA warp + MMA warp + these).  The GELU' epilogue (dgrad of c_proj) has the longest
+// per-element dependency chain (unpack, 6 packed fp32 ops, tanh, pack) and was latency-bound on 2 warps per
+// scheduler (ncu: issue slots 39 % busy, stall_wait dominant): it runs 16 warps at <= 112 registers, with a
+// single accumulator register set (4 warps per scheduler hide the TMEM load instead of a second set).
+template <int MODE> struct EpiWarps { static constexpr int value = (MODE == 4 /*EPI_GELU_BWD*/) ? 16 : 8; };
+template <int MODE> struct GemmThreads { static constexpr int value = 64 + 32 * EpiWarps<MODE>::value; };
 
 // TWO = CTA pair (cta_group::2): the pair computes a 256 x BN tile, each CTA holds 128 rows of A
 // and BN/2 rows of B per stage, so the B half that an SM reads from its shared memory feeds both
@@ -67,7 +71,7 @@ struct GemmCfg {
   // fp32 outputs: a 32-column box is 4 KB (two units), double-buffered
   static constexpr int kUnitsPerWarp = (MODE == EPI_GELU || (F32Epi<MODE>::value && MODE != EPI_RESID_DEEP)) ? 4 : 2;
   static constexpr int kWarpStaging = RowEpi<MODE>::value ? kUnitsPerWarp * kUnitBytes : 32 * 32 * 4;
-  static constexpr int kStagingBytes = EPI_WARPS * kWarpStaging;
+  static constexpr int kStagingBytes = EpiWarps<MODE>::value * kWarpStaging;
   static constexpr int kBarBytes = 512;
   static constexpr int kFit = (kMaxSmem - kStagingBytes - 1024 - kBarBytes) / kStageBytes;
   static constexpr int kStages = kFit < 6 ? kFit : 6;
@@ -195,9 +199,10 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
                                               uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const int warp,
                                               const int lane) {
   constexpr int TM = TWO ? 2 * BM : BM;
-  constexpr int kCols = BN / 2;       // columns per warp
-  constexpr int kBoxes = kCols / 32;  // boxes per warp and tile
-  const int quad = warp & 3, half = (warp - 2) >> 2;
+  constexpr int kParts = EpiWarps<MODE>::value / 4;  // warps per TMEM lane quadrant
+  constexpr int kCols = BN / kParts;                 // columns per warp
+  constexpr int kBoxes = kCols / 32;                 // boxes per warp and tile
+  const int quad = warp & 3, half = (warp - 2) >> 2;  // half = which column part of the tile
   auto box_origin = [&](int tile, int& row, int& col0) {
     const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
     row = m_blk * TM + static_cast<int>(rank) * BM + quad * 32;
@@ -242,8 +247,10 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
   const bool has_bias = ep.bias != nullptr;
   // one box: r = 32 accumulator columns of this thread's row
   auto process = [&](uint32_t (&r)[32], int row, int col) {
-    float4 bv[8];
-    if (has_bias && col + 32 <= N) {  // the common case: no per-load guards
+    float4 bv[MODE == EPI_GELU_BWD ? 1 : 8];
+    if constexpr (MODE == EPI_GELU_BWD) {
+      // (loaded per 8-column group below: dgrad GEMMs have no bias, and 32 live registers would not fit 16 warps)
+    } else if (has_bias && col + 32 <= N) {  // the common case: no per-load guards
       const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
 #pragma unroll
       for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
@@ -369,9 +376,9 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
         for (int q = 0; q < 4; ++q) {
           const int e = 8 * j + 2 * q;
           f32x2 v = f2_pack_u(r[e], r[e + 1]);
-          if (has_bias) {  // (dgrad GEMMs have none: warp-uniform)
-            const float4 b4 = bv[e >> 2];
-            v = f2_add(v, (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y));
+          if (has_bias && col + 8 * j < N) {  // (dgrad GEMMs have none: warp-uniform)
+            const float2 b2 = __ldg(reinterpret_cast<const float2*>(ep.bias + col + e));
+            v = f2_add(v, f2_pack(b2.x, b2.y));
           }
           const f32x2 h = f2_pack_u(hw[q] << 16, hw[q] & 0xffff0000u);  // bf16 pair -> fp32 pair
           o[q] = pack_bf16_2(mul_quick_gelu_grad2(v, h));
@@ -402,6 +409,20 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
         else mbar_arrive(&tmem_empty_bar[acc]);
       }
     };
+    if constexpr (EpiWarps<MODE>::value > 8) {
+      // 4 warps per scheduler: one accumulator register set, no TMEM prefetch
+      uint32_t ra[32];
+      if (nb == 0) release_acc();
+#pragma unroll 1
+      for (int b = 0; b < nb; ++b) {
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(b * 32), ra);
+        tmem_ld_wait_regs(ra);
+        if (b + 1 == nb) release_acc();
+        process(ra, row, col0 + b * 32);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      continue;
+    }
     uint32_t ra[32], rb[32];
     if (nb > 0) tmem_ld_32x32(taddr, ra);
     else release_acc();
@@ -427,7 +448,7 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
 // The kernel
 // ---------------------------------------------------------------------------------------
 template <int BN, int MODE, bool TWO>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmThreads<MODE>::value, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                        const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1,
                        const __grid_constant__ CUtensorMap tma_ex, const GemmEpilogue ep, const int M, const int N,
@@ -451,7 +472,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* extra_bar = tmem_empty_bar + 2;  // [EPI_WARPS][2]: pre-activation boxes of the GELU' epilogue
+  constexpr int EPI_WARPS = EpiWarps<MODE>::value;
+  uint64_t* extra_bar = tmem_empty_bar + 2;  // [EPI_WARPS][2]: pre-activation / residual boxes of the row epilogues
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(extra_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
@@ -777,7 +799,7 @@ static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, cons
   const int grid = (tiles < units ? tiles : units) * (TWO ? 2 : 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(GemmThreads<MODE>::value);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
