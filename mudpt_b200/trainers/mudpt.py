@@ -86,6 +86,26 @@ except Exception:  # pragma: no cover - exercised on boxes without dassl
                 if s is not None:
                     s.step()
 
+        def save_model(self, epoch, directory, is_best=False, val_result=None, model_name=""):
+            """Dassl's checkpoint layout (TrainerBase.save_model / dassl.utils.save_checkpoint):
+            <directory>/<model name>/model.pth.tar-<epoch + 1> holding {"state_dict", "epoch", "optimizer",
+            "scheduler", "val_result"} plus a "checkpoint" file naming it; `load_model` below reads it back."""
+            for name in self.get_model_names():
+                model = self._models[name]
+                optim, sched = self._optims.get(name), self._scheds.get(name)
+                fdir = osp.join(directory, name)
+                os.makedirs(fdir, exist_ok=True)
+                fname = model_name or ("model.pth.tar-" + str(epoch + 1))
+                torch.save({"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "epoch": epoch + 1,
+                            "optimizer": optim.state_dict() if optim is not None else None,
+                            "scheduler": sched.state_dict() if sched is not None else None, "val_result": val_result},
+                           osp.join(fdir, fname))
+                with open(osp.join(fdir, "checkpoint"), "w") as f:
+                    f.write(fname + "\n")
+                if is_best:
+                    import shutil
+                    shutil.copy(osp.join(fdir, fname), osp.join(fdir, "model-best.pth.tar"))
+
     def build_optimizer(model, optim_cfg):
         """Dassl's SGD defaults (momentum 0.9, weight decay 5e-4); on a CUDA model the update runs as one
         native multi-tensor launch (mudpt_b200.optim.FusedSGD, same torch.optim.SGD semantics and state)."""

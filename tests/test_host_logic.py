@@ -173,3 +173,51 @@ def test_variant_prompt_algebra_matches_reference():
         f_txt = orc.text_features_from_stack(sd, emb, eot, P_t, 77, 0)
         logits, _ = orc.logits_and_loss(f_img, f_txt, sd["logit_scale"])
         assert float((logits - torch.from_numpy(c["golden"]["logits"])).abs().max()) <= 1e-4, name
+
+
+def test_checkpoint_round_trip_dassl_layout(tmp_path):
+    """a checkpoint written in Dassl's layout (model.pth.tar-N under <dir>/<model name>/) loads back
+    through the reference-shaped `load_model` (trainers/mudpt.py:270-302): trained tensors restored, the fixed token
+    vectors of the CHECKPOINT ignored (they belong to its class names, :294-298)."""
+    import torch
+    from mudpt_b200 import clip
+    from mudpt_b200.trainers import mudpt as M
+    from tests import golden_util as gu
+    c = gu.load("tiny_c")
+
+    def make(classnames):
+        cfg = gu.make_cfg(c["n_ctx"], c["depth"], "", c["arch"].image_resolution)
+        from mudpt_b200 import synthetic as syn
+        clip_model = clip.CLIP(*c["arch"].astuple(), cfg).float()
+        t = M.MuDPT.__new__(M.MuDPT)
+        M.TrainerX.__init__(t, None, None, "cpu")
+        t.cfg = cfg
+        t.model = M.CustomCLIP(cfg, classnames, clip_model, tokenizer=syn.synthetic_tokenize)
+        for n, p in t.model.named_parameters():
+            if "prompt_learner" not in n:
+                p.requires_grad_("visual_ctx" in n)
+        t.optim = torch.optim.SGD([p for p in t.model.parameters() if p.requires_grad], lr=0.1, momentum=0.9)
+        t.sched = None
+        t.register_model("MultimodalDeepPromptTuning", t.model, t.optim, t.sched)
+        return t
+
+    a = make(["class 0", "class 1", "class 2"])
+    with torch.no_grad():
+        for n, p in a.model.named_parameters():
+            if p.requires_grad:
+                p.add_(torch.randn_like(p))
+    a.save_model(4, str(tmp_path))
+    path = tmp_path / "MultimodalDeepPromptTuning" / "model.pth.tar-5"
+    assert path.exists()
+    ck = torch.load(str(path), map_location="cpu", weights_only=False)
+    assert set(ck) == {"state_dict", "epoch", "optimizer", "scheduler", "val_result"} and ck["epoch"] == 5
+    b = make(["dog", "cat", "bird", "fish"])   # other class names: 4 instead of 3 classes
+    before = b.model.mudpt_prompt_learner.token_prefix.clone()
+    b.load_model(str(tmp_path), epoch=5)
+    for (n, p), (_, q) in zip(a.model.named_parameters(), b.model.named_parameters()):
+        if p.requires_grad:
+            assert torch.equal(p, q), n
+    assert torch.equal(b.model.mudpt_prompt_learner.token_prefix, before)
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        b.load_model(str(tmp_path), epoch=99)
