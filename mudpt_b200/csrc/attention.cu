@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_dkv_kernel(const bf16* __rest
 // so the softmax is a single pass (no running max / rescale) and the code is straight-line per T
 // (dispatch on T: no per-group guards -- the generic kernels above spend ~2/3 of their issue
 // slots on those).  The backward is ONE kernel: phase 1 (rows = queries) computes S, P, dP, dS
-// once, dQ = dS K, and parks P / dS as bf16 in shared memory (over the dead K / V / O tiles);
+// once (D = rowsum(P dP): O is not loaded), dQ = dS K, and parks P / dS as bf16 in shared memory (over the dead K / V tiles);
 // phase 2 (rows = keys) reads them transposed with ldmatrix.trans: dV = P^T dO, dK = dS^T Q.
 // 5 MMA products instead of 7, one exp per score instead of two, a third of the tile loads.
 // =======================================================================================
@@ -612,8 +612,8 @@ __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, false)) attn_s
 // fragment layout) in pp / ds.
 template <bool CAUSAL, int T, int MAXT>
 __device__ __forceinline__ void short_bwd_phase1(uint32_t sQ, uint32_t sdO, uint32_t sK, uint32_t sV, int t, int L, int lane,
-                                                 float scale_log2e, float lse0, float lse1, float D0, float D1,
-                                                 float (&dq)[8][4], uint32_t (&pp)[2 * MAXT][2], uint32_t (&ds)[2 * MAXT][2]) {
+                                                 float scale_log2e, float lse0, float lse1, float (&dq)[8][4],
+                                                 uint32_t (&pp)[2 * MAXT][2], uint32_t (&ds)[2 * MAXT][2]) {
   const int row0 = t * 16;
   float sc[2 * T][4], dp[2 * T][4];
   zero_acc(sc);
@@ -638,7 +638,9 @@ __device__ __forceinline__ void short_bwd_phase1(uint32_t sQ, uint32_t sdO, uint
   const int qr = row0 + (lane >> 2);
   const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
   const f32x2 nl[2] = {f2_pack(-lse0, -lse0), f2_pack(-lse1, -lse1)};
-  const f32x2 nD[2] = {f2_pack(-D0, -D0), f2_pack(-D1, -D1)};
+  // P in place of the scores; D_i = sum_j P_ij dP_ij (== sum_k dO_ik O_ik, without loading O: the whole row
+  // block is in registers here)
+  f32x2 dsum2[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
 #pragma unroll
   for (int nt = 0; nt < 2 * T; ++nt) {
 #pragma unroll
@@ -653,10 +655,29 @@ __device__ __forceinline__ void short_bwd_phase1(uint32_t sQ, uint32_t sdO, uint
         a = col <= lim ? a : 0.f;
         b = col + 1 <= lim ? b : 0.f;
       }
-      const f32x2 p2 = f2_pack(a, b);
+      sc[nt][2 * r] = a;
+      sc[nt][2 * r + 1] = b;
+      dsum2[r] = f2_fma(f2_pack(a, b), f2_pack(dp[nt][2 * r], dp[nt][2 * r + 1]), dsum2[r]);
+    }
+  }
+  f32x2 nD[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float a, b;
+    f2_unpack(dsum2[r], a, b);
+    float D = a + b;
+    D += __shfl_xor_sync(0xffffffffu, D, 1);
+    D += __shfl_xor_sync(0xffffffffu, D, 2);
+    nD[r] = f2_pack(-D, -D);
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2 * T; ++nt) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const f32x2 p2 = f2_pack(sc[nt][2 * r], sc[nt][2 * r + 1]);
       float x, y;
       f2_unpack(f2_mul(p2, f2_add(f2_pack(dp[nt][2 * r], dp[nt][2 * r + 1]), nD[r])), x, y);  // dS (unscaled)
-      pp[nt][r] = pack_bf16(a, b);
+      pp[nt][r] = pack_bf16(sc[nt][2 * r], sc[nt][2 * r + 1]);
       ds[nt][r] = pack_bf16(x, y);
     }
   }
@@ -684,9 +705,9 @@ __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, true)) attn_sh
   const int nw = blockDim.x >> 5, Lp = nw * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sh = blockIdx.x, s = sh / H, h = sh - s * H;
-  // [Q | dO | K | V | O ...]; after phase 1 the K/V/O region is reused for P and dS
+  // [Q | dO | K | V | pad]; after phase 1 the K / V / pad region is reused for P and dS
   const uint32_t tile_bytes = Lp * ROW_BYTES;
-  const uint32_t sQ = smem_u32(smem), sdO = sQ + tile_bytes, sK = sdO + tile_bytes, sV = sK + tile_bytes, sO = sV + tile_bytes;
+  const uint32_t sQ = smem_u32(smem), sdO = sQ + tile_bytes, sK = sdO + tile_bytes, sV = sK + tile_bytes;
   const int ld = 3 * d;
   const size_t seq_row = static_cast<size_t>(s) * L;
   const bf16* base = qkv + seq_row * ld + h * DH;
@@ -696,44 +717,21 @@ __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, true)) attn_sh
   load_tile(sdO, d_o + seq_row * d + h * DH, d, 0, L, Lp);
   load_tile(sK, base + d, ld, 0, L, Lp);
   load_tile(sV, base + 2 * d, ld, 0, L, Lp);
-  load_tile(sO, o + seq_row * d + h * DH, d, 0, L, Lp);
   cp_async_commit();
   const int row0 = warp * 16;
   const int qr = row0 + (lane >> 2);
   const size_t stat_base = (static_cast<size_t>(s) * H + h) * L;
-  // rows >= L: lse = 0 with zero Q / dO rows gives finite p and dS = 0, dO = 0: no contribution to dK / dV
+  // rows >= L: lse = 0 with zero Q / dO rows gives finite p, dP = 0, hence D = 0 and dS = 0: no contribution to dK / dV
   const float lse0 = qr < L ? lse2[stat_base + qr] : 0.f;
   const float lse1 = qr + 8 < L ? lse2[stat_base + qr + 8] : 0.f;
   cp_async_wait_all();
   __syncthreads();
 
-  // D_i = sum_j dO_ij O_ij for the warp's 16 rows: lane -> (row = lane/2, half = lane%2)
-  float dpart = 0.f;
-  {
-    const int r = row0 + (lane >> 1);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int chunk = (lane & 1) * 4 + c;
-      const uint4 a = *reinterpret_cast<const uint4*>(smem + (sdO - sQ) + swz(r, chunk));
-      const uint4 b = *reinterpret_cast<const uint4*>(smem + (sO - sQ) + swz(r, chunk));
-      const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
-      const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 x = unpack_bf16(pa[i]), y = unpack_bf16(pb[i]);
-        dpart += x.x * y.x + x.y * y.y;
-      }
-    }
-    dpart += __shfl_xor_sync(0xffffffffu, dpart, 1);
-  }
-  const float D0 = __shfl_sync(0xffffffffu, dpart, (lane >> 2) * 2);
-  const float D1 = __shfl_sync(0xffffffffu, dpart, ((lane >> 2) + 8) * 2);
-
   float dq[8][4];
   uint32_t pp[2 * MAXT][2], ds[2 * MAXT][2];
   const int T = CAUSAL ? warp + 1 : nw;
 #define MUDPT_BWD_CASE(k) \
-  case k: if constexpr (MAXT >= k) short_bwd_phase1<CAUSAL, k, MAXT>(sQ, sdO, sK, sV, warp, L, lane, scale_log2e, lse0, lse1, D0, D1, dq, pp, ds); break;
+  case k: if constexpr (MAXT >= k) short_bwd_phase1<CAUSAL, k, MAXT>(sQ, sdO, sK, sV, warp, L, lane, scale_log2e, lse0, lse1, dq, pp, ds); break;
   switch (T) {
     MUDPT_BWD_CASE(1) MUDPT_BWD_CASE(2) MUDPT_BWD_CASE(3) MUDPT_BWD_CASE(4)
     MUDPT_BWD_CASE(5) MUDPT_BWD_CASE(6) MUDPT_BWD_CASE(7) MUDPT_BWD_CASE(8)
@@ -797,7 +795,7 @@ __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, true)) attn_sh
 }
 
 static size_t short_bwd_smem(int Lp) {
-  const size_t tiles = 5u * Lp * ROW_BYTES;                       // Q dO K V O
+  const size_t tiles = 4u * Lp * ROW_BYTES;                       // Q dO K V
   const size_t need = 2u * Lp * ROW_BYTES + 2u * Lp * (2 * Lp + 16);  // Q dO P dS
   return tiles > need ? tiles : need;
 }
