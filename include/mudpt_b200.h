@@ -146,6 +146,28 @@ int mudpt_sgd_step(void* const* params, const void* const* grads, void* const* b
                    float lr, float momentum, float dampening, float weight_decay, int32_t nesterov, int32_t first_step,
                    void* stream);
 
+/* ---- input pipeline in front of the vision tower -------------------------------
+ * Replaces, for the tensor MuDPT.parse_batch_train receives (trainers/mudpt.py:263-268), the CPU transform
+ * the yaml names (configs/trainers/MuDPT/vit_b16_bz4_ep10_nctx2_depth9.yaml:8-13: random_resized_crop,
+ * random_flip, normalize, bicubic) -- Dassl's builder maps it onto torchvision transforms on PIL images:
+ * crop -> PIL.Image.resize(BICUBIC) -> window (CenterCrop at evaluation) -> hflip -> /255 -> (x - mean) / std.
+ * Output is bit-identical to that pipeline.  Random parameters are drawn by the caller. */
+typedef struct mudpt_image_desc {
+  const uint8_t* src;                  /* DEVICE pointer: 8-bit RGB, HWC, rows `pitch` bytes apart */
+  int32_t height, width, pitch;
+  int32_t box_x, box_y, box_w, box_h;  /* crop box (PIL.Image.crop); resampling clamps at its edges */
+  int32_t rs_w, rs_h;                  /* size the crop is resampled to (PIL.Image.resize) */
+  int32_t win_x, win_y;                /* top-left of the out_h x out_w window of the resampled image */
+  int32_t flip;                        /* != 0: mirror the window horizontally */
+  int32_t reserved[2];
+} mudpt_image_desc;                    /* 64 bytes */
+/* device workspace (bytes) mudpt_augment_images needs for this batch; negative on a bad descriptor */
+int64_t mudpt_augment_workspace_bytes(const mudpt_image_desc* descs_host, int32_t n, int32_t out_h, int32_t out_w);
+/* descs: DEVICE copy of descs_host[n]; mean_host / std_host: 3 floats; out: fp32 [n, 3, out_h, out_w] */
+int mudpt_augment_images(const mudpt_image_desc* descs, const mudpt_image_desc* descs_host, int32_t n, int32_t out_h,
+                         int32_t out_w, const float* mean_host, const float* std_host, void* workspace,
+                         int64_t workspace_bytes, float* out, void* stream);
+
 /* ---- introspection for tests / profiling --------------------------------------------------------
  * name in {"x_in","x_mid","qkv","o","h","lse","dx"}; layer ignored for "dx". */
 int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t layer, void** ptr, int64_t* numel);

@@ -49,6 +49,9 @@ SIGNATURES = {
     "mudpt_cast_bf16": (C.c_int, [c_f32p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mudpt_sgd_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                  C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
+    "mudpt_augment_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "mudpt_augment_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), C.c_void_p, C.c_int64, c_f32p, C.c_void_p]),
     "mudpt_debug_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mudpt_profile_begin": (C.c_int, [C.c_void_p]),
     "mudpt_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),

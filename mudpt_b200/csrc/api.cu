@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "attention.h"
+#include "augment.h"
 #include "gemm.h"
 #include "head.h"
 #include "launch_count.h"
@@ -612,6 +613,20 @@ int mudpt_sgd_step(void* const* params, const void* const* grads, void* const* b
   if (!params || !grads || !numel || (momentum != 0.f && !bufs)) return fail(nullptr, "mudpt_sgd_step: null argument");
   CKG(sgd_step(params, grads, bufs, reinterpret_cast<const long long*>(numel), n, lr, momentum, dampening, weight_decay,
                nesterov != 0, first_step != 0, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int64_t mudpt_augment_workspace_bytes(const mudpt_image_desc* descs_host, int32_t n, int32_t out_h, int32_t out_w) {
+  const char* e = nullptr;
+  const long long b = augment_workspace_bytes(descs_host, n, out_h, out_w, &e);
+  if (e) return fail(nullptr, "%s", e);
+  return b;
+}
+int mudpt_augment_images(const mudpt_image_desc* descs, const mudpt_image_desc* descs_host, int32_t n, int32_t out_h,
+                         int32_t out_w, const float* mean_host, const float* std_host, void* workspace,
+                         int64_t workspace_bytes, float* out, void* stream) {
+  CKG(augment_images(descs, descs_host, n, out_h, out_w, mean_host, std_host, workspace, workspace_bytes, out,
+                     static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -1,0 +1,205 @@
+"""Input pipeline: crop -> bicubic resample -> window -> flip -> normalize.
+
+CPU (`-m "not gpu"`): the oracle (oracle/input_pipeline_oracle.py) against the golden fixture made from
+torchvision + PIL and, when those are importable, against them live; the host-side random draws against
+torchvision under the same seed; descriptor validation through the C ABI (host-only entry point).
+GPU (`-m gpu`): the CUDA kernels through the C ABI against the oracle and the fixture.
+Bar: BIT-EXACT everywhere (8-bit resampling is integer work; /255 and (x - mean) / std are single IEEE fp32 ops).
+"""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import input_pipeline_oracle as ipo
+from tests import input_cases as ic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_pipeline.npz")
+
+
+def _oracle_case(case):
+    name, seed, H, W, size, mode, box, flip = case
+    img = ic.make_image(seed, H, W)
+    if mode == "train":
+        return ipo.train_transform(img, *box, flip, size, ic.MEAN, ic.STD)
+    return ipo.eval_transform(img, size, ic.MEAN, ic.STD)
+
+
+def _check_against_golden(case, y, g):
+    name = case[0]
+    assert y.dtype == np.float32
+    if name in ic.SMALL:
+        assert np.array_equal(y, g[name]), f"{name}: max abs diff {np.abs(y - g[name]).max()}"
+    else:
+        assert np.array_equal(y[:, ::16, ::16], g[name + "_sample"]), name
+        assert hashlib.sha256(np.ascontiguousarray(y).tobytes()).hexdigest() == str(g[name + "_sha256"]), name
+
+
+# ------------------------------------------------------------------------------------------- CPU
+@pytest.mark.parametrize("case", ic.CASES, ids=[c[0] for c in ic.CASES])
+def test_oracle_matches_golden(case):
+    g = np.load(GOLDEN, allow_pickle=False)
+    _check_against_golden(case, _oracle_case(case), g)
+
+
+def test_oracle_resample_matches_pil_live():
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(0)
+    for it in range(40):
+        H, W = (int(v) for v in rng.integers(6, 260, 2))
+        img = ic.make_image(100 + it, H, W)
+        ow, oh = (int(v) for v in rng.integers(3, 200, 2))
+        if it % 4 == 0:
+            ow = W  # horizontal pass skipped
+        if it % 5 == 0:
+            oh = H
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BICUBIC))
+        assert np.array_equal(ipo.resample_u8(img, ow, oh), ref), (H, W, ow, oh)
+
+
+def test_oracle_pipeline_matches_torchvision_live():
+    T = pytest.importorskip("torchvision.transforms")
+    Image = pytest.importorskip("PIL.Image")
+    bic = T.InterpolationMode.BICUBIC
+    rng = np.random.default_rng(1)
+    for it in range(6):
+        H, W = (int(v) for v in rng.integers(40, 300, 2))
+        img = ic.make_image(200 + it, H, W)
+        pil = Image.fromarray(img)
+        size = (56, 56)
+        # training: same seed -> same draws -> same pixels
+        tf = T.Compose([T.RandomResizedCrop(size, scale=(0.08, 1.0), interpolation=bic), T.RandomHorizontalFlip(),
+                        T.ToTensor(), T.Normalize(ic.MEAN, ic.STD)])
+        torch.manual_seed(it)
+        ref = tf(pil).numpy()
+        from mudpt_b200 import input_pipeline as ip
+        torch.manual_seed(it)
+        bx, by, bw, bh, rw, rh, wx, wy, flip = ip.draw_geometry(H, W, size, True)
+        assert (rw, rh, wx, wy) == (56, 56, 0, 0)
+        got = ipo.train_transform(img, by, bx, bh, bw, bool(flip), size, ic.MEAN, ic.STD)
+        assert np.array_equal(got, ref)
+        ev = T.Compose([T.Resize(max(size), interpolation=bic), T.CenterCrop(size), T.ToTensor(), T.Normalize(ic.MEAN, ic.STD)])
+        assert np.array_equal(ipo.eval_transform(img, size, ic.MEAN, ic.STD), ev(pil).numpy())
+
+
+def test_random_draws_match_torchvision():
+    T = pytest.importorskip("torchvision.transforms")
+    from mudpt_b200 import input_pipeline as ip
+    for seed, (H, W) in enumerate([(375, 500), (500, 333), (64, 64), (10, 400), (400, 10), (1, 1)]):
+        torch.manual_seed(seed)
+        ref = [T.RandomResizedCrop.get_params(torch.empty(3, H, W), [0.08, 1.0], [3 / 4, 4 / 3]) for _ in range(5)]
+        ref_flip = bool(torch.rand(1) < 0.5)
+        torch.manual_seed(seed)
+        got = [ip.random_resized_crop_params(H, W) for _ in range(5)]
+        assert got == [tuple(r) for r in ref]
+        assert ip.random_flip() == ref_flip
+    # evaluation geometry == torchvision's Resize(int) + center_crop arithmetic
+    import torchvision.transforms.functional as F
+    for H, W in [(150, 233), (301, 170), (224, 224), (225, 224), (480, 640)]:
+        assert list(ip.resized_output_size(H, W, 224)) == F._compute_resized_output_size((H, W), [224])
+        g = ip.draw_geometry(H, W, (224, 224), False)
+        nh, nw = ip.resized_output_size(H, W, 224)
+        assert g == (0, 0, W, H, nw, nh, int(round((nw - 224) / 2.0)), int(round((nh - 224) / 2.0)), 0)
+
+
+def test_desc_struct_and_validation_through_abi():
+    """mudpt_augment_workspace_bytes is host-only: descriptor layout and error paths are checkable without a GPU."""
+    from mudpt_b200 import _lib, input_pipeline as ip
+    lib = _lib.load()
+    assert ip.DESC_DTYPE.itemsize == 64
+    d = np.zeros(2, ip.DESC_DTYPE)
+    d[0] = (0x1000, 100, 200, 600, 10, 20, 150, 60, 224, 224, 0, 0, 1, (0, 0))
+    d[1] = (0x2000, 500, 400, 1200, 0, 0, 400, 500, 224, 280, 0, 28, 0, (0, 0))
+    need = lib.mudpt_augment_workspace_bytes(d.ctypes.data_as(C.c_void_p), 2, 224, 224)
+    kmax = max(ipo.precompute_coeffs(w, 0, w, o)[0] for w, o in [(150, 224), (60, 224), (400, 224), (500, 280)])
+    assert need == 2 * 2 * 224 * (8 + 4 * kmax)
+    bad = d.copy()
+    bad[1]["box_w"] = 401  # outside the image
+    assert lib.mudpt_augment_workspace_bytes(bad.ctypes.data_as(C.c_void_p), 2, 224, 224) < 0
+    assert b"crop box" in lib.mudpt_global_last_error()
+    bad = d.copy()
+    bad[0]["win_x"] = 1  # window leaves the resampled image
+    assert lib.mudpt_augment_workspace_bytes(bad.ctypes.data_as(C.c_void_p), 2, 224, 224) < 0
+    assert b"window" in lib.mudpt_global_last_error()
+    bad = d.copy()
+    bad[0]["pitch"] = 599
+    assert lib.mudpt_augment_workspace_bytes(bad.ctypes.data_as(C.c_void_p), 2, 224, 224) < 0
+    with pytest.raises(NotImplementedError):
+        ip.GpuTransform(interpolation="bilinear")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ip.GpuTransform(device="cpu")
+
+
+# ------------------------------------------------------------------------------------------- GPU
+def _geometry_of(case):
+    from mudpt_b200 import input_pipeline as ip
+    name, seed, H, W, size, mode, box, flip = case
+    if mode == "train":
+        top, left, h, w = box
+        return (left, top, w, h, size[1], size[0], 0, 0, int(flip))
+    return ip.draw_geometry(H, W, size, False)
+
+
+@pytest.mark.gpu
+def test_gpu_cases_bit_exact_vs_golden_and_oracle():
+    from mudpt_b200 import input_pipeline as ip
+    g = np.load(GOLDEN, allow_pickle=False)
+    by_size = {}
+    for case in ic.CASES:
+        by_size.setdefault(case[4], []).append(case)
+    for size, cases in by_size.items():  # one ragged batch per output size
+        tf = ip.GpuTransform(size=size, is_train=True, mean=ic.MEAN, std=ic.STD)
+        imgs = [torch.from_numpy(ic.make_image(c[1], c[2], c[3])).cuda() for c in cases]
+        out = tf(imgs, params=[_geometry_of(c) for c in cases]).cpu().numpy()
+        for c, y in zip(cases, out):
+            _check_against_golden(c, y, g)
+            assert np.array_equal(y, _oracle_case(c)), c[0]
+
+
+@pytest.mark.gpu
+def test_gpu_random_ragged_batch_bit_exact():
+    """Seeded random crops at 224 x 224 (the training transform as the trainer would call it), pinned host images
+    uploaded by the transform, evaluation transform on the same images, a strided (pitched) source."""
+    from mudpt_b200 import input_pipeline as ip
+    rng = np.random.default_rng(7)
+    shapes = [(int(h), int(w)) for h, w in zip(rng.integers(30, 520, 12), rng.integers(30, 520, 12))] + [(224, 224), (500, 375)]
+    host = [ic.make_image(300 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    tf = ip.GpuTransform(size=(224, 224), is_train=True, mean=ic.MEAN, std=ic.STD)
+    torch.manual_seed(3)
+    geo = [ip.draw_geometry(h, w, (224, 224), True) for h, w in shapes]
+    torch.manual_seed(3)
+    out = tf([torch.from_numpy(a).pin_memory() for a in host]).cpu().numpy()  # draws its own (same seed)
+    for a, (bx, by, bw, bh, rw, rh, wx, wy, flip), y in zip(host, geo, out):
+        assert np.array_equal(y, ipo.train_transform(a, by, bx, bh, bw, bool(flip), (224, 224), ic.MEAN, ic.STD))
+    big = [a for a in host if min(a.shape[:2]) >= 100]
+    ev = ip.GpuTransform(size=(224, 224), is_train=False, mean=ic.MEAN, std=ic.STD)
+    out = ev([torch.from_numpy(a).cuda() for a in big]).cpu().numpy()
+    for a, y in zip(big, out):
+        assert np.array_equal(y, ipo.eval_transform(a, (224, 224), ic.MEAN, ic.STD))
+    # pitched source: a view into a wider image
+    wide = torch.from_numpy(ic.make_image(77, 200, 300)).cuda()
+    view = wide[10:190, 20:260]
+    y = tf([view], params=[(5, 6, 200, 150, 224, 224, 0, 0, 1)]).cpu().numpy()[0]
+    ref = ipo.train_transform(view.cpu().numpy(), 6, 5, 150, 200, True, (224, 224), ic.MEAN, ic.STD)
+    assert np.array_equal(y, ref)
+
+
+@pytest.mark.gpu
+def test_gpu_extreme_scales_bit_exact():
+    """Heavy down-scaling (wide filters; the narrow-band launch when the 8-row band no longer fits shared memory)
+    and heavy up-scaling."""
+    from mudpt_b200 import input_pipeline as ip
+    tf = ip.GpuTransform(size=(224, 224), is_train=True, mean=ic.MEAN, std=ic.STD)
+    for seed, (H, W), box in [(1, (1400, 1300), (0, 0, 1300, 1400)),     # scale ~6: 8-row bands
+                              (2, (6400, 240), (0, 0, 240, 6400)),       # vertical scale 28.6: 2-row bands
+                              (3, (40, 40), (10, 12, 9, 7))]:            # up-scaling x25 / x32
+        a = ic.make_image(seed, H, W)
+        bx, by, bw, bh = box
+        y = tf([torch.from_numpy(a).cuda()], params=[(bx, by, bw, bh, 224, 224, 0, 0, 0)]).cpu().numpy()[0]
+        assert np.array_equal(y, ipo.train_transform(a, by, bx, bh, bw, False, (224, 224), ic.MEAN, ic.STD)), (H, W)
+    with pytest.raises(RuntimeError, match="crop box"):
+        tf([torch.zeros(50, 50, 3, dtype=torch.uint8, device="cuda")], params=[(0, 0, 51, 50, 224, 224, 0, 0, 0)])
