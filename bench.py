@@ -441,7 +441,7 @@ def input_pipeline_bench(device, peaks, batch=BATCH_PER_GPU, reps=20):
         ts.append(e0.elapsed_time(e1))
     ms = statistics.median(ts)
     nbytes = sum(int(x[2]) * int(x[3]) * 3 for x in geo) + batch * 3 * 224 * 224 * 4
-    return {"kernels": "resample_coeffs_kernel + augment_kernel (bit-exact vs torchvision/PIL bicubic pipeline)",
+    return {"kernels": "resample_coeffs_kernel + augment_smem_kernel (bit-exact vs torchvision/PIL bicubic pipeline)",
             "batch": batch, "us_per_batch": round(ms * 1e3, 1), "imgs_per_s": round(batch / (ms * 1e-3), 0),
             "algorithmic_bytes": nbytes, "gbs_algorithmic": round(nbytes / (ms * 1e-3) / 1e9, 1),
             "frac_of_hbm_peak": round(nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"], 4), "l2": "flushed between launches",

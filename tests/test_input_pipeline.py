@@ -196,7 +196,11 @@ def test_gpu_extreme_scales_bit_exact():
     tf = ip.GpuTransform(size=(224, 224), is_train=True, mean=ic.MEAN, std=ic.STD)
     for seed, (H, W), box in [(1, (1400, 1300), (0, 0, 1300, 1400)),     # scale ~6: 8-row bands
                               (2, (6400, 240), (0, 0, 240, 6400)),       # vertical scale 28.6: 2-row bands
-                              (3, (40, 40), (10, 12, 9, 7))]:            # up-scaling x25 / x32
+                              (3, (40, 40), (10, 12, 9, 7)),             # up-scaling x25 / x32
+                              # staged-rows kernel, horizontal filter widths 9 / 11 / 13 / 17 taps (register-weight
+                              # variants and the generic loop), short crops so that the rows fit shared memory
+                              (4, (160, 420), (3, 2, 400, 150)), (5, (170, 520), (11, 5, 500, 150)),
+                              (6, (160, 650), (1, 0, 640, 150)), (7, (120, 900), (50, 10, 800, 100))]:
         a = ic.make_image(seed, H, W)
         bx, by, bw, bh = box
         y = tf([torch.from_numpy(a).cuda()], params=[(bx, by, bw, bh, 224, 224, 0, 0, 0)]).cpu().numpy()[0]
