@@ -121,9 +121,9 @@ class GpuTransform:
             if n not in cls.SUPPORTED_TRAIN:
                 raise NotImplementedError(f"transform {n!r} is not used by the reference's MuDPT configs")
         scale = tuple(getattr(inp, "RRCROP_SCALE", (0.08, 1.0)))
-        return cls(size=tuple(inp.SIZE), is_train=is_train, scale=scale, mean=tuple(inp.PIXEL_MEAN),
-                   std=tuple(inp.PIXEL_STD), interpolation=getattr(inp, "INTERPOLATION", "bicubic"), device=device,
-                   flip_p=0.5 if "random_flip" in names else 0.0)
+        return cls(size=tuple(inp.SIZE), is_train=is_train, scale=scale, mean=tuple(getattr(inp, "PIXEL_MEAN", CLIP_MEAN)),
+                   std=tuple(getattr(inp, "PIXEL_STD", CLIP_STD)), interpolation=getattr(inp, "INTERPOLATION", "bicubic"),
+                   device=device, flip_p=0.5 if "random_flip" in names else 0.0)
 
     def draw(self, height: int, width: int):
         return draw_geometry(height, width, self.size, self.is_train, self.scale, self.ratio, self.flip_p)

@@ -456,9 +456,12 @@ class MuDPT(TrainerX):
             # fused loss + backward in the native head; same update as model_backward_and_update(loss).
             # Host batches go in as they are: the fused step uploads them on its vision stream
             # (parse_batch_train's blocking .to(device) would put the PCIe copy on the critical path).
-            image, label = batch["img"], batch["label"]
-            if not (image.device.type == "cpu" and self.device.type == "cuda"):
-                image, label = self.parse_batch_train(batch)
+            if "img" not in batch:
+                image, label = self.parse_batch_train(batch)  # raw 8-bit images: GPU input pipeline
+            else:
+                image, label = batch["img"], batch["label"]
+                if not (image.device.type == "cpu" and self.device.type == "cuda"):
+                    image, label = self.parse_batch_train(batch)
             self.optim.zero_grad()
             loss, _ = self.model.forward_backward(image, label)
             # the loss value is on the host as soon as the head has run (the backward is still in flight):
@@ -481,9 +484,23 @@ class MuDPT(TrainerX):
         return loss_summary
 
     def parse_batch_train(self, batch):
+        if "img" not in batch:
+            # batch["img_u8"] = list of decoded 8-bit RGB images [H, W, 3] (any sizes, host or
+            # device).  The transform the yaml names (random_resized_crop, random_flip, normalize; bicubic) runs on
+            # the GPU, bit-identical to the torchvision / PIL pipeline of the reference's data loader.
+            input = self.input_transform()(batch["img_u8"])
+            return input, batch["label"].to(self.device)
         input = batch["img"].to(self.device)
         label = batch["label"].to(self.device)
         return input, label
+
+    def input_transform(self, is_train: bool = True):
+        """GpuTransform built from cfg.INPUT (mudpt_b200/input_pipeline.py), one per mode, created on first use."""
+        cache = self.__dict__.setdefault("_input_transforms", {})
+        if is_train not in cache:
+            from ..input_pipeline import GpuTransform
+            cache[is_train] = GpuTransform.from_cfg(self.cfg, is_train, device=self.device)
+        return cache[is_train]
 
     def load_model(self, directory, epoch=None):
         if not directory:

@@ -207,3 +207,49 @@ def test_gpu_extreme_scales_bit_exact():
         assert np.array_equal(y, ipo.train_transform(a, by, bx, bh, bw, False, (224, 224), ic.MEAN, ic.STD)), (H, W)
     with pytest.raises(RuntimeError, match="crop box"):
         tf([torch.zeros(50, 50, 3, dtype=torch.uint8, device="cuda")], params=[(0, 0, 51, 50, 224, 224, 0, 0, 0)])
+
+
+@pytest.mark.gpu
+def test_gpu_trainer_takes_raw_images():
+    """MuDPT.forward_backward({"img_u8": [...], "label": ...}): the trainer's parse_batch_train runs the transform
+    named by cfg.INPUT on the GPU; the batch it feeds the model is bit-identical to the torchvision-pinned oracle
+    under the same seed, and the step equals the step on that float batch."""
+    from mudpt_b200 import input_pipeline as ip
+    from mudpt_b200.trainers import mudpt as M
+    from tests import golden_util as gu
+    case = gu.load("tiny_a")
+    R = case["arch"].image_resolution
+    raws = [ic.make_image(400 + i, h, w) for i, (h, w) in enumerate([(40, 61), (90, 33), (R, R)][:case["batch"]])]
+    assert len(raws) == case["batch"]
+
+    def make_trainer():
+        model, cfg = gu.build_model(case, "cuda")
+        cfg.INPUT["INTERPOLATION"] = "bicubic"
+        cfg.INPUT["PIXEL_MEAN"], cfg.INPUT["PIXEL_STD"] = list(ic.MEAN), list(ic.STD)
+        cfg.INPUT["TRANSFORMS"] = ["random_resized_crop", "random_flip", "normalize"]
+        t = M.MuDPT.__new__(M.MuDPT)
+        M.TrainerX.__init__(t, None, None, torch.device("cuda"))
+        t.cfg, t.model = cfg, model
+        t.optim = M.build_optimizer(model, cfg.OPTIM)
+        t.sched = M.build_lr_scheduler(t.optim, cfg.OPTIM)
+        t.register_model("MultimodalDeepPromptTuning", model, t.optim, t.sched)
+        t.batch_idx, t.num_batches = 0, 10 ** 9
+        return t
+
+    torch.manual_seed(11)
+    geo = [ip.draw_geometry(a.shape[0], a.shape[1], (R, R), True) for a in raws]
+    ref = np.stack([ipo.train_transform(a, by, bx, bh, bw, bool(f), (R, R), ic.MEAN, ic.STD)
+                    for a, (bx, by, bw, bh, _, _, _, _, f) in zip(raws, geo)])
+    batch_u8 = {"img_u8": [torch.from_numpy(a) for a in raws], "label": case["labels"]}
+    t1 = make_trainer()
+    torch.manual_seed(11)
+    image, label = t1.parse_batch_train(batch_u8)
+    assert np.array_equal(image.cpu().numpy(), ref)
+    torch.manual_seed(11)
+    loss_u8 = t1.forward_backward(batch_u8)["loss"]
+    t2 = make_trainer()
+    loss_f = t2.forward_backward({"img": torch.from_numpy(ref), "label": case["labels"]})["loss"]
+    assert loss_u8 == loss_f and np.isfinite(loss_u8)
+    for (n1, p1), (_, p2) in zip(t1.model.named_parameters(), t2.model.named_parameters()):
+        if p1.requires_grad:
+            assert torch.equal(p1, p2), n1
