@@ -86,6 +86,32 @@ except Exception:  # pragma: no cover - exercised on boxes without dassl
                 if s is not None:
                     s.step()
 
+        def parse_batch_test(self, batch):
+            return batch["img"].to(self.device), batch["label"].to(self.device)
+
+        def model_inference(self, input):
+            return self.model(input)
+
+        @torch.no_grad()
+        def test(self, data_loader=None, split=None):
+            """Dassl's TrainerX.test loop (parse_batch_test -> model_inference -> evaluator) with the Classification
+            evaluator's top-1 accuracy (100 * correct / total) kept on the device: one host read for the whole split
+            instead of a `.item()` per batch."""
+            if data_loader is None:
+                raise ValueError("the stand-in trainer has no data manager: pass the test loader")
+            for m in self._models.values():
+                m.eval()
+            correct, total = None, 0
+            for batch in data_loader:
+                input, label = self.parse_batch_test(batch)
+                output = self.model_inference(input)
+                hits = (output.argmax(dim=1) == label).sum()
+                correct = hits if correct is None else correct + hits
+                total += int(label.shape[0])
+            acc = 100.0 * float(correct) / max(total, 1) if correct is not None else 0.0
+            self.last_test_result = {"accuracy": acc, "error_rate": 100.0 - acc, "total": total}
+            return acc
+
         def save_model(self, epoch, directory, is_best=False, val_result=None, model_name=""):
             """Dassl's checkpoint layout (TrainerBase.save_model / dassl.utils.save_checkpoint):
             <directory>/<model name>/model.pth.tar-<epoch + 1> holding {"state_dict", "epoch", "optimizer",
@@ -317,6 +343,7 @@ class CustomCLIP(nn.Module):
         device = self.logit_scale.device if host_batch else image.device
         eng = self._engine(device)
         self._register_classes(device)
+        self._cached_text_features = None  # the parameters are about to change: evaluation recomputes them
         world = mdist.world_size() if self.shard_classes else 1
         P_v, P_t = self.prompt_stacks()
         n_cls = self.mudpt_prompt_learner.n_cls
@@ -493,6 +520,19 @@ class MuDPT(TrainerX):
         input = batch["img"].to(self.device)
         label = batch["label"].to(self.device)
         return input, label
+
+    def parse_batch_test(self, batch):
+        """Dassl TrainerX.parse_batch_test; raw 8-bit images go through the evaluation transform
+        (Resize(max(size)) -> CenterCrop -> normalize) on the GPU."""
+        if "img" not in batch:
+            return self.input_transform(False)(batch["img_u8"]), batch["label"].to(self.device)
+        return batch["img"].to(self.device), batch["label"].to(self.device)
+
+    def model_inference(self, input):
+        """Dassl TrainerX.model_inference (`self.model(input)` in the reference, which recomputes the text tower for
+        every test batch): the text features depend only on parameters, so they are computed once per evaluation
+         -- the cache is dropped by every training step."""
+        return self.model.inference(input)
 
     def input_transform(self, is_train: bool = True):
         """GpuTransform built from cfg.INPUT (mudpt_b200/input_pipeline.py), one per mode, created on first use."""

@@ -221,3 +221,30 @@ def test_checkpoint_round_trip_dassl_layout(tmp_path):
     import pytest
     with pytest.raises(FileNotFoundError):
         b.load_model(str(tmp_path), epoch=99)
+
+
+def test_trainer_test_loop_uses_cached_text_features():
+    """Dassl-shaped test() -> parse_batch_test -> model_inference on cached text features, top-1 accuracy
+    accumulated on the device; a training step drops the cache."""
+    from mudpt_b200.trainers import mudpt as M
+    c = gu.load("tiny_a")
+    model, cfg = gu.build_model(c, "cpu")
+    fake_engine.attach(model, c)
+    t = M.MuDPT.__new__(M.MuDPT)
+    M.TrainerX.__init__(t, None, None, "cpu")
+    t.cfg, t.model = cfg, model
+    t.optim = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.01)
+    t.sched = None
+    t.register_model("MultimodalDeepPromptTuning", model, t.optim, t.sched)
+    golden_pred = torch.from_numpy(c["golden"]["logits"]).argmax(1)
+    labels = golden_pred.clone()
+    labels[0] = (labels[0] + 1) % len(c["classnames"])  # one deliberate miss
+    loader = [{"img": c["image"][i:i + 1], "label": labels[i:i + 1]} for i in range(c["batch"])]
+    acc = t.test(loader)
+    assert acc == pytest.approx(100.0 * (c["batch"] - 1) / c["batch"])
+    assert t.last_test_result["total"] == c["batch"]
+    assert model._cached_text_features is not None
+    model.forward_backward(c["image"], c["labels"])
+    assert model._cached_text_features is None
+    with pytest.raises(ValueError):
+        t.test()

@@ -253,3 +253,29 @@ def test_gpu_trainer_takes_raw_images():
     for (n1, p1), (_, p2) in zip(t1.model.named_parameters(), t2.model.named_parameters()):
         if p1.requires_grad:
             assert torch.equal(p1, p2), n1
+
+
+@pytest.mark.gpu
+def test_gpu_trainer_evaluates_raw_images():
+    """test() over raw 8-bit images: evaluation transform on the GPU (bit-identical to the oracle), logits from the
+    cached text features, accuracy accumulated on the device."""
+    from mudpt_b200.trainers import mudpt as M
+    from tests import golden_util as gu
+    case = gu.load("tiny_d")
+    R = case["arch"].image_resolution
+    model, cfg = gu.build_model(case, "cuda")
+    cfg.INPUT["PIXEL_MEAN"], cfg.INPUT["PIXEL_STD"] = list(ic.MEAN), list(ic.STD)
+    t = M.MuDPT.__new__(M.MuDPT)
+    M.TrainerX.__init__(t, None, None, torch.device("cuda"))
+    t.cfg, t.model = cfg, model
+    t.register_model("MultimodalDeepPromptTuning", model, None, None)
+    raws = [ic.make_image(500 + i, h, w) for i, (h, w) in enumerate([(70, 90), (R, R), (120, 64), (55, 200), (99, 98)])]
+    ref = torch.from_numpy(np.stack([ipo.eval_transform(a, (R, R), ic.MEAN, ic.STD) for a in raws])).cuda()
+    with torch.no_grad():
+        full = model(ref)  # full forward on the oracle's batch
+    labels = full.argmax(1).cpu()
+    labels[2] = (labels[2] + 1) % full.shape[1]
+    loader = [{"img_u8": [torch.from_numpy(a) for a in raws[i:i + 2]], "label": labels[i:i + 2]} for i in range(0, 5, 2)]
+    image, _ = t.parse_batch_test(loader[0])
+    assert torch.equal(image, ref[:2])
+    assert t.test(loader) == pytest.approx(80.0)
