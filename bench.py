@@ -457,10 +457,18 @@ def main():
     ap.add_argument("--classes", type=int, default=N_CLASSES, help="--quick only: classes on this GPU")
     ap.add_argument("--no-overlap", action="store_true", help="--quick only: towers on one stream")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version
+    # banner to fd 1 at the first communicator): point fd 1 at stderr for the run and keep the real stdout
+    # for the JSON line(s) this script prints itself.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
