@@ -86,8 +86,11 @@ def group_gemm(res):
     shapes = [(128, 128, 64), (128, 128, 256), (128, 256, 64), (256, 512, 128), (6368, 2304, 768), (6368, 768, 3072),
               (900, 1536, 512), (77, 64, 64), (300, 136, 200), (21, 384, 128), (784, 768, 592),
               # strip-scheduler stress: ragged N (not a multiple of 32 / 256), M tails in both tile engines
-              (4000, 1544, 256), (9625, 520, 128), (513, 96, 64), (2500, 40, 64)]
-    all_modes = [(128, 128, 64), (6368, 2304, 768), (300, 136, 200), (4000, 1544, 256), (9625, 520, 128)]
+              (4000, 1544, 256), (9625, 520, 128), (513, 96, 64), (2500, 40, 64),
+              # long-K N = d shapes whose tile count is just above whole waves (75 / 76 pair tiles on 74 pairs)
+              (9625, 512, 2048), (6368, 768, 2304), (19000, 768, 1024)]
+    all_modes = [(128, 128, 64), (6368, 2304, 768), (300, 136, 200), (4000, 1544, 256), (9625, 520, 128),
+                 (9625, 512, 2048), (6368, 768, 3072)]
     for (M, N, K) in shapes:
         for mode in ([0, 1, 2, 3, 4] if (M, N, K) in all_modes else [0]):
             key = f"gemm_{M}x{N}x{K}_m{mode}"
