@@ -52,7 +52,8 @@ struct Tower {
   std::vector<float*> lse;
   // transients
   bf16 *a_buf = nullptr, *g_buf = nullptr, *dh_buf = nullptr, *do_buf = nullptr, *dqkv_buf = nullptr, *dx_bf16 = nullptr;
-  float *dx = nullptr, *dsum = nullptr, *splice_ws = nullptr, *head_ws = nullptr;  // head_ws: [rows] floats >= S*d
+  float *dx = nullptr, *dsum = nullptr, *splice_ws = nullptr, *head_ws = nullptr;  // head_ws: feature_head_workspace_floats(S, d, e)
+  size_t head_cap = 0;  // floats in head_ws (sized by the sequence count, which may grow while rows = S * L shrinks)
   bool fwd_done = false;
   int first_splice = 0;  // 0: layer 0 splices prompts[0]; 1: layer-0 rows kept as given
 };
@@ -145,6 +146,11 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
   const size_t rows = static_cast<size_t>(S) * L;
   t.S = S;
   t.L = L;
+  const size_t head_need = feature_head_workspace_floats(S, t.d, h->cfg.embed_dim);
+  if (head_need > t.head_cap) {  // gathered CLS / EOT rows of the feature head + split-K partials
+    CUDA_OK(h, dev_alloc(h, &t.head_ws, head_need));
+    t.head_cap = head_need;
+  }
   if (rows <= t.cap_rows) return 0;
   // grow: leak-free enough for a workspace that is sized once per configuration (old buffers stay
   // registered in h->allocs and are released in mudpt_destroy)
@@ -173,7 +179,6 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
   CUDA_OK(h, dev_alloc(h, &t.dx, rows * d));
   CUDA_OK(h, dev_alloc(h, &t.dsum, rows * t.H));
   if (!t.splice_ws) CUDA_OK(h, dev_alloc(h, &t.splice_ws, splice_bwd_workspace_floats(t.n_ctx > 0 ? t.n_ctx : 1, t.d)));
-  CUDA_OK(h, dev_alloc(h, &t.head_ws, static_cast<size_t>(S) * d));  // gathered CLS / EOT rows of the feature head
   t.cap_rows = rows;
   t.fwd_done = false;
   return 0;

@@ -19,9 +19,18 @@ namespace mudpt {
 // ------------------------------------------------------------------ small fp32 GEMM
 // C[m, n] = alpha * sum_k A(m, k) * B(k, n),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn],
 // C row-major [M, N].  64 x 64 tile per block, 256 threads, 4 x 4 outputs per thread, k-step 16.
+// Split-K: the head GEMMs are tiny (32 x 512 x 768 ...) and sit on the critical path between the towers'
+// forward and backward, where nothing else can run; 8-16 CTAs walking K in 16-wide slices were pure latency
+// (33-44 us each).  With `partial` != nullptr, blockIdx.z owns K-slice [z * kchunk, (z + 1) * kchunk) and writes
+// its unscaled tile to partial[z][M][N]; splitk_reduce_kernel adds the slices in order.  The slice width is a
+// constant (never a function of M), so a row's result does not depend on how many rows the call has: class
+// shards stay bit-identical to the unsharded tower.
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                             float* __restrict__ C, int M, int N, int K, long sam, long sak,
-                                                            long sbk, long sbn, float alpha) {
+                                                            long sbk, long sbn, float alpha, float* __restrict__ partial,
+                                                            int kchunk) {
+  const int k_begin = blockIdx.z * kchunk;
+  const int k_end = min(K, k_begin + kchunk);
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -44,9 +53,9 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
       if (sak == 1) { ak = idx & 15; am = idx >> 4; } else { am = idx & 63; ak = idx >> 6; }
       if (sbn == 1) { bn = idx & 63; bk = idx >> 6; } else { bk = idx & 15; bn = idx >> 4; }
       const int gm = m0 + am, gk = k0 + ak;
-      ra[i] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
+      ra[i] = (gm < M && gk < k_end) ? A[gm * sam + gk * sak] : 0.f;
       const int gn = n0 + bn, gk2 = k0 + bk;
-      rb[i] = (gn < N && gk2 < K) ? B[gk2 * sbk + gn * sbn] : 0.f;
+      rb[i] = (gn < N && gk2 < k_end) ? B[gk2 * sbk + gn * sbn] : 0.f;
     }
   };
   auto stash = [&]() {
@@ -60,11 +69,11 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
       Bs[bk][bn] = rb[i];
     }
   };
-  fetch(0);
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
     stash();
     __syncthreads();
-    if (k0 + 16 < K) fetch(k0 + 16);
+    if (k0 + 16 < k_end) fetch(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       float a[4], b[4];
@@ -86,15 +95,44 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;
-      if (gn < N) C[static_cast<size_t>(gm) * N + gn] = alpha * acc[i][j];
+      if (gn >= N) continue;
+      if (partial != nullptr) partial[(static_cast<size_t>(blockIdx.z) * M + gm) * N + gn] = acc[i][j];
+      else C[static_cast<size_t>(gm) * N + gn] = alpha * acc[i][j];
     }
   }
 }
 
+// C[i] = alpha * (((p[0][i] + p[1][i]) + p[2][i]) + ...): fixed order, deterministic
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, size_t mn,
+                                                            int slices, float alpha) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= mn) return;
+  float s = partial[i];
+  for (int z = 1; z < slices; ++z) s += partial[static_cast<size_t>(z) * mn + i];
+  C[i] = alpha * s;
+}
+
+static constexpr int kSplitChunk = 64;  // K-slice of one CTA (4 k-steps)
+static int splitk_slices(int K) { return K >= 2 * kSplitChunk ? (K + kSplitChunk - 1) / kSplitChunk : 1; }
+static size_t sgemm_scratch_floats(int M, int N, int K) {
+  const int z = splitk_slices(K);
+  return z > 1 ? static_cast<size_t>(z) * M * N : 0;
+}
+
+// scratch: sgemm_scratch_floats(M, N, K) floats (may be nullptr when that is 0)
 static void sgemm(const float* A, const float* B, float* C, int M, int N, int K, long sam, long sak, long sbk, long sbn,
-                  float alpha, cudaStream_t st) {
-  sgemm_strided_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, alpha);
-  count_launch(1);
+                  float alpha, float* scratch, cudaStream_t st) {
+  const int z = scratch != nullptr ? splitk_slices(K) : 1;
+  const dim3 grid((N + 63) / 64, (M + 63) / 64, z);
+  if (z == 1) {
+    sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, alpha, nullptr, K);
+    count_launch(1);
+    return;
+  }
+  sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, alpha, scratch, kSplitChunk);
+  const size_t mn = static_cast<size_t>(M) * N;
+  splitk_reduce_kernel<<<static_cast<unsigned>((mn + 255) / 256), 256, 0, st>>>(scratch, C, mn, z, alpha);
+  count_launch(2);
 }
 
 // ------------------------------------------------------------------ feature head
@@ -149,22 +187,25 @@ __global__ void __launch_bounds__(256) scatter_ln_bwd_kernel(const float* __rest
   }
 }
 
-size_t feature_head_workspace_floats(int S, int d) { return static_cast<size_t>(S) * d; }
+size_t feature_head_workspace_floats(int S, int d, int e) {
+  const size_t a = sgemm_scratch_floats(S, e, d), b = sgemm_scratch_floats(S, d, e);
+  return static_cast<size_t>(S) * d + (a > b ? a : b);
+}
 
-// proj is [d, e] row-major (x @ proj).  ws: S*d floats.
+// proj is [d, e] row-major (x @ proj).  ws: feature_head_workspace_floats(S, d, e) floats.
 const char* feature_head_fwd(const float* x, const int* rows, const float* gamma, const float* beta, const float* proj,
                              float* f, float* ws, int S, int L, int d, int e, float eps, cudaStream_t stream) {
   if (S <= 0) return nullptr;
   gather_ln_kernel<<<(S + 7) / 8, 256, 0, stream>>>(x, rows, gamma, beta, ws, S, L, d, eps);
   count_launch(1);
-  sgemm(ws, proj, f, S, e, d, d, 1, e, 1, 1.f, stream);  // f = y @ proj
+  sgemm(ws, proj, f, S, e, d, d, 1, e, 1, 1.f, ws + static_cast<size_t>(S) * d, stream);  // f = y @ proj
   return launch_status("feature head fwd launch failed");
 }
 
 const char* feature_head_bwd(const float* df, const float* x, const int* rows, const float* gamma, const float* proj,
                              float* dx, bf16* dx_bf16, float* ws, int S, int L, int d, int e, float eps, cudaStream_t stream) {
   if (S <= 0) return nullptr;
-  sgemm(df, proj, ws, S, d, e, e, 1, 1, e, 1.f, stream);  // g = df @ proj^T : B(k = j, n = c) = proj[c*e + j]
+  sgemm(df, proj, ws, S, d, e, e, 1, 1, e, 1.f, ws + static_cast<size_t>(S) * d, stream);  // g = df @ proj^T : B(k = j, n = c) = proj[c*e + j]
   scatter_ln_bwd_kernel<<<(S + 7) / 8, 256, 0, stream>>>(ws, x, rows, gamma, dx, dx_bf16, S, L, d, eps);
   count_launch(1);
   return launch_status("feature head bwd launch failed");
@@ -229,8 +270,15 @@ __global__ void sum_scale_kernel(const float* __restrict__ v, float* __restrict_
   if (threadIdx.x == 0) out[0] = s * scale;
 }
 
-size_t logits_head_workspace_floats(int B, int C, int e) {
+static size_t logits_head_fixed_floats(int B, int C, int e) {
   return static_cast<size_t>(B) * e + static_cast<size_t>(C) * e + B + C + B + static_cast<size_t>(B) * C;
+}
+size_t logits_head_workspace_floats(int B, int C, int e) {
+  size_t sc = sgemm_scratch_floats(B, C, e);
+  const size_t s2 = sgemm_scratch_floats(B, e, C), s3 = sgemm_scratch_floats(C, e, B);
+  sc = s2 > sc ? s2 : sc;
+  sc = s3 > sc ? s3 : sc;
+  return logits_head_fixed_floats(B, C, e) + sc;
 }
 
 const char* logits_head(const float* f_img, const float* f_txt, const long long* labels, float scale, int B, int C, int e,
@@ -244,21 +292,22 @@ const char* logits_head(const float* f_img, const float* f_txt, const long long*
   float* inv_t = inv_i + B;
   float* loss_rows = inv_t + C;
   float* dlogits = loss_rows + B;
+  float* scratch = ws + logits_head_fixed_floats(B, C, e);  // split-K partials of the three small GEMMs
   l2norm_kernel<<<(B + 7) / 8, 256, 0, stream>>>(f_img, in_hat, inv_i, B, e);
   l2norm_kernel<<<(C + 7) / 8, 256, 0, stream>>>(f_txt, tn_hat, inv_t, C, e);
   count_launch(2);
-  sgemm(in_hat, tn_hat, logits, B, C, e, e, 1, 1, e, scale, stream);  // logits = scale * i_hat @ t_hat^T
+  sgemm(in_hat, tn_hat, logits, B, C, e, e, 1, 1, e, scale, scratch, stream);  // logits = scale * i_hat @ t_hat^T
   if (labels != nullptr) {
     ce_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(logits, labels, loss_rows, dlogits, B, C, inv_global_batch);
     sum_scale_kernel<<<1, 32, 0, stream>>>(loss_rows, loss, B, inv_global_batch);
     count_launch(2);
     if (d_f_img) {
-      sgemm(dlogits, tn_hat, d_f_img, B, e, C, C, 1, e, 1, scale, stream);  // scale * dl @ t_hat
+      sgemm(dlogits, tn_hat, d_f_img, B, e, C, C, 1, e, 1, scale, scratch, stream);  // scale * dl @ t_hat
       normalize_bwd_kernel<<<(B + 7) / 8, 256, 0, stream>>>(d_f_img, in_hat, inv_i, B, e);
       count_launch(1);
     }
     if (d_f_txt) {
-      sgemm(dlogits, in_hat, d_f_txt, C, e, B, 1, C, e, 1, scale, stream);  // scale * dl^T @ i_hat : A(m = c, k = b) = dl[b*C + c]
+      sgemm(dlogits, in_hat, d_f_txt, C, e, B, 1, C, e, 1, scale, scratch, stream);  // scale * dl^T @ i_hat : A(m = c, k = b) = dl[b*C + c]
       normalize_bwd_kernel<<<(C + 7) / 8, 256, 0, stream>>>(d_f_txt, tn_hat, inv_t, C, e);
       count_launch(1);
     }
@@ -275,12 +324,13 @@ const char* logits_head_bwd(const float* f_img, const float* f_txt, const float*
   float* tn_hat = in_hat + static_cast<size_t>(B) * e;
   float* inv_i = tn_hat + static_cast<size_t>(C) * e;
   float* inv_t = inv_i + B;
+  float* scratch = ws + logits_head_fixed_floats(B, C, e);
   l2norm_kernel<<<(B + 7) / 8, 256, 0, stream>>>(f_img, in_hat, inv_i, B, e);
   l2norm_kernel<<<(C + 7) / 8, 256, 0, stream>>>(f_txt, tn_hat, inv_t, C, e);
   count_launch(2);
-  sgemm(dlogits, tn_hat, d_f_img, B, e, C, C, 1, e, 1, scale, stream);
+  sgemm(dlogits, tn_hat, d_f_img, B, e, C, C, 1, e, 1, scale, scratch, stream);
   normalize_bwd_kernel<<<(B + 7) / 8, 256, 0, stream>>>(d_f_img, in_hat, inv_i, B, e);
-  sgemm(dlogits, in_hat, d_f_txt, C, e, B, 1, C, e, 1, scale, stream);
+  sgemm(dlogits, in_hat, d_f_txt, C, e, B, 1, C, e, 1, scale, scratch, stream);
   normalize_bwd_kernel<<<(C + 7) / 8, 256, 0, stream>>>(d_f_txt, tn_hat, inv_t, C, e);
   count_launch(2);
   return launch_status("logits head bwd launch failed");

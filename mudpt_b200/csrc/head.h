@@ -5,8 +5,8 @@
 #include <stddef.h>
 
 namespace mudpt {
-size_t feature_head_workspace_floats(int S, int d);
-// ws: S*d floats of scratch (gathered + normalised rows / their gradient)
+size_t feature_head_workspace_floats(int S, int d, int e);
+// ws: feature_head_workspace_floats(S, d, e) floats (gathered + normalised rows / their gradient, split-K partials)
 const char* feature_head_fwd(const float* x, const int* rows, const float* gamma, const float* beta, const float* proj,
                              float* f, float* ws, int S, int L, int d, int e, float eps, cudaStream_t stream);
 const char* feature_head_bwd(const float* df, const float* x, const int* rows, const float* gamma, const float* proj,
