@@ -279,3 +279,24 @@ def test_gpu_trainer_evaluates_raw_images():
     image, _ = t.parse_batch_test(loader[0])
     assert torch.equal(image, ref[:2])
     assert t.test(loader) == pytest.approx(80.0)
+
+
+def test_oracle_resample_property_vs_pil():
+    """Property test of the pin: random sizes (incl. 1-pixel axes, x30 down-scaling, x40 up-scaling) and crop boxes,
+    the numpy restatement equals PIL.Image.resize bit for bit."""
+    Image = pytest.importorskip("PIL.Image")
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=30, deadline=None, derandomize=True)
+    @hyp.given(st.integers(1, 300), st.integers(1, 300), st.integers(1, 64), st.integers(1, 64), st.integers(0, 10 ** 6))
+    def check(H, W, oh, ow, seed):
+        rng = np.random.default_rng(seed)
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        x0, y0 = int(rng.integers(0, W)), int(rng.integers(0, H))
+        x1, y1 = int(rng.integers(x0 + 1, W + 1)), int(rng.integers(y0 + 1, H + 1))
+        crop = img[y0:y1, x0:x1]
+        ref = np.asarray(Image.fromarray(crop).resize((ow, oh), Image.BICUBIC))
+        assert np.array_equal(ipo.resample_u8(crop, ow, oh), ref)
+
+    check()
