@@ -356,12 +356,16 @@ def run_ours(args):
 
     h2d = B * 3 * 224 * 224 * 4 + B * 8
     cb = cpu_time_steps(3, 1) if world == 1 else None  # rank 0 at N=1 only (torchrun pins OMP threads to 1)
-    pipe = None
+    pipe = infer = None
     if world == 1:
         try:
             pipe = input_pipeline_bench(device, peaks)
         except Exception as e:  # an aside to the contract line: never lose the headline over it
             pipe = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            infer = inference_bench(device)
+        except Exception as e:
+            infer = {"error": f"{type(e).__name__}: {e}"}
     line = {
         "metric": METRIC, "value": gB / (full["ms"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": full["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -398,6 +402,7 @@ def run_ours(args):
         "clocks": clocks,
         "cpu_baseline": cb,
         "input_pipeline": pipe,
+        "inference_cfg3": infer,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -446,6 +451,35 @@ def input_pipeline_bench(device, peaks, batch=BATCH_PER_GPU, reps=20):
             "algorithmic_bytes": nbytes, "gbs_algorithmic": round(nbytes / (ms * 1e-3) / 1e9, 1),
             "frac_of_hbm_peak": round(nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"], 4), "l2": "flushed between launches",
             "gpu_launches_per_batch": 2}
+
+
+def inference_bench(device, batch=256, reps=10):
+    """BASELINE configs[2] beside the headline: ViT-B/16 inference with cached text features (1000 classes), batch
+    256 per GPU, images resident in HBM (two rotating batches, 308 MB > L2), CUDA events on the launch stream."""
+    import torch
+    from mudpt_b200 import synthetic as syn
+    trainer = build_trainer(device, True)
+    model = trainer.model
+    imgs = [syn.synthetic_images(batch, 224, seed=200 + i).to(device) for i in range(2)]
+    with torch.no_grad():
+        model.cache_text_features(device)
+        for i in range(3):
+            logits = model.inference(imgs[i % 2])
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            logits = model.inference(imgs[i % 2])
+        e1.record()
+        torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    flops = batch * 35.50e9  # SURVEY.md 8d: vision tower forward, reference formulation
+    out = {"workload": "MuDPT ViT-B/16 inference, cached text features, 1000 classes (BASELINE configs[2])", "batch": batch,
+           "ms_per_batch": round(ms, 3), "imgs_per_s": round(batch / (ms * 1e-3), 0),
+           "tflops_reference_formulation": round(flops / (ms * 1e-3) / 1e12, 1), "finite": bool(torch.isfinite(logits).all())}
+    del trainer, model, imgs
+    torch.cuda.empty_cache()
+    return out
 
 def main():
     ap = argparse.ArgumentParser()
