@@ -182,8 +182,7 @@ def build_trainer(device, truncate: bool, n_classes: int = N_CLASSES):
     import torch
     from mudpt_b200 import synthetic as syn
     from mudpt_b200.trainers import mudpt as M
-    from tests.golden_util import make_cfg
-    cfg = make_cfg(N_CTX, DEPTH, "a photo of a", 224, "ViT-B/16")
+    cfg = syn.make_cfg(N_CTX, DEPTH, "a photo of a", 224, "ViT-B/16")
     arch = syn.ARCHS["ViT-B/16"]
     torch.manual_seed(0)  # prompt parameters are torch-initialised: identical replicas on every rank
     clip_model = M.clip.CLIP(*arch.astuple(), cfg).float()

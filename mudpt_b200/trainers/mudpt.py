@@ -282,6 +282,14 @@ class CustomCLIP(nn.Module):
     def _engine(self, device):
         return self._clip_ref[0].engine(device)
 
+    def invalidate_cache(self):
+        """Drop the evaluation-time text-feature cache (and the class set resident in the native text tower):
+        call after anything that changes parameters outside forward_backward (load_state_dict, a manual update)."""
+        self._cached_text_features = None
+        eng = getattr(self._clip_ref[0], "_engine", None)
+        if eng is not None:
+            eng.class_key = None
+
     def _class_range(self) -> Tuple[int, int]:
         n = self.mudpt_prompt_learner.n_cls
         if self.shard_classes and mdist.world_size() > 1:
@@ -326,6 +334,8 @@ class CustomCLIP(nn.Module):
         """image [B, 3, H, W] -> logits [B, C] (trainers/mudpt.py:170-184), differentiable w.r.t. the prompts."""
         device = image.device
         eng = self._engine(device)
+        if self.training or torch.is_grad_enabled():
+            self._cached_text_features = None  # an optimizer step may follow: evaluation must recompute the text features
         self._register_classes(device)
         P_v, P_t = self.prompt_stacks()
         image_features = VisionTowerFn.apply(eng, image.type(self.dtype), P_v)
@@ -503,8 +513,22 @@ class MuDPT(TrainerX):
         else:
             image, label = self.parse_batch_train(batch)
             output = self.model(image)
+            world = mdist.world_size() if getattr(self.model, "shard_classes", False) else 1
             loss = F.cross_entropy(output, label)
-            self.model_backward_and_update(loss)
+            if world > 1:
+                # class-sharded text tower + data-parallel images: the update must be the GLOBAL-batch mean
+                # (nn.DataParallel semantics, trainers/mudpt.py:230-233), summed over ranks before the step
+                for o in self._optims.values():
+                    o.zero_grad()
+                (loss / world).backward()
+                mdist.all_reduce_grads([p for p in self.model.parameters() if p.requires_grad])
+                loss = mdist.all_reduce_sum(loss.detach()) / world
+                if not torch.isfinite(loss).all():
+                    raise FloatingPointError("Loss is infinite or NaN!")
+                for o in self._optims.values():
+                    o.step()
+            else:
+                self.model_backward_and_update(loss)
         loss_summary = {"loss": loss.item()}
         if (self.batch_idx + 1) == self.num_batches:
             self.update_lr()
@@ -557,9 +581,12 @@ class MuDPT(TrainerX):
             checkpoint = load_checkpoint(model_path)
             state_dict = checkpoint["state_dict"]
             epoch = checkpoint["epoch"]
-            # class names may differ (base -> new): ignore the fixed token vectors
-            state_dict.pop("mudpt_prompt_learner.token_prefix", None)
-            state_dict.pop("mudpt_prompt_learner.token_suffix", None)
+            # class names may differ (base -> new): ignore the fixed token vectors, whatever the learner is called
+            # (mudpt_ / umudpt_ / uumudpt_prompt_learner: trainers/mudpt.py:294-298, umudpt.py:337-341, uumudpt.py:343-347)
+            for key in [k for k in state_dict
+                        if k.endswith("prompt_learner.token_prefix") or k.endswith("prompt_learner.token_suffix")]:
+                del state_dict[key]
             print('Loading weights to {} from "{}" (epoch = {})'.format(name, model_path, epoch))
             self._models[name].load_state_dict(state_dict, strict=False)
             self._models[name]._clip_ref[0].refresh_engine_weights()
+            self._models[name].invalidate_cache()  # cached text features / resident class set belong to the old weights

@@ -31,21 +31,7 @@ def load(name):
     return case
 
 
-def make_cfg(n_ctx, depth, ctx_init, size, arch_name="ViT-B/16"):
-    """The subset of the yacs tree the hot path reads (train.py:114-119); plain attribute dicts."""
-    class N(dict):
-        def __getattr__(self, k):
-            try:
-                return self[k]
-            except KeyError as e:
-                raise AttributeError(k) from e
-        __setattr__ = dict.__setitem__
-    cfg = N()
-    cfg.TRAINER = N(NAME="MuDPT", MUDPT=N(N_CTX=n_ctx, CTX_INIT=ctx_init, DEEP_PROMPT_DEPTH=depth, PREC="fp32"))
-    cfg.INPUT = N(SIZE=(size, size))
-    cfg.MODEL = N(BACKBONE=N(NAME=arch_name, PATH=""), INIT_WEIGHTS="")
-    cfg.OPTIM = N(LR=0.0025, MAX_EPOCH=10)
-    return cfg
+make_cfg = syn.make_cfg  # the yacs subset the hot path reads lives with the product (bench.py uses it too)
 
 
 def build_model(case, device="cuda"):

@@ -248,3 +248,49 @@ def test_trainer_test_loop_uses_cached_text_features():
     assert model._cached_text_features is None
     with pytest.raises(ValueError):
         t.test()
+
+
+@pytest.mark.parametrize("variant", ["UMuDPT", "UUMuDPT"])
+@pytest.mark.parametrize("new_names", [["dog", "cat", "bird"], ["dog", "cat", "bird", "fish"]])
+def test_variant_checkpoint_reload_with_other_class_names(tmp_path, variant, new_names):
+    """Base -> new evaluation for the UMuDPT / UUMuDPT trainers: their checkpoints store the class-name token vectors
+    under `umudpt_prompt_learner.*` / `uumudpt_prompt_learner.*` (trainers/umudpt.py:337-341, uumudpt.py:343-347);
+    load_model must drop them whatever the class count (equal count: no silent overwrite; unequal: no size error)."""
+    import importlib
+    from mudpt_b200 import clip, synthetic as syn
+    from mudpt_b200.trainers import mudpt as M
+    mod = importlib.import_module("mudpt_b200.trainers." + variant.lower())
+    arch = syn.ARCHS["tiny"] if "tiny" in syn.ARCHS else gu.load("tiny_c")["arch"]
+
+    def make(classnames):
+        cfg = gu.make_cfg(2, 2, "", arch.image_resolution)
+        cfg.TRAINER["NAME"] = variant
+        cfg.TRAINER[variant.upper()] = type(cfg)(N_CTX=2, CTX_INIT="", DEEP_PROMPT_DEPTH=2, PREC="fp32")
+        clip_model = clip.CLIP(*arch.astuple(), cfg).float()
+        t = getattr(mod, variant).__new__(getattr(mod, variant))
+        M.TrainerX.__init__(t, None, None, "cpu")
+        t.cfg = cfg
+        t.model = mod.CustomCLIP(cfg, classnames, clip_model, tokenizer=syn.synthetic_tokenize)
+        t.optim = torch.optim.SGD([p for p in t.model.parameters() if p.requires_grad], lr=0.1)
+        t.sched = None
+        t.register_model(t.MODEL_NAME, t.model, t.optim, t.sched)
+        return t
+
+    a = make(["class 0", "class 1", "class 2"])
+    with torch.no_grad():
+        for p in a.model.parameters():
+            if p.requires_grad:
+                p.add_(torch.randn_like(p))
+    a.save_model(0, str(tmp_path))
+    ck = torch.load(str(tmp_path / a.MODEL_NAME / "model.pth.tar-1"), map_location="cpu", weights_only=False)
+    assert any(k.endswith("prompt_learner.token_prefix") and not k.startswith("mudpt_") for k in ck["state_dict"])
+    b = make(new_names)
+    pl = b.model.mudpt_prompt_learner
+    prefix, suffix = pl.token_prefix.clone(), pl.token_suffix.clone()
+    b.model._cached_text_features = torch.zeros(1)  # a stale evaluation cache from before the load
+    b.load_model(str(tmp_path), epoch=1)
+    assert torch.equal(pl.token_prefix, prefix) and torch.equal(pl.token_suffix, suffix)
+    assert b.model._cached_text_features is None
+    for (n, p), (_, q) in zip(a.model.named_parameters(), b.model.named_parameters()):
+        if p.requires_grad:
+            assert torch.equal(p, q), n
