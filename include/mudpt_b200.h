@@ -62,6 +62,13 @@ const char* mudpt_global_last_error(void);
 
 int mudpt_create(const mudpt_config* cfg, mudpt_handle** out);
 void mudpt_destroy(mudpt_handle* h);
+/* Options (name, integer value):
+ *   "ln_fused"  1 (default; env MUDPT_LN_FUSED) LayerNorm folded into the GEMM epilogues, 0 stand-alone LN kernels
+ *               (for checkpoints whose residual rows have |mean| >> std: the fused form feeds bf16(x), not
+ *               bf16(LN(x)), to the tensor cores)
+ *   "prune"     1 (default; env MUDPT_PRUNE) exact work skipping: the last block's out-proj / MLP (forward and
+ *               dgrad) run on the CLS / EOT rows only (clip/model.py:548, trainers/mudpt.py:154), 0 = every row */
+int mudpt_set_option(mudpt_handle* h, const char* name, int32_t value);
 const char* mudpt_last_error(mudpt_handle* h);
 
 /* Frozen CLIP weights, one call per tensor, `name` = key of the reference CLIP.state_dict()
@@ -132,6 +139,52 @@ int mudpt_attention_backward(const uint16_t* qkv, const uint16_t* o, const uint1
 int mudpt_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, int32_t K, int32_t mode, void* out0,
                     void* out1, const float* bias, const float* resid, const void* aux, int32_t ldc, int32_t patch_np,
                     int32_t patch_L, void* stream);
+/* The same GEMM with every epilogue the towers use, incl. the LayerNorm-fused forms (clip/model.py:164-170 folded
+ * into :273 / :299-300 and their dgrads).  Modes 0-5 as above, plus
+ *   7  bf16 = rstd*(acc - mean*colsum) + bias            LN1 + in-proj   (A = bf16 LN input, B = gamma-folded weight)
+ *   8  out0 = h = (same), out1 = QuickGELU(h)            LN2 + c_fc
+ *   9  f32 = acc + bias + resid; out2 = bf16 copy; stats_out[row, col/64] = (sum, M2) of the new row; rows
+ *      (r % splice_L) in [splice_row0, splice_row0 + splice_n) take splice_prompt (deep-prompt splice, :281-297)
+ *   10 f32 = resid + rstd*(acc - c1 - xhat*c2) (+ bf16 copy): LayerNorm dgrad in the dgrad GEMM's epilogue,
+ *      c1 = sum_p dots[row,p].x / ln_width, c2 = sum_p dots[row,p].y / ln_width, xhat from x2 and ln_stats
+ *   11 mode 4 + dots_out[row, col/span] = (sum dh*colsum, sum dh*(h - bias')) with sb = interleaved (colsum, bias')
+ * stream_k: 0 = whole tiles only, 1 = cut the tail wave into k-block ranges whenever possible, -1 = cost model. */
+typedef struct mudpt_gemm_epilogue {
+  int32_t mode, ldc;
+  void* out0;
+  void* out1;
+  void* out2;
+  const float* bias;
+  const float* resid;
+  const void* aux;
+  const float* ln_stats;   /* [M, ln_parts, 2] */
+  int32_t ln_parts, ln_width;
+  float ln_eps;
+  int32_t dot_parts;
+  const float* colsum;
+  float* stats_out;        /* [M, N/64, 2] */
+  const float* splice_prompt;
+  int32_t splice_row0, splice_n, splice_L, stream_k;
+  const void* x2;          /* bf16 [M, ldc] */
+  const float* dots;       /* [M, dot_parts, 2] */
+  const float* sb;         /* [N, 2] */
+  float* dots_out;         /* [M, N/mudpt_gemm_dots_span(N), 2] */
+} mudpt_gemm_epilogue;
+int mudpt_gemm_fused(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, int32_t K, const mudpt_gemm_epilogue* ep,
+                     void* stream);
+int32_t mudpt_gemm_dots_span(int32_t N);
+/* xb = bf16(x), stats[row, p] = (sum, M2 about the partial mean) of columns [64p, 64p+64): the form in which the
+ * fused-LayerNorm GEMMs take their LN input */
+int mudpt_rowstats(const float* x, uint16_t* xb, float* stats, int32_t rows, int32_t width, void* stream);
+/* W [N, K], gamma/beta [K], bias [N] -> W' = bf16(W gamma) [N, K] and its transpose [K, N], bias' = bias + W beta,
+ * colsum[n] = sum_k W'[n,k], sb = interleaved (colsum, bias') */
+int mudpt_fold_layernorm(const float* W, const float* gamma, const float* beta, const float* bias, uint16_t* Wl,
+                         uint16_t* Wlt, float* bias_l, float* colsum, float* sb, int32_t N, int32_t K, void* stream);
+/* attention backward that also emits the row dots of dqkv for the fused LayerNorm backward of the in-proj:
+ * ln_sb [3*width, 2] = (colsum, bias'), ln_dots [S*L, 3*H, 2] */
+int mudpt_attention_backward_dots(const uint16_t* qkv, const uint16_t* o, const uint16_t* d_o, const float* lse2,
+                                  float* dsum_scratch, uint16_t* dqkv, int32_t S, int32_t L, int32_t H, int32_t causal,
+                                  const float* ln_sb, float* ln_dots, void* stream);
 int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream);
 int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream);
 

@@ -45,6 +45,14 @@ SIGNATURES = {
                                            C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "mudpt_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "mudpt_gemm_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mudpt_gemm_dots_span": (C.c_int32, [C.c_int32]),
+    "mudpt_rowstats": (C.c_int, [c_f32p, C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
+    "mudpt_fold_layernorm": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, c_f32p, c_f32p, c_f32p,
+                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "mudpt_attention_backward_dots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int32,
+                                                C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
     "mudpt_im2col": (C.c_int, [c_f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_cast_bf16": (C.c_int, [c_f32p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mudpt_sgd_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
@@ -65,6 +73,16 @@ class Config(C.Structure):
         "embed_dim", "image_resolution", "vision_layers", "vision_width", "vision_patch_size",
         "context_length", "transformer_width", "transformer_heads", "transformer_layers",
         "n_ctx", "prompt_depth", "device")]
+
+
+class GemmEpilogue(C.Structure):
+    """mudpt_gemm_epilogue (include/mudpt_b200.h): every epilogue of the tcgen05 GEMM, for tests and profiling."""
+    _fields_ = [("mode", C.c_int32), ("ldc", C.c_int32), ("out0", C.c_void_p), ("out1", C.c_void_p), ("out2", C.c_void_p),
+                ("bias", C.c_void_p), ("resid", C.c_void_p), ("aux", C.c_void_p), ("ln_stats", C.c_void_p),
+                ("ln_parts", C.c_int32), ("ln_width", C.c_int32), ("ln_eps", C.c_float), ("dot_parts", C.c_int32),
+                ("colsum", C.c_void_p), ("stats_out", C.c_void_p), ("splice_prompt", C.c_void_p),
+                ("splice_row0", C.c_int32), ("splice_n", C.c_int32), ("splice_L", C.c_int32), ("stream_k", C.c_int32),
+                ("x2", C.c_void_p), ("dots", C.c_void_p), ("sb", C.c_void_p), ("dots_out", C.c_void_p)]
 
 
 def library_path() -> str:

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -36,6 +37,12 @@ struct Layer {
   bf16 *w_fc = nullptr, *w_fc_t = nullptr, *w_pr = nullptr, *w_pr_t = nullptr;
   float *b_in = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_pr = nullptr;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  // LayerNorm folded into the Linear that follows it (rowops.cu fold_layernorm): fp32 sources kept for re-folding,
+  // folded bf16 weight (+ transposed), folded bias, column sums, interleaved (colsum, bias')
+  float *w_in_f32 = nullptr, *w_fc_f32 = nullptr;
+  bf16 *w_in_ln = nullptr, *w_in_t_ln = nullptr, *w_fc_ln = nullptr, *w_fc_t_ln = nullptr;
+  float *b_in_ln = nullptr, *b_fc_ln = nullptr, *cs_in = nullptr, *cs_fc = nullptr;
+  float2 *sb_in = nullptr, *sb_fc = nullptr;
   int have = 0;  // bit per tensor
 };
 
@@ -46,15 +53,24 @@ struct Tower {
   int S = 0;        // current sequences
   size_t cap_rows = 0;
   std::vector<Layer> lw;
+  bool fold_dirty = true;  // a tensor that enters the LayerNorm folding changed since the last fold
   // saved activations, per layer
   std::vector<float*> x_in, x_mid;
   std::vector<bf16*> qkv, o, h;
   std::vector<float*> lse;
+  // fused LayerNorm: bf16 copies of the LN inputs (GEMM A operands) + their per-64-column partial statistics
+  std::vector<bf16*> xb_in, xb_mid;
+  std::vector<float2*> st_in, st_mid;
+  float2* dots = nullptr;  // row dots for the fused LayerNorm backward [rows, dot_cap]
+  int dot_cap = 0;
   // transients
   bf16 *a_buf = nullptr, *g_buf = nullptr, *dh_buf = nullptr, *do_buf = nullptr, *dqkv_buf = nullptr, *dx_bf16 = nullptr;
   float *dx = nullptr, *dsum = nullptr, *splice_ws = nullptr, *head_ws = nullptr;  // head_ws: feature_head_workspace_floats(S, d, e)
   size_t head_cap = 0;  // floats in head_ws (sized by the sequence count, which may grow while rows = S * L shrinks)
+  std::vector<void*> ws_allocs;  // everything sized by cap_rows: released when the tower outgrows it
+  GemmWorkspace gws;             // stream-K scratch of this tower's stream
   bool fwd_done = false;
+  bool fwd_fused = false;  // the saved activations belong to the fused-LayerNorm formulation
   int first_splice = 0;  // 0: layer 0 splices prompts[0]; 1: layer-0 rows kept as given
 };
 
@@ -94,6 +110,12 @@ struct mudpt_handle {
   size_t head_ws_cap = 0;
   std::vector<void*> allocs;
   long long launches_at_create = 0;
+  // options (mudpt_set_option): LayerNorm folded into the GEMMs (default) or the stand-alone LN kernels -- the
+  // fallback for checkpoints whose residual stream has a row mean far above its spread (bf16(x) instead of
+  // bf16(LN(x)) as the GEMM operand would lose the signal there)
+  bool ln_fused = true;
+  // exact work skipping: the last block's out-proj / MLP on the CLS / EOT rows only
+  bool prune = true;
 };
 
 namespace {
@@ -132,13 +154,18 @@ int fail(mudpt_handle* h, const char* fmt, ...) {
   } while (0)
 
 template <typename T>
-cudaError_t dev_alloc(mudpt_handle* h, T** p, size_t n) {
+cudaError_t dev_alloc(mudpt_handle* h, T** p, size_t n, std::vector<void*>* group = nullptr) {
   void* q = nullptr;
   cudaError_t c = cudaMalloc(&q, n * sizeof(T) + 256);
   if (c != cudaSuccess) return c;
-  h->allocs.push_back(q);
+  (group ? *group : h->allocs).push_back(q);
   *p = reinterpret_cast<T*>(q);
   return cudaSuccess;
+}
+
+bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) != 0 : dflt;
 }
 
 // (re)allocate the activation workspace of a tower for S sequences of L tokens
@@ -151,33 +178,55 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
     CUDA_OK(h, dev_alloc(h, &t.head_ws, head_need));
     t.head_cap = head_need;
   }
+  if (!t.gws.partials) {
+    CUDA_OK(h, dev_alloc(h, &t.gws.partials, gemm_workspace_partial_bytes() / sizeof(float)));
+    CUDA_OK(h, dev_alloc(h, &t.gws.flags, gemm_workspace_flag_bytes() / sizeof(unsigned)));
+    CUDA_OK(h, cudaMemset(t.gws.flags, 0, gemm_workspace_flag_bytes()));
+  }
   if (rows <= t.cap_rows) return 0;
-  // grow: leak-free enough for a workspace that is sized once per configuration (old buffers stay
-  // registered in h->allocs and are released in mudpt_destroy)
+  // grow: the outgrown buffers are released first (cudaFree waits for the device, so nothing in flight uses them);
+  // a CoCoOp-style caller whose B x C changes would otherwise pile up GBs until mudpt_destroy
+  for (void* p : t.ws_allocs) cudaFree(p);
+  t.ws_allocs.clear();
   gemm_clear_tensor_map_cache();
   const size_t d = t.d;
+  const size_t parts = d / 64;
+  std::vector<void*>* g = &t.ws_allocs;
   t.x_in.assign(t.layers + 1, nullptr);
   t.x_mid.assign(t.layers, nullptr);
   t.qkv.assign(t.layers, nullptr);
   t.o.assign(t.layers, nullptr);
   t.h.assign(t.layers, nullptr);
   t.lse.assign(t.layers, nullptr);
-  for (int i = 0; i <= t.layers; ++i) CUDA_OK(h, dev_alloc(h, &t.x_in[i], rows * d));
-  for (int i = 0; i < t.layers; ++i) {
-    CUDA_OK(h, dev_alloc(h, &t.x_mid[i], rows * d));
-    CUDA_OK(h, dev_alloc(h, &t.qkv[i], rows * 3 * d));
-    CUDA_OK(h, dev_alloc(h, &t.o[i], rows * d));
-    CUDA_OK(h, dev_alloc(h, &t.h[i], rows * 4 * d));
-    CUDA_OK(h, dev_alloc(h, &t.lse[i], rows * t.H));
+  t.xb_in.assign(t.layers + 1, nullptr);
+  t.xb_mid.assign(t.layers, nullptr);
+  t.st_in.assign(t.layers + 1, nullptr);
+  t.st_mid.assign(t.layers, nullptr);
+  for (int i = 0; i <= t.layers; ++i) {
+    CUDA_OK(h, dev_alloc(h, &t.x_in[i], rows * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.xb_in[i], rows * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.st_in[i], rows * parts, g));
   }
-  CUDA_OK(h, dev_alloc(h, &t.a_buf, rows * d));
-  CUDA_OK(h, dev_alloc(h, &t.g_buf, rows * 4 * d));
-  CUDA_OK(h, dev_alloc(h, &t.dh_buf, rows * 4 * d));
-  CUDA_OK(h, dev_alloc(h, &t.do_buf, rows * d));
-  CUDA_OK(h, dev_alloc(h, &t.dqkv_buf, rows * 3 * d));
-  CUDA_OK(h, dev_alloc(h, &t.dx_bf16, rows * d));
-  CUDA_OK(h, dev_alloc(h, &t.dx, rows * d));
-  CUDA_OK(h, dev_alloc(h, &t.dsum, rows * t.H));
+  for (int i = 0; i < t.layers; ++i) {
+    CUDA_OK(h, dev_alloc(h, &t.x_mid[i], rows * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.xb_mid[i], rows * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.st_mid[i], rows * parts, g));
+    CUDA_OK(h, dev_alloc(h, &t.qkv[i], rows * 3 * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.o[i], rows * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.h[i], rows * 4 * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.lse[i], rows * t.H, g));
+  }
+  const int dots_mlp = (4 * t.d + gemm_dots_span(4 * t.d) - 1) / gemm_dots_span(4 * t.d);
+  t.dot_cap = dots_mlp > 3 * t.H ? dots_mlp : 3 * t.H;
+  CUDA_OK(h, dev_alloc(h, &t.dots, rows * t.dot_cap, g));
+  CUDA_OK(h, dev_alloc(h, &t.a_buf, rows * d, g));
+  CUDA_OK(h, dev_alloc(h, &t.g_buf, rows * 4 * d, g));
+  CUDA_OK(h, dev_alloc(h, &t.dh_buf, rows * 4 * d, g));
+  CUDA_OK(h, dev_alloc(h, &t.do_buf, rows * d, g));
+  CUDA_OK(h, dev_alloc(h, &t.dqkv_buf, rows * 3 * d, g));
+  CUDA_OK(h, dev_alloc(h, &t.dx_bf16, rows * d, g));
+  CUDA_OK(h, dev_alloc(h, &t.dx, rows * d, g));
+  CUDA_OK(h, dev_alloc(h, &t.dsum, rows * t.H, g));
   if (!t.splice_ws) CUDA_OK(h, dev_alloc(h, &t.splice_ws, splice_bwd_workspace_floats(t.n_ctx > 0 ? t.n_ctx : 1, t.d)));
   t.cap_rows = rows;
   t.fwd_done = false;
@@ -223,11 +272,19 @@ int set_block_weight(mudpt_handle* h, Tower& t, int layer, const char* sub, cons
   Layer& l = t.lw[layer];
   const int d = t.d;
   int rc = 0;
-  if (!strcmp(sub, "attn.in_proj_weight")) { rc = store_gemm_weight(h, &l.w_in, &l.w_in_t, data, numel, 3 * d, d, full, st); l.have |= LB_W_IN; }
+  if (!strcmp(sub, "attn.in_proj_weight")) {
+    rc = store_gemm_weight(h, &l.w_in, &l.w_in_t, data, numel, 3 * d, d, full, st);
+    if (!rc) rc = store_f32(h, &l.w_in_f32, data, numel, static_cast<int64_t>(3) * d * d, full, st);
+    l.have |= LB_W_IN;
+  }
   else if (!strcmp(sub, "attn.in_proj_bias")) { rc = store_f32(h, &l.b_in, data, numel, 3 * d, full, st); l.have |= LB_B_IN; }
   else if (!strcmp(sub, "attn.out_proj.weight")) { rc = store_gemm_weight(h, &l.w_out, &l.w_out_t, data, numel, d, d, full, st); l.have |= LB_W_OUT; }
   else if (!strcmp(sub, "attn.out_proj.bias")) { rc = store_f32(h, &l.b_out, data, numel, d, full, st); l.have |= LB_B_OUT; }
-  else if (!strcmp(sub, "mlp.c_fc.weight")) { rc = store_gemm_weight(h, &l.w_fc, &l.w_fc_t, data, numel, 4 * d, d, full, st); l.have |= LB_W_FC; }
+  else if (!strcmp(sub, "mlp.c_fc.weight")) {
+    rc = store_gemm_weight(h, &l.w_fc, &l.w_fc_t, data, numel, 4 * d, d, full, st);
+    if (!rc) rc = store_f32(h, &l.w_fc_f32, data, numel, static_cast<int64_t>(4) * d * d, full, st);
+    l.have |= LB_W_FC;
+  }
   else if (!strcmp(sub, "mlp.c_fc.bias")) { rc = store_f32(h, &l.b_fc, data, numel, 4 * d, full, st); l.have |= LB_B_FC; }
   else if (!strcmp(sub, "mlp.c_proj.weight")) { rc = store_gemm_weight(h, &l.w_pr, &l.w_pr_t, data, numel, d, 4 * d, full, st); l.have |= LB_W_PR; }
   else if (!strcmp(sub, "mlp.c_proj.bias")) { rc = store_f32(h, &l.b_pr, data, numel, d, full, st); l.have |= LB_B_PR; }
@@ -236,73 +293,166 @@ int set_block_weight(mudpt_handle* h, Tower& t, int layer, const char* sub, cons
   else if (!strcmp(sub, "ln_2.weight")) { rc = store_f32(h, &l.ln2_g, data, numel, d, full, st); l.have |= LB_LN2_G; }
   else if (!strcmp(sub, "ln_2.bias")) { rc = store_f32(h, &l.ln2_b, data, numel, d, full, st); l.have |= LB_LN2_B; }
   else return 1;
+  t.fold_dirty = true;
   return rc;
 }
 
+// LayerNorm -> Linear folding of every block (once per weight load)
+int ensure_folded(mudpt_handle* h, Tower& t, cudaStream_t st) {
+  if (!t.fold_dirty) return 0;
+  const int d = t.d;
+  for (Layer& l : t.lw) {
+    if (!l.w_in_ln) {
+      CUDA_OK(h, dev_alloc(h, &l.w_in_ln, static_cast<size_t>(3) * d * d));
+      CUDA_OK(h, dev_alloc(h, &l.w_in_t_ln, static_cast<size_t>(3) * d * d));
+      CUDA_OK(h, dev_alloc(h, &l.w_fc_ln, static_cast<size_t>(4) * d * d));
+      CUDA_OK(h, dev_alloc(h, &l.w_fc_t_ln, static_cast<size_t>(4) * d * d));
+      CUDA_OK(h, dev_alloc(h, &l.b_in_ln, static_cast<size_t>(3) * d));
+      CUDA_OK(h, dev_alloc(h, &l.b_fc_ln, static_cast<size_t>(4) * d));
+      CUDA_OK(h, dev_alloc(h, &l.cs_in, static_cast<size_t>(3) * d));
+      CUDA_OK(h, dev_alloc(h, &l.cs_fc, static_cast<size_t>(4) * d));
+      CUDA_OK(h, dev_alloc(h, &l.sb_in, static_cast<size_t>(3) * d));
+      CUDA_OK(h, dev_alloc(h, &l.sb_fc, static_cast<size_t>(4) * d));
+    }
+    CK(h, fold_layernorm(l.w_in_f32, l.ln1_g, l.ln1_b, l.b_in, l.w_in_ln, l.w_in_t_ln, l.b_in_ln, l.cs_in, l.sb_in, 3 * d, d, st));
+    CK(h, fold_layernorm(l.w_fc_f32, l.ln2_g, l.ln2_b, l.b_fc, l.w_fc_ln, l.w_fc_t_ln, l.b_fc_ln, l.cs_fc, l.sb_fc, 4 * d, d, st));
+  }
+  t.fold_dirty = false;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------- tower passes
+// Per block (clip/model.py:275-301): [splice] ; x += attn(ln_1(x)) ; x += c_proj(QuickGELU(c_fc(ln_2(x)))).
+//
+// Fused formulation (default): no LayerNorm kernel and no splice kernel inside the layer loop.  The residual GEMMs
+// (out-proj, c_proj) write the new residual row as fp32 + bf16 + partial statistics (and the NEXT block's spliced
+// prompt rows in place of the computed ones); the QKV / c_fc GEMMs read the bf16 row as their A operand and apply
+// the normalisation in their epilogue (EPI_LN_*: gamma folded into the weight, mean as a rank-1 correction).
+// Precondition of the fused path: x_in[0], xb_in[0], st_in[0] hold the tower input (layer-0 splice excepted).
 int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_splice_layer, cudaStream_t st) {
   const int M = t.S * t.L, d = t.d;
   const double Md = static_cast<double>(M), dd = d;
   const double attn_fl = 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // QK^T + PV, dense count
+  const bool fused = h->ln_fused;
+  const int parts = d / 64;
+  auto spliced = [&](int i) { return i < t.depth && i >= first_splice_layer && t.n_ctx > 0 && i < t.layers; };
+  if (fused && ensure_folded(h, t, st)) return -1;
   for (int i = 0; i < t.layers; ++i) {
     const Layer& w = t.lw[i];
-    if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
-      CKP(h, st, PC_SPLICE, 0, 2.0 * t.S * t.n_ctx * dd * 4,
-          splice_fwd(t.x_in[i], prompts + static_cast<size_t>(i) * t.n_ctx * d, t.S, t.L, t.row0, t.n_ctx, d, st));
+    if (spliced(i) && (!fused || i == 0)) {
+      const float* pr = prompts + static_cast<size_t>(i) * t.n_ctx * d;
+      if (fused)
+        CKP(h, st, PC_SPLICE, 0, 2.0 * t.S * t.n_ctx * dd * 4, splice_fwd_stats(t.x_in[i], t.xb_in[i], t.st_in[i], pr, t.S, t.L, t.row0, t.n_ctx, d, st));
+      else
+        CKP(h, st, PC_SPLICE, 0, 2.0 * t.S * t.n_ctx * dd * 4, splice_fwd(t.x_in[i], pr, t.S, t.L, t.row0, t.n_ctx, d, st));
+    }
     // x + attn(ln_1(x))   (clip/model.py:299)
-    CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_in[i], w.ln1_g, w.ln1_b, t.a_buf, true, M, d, kLnEps, st));
     GemmEpilogue e1;
-    e1.mode = EPI_BF16; e1.out0 = t.qkv[i]; e1.bias = w.b_in; e1.ldc = 3 * d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
-        gemm_bf16_tn(t.a_buf, d, w.w_in, d, e1, M, 3 * d, d, st));
+    e1.out0 = t.qkv[i]; e1.ldc = 3 * d;
+    if (fused) {
+      e1.mode = EPI_LN_BF16; e1.bias = w.b_in_ln; e1.colsum = w.cs_in; e1.ln_stats = t.st_in[i]; e1.ln_parts = parts; e1.ln_width = d; e1.ln_eps = kLnEps;
+      CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
+          gemm_bf16_tn(t.xb_in[i], d, w.w_in_ln, d, e1, M, 3 * d, d, st, &t.gws));
+    } else {
+      CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_in[i], w.ln1_g, w.ln1_b, t.a_buf, true, M, d, kLnEps, st));
+      e1.mode = EPI_BF16; e1.bias = w.b_in;
+      CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
+          gemm_bf16_tn(t.a_buf, d, w.w_in, d, e1, M, 3 * d, d, st, &t.gws));
+    }
     CKP(h, st, PC_ATTN_FWD, attn_fl, Md * dd * 2 * 4, attention_fwd(t.qkv[i], t.o[i], t.lse[i], t.S, t.L, t.H, d, t.causal, st));
     GemmEpilogue e2;
-    e2.mode = EPI_RESID_F32; e2.out0 = t.x_mid[i]; e2.bias = w.b_out; e2.resid = t.x_in[i]; e2.ldc = d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (Md * dd + dd * dd) + 8 * Md * dd,
-        gemm_bf16_tn(t.o[i], d, w.w_out, d, e2, M, d, d, st));
+    e2.out0 = t.x_mid[i]; e2.bias = w.b_out; e2.resid = t.x_in[i]; e2.ldc = d;
+    if (fused) { e2.mode = EPI_RESID_STATS; e2.out2 = t.xb_mid[i]; e2.stats_out = t.st_mid[i]; }
+    else e2.mode = EPI_RESID_F32;
+    CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (Md * dd + dd * dd) + (fused ? 10 : 8) * Md * dd,
+        gemm_bf16_tn(t.o[i], d, w.w_out, d, e2, M, d, d, st, &t.gws));
     // x + c_proj(QuickGELU(c_fc(ln_2(x))))   (clip/model.py:300)
-    CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_mid[i], w.ln2_g, w.ln2_b, t.a_buf, true, M, d, kLnEps, st));
     GemmEpilogue e3;
-    e3.mode = EPI_GELU; e3.out0 = t.h[i]; e3.out1 = t.g_buf; e3.bias = w.b_fc; e3.ldc = 4 * d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
-        gemm_bf16_tn(t.a_buf, d, w.w_fc, d, e3, M, 4 * d, d, st));
+    e3.out0 = t.h[i]; e3.out1 = t.g_buf; e3.ldc = 4 * d;
+    if (fused) {
+      e3.mode = EPI_LN_GELU; e3.bias = w.b_fc_ln; e3.colsum = w.cs_fc; e3.ln_stats = t.st_mid[i]; e3.ln_parts = parts; e3.ln_width = d; e3.ln_eps = kLnEps;
+      CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
+          gemm_bf16_tn(t.xb_mid[i], d, w.w_fc_ln, d, e3, M, 4 * d, d, st, &t.gws));
+    } else {
+      CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_mid[i], w.ln2_g, w.ln2_b, t.a_buf, true, M, d, kLnEps, st));
+      e3.mode = EPI_GELU; e3.bias = w.b_fc;
+      CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
+          gemm_bf16_tn(t.a_buf, d, w.w_fc, d, e3, M, 4 * d, d, st, &t.gws));
+    }
     GemmEpilogue e4;
-    e4.mode = EPI_RESID_F32; e4.out0 = t.x_in[i + 1]; e4.bias = w.b_pr; e4.resid = t.x_mid[i]; e4.ldc = d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 8 * Md * dd,
-        gemm_bf16_tn(t.g_buf, 4 * d, w.w_pr, 4 * d, e4, M, d, 4 * d, st));
+    e4.out0 = t.x_in[i + 1]; e4.bias = w.b_pr; e4.resid = t.x_mid[i]; e4.ldc = d;
+    if (fused) {
+      e4.mode = EPI_RESID_STATS; e4.out2 = t.xb_in[i + 1]; e4.stats_out = t.st_in[i + 1];
+      if (spliced(i + 1)) {  // the next block's prompt rows replace the computed ones (they get no gradient: splice_bwd)
+        e4.splice_prompt = prompts + static_cast<size_t>(i + 1) * t.n_ctx * d;
+        e4.splice_row0 = t.row0; e4.splice_n = t.n_ctx; e4.splice_L = t.L;
+      }
+    } else {
+      e4.mode = EPI_RESID_F32;
+    }
+    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + (fused ? 10 : 8) * Md * dd,
+        gemm_bf16_tn(t.g_buf, 4 * d, w.w_pr, 4 * d, e4, M, d, 4 * d, st, &t.gws));
   }
   t.fwd_done = true;
+  t.fwd_fused = fused;
   return 0;
 }
 
 // Precondition: t.dx / t.dx_bf16 hold the gradient w.r.t. the tower output x_in[layers].
+//
+// Fused formulation: the LayerNorm dgrad  dx += rstd (g - mean(g) - xhat mean(g xhat)),  g = dy gamma, runs in the
+// epilogue of the dgrad GEMM that produces g (through the gamma-folded weight).  Its two row means do not need g:
+//   mean(g) = (1/d) dout . colsum,   mean(g xhat) = (1/d) dout . (y - b')      (dout = the GEMM's A operand, y = the
+// saved output of the forward LN-GEMM), so the PRODUCER of dout (GELU' epilogue, attention backward) emits them.
 int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice_layer, cudaStream_t st) {
   const int M = t.S * t.L, d = t.d;
   const double Md = static_cast<double>(M), dd = d;
   const double attn_fl = 2.5 * 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // 2.5x forward
+  const bool fused = t.fwd_fused;
+  const int parts = d / 64;
+  const int dots_mlp = (4 * d + gemm_dots_span(4 * d) - 1) / gemm_dots_span(4 * d);
   for (int i = t.layers - 1; i >= 0; --i) {
     const Layer& w = t.lw[i];
     // MLP branch: dg = dx W_pr ; dh = dg * GELU'(h) ; dm = dh W_fc ; dx += LN2_bwd(dm)
     GemmEpilogue e1;
-    e1.mode = EPI_GELU_BWD; e1.out0 = t.dh_buf; e1.aux = t.h[i]; e1.ldc = 4 * d;
+    e1.out0 = t.dh_buf; e1.aux = t.h[i]; e1.ldc = 4 * d;
+    if (fused) { e1.mode = EPI_GELU_BWD_DOTS; e1.sb = w.sb_fc; e1.dots_out = t.dots; }
+    else e1.mode = EPI_GELU_BWD;
     CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
-        gemm_bf16_tn(t.dx_bf16, d, w.w_pr_t, d, e1, M, 4 * d, d, st));
+        gemm_bf16_tn(t.dx_bf16, d, w.w_pr_t, d, e1, M, 4 * d, d, st, &t.gws));
     GemmEpilogue e2;
-    e2.mode = EPI_BF16; e2.out0 = t.a_buf; e2.ldc = d;  // a_buf: forward transient, free during the backward
-    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 2 * Md * dd,
-        gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st));
-    CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    e2.ldc = d;
+    if (fused) {
+      e2.mode = EPI_LN_BWD; e2.out0 = t.dx; e2.resid = t.dx; e2.out2 = t.dx_bf16; e2.x2 = t.xb_mid[i];
+      e2.ln_stats = t.st_mid[i]; e2.ln_parts = parts; e2.ln_width = d; e2.ln_eps = kLnEps; e2.dots = t.dots; e2.dot_parts = dots_mlp;
+      CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 12 * Md * dd,
+          gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t_ln, 4 * d, e2, M, d, 4 * d, st, &t.gws));
+    } else {
+      e2.mode = EPI_BF16; e2.out0 = t.a_buf;  // a_buf: forward transient, free during the backward
+      CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 2 * Md * dd,
+          gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st, &t.gws));
+      CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    }
     // attention branch: dO = dx W_out ; (dQ,dK,dV) ; da = dQKV W_in ; dx += LN1_bwd(da)
     GemmEpilogue e3;
     e3.mode = EPI_BF16; e3.out0 = t.do_buf; e3.ldc = d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (2 * Md * dd + dd * dd), gemm_bf16_tn(t.dx_bf16, d, w.w_out_t, d, e3, M, d, d, st));
+    CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (2 * Md * dd + dd * dd), gemm_bf16_tn(t.dx_bf16, d, w.w_out_t, d, e3, M, d, d, st, &t.gws));
     CKP(h, st, PC_ATTN_BWD, attn_fl, Md * dd * 2 * 8,
-        attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st));
+        attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st,
+                      fused ? w.sb_in : nullptr, fused ? t.dots : nullptr));
     GemmEpilogue e4;
-    e4.mode = EPI_BF16; e4.out0 = t.a_buf; e4.ldc = d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 2 * Md * dd,
-        gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st));
-    CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_in[i], w.ln1_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    e4.ldc = d;
+    if (fused) {
+      e4.mode = EPI_LN_BWD; e4.out0 = t.dx; e4.resid = t.dx; e4.out2 = t.dx_bf16; e4.x2 = t.xb_in[i];
+      e4.ln_stats = t.st_in[i]; e4.ln_parts = parts; e4.ln_width = d; e4.ln_eps = kLnEps; e4.dots = t.dots; e4.dot_parts = 3 * t.H;
+      CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 12 * Md * dd,
+          gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t_ln, 3 * d, e4, M, d, 3 * d, st, &t.gws));
+    } else {
+      e4.mode = EPI_BF16; e4.out0 = t.a_buf;
+      CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 2 * Md * dd,
+          gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st, &t.gws));
+      CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_in[i], w.ln1_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+    }
     // splice backward: the inserted prompt rows collect the batch-summed gradient; the rows
     // they overwrote get none (clip/model.py:281-297)
     if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
@@ -356,6 +506,8 @@ int mudpt_create(const mudpt_config* cfg, mudpt_handle** out) {
   t.lw.resize(t.layers);
   h->Kp = (3 * cfg->vision_patch_size * cfg->vision_patch_size + 7) & ~7;
   h->launches_at_create = g_launch_counter.load();
+  h->ln_fused = env_flag("MUDPT_LN_FUSED", true);
+  h->prune = env_flag("MUDPT_PRUNE", true);
   *out = h;
   return 0;
 }
@@ -364,10 +516,21 @@ void mudpt_destroy(mudpt_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->vis.ws_allocs) cudaFree(p);
+  for (void* p : h->txt.ws_allocs) cudaFree(p);
   for (ProfRec& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
   gemm_clear_tensor_map_cache();
   delete h;
+}
+
+int mudpt_set_option(mudpt_handle* h, const char* name, int32_t value) {
+  if (!h || !name) return fail(h, "mudpt_set_option: null argument");
+  if (!strcmp(name, "ln_fused")) h->ln_fused = value != 0;
+  else if (!strcmp(name, "prune")) h->prune = value != 0;
+  else return fail(h, "mudpt_set_option: unknown option %s", name);
+  h->vis.fwd_done = h->txt.fwd_done = false;  // saved activations belong to the previous formulation
+  return 0;
 }
 
 int mudpt_set_weight(mudpt_handle* h, const char* name, const float* data, int64_t numel, void* stream) {
@@ -449,6 +612,7 @@ int mudpt_vision_forward(mudpt_handle* h, const float* images, int32_t B, const 
   // ln_pre in place (:541); the prompt rows are overwritten by the layer-0 splice with
   // prompts[0] = ln_pre(visual_ctx + shared_ctx), which is identical for every image
   CK(h, layernorm_fwd(t.x_in[0], h->ln_pre_g, h->ln_pre_b, t.x_in[0], false, B * t.L, t.d, kLnEps, st));
+  if (h->ln_fused) CK(h, rowstats(t.x_in[0], t.xb_in[0], t.st_in[0], B * t.L, t.d, st));  // tower input as fp32 + bf16 + statistics
   if (tower_forward(h, t, prompts, 0, st)) return -1;
   CK(h, feature_head_fwd(t.x_in[t.layers], nullptr, h->ln_post_g, h->ln_post_b, h->proj_v, f_img, t.head_ws, B, t.L, t.d, c.embed_dim, kLnEps, st));
   return 0;
@@ -488,6 +652,7 @@ int mudpt_text_set_classes(mudpt_handle* h, const float* embeddings, int32_t C, 
   CUDA_OK(h, cudaMemcpyAsync(h->eot, eot_host, C * sizeof(int), cudaMemcpyHostToDevice, st));
   CUDA_OK(h, cudaStreamSynchronize(st));  // eot_host may be freed by the caller after return
   CK(h, add_positional(t.x_in[0], embeddings, h->pos_t, C, seq_len, src_len, t.d, st));
+  CK(h, rowstats(t.x_in[0], t.xb_in[0], t.st_in[0], C * seq_len, t.d, st));  // (the prompt rows are rewritten every step)
   t.fwd_done = false;
   return 0;
 }
@@ -594,13 +759,65 @@ int mudpt_attention_backward(const uint16_t* qkv, const uint16_t* o, const uint1
                     lse2, dsum, reinterpret_cast<bf16*>(dqkv), S, L, H, H * 64, causal != 0, static_cast<cudaStream_t>(stream)));
   return 0;
 }
+// stream-K scratch of the handle-less GEMM entry points (tests, one stream at a time)
+static GemmWorkspace* unit_workspace() {
+  static GemmWorkspace ws;
+  if (!ws.partials) {
+    void *p = nullptr, *f = nullptr;
+    if (cudaMalloc(&p, gemm_workspace_partial_bytes()) != cudaSuccess || cudaMalloc(&f, gemm_workspace_flag_bytes()) != cudaSuccess)
+      return nullptr;
+    cudaMemset(f, 0, gemm_workspace_flag_bytes());
+    ws.partials = static_cast<float*>(p);
+    ws.flags = static_cast<unsigned*>(f);
+  }
+  return &ws;
+}
+
+int mudpt_gemm_fused(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, int32_t K, const mudpt_gemm_epilogue* e,
+                     void* stream) {
+  if (!A || !B || !e) return fail(nullptr, "mudpt_gemm_fused: null argument");
+  GemmEpilogue ep;
+  ep.mode = e->mode; ep.ldc = e->ldc; ep.out0 = e->out0; ep.out1 = e->out1; ep.out2 = e->out2; ep.bias = e->bias;
+  ep.resid = e->resid; ep.aux = e->aux; ep.ln_stats = reinterpret_cast<const float2*>(e->ln_stats); ep.ln_parts = e->ln_parts;
+  ep.ln_width = e->ln_width; ep.ln_eps = e->ln_eps; ep.dot_parts = e->dot_parts; ep.colsum = e->colsum;
+  ep.stats_out = reinterpret_cast<float2*>(e->stats_out); ep.splice_prompt = e->splice_prompt; ep.splice_row0 = e->splice_row0;
+  ep.splice_n = e->splice_n; ep.splice_L = e->splice_L > 0 ? e->splice_L : 1; ep.x2 = e->x2;
+  ep.dots = reinterpret_cast<const float2*>(e->dots); ep.sb = reinterpret_cast<const float2*>(e->sb);
+  ep.dots_out = reinterpret_cast<float2*>(e->dots_out);
+  gemm_set_stream_k(e->stream_k);
+  const char* err = gemm_bf16_tn(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, ep, M, N, K,
+                                 static_cast<cudaStream_t>(stream), e->stream_k != 0 ? unit_workspace() : nullptr);
+  gemm_set_stream_k(-2);  // back to the process default
+  if (err) return fail(nullptr, "%s", err);
+  return 0;
+}
+int32_t mudpt_gemm_dots_span(int32_t N) { return gemm_dots_span(N); }
+int mudpt_rowstats(const float* x, uint16_t* xb, float* stats, int32_t rows, int32_t width, void* stream) {
+  CKG(rowstats(x, reinterpret_cast<bf16*>(xb), reinterpret_cast<float2*>(stats), rows, width, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_fold_layernorm(const float* W, const float* gamma, const float* beta, const float* bias, uint16_t* Wl,
+                         uint16_t* Wlt, float* bias_l, float* colsum, float* sb, int32_t N, int32_t K, void* stream) {
+  CKG(fold_layernorm(W, gamma, beta, bias, reinterpret_cast<bf16*>(Wl), reinterpret_cast<bf16*>(Wlt), bias_l, colsum,
+                     reinterpret_cast<float2*>(sb), N, K, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_attention_backward_dots(const uint16_t* qkv, const uint16_t* o, const uint16_t* d_o, const float* lse2,
+                                  float* dsum, uint16_t* dqkv, int32_t S, int32_t L, int32_t H, int32_t causal,
+                                  const float* ln_sb, float* ln_dots, void* stream) {
+  CKG(attention_bwd(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o),
+                    lse2, dsum, reinterpret_cast<bf16*>(dqkv), S, L, H, H * 64, causal != 0, static_cast<cudaStream_t>(stream),
+                    reinterpret_cast<const float2*>(ln_sb), reinterpret_cast<float2*>(ln_dots)));
+  return 0;
+}
 int mudpt_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, int32_t K, int32_t mode, void* out0,
                     void* out1, const float* bias, const float* resid, const void* aux, int32_t ldc, int32_t patch_np,
                     int32_t patch_L, void* stream) {
   GemmEpilogue ep;
   ep.mode = mode; ep.out0 = out0; ep.out1 = out1; ep.bias = bias; ep.resid = resid; ep.aux = aux; ep.ldc = ldc;
   ep.patch_np = patch_np > 0 ? patch_np : 1; ep.patch_L = patch_L > 0 ? patch_L : 1;
-  CKG(gemm_bf16_tn(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, ep, M, N, K, static_cast<cudaStream_t>(stream)));
+  CKG(gemm_bf16_tn(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, ep, M, N, K, static_cast<cudaStream_t>(stream),
+                   unit_workspace()));
   return 0;
 }
 int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream) {

@@ -106,11 +106,21 @@ __device__ __forceinline__ void mma_p_x_tile(float (&out)[8][4], const float (&p
   }
 }
 
+// Optional by-product of the backward stores (fused LayerNorm backward, gemm.h EPI_LN_BWD): the row dots of the
+// stored gradient slice with the column sums of the LN-folded in-proj weight and with (y - b'), y = the saved
+// forward value of the same slice (q, k or v).  One partial per (row, slice): dots[row * parts + part].
+struct RowDots {
+  const float2* sb = nullptr;  // (colsum, b') of the slice's 64 columns
+  const bf16* y = nullptr;     // forward values, same indexing as the gradient slice
+  float2* out = nullptr;       // null: no dots
+  int parts = 0, part = 0;
+};
+
 // Write a warp's 16 x 64 fp32 accumulator (scaled) as bf16 to global rows, staged through the
 // warp's own (no longer needed) 16 smem rows so the global stores are 16 B and coalesced.
 __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float scale0, float scale1, uint8_t* smem_gen,
                                                 uint32_t tile_off, int row0, bf16* g, int ld, int grow0, int row_limit,
-                                                int lane) {
+                                                int lane, const RowDots dots = RowDots()) {
   __syncwarp();
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
@@ -125,9 +135,28 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float 
     const int idx = i * 32 + lane;
     const int r = idx >> 3, c = idx & 7;
     const int gr = grow0 + r;
-    if (gr < row_limit) {
-      uint4 v = *reinterpret_cast<const uint4*>(smem_gen + tile_off + swz(row0 + r, c));
-      *reinterpret_cast<uint4*>(g + static_cast<size_t>(gr) * ld + c * 8) = v;
+    const bool valid = gr < row_limit;
+    uint4 v = *reinterpret_cast<const uint4*>(smem_gen + tile_off + swz(row0 + r, c));
+    if (valid) *reinterpret_cast<uint4*>(g + static_cast<size_t>(gr) * ld + c * 8) = v;
+    if (dots.out != nullptr) {  // (warp-uniform) 8 lanes share a row: the rounded values that the dgrad GEMM will read
+      float d1 = 0.f, d2 = 0.f;
+      if (valid) {
+        const uint4 y = *reinterpret_cast<const uint4*>(dots.y + static_cast<size_t>(gr) * ld + c * 8);
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 sb2 = __ldg(reinterpret_cast<const float4*>(dots.sb + c * 8 + 2 * q));  // (cs, b', cs, b') of 2 columns
+          const float2 gv = unpack_bf16(vw[q]), yv = unpack_bf16(yw[q]);
+          d1 += gv.x * sb2.x + gv.y * sb2.z;
+          d2 += gv.x * (yv.x - sb2.y) + gv.y * (yv.y - sb2.w);
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+      }
+      if (valid && c == 0) dots.out[static_cast<size_t>(gr) * dots.parts + dots.part] = make_float2(d1, d2);
     }
   }
 }
@@ -271,7 +300,8 @@ template <bool CAUSAL>
 __global__ void __launch_bounds__(256, 2) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
                                                              const bf16* __restrict__ d_o, const float* __restrict__ lse2,
                                                              float* __restrict__ dsum, bf16* __restrict__ dqkv, int L,
-                                                             int H, int d, float scale, float scale_log2e) {
+                                                             int H, int d, float scale, float scale_log2e,
+                                                             const float2* __restrict__ ln_sb, float2* __restrict__ ln_dots) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nwarps = blockDim.x >> 5, BQ = nwarps * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -373,7 +403,9 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_dq_kernel(const bf16* __restr
     if (g_hi == 2 && !need_mask) chunk(std::true_type{}, c0, 2);
     else chunk(std::false_type{}, c0, g_hi);
   }
-  store_rows_bf16(dq, scale, scale, smem, 0, row0, dqkv + seq_row * ld + h * DH, ld, q0 + row0, L, lane);
+  RowDots rd;
+  if (ln_dots != nullptr) { rd.sb = ln_sb + h * DH; rd.y = base; rd.out = ln_dots + seq_row * 3 * H; rd.parts = 3 * H; rd.part = h; }
+  store_rows_bf16(dq, scale, scale, smem, 0, row0, dqkv + seq_row * ld + h * DH, ld, q0 + row0, L, lane, rd);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -383,7 +415,8 @@ template <bool CAUSAL>
 __global__ void __launch_bounds__(256, 2) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
                                                               const float* __restrict__ lse2, const float* __restrict__ dsum,
                                                               bf16* __restrict__ dqkv, int L, int H, int d, float scale,
-                                                              float scale_log2e) {
+                                                              float scale_log2e, const float2* __restrict__ ln_sb,
+                                                              float2* __restrict__ ln_dots) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nwarps = blockDim.x >> 5, BKV = nwarps * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -465,8 +498,13 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_dkv_kernel(const bf16* __rest
     else chunk(std::false_type{}, c0, g_lo, g_hi);
   }
   bf16* out = dqkv + seq_row * ld + h * DH;
-  store_rows_bf16(dk, scale, scale, smem, 0, row0, out + d, ld, k0 + row0, L, lane);
-  store_rows_bf16(dv, 1.f, 1.f, smem, BKV * ROW_BYTES, row0, out + 2 * d, ld, k0 + row0, L, lane);
+  RowDots rk, rv;
+  if (ln_dots != nullptr) {
+    rk.sb = ln_sb + d + h * DH; rk.y = base + d; rk.out = ln_dots + seq_row * 3 * H; rk.parts = 3 * H; rk.part = H + h;
+    rv = rk; rv.sb = ln_sb + 2 * d + h * DH; rv.y = base + 2 * d; rv.part = 2 * H + h;
+  }
+  store_rows_bf16(dk, scale, scale, smem, 0, row0, out + d, ld, k0 + row0, L, lane, rk);
+  store_rows_bf16(dv, 1.f, 1.f, smem, BKV * ROW_BYTES, row0, out + 2 * d, ld, k0 + row0, L, lane, rv);
 }
 
 // =======================================================================================
@@ -700,7 +738,9 @@ __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, true)) attn_sh
                                                                               const bf16* __restrict__ d_o,
                                                                               const float* __restrict__ lse2,
                                                                               bf16* __restrict__ dqkv, int L, int H, int d,
-                                                                              float scale, float scale_log2e) {
+                                                                              float scale, float scale_log2e,
+                                                                              const float2* __restrict__ ln_sb,
+                                                                              float2* __restrict__ ln_dots) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5, Lp = nw * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -787,10 +827,16 @@ __global__ void __launch_bounds__(MAXT * 32, short_min_ctas(MAXT, true)) attn_sh
   __syncthreads();  // all reads of Q / dO / P / dS are done: the Q and dO tiles become store staging
   bf16* out = dqkv + seq_row * ld + h * DH;
   if (row0 < L) {
-    store_rows_bf16(dq, scale, scale, smem, 0, row0, out, ld, row0, L, lane);
-    store_rows_bf16(dk, scale, scale, smem, tile_bytes, row0, out + d, ld, row0, L, lane);
+    RowDots rq, rk, rv;
+    if (ln_dots != nullptr) {
+      rq.sb = ln_sb + h * DH; rq.y = base; rq.out = ln_dots + seq_row * 3 * H; rq.parts = 3 * H; rq.part = h;
+      rk = rq; rk.sb = ln_sb + d + h * DH; rk.y = base + d; rk.part = H + h;
+      rv = rq; rv.sb = ln_sb + 2 * d + h * DH; rv.y = base + 2 * d; rv.part = 2 * H + h;
+    }
+    store_rows_bf16(dq, scale, scale, smem, 0, row0, out, ld, row0, L, lane, rq);
+    store_rows_bf16(dk, scale, scale, smem, tile_bytes, row0, out + d, ld, row0, L, lane, rk);
     __syncwarp();
-    store_rows_bf16(dv, 1.f, 1.f, smem, 0, row0, out + 2 * d, ld, row0, L, lane);
+    store_rows_bf16(dv, 1.f, 1.f, smem, 0, row0, out + 2 * d, ld, row0, L, lane, rv);
   }
 }
 
@@ -876,7 +922,7 @@ const char* attention_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L, i
 }
 
 const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv,
-                          int S, int L, int H, int d, bool causal, cudaStream_t stream) {
+                          int S, int L, int H, int d, bool causal, cudaStream_t stream, const float2* ln_sb, float2* ln_dots) {
   if (S <= 0 || L <= 0) return nullptr;
   if (d != H * DH) return "attention: head width must be 64";
   if (use_short(L)) {
@@ -887,7 +933,7 @@ const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const
 #define MUDPT_LAUNCH_BWD(C, MT)                                                                                  \
   do {                                                                                                           \
     if ((es = set_smem(attn_short_bwd_kernel<C, MT>, sm))) return es;                                            \
-    launch_pdl(attn_short_bwd_kernel<C, MT>, dim3(S * H), dim3(tiles * 32), sm, stream, qkv, o, d_o, lse2, dqkv, L, H, d, sc, sl2s); \
+    launch_pdl(attn_short_bwd_kernel<C, MT>, dim3(S * H), dim3(tiles * 32), sm, stream, qkv, o, d_o, lse2, dqkv, L, H, d, sc, sl2s, ln_sb, ln_dots); \
   } while (0)
     if (causal) { if (tiles <= 2) MUDPT_LAUNCH_BWD(true, 2); else if (tiles <= 5) MUDPT_LAUNCH_BWD(true, 5); else MUDPT_LAUNCH_BWD(true, 8); }
     else { if (tiles <= 2) MUDPT_LAUNCH_BWD(false, 2); else if (tiles <= 5) MUDPT_LAUNCH_BWD(false, 5); else MUDPT_LAUNCH_BWD(false, 8); }
@@ -904,13 +950,13 @@ const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const
   if (causal) {
     if ((e = set_smem(attn_bwd_dq_kernel<true>, smem_q))) return e;
     if ((e = set_smem(attn_bwd_dkv_kernel<true>, smem_kv))) return e;
-    launch_pdl(attn_bwd_dq_kernel<true>, grid, dim3(nw * 32), smem_q, stream, qkv, o, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
-    launch_pdl(attn_bwd_dkv_kernel<true>, grid, dim3(nw * 32), smem_kv, stream, qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
+    launch_pdl(attn_bwd_dq_kernel<true>, grid, dim3(nw * 32), smem_q, stream, qkv, o, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2, ln_sb, ln_dots);
+    launch_pdl(attn_bwd_dkv_kernel<true>, grid, dim3(nw * 32), smem_kv, stream, qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2, ln_sb, ln_dots);
   } else {
     if ((e = set_smem(attn_bwd_dq_kernel<false>, smem_q))) return e;
     if ((e = set_smem(attn_bwd_dkv_kernel<false>, smem_kv))) return e;
-    launch_pdl(attn_bwd_dq_kernel<false>, grid, dim3(nw * 32), smem_q, stream, qkv, o, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
-    launch_pdl(attn_bwd_dkv_kernel<false>, grid, dim3(nw * 32), smem_kv, stream, qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2);
+    launch_pdl(attn_bwd_dq_kernel<false>, grid, dim3(nw * 32), smem_q, stream, qkv, o, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2, ln_sb, ln_dots);
+    launch_pdl(attn_bwd_dkv_kernel<false>, grid, dim3(nw * 32), smem_kv, stream, qkv, d_o, lse2, dsum, dqkv, L, H, d, scale, sl2, ln_sb, ln_dots);
   }
   count_launch(2);
   return launch_status("attention bwd launch failed");

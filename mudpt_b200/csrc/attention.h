@@ -9,6 +9,10 @@ namespace mudpt {
 const char* attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* o, float* lse2, int S, int L, int H, int d,
                           bool causal, cudaStream_t stream);
 // dsum [S, H, L] fp32 scratch (rowsum(dO*O)), dqkv [S*L, 3d] bf16 out.
+// ln_dots != null (fused LayerNorm backward of the in-proj, gemm.h EPI_LN_BWD): also ln_dots[row, which*H + h] =
+// (sum_c g_c colsum_c, sum_c g_c (y_c - b'_c)) over the 64 columns of head h of dq / dk / dv (which = 0 / 1 / 2),
+// with ln_sb [3d] = (colsum, b') of the LN-folded in-proj and y = the saved qkv.
 const char* attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
-                          float* dsum, __nv_bfloat16* dqkv, int S, int L, int H, int d, bool causal, cudaStream_t stream);
+                          float* dsum, __nv_bfloat16* dqkv, int S, int L, int H, int d, bool causal, cudaStream_t stream,
+                          const float2* ln_sb = nullptr, float2* ln_dots = nullptr);
 }  // namespace mudpt

@@ -7,19 +7,30 @@
 // trainers/mudpt.py:205-212, so there is no wgrad and the transpose is free).
 //
 // Replaces the `addmm`/`mm` call sites of clip/model.py:273 (in-proj), :299 (out-proj),
-// :300 (c_fc, c_proj), :527 (conv1 as a GEMM) and their autograd dgrads.
+// :300 (c_fc, c_proj), :527 (conv1 as a GEMM), their autograd dgrads, and -- through the EPI_LN_* /
+// EPI_RESID_STATS epilogues -- the LayerNorms in front of them (:164-170) and the deep-prompt splice (:281-297).
 //
 // Structure (one persistent CTA per SM, 320 threads; CTA pairs in cta_group::2 mode):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles (128B swizzle) into a smem ring
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (128|256 x BN x 16), fp32
 //                                accumulators in TMEM, double-buffered (2 x BN columns)
 //   warps 2..9  epilogue       : tcgen05.ld the accumulator, apply the fused epilogue
-//                                (bias / QuickGELU / residual / GELU' / patch-embed scatter),
+//                                (bias / QuickGELU / residual / GELU' / LayerNorm forms / patch-embed scatter),
 //                                hand 32 x 32 boxes to the TMA (UTMASTG; residual / saved
 //                                pre-activation boxes arrive by UTMALDG one box ahead)
 // The epilogue of tile i overlaps the MMAs of tile i+1 through the second TMEM buffer.  The kernel
 // is launched with programmatic stream serialization: its prologue (barriers, TMEM allocation,
 // descriptor prefetch) overlaps the tail of the previous kernel (pdl_wait() in common.cuh).
+//
+// Work decomposition (stream-K hybrid).  Whole tiles are dealt round-robin to the units (CTAs or CTA pairs) for
+// as many full waves as there are; the tiles of the last full wave plus the remainder are cut into ONE contiguous
+// range of k-blocks per unit (75 pair tiles on 74 pairs: 1.014 tile-times instead of 2).  A unit walks its range
+// from the high end down, so the part of a tile that ends at the tile's last k-block comes last in its range: that
+// unit ("finisher") runs the epilogue, after adding the fp32 partial accumulators that the lower-numbered
+// unit(s) holding the rest of the tile wrote to an L2-resident scratch slot at the START of their ranges (one slot per
+// CTA, one ready flag per epilogue warp: warp w of the finisher reads exactly what warp w of the contributor wrote,
+// so the hand-over is warp to warp).  A finisher only ever waits for lower-numbered units, which the hardware
+// dispatches first: no deadlock when another stream's kernel holds part of the machine.
 #include "gemm.h"
 
 #include <cstdio>
@@ -34,11 +45,13 @@ namespace mudpt {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int kStatSpan = 64;  // columns per partial LayerNorm statistic (EPI_RESID_STATS -> EPI_LN_*)
 // Epilogue warps per CTA (TMA warp + MMA warp + these).  The GELU' epilogue (dgrad of c_proj) has the longest
 // per-element dependency chain (unpack, 6 packed fp32 ops, tanh, pack) and was latency-bound on 2 warps per
 // scheduler (ncu: issue slots 39 % busy, stall_wait dominant): it runs 16 warps at <= 112 registers, with a
 // single accumulator register set (4 warps per scheduler hide the TMEM load instead of a second set).
-template <int MODE> struct EpiWarps { static constexpr int value = (MODE == 4 /*EPI_GELU_BWD*/) ? 16 : 8; };
+template <int MODE> struct GeluBwd { static constexpr bool value = (MODE == EPI_GELU_BWD || MODE == EPI_GELU_BWD_DOTS); };
+template <int MODE> struct EpiWarps { static constexpr int value = GeluBwd<MODE>::value ? 16 : 8; };
 template <int MODE> struct GemmThreads { static constexpr int value = 64 + 32 * EpiWarps<MODE>::value; };
 
 // TWO = CTA pair (cta_group::2): the pair computes a 256 x BN tile, each CTA holds 128 rows of A
@@ -46,17 +59,20 @@ template <int MODE> struct GemmThreads { static constexpr int value = 64 + 32 * 
 // tensor cores: 1/3 less operand traffic through shared memory per FLOP than two independent
 // 128 x BN tiles (the 1-CTA mainloop is bound by exactly that traffic).
 // Epilogue flavour per mode.  "Row" epilogues keep the TMEM layout (thread = accumulator row, 32
-// consecutive columns in registers), do the fused math on packed fp32 pairs and hand 32 x 32 bf16
-// boxes to the TMA (store; for GELU' also the load of the saved pre-activation) through 2 KB
-// 64B-swizzled staging units: ~1/3 of the instructions of the transposing epilogue below, which the
-// fp32-output modes still use (their boxes would be twice as large and they are HBM-bound anyway).
-template <int MODE> struct RowEpi { static constexpr bool value = (MODE != EPI_PATCH && MODE != 6 /*EPI_RESID_DEEP*/); };
-// internal variant of EPI_RESID_F32 for long-K GEMMs (c_proj, K >= 1024): these keep the transposing epilogue
-// (coalesced residual loads straight from global memory, 6 operand stages) -- measured 134 us against 139 us for
-// the row-layout / TMA version, whose gain is the short-K out-proj (93 -> 78 us)
-static constexpr int EPI_RESID_DEEP = 6;
-template <int MODE> struct F32Epi { static constexpr bool value = (MODE == EPI_F32 || MODE == EPI_RESID_F32 || MODE == EPI_RESID_DEEP); };
-template <int MODE> struct ResidEpi { static constexpr bool value = (MODE == EPI_RESID_F32 || MODE == EPI_RESID_DEEP); };
+// consecutive columns in registers), do the fused math on packed fp32 pairs and hand 32 x 32
+// boxes to the TMA (store; also the loads of residual / saved pre-activation / LN input) through 2 KB
+// 64B-swizzled (bf16) or 4 KB 128B-swizzled (fp32) staging boxes.  Only the patch-embedding scatter keeps the
+// transposing epilogue below.
+template <int MODE> struct RowEpi { static constexpr bool value = (MODE != EPI_PATCH); };
+template <int MODE> struct LnFwd { static constexpr bool value = (MODE == EPI_LN_BF16 || MODE == EPI_LN_GELU); };
+template <int MODE> struct GeluFwd { static constexpr bool value = (MODE == EPI_GELU || MODE == EPI_LN_GELU); };
+template <int MODE> struct Bf16Fwd { static constexpr bool value = (MODE == EPI_BF16 || MODE == EPI_LN_BF16); };
+// fp32 output box with an optional second (bf16) box: residual + statistics, LayerNorm backward
+template <int MODE> struct DualEpi { static constexpr bool value = (MODE == EPI_RESID_STATS || MODE == EPI_LN_BWD); };
+template <int MODE> struct F32Epi { static constexpr bool value = (MODE == EPI_F32 || MODE == EPI_RESID_F32 || DualEpi<MODE>::value); };
+// an fp32 box (residual / residual gradient) is TMA-loaded one box ahead and rewritten in place
+template <int MODE> struct ResidEpi { static constexpr bool value = (MODE == EPI_RESID_F32 || DualEpi<MODE>::value); };
+template <int MODE> struct PrefetchEpi { static constexpr bool value = (ResidEpi<MODE>::value || GeluBwd<MODE>::value); };
 static constexpr int kUnitBytes = 32 * 64;  // 32 rows x 32 bf16, SWIZZLE_64B
 static constexpr int kMaxSmem = 227 * 1024;
 
@@ -67,20 +83,81 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTxBytes = TWO ? 2 * kStageBytes : kStageBytes;  // credited to the leader's barrier
-  // staging per epilogue warp: one 4 KB transpose buffer, or 2 (4 for the two-output c_fc) TMA units
-  // fp32 outputs: a 32-column box is 4 KB (two units), double-buffered
-  static constexpr int kUnitsPerWarp = (MODE == EPI_GELU || (F32Epi<MODE>::value && MODE != EPI_RESID_DEEP)) ? 4 : 2;
+  // staging per epilogue warp: one 4 KB transpose buffer (patch embedding), or TMA boxes: 2 bf16 units (4 for the
+  // two-output c_fc), 2 fp32 boxes (= 4 units), or 2 fp32 boxes + 2 bf16 units for the dual-output modes
+  static constexpr int kUnitsPerWarp = DualEpi<MODE>::value ? 6 : (GeluFwd<MODE>::value || F32Epi<MODE>::value) ? 4 : 2;
   static constexpr int kWarpStaging = RowEpi<MODE>::value ? kUnitsPerWarp * kUnitBytes : 32 * 32 * 4;
   static constexpr int kStagingBytes = EpiWarps<MODE>::value * kWarpStaging;
   static constexpr int kBarBytes = 512;
   static constexpr int kFit = (kMaxSmem - kStagingBytes - 1024 - kBarBytes) / kStageBytes;
   static constexpr int kStages = kFit < 6 ? kFit : 6;
+  static_assert(kStages >= 2, "operand ring too shallow");
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + kBarBytes;
   static constexpr int kTmemCols = 2 * BN;
 };
 
 // ---------------------------------------------------------------------------------------
-// Fused epilogue on 4 consecutive columns of one row (one lane of the coalesced phase).
+// Work decomposition shared by the three warp roles
+// ---------------------------------------------------------------------------------------
+struct SkArgs {
+  int dp_tiles;   // tiles [0, dp_tiles) are dealt whole, round-robin (a multiple of the unit count, or all tiles)
+  int sk_tiles;   // tiles [dp_tiles, dp_tiles + sk_tiles) are cut into sk_units contiguous k-block ranges
+  int sk_units;
+  float* partials;  // one slot of 128 x BN floats per CTA
+  unsigned* flags;  // [CTA][16]
+};
+
+struct Seg {
+  int tile, kb0, kb1;  // k-blocks [kb0, kb1) of `tile`
+  bool finish;         // holds the tile's last k-block: runs the epilogue
+  int n_contrib;       // finisher: partials to add, written by units unit-1 ... unit-n_contrib
+};
+
+// Only the two cursors are state; everything else is re-derived from kernel parameters (uniform registers /
+// constant bank) on each step -- three roles hold an iterator each and the 16-warp epilogues have 96 registers.
+struct SegIter {
+  int dp_next, q;
+  __device__ __forceinline__ static int cut(int u, const SkArgs& a, int num_kb) {  // lower end of unit u's k-block range
+    return static_cast<int>(static_cast<long long>(u) * (a.sk_tiles * num_kb) / a.sk_units);
+  }
+  __device__ __forceinline__ void init(int unit, int num_kb, const SkArgs& a) {
+    dp_next = unit;
+    q = (a.sk_tiles > 0 && unit < a.sk_units) ? cut(unit + 1, a, num_kb) : 0;
+  }
+  __device__ __forceinline__ bool next(Seg& s, int unit, int stride, int num_kb, const SkArgs& a) {
+    if (dp_next < a.dp_tiles) {
+      s.tile = dp_next; s.kb0 = 0; s.kb1 = num_kb; s.finish = true; s.n_contrib = 0;
+      dp_next += stride;
+      return true;
+    }
+    if (q > 0) {  // the unit's stream-K range, walked from the high end down (q == 0: none, or done)
+      const int q_lo = cut(unit, a, num_kb);
+      const int ts = (q - 1) / num_kb, t0 = ts * num_kb;
+      const int lo = q_lo > t0 ? q_lo : t0;
+      s.tile = a.dp_tiles + ts; s.kb0 = lo - t0; s.kb1 = q - t0; s.finish = (s.kb1 == num_kb); s.n_contrib = 0;
+      if (s.finish && s.kb0 > 0) {
+        int v = unit;
+        do { --v; ++s.n_contrib; } while (cut(v, a, num_kb) > t0);
+      }
+      q = lo > q_lo ? lo : 0;  // (lo == q_lo: range exhausted)
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ void flag_release(unsigned* f) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+}
+__device__ __forceinline__ unsigned flag_acquire(const unsigned* f) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused epilogue on 4 consecutive columns of one row (transposing epilogue of the patch embedding
+// and the bring-up SIMT kernel).
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint2 pack4_bf16(const float4& v) {
   uint2 u;
@@ -148,14 +225,15 @@ __device__ __forceinline__ void epilogue4(const GemmEpilogue& ep, int row, int c
 
 
 // ---------------------------------------------------------------------------------------
-// Row-layout epilogue (EPI_BF16 / EPI_GELU / EPI_GELU_BWD), one call per epilogue warp.
+// Row-layout epilogue, one call per epilogue warp.
 //   quad = warp % 4 selects the 32 TMEM lanes (accumulator rows) the warp may read, half selects
-//   which contiguous half of the tile's BN columns it drains, in boxes of 32 columns:
-//     tcgen05.ld 32x32b.x32 (thread = row)  ->  bias / QuickGELU / GELU' on packed fp32 pairs
-//     ->  bf16, 4 x STS.128 into a 2 KB unit (64B swizzle: conflict-free)  ->  TMA store.
+//   which contiguous part of the tile's BN columns it drains, in boxes of 32 columns:
+//     tcgen05.ld 32x32b.x32 (thread = row)  ->  fused math on packed fp32 pairs
+//     ->  bf16: 4 x STS.128 into a 2 KB unit (64B swizzle), fp32: 8 x STS.128 into a 4 KB box (128B swizzle)
+//     ->  TMA store.
 //   The next box's accumulator columns are in flight (second register set) during the math.
-//   EPI_GELU_BWD additionally TMA-loads the saved pre-activation box into the unit one box ahead
-//   (also across tiles) and rewrites it in place.
+//   Modes with an extra per-element operand TMA-load its box into the staging one box ahead
+//   (also across tiles) and rewrite it in place.
 //   TMA clips stores / zero-fills loads at the M and N tails, so there are no per-element predicates.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t unit_slot(int lane, int j) {  // byte offset of 16 B chunk j of row `lane`
@@ -190,19 +268,49 @@ __device__ __forceinline__ uint32_t pack_bf16_2(f32x2 v) {
   f2_unpack(v, lo, hi);
   return pack_bf16(lo, hi);
 }
+__device__ __forceinline__ float f2_hsum(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return lo + hi;
+}
+
+// Row statistics from the per-64-column partials (sum, M2 about the partial's own mean) written by
+// EPI_RESID_STATS / the row kernels: Chan's pairwise update, so a large row mean costs no precision.
+__device__ __forceinline__ void row_mean_rstd(const float2* __restrict__ st, int parts, int width, float eps, float& mean,
+                                              float& rstd) {
+  float n = 0.f, mu = 0.f, m2 = 0.f;
+  for (int p = 0; p < parts; ++p) {
+    const float2 v = __ldg(st + p);
+    const int rem = width - p * kStatSpan;
+    const float np = static_cast<float>(rem < kStatSpan ? rem : kStatSpan);
+    const float nn = n + np;
+    const float delta = v.x / np - mu;
+    mu += delta * (np / nn);
+    m2 += v.y + delta * delta * (n * np / nn);
+    n = nn;
+  }
+  mean = mu;
+  rstd = rsqrtf(m2 / static_cast<float>(width) + eps);
+}
+
+struct EpiMaps {
+  const CUtensorMap *o0, *o1, *ex, *x2, *o2;
+};
 
 template <int BN, int MODE, bool TWO>
-__device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const CUtensorMap* tma_o1, const CUtensorMap* tma_ex,
-                                              const GemmEpilogue& ep, const int M, const int N, const int num_n,
-                                              const int num_tiles, const int unit, const int unit_stride, const uint32_t rank,
-                                              const uint32_t tmem_base, uint8_t* units, uint64_t* ex_bar,
+__device__ __forceinline__ void epilogue_rows(const EpiMaps mp, const GemmEpilogue& ep, const SkArgs& sk, const int M, const int N,
+                                              const int num_n, const int num_kb, const int unit, const int unit_stride,
+                                              const uint32_t rank, const uint32_t tmem_base, uint8_t* units, uint64_t* ex_bar,
                                               uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const int warp,
                                               const int lane) {
   constexpr int TM = TWO ? 2 * BM : BM;
-  constexpr int kParts = EpiWarps<MODE>::value / 4;  // warps per TMEM lane quadrant
-  constexpr int kCols = BN / kParts;                 // columns per warp
-  constexpr int kBoxes = kCols / 32;                 // boxes per warp and tile
-  const int quad = warp & 3, half = (warp - 2) >> 2;  // half = which column part of the tile
+  constexpr int EW = EpiWarps<MODE>::value;
+  constexpr int kParts = EW / 4;        // warps per TMEM lane quadrant
+  constexpr int kCols = BN / kParts;    // columns per warp
+  constexpr int kBoxes = kCols / 32;    // boxes per warp and tile
+  constexpr int kBoxFloats = 32 * 32;
+  const int we = warp - 2;
+  const int quad = warp & 3, half = we >> 2;  // half = which column part of the tile
   auto box_origin = [&](int tile, int& row, int& col0) {
     const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
     row = m_blk * TM + static_cast<int>(rank) * BM + quad * 32;
@@ -215,118 +323,295 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
     const int nb = (N - col0 + 31) >> 5;
     return nb < kBoxes ? nb : kBoxes;
   };
-  // EPI_GELU_BWD: lane 0 walks one box ahead of the warp and issues the pre-activation loads
-  int pf_tile = unit, pf_b = -1;
-  uint32_t pf_k = 0;
-  auto prefetch_next = [&]() {
+  const bool has_resid = ep.resid != nullptr;
+  // Modes with a TMA-loaded operand box: lane 0 walks one box ahead of the warp (over the tiles this unit
+  // FINISHES, in order) and issues the loads
+  SegIter pit;
+  Seg psg;
+  bool pf_valid = false;
+  int pf_b = -1, pf_nb = 0;
+  auto pf_advance = [&]() {
+    bool ok;
+    do { ok = pit.next(psg, unit, unit_stride, num_kb, sk); } while (ok && !psg.finish);
+    pf_valid = ok;
+    pf_nb = ok ? boxes_of(psg.tile) : 0;
+  };
+  auto prefetch_next = [&](const uint32_t pf_k) {  // pf_k = index of the box being requested (one ahead of the warp)
     for (;;) {
       ++pf_b;
-      while (pf_tile < num_tiles && pf_b >= boxes_of(pf_tile)) { pf_tile += unit_stride; pf_b = 0; }
-      if (pf_tile >= num_tiles) return;
+      while (pf_valid && pf_b >= pf_nb) { pf_advance(); pf_b = 0; }
+      if (!pf_valid) return;
       int row, col0;
-      box_origin(pf_tile, row, col0);
+      box_origin(psg.tile, row, col0);
       uint64_t* bar = &ex_bar[pf_k & 1];
-      if constexpr (ResidEpi<MODE>::value) {  // fp32 residual: one 32 x 32 fp32 box (128 B rows, 4 KB = two units)
-        constexpr uint32_t kBufMask = MODE == EPI_RESID_DEEP ? 0u : 1u;
-        bar = &ex_bar[pf_k & kBufMask];
+      if constexpr (MODE == EPI_LN_BWD) {
+        // residual gradient (fp32 box, optional) + LN input x (bf16 box): one barrier
+        mbar_expect_tx(bar, kUnitBytes + (has_resid ? 2 * kUnitBytes : 0));
+        if (has_resid) tma_load_2d(units + (pf_k & 1) * 2 * kUnitBytes, mp.ex, bar, col0 + pf_b * 32, row);
+        tma_load_2d(units + 4 * kUnitBytes + (pf_k & 1) * kUnitBytes, mp.x2, bar, col0 + pf_b * 32, row);
+      } else if constexpr (ResidEpi<MODE>::value) {  // fp32 residual: one 32 x 32 fp32 box (128 B rows, 4 KB = two units)
         mbar_expect_tx(bar, 2 * kUnitBytes);
-        tma_load_2d(units + (pf_k & kBufMask) * 2 * kUnitBytes, tma_ex, bar, col0 + pf_b * 32, row);
+        tma_load_2d(units + (pf_k & 1) * 2 * kUnitBytes, mp.ex, bar, col0 + pf_b * 32, row);
       } else {
         mbar_expect_tx(bar, kUnitBytes);
-        tma_load_2d(units + (pf_k & 1) * kUnitBytes, tma_ex, bar, col0 + pf_b * 32, row);
+        tma_load_2d(units + (pf_k & 1) * kUnitBytes, mp.ex, bar, col0 + pf_b * 32, row);
       }
-      ++pf_k;
       return;
     }
   };
-  if constexpr (MODE == EPI_GELU_BWD || MODE == EPI_RESID_F32) {
-    if (lane == 0) prefetch_next();
+  if constexpr (PrefetchEpi<MODE>::value) {
+    if (lane == 0) {
+      pit.init(unit, num_kb, sk);
+      pf_advance();
+      prefetch_next(0u);
+    }
   }
 
   uint32_t k = 0;  // boxes processed so far by this warp
   const bool has_bias = ep.bias != nullptr;
-  // one box: r = 32 accumulator columns of this thread's row
-  auto process = [&](uint32_t (&r)[32], int row, int col) {
-    float4 bv[MODE == EPI_GELU_BWD ? 1 : 8];
-    if constexpr (MODE == EPI_GELU_BWD) {
-      // (loaded per 8-column group below: dgrad GEMMs have no bias, and 32 live registers would not fit 16 warps)
-    } else if (has_bias && col + 32 <= N) {  // the common case: no per-load guards
-      const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_bias && col + 4 * i < N) bv[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i);
+  // per-row state of the tile being finished (thread = accumulator row)
+  int trow = 0;                               // this thread's global row
+  float ln_a = 1.f, ln_b = 0.f;               // LayerNorm forward: rstd, -rstd * mean
+  float bw_a1 = 0.f, bw_a0 = 0.f;             // LayerNorm backward: out = resid + ln_a * acc + bw_a1 * x + bw_a0
+  int prow = -1;                              // EPI_RESID_STATS: spliced prompt row, or -1
+  float g_sum = 0.f, g_m2 = 0.f, g_mean = 0.f;  // EPI_RESID_STATS: first box of the current 64-column granule
+  f32x2 dot1 = f2_pack(0.f, 0.f), dot2 = f2_pack(0.f, 0.f);  // EPI_GELU_BWD_DOTS
+  auto row_setup = [&](int row) {
+    trow = row + lane;
+    const int rc = trow < M ? trow : M - 1;
+    if constexpr (LnFwd<MODE>::value || MODE == EPI_LN_BWD) {
+      float mean, rstd;
+      row_mean_rstd(ep.ln_stats + static_cast<size_t>(rc) * ep.ln_parts, ep.ln_parts, ep.ln_width, ep.ln_eps, mean, rstd);
+      ln_a = rstd;
+      ln_b = -rstd * mean;
+      if constexpr (MODE == EPI_LN_BWD) {
+        float c1 = 0.f, c2 = 0.f;
+        const float2* dp = ep.dots + static_cast<size_t>(rc) * ep.dot_parts;
+        for (int p = 0; p < ep.dot_parts; ++p) {
+          const float2 v = __ldg(dp + p);
+          c1 += v.x;
+          c2 += v.y;
+        }
+        const float inv = 1.f / static_cast<float>(ep.ln_width);
+        c1 *= inv;
+        c2 *= inv;
+        bw_a1 = -rstd * rstd * c2;
+        bw_a0 = rstd * (rstd * c2 * mean - c1);
       }
     }
-    if constexpr (MODE == EPI_BF16) {
-      uint8_t* u = units + (k & 1) * kUnitBytes;
-      if (lane == 0) bulk_wait_read<1>();  // the store issued from this unit two boxes ago has read it
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int e = 8 * j + 2 * q;
-          f32x2 v = f2_pack_u(r[e], r[e + 1]);
-          if (has_bias) {  // (dgrad GEMMs have none: warp-uniform)
-            const float4 b4 = bv[e >> 2];
-            v = f2_add(v, (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y));
-          }
-          o[q] = pack_bf16_2(v);
-        }
-        *reinterpret_cast<uint4*>(u + unit_slot(lane, j)) = make_uint4(o[0], o[1], o[2], o[3]);
+    if constexpr (MODE == EPI_RESID_STATS) {
+      prow = -1;
+      if (ep.splice_n > 0 && trow < M) {
+        const int pos = trow % ep.splice_L - ep.splice_row0;
+        if (pos >= 0 && pos < ep.splice_n) prow = pos;
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) { tma_store_2d(tma_o0, u, col, row); bulk_commit(); }
-    } else if constexpr (MODE == EPI_GELU) {
-      // units {0,1} / {2,3} alternate per box: h and QuickGELU(h)
-      uint8_t* uh = units + (k & 1) * 2 * kUnitBytes;
-      uint8_t* ug = uh + kUnitBytes;
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
+    }
+  };
+  // one box: r = 32 accumulator columns of this thread's row
+  auto process = [&](uint32_t (&r)[32], int row, int col) {
+    if constexpr (Bf16Fwd<MODE>::value || GeluFwd<MODE>::value) {
+      constexpr bool LN = LnFwd<MODE>::value;
+      float4 bv[8], sv[LN ? 8 : 1];
+      if ((has_bias || LN) && col + 32 <= N) {  // the common case: no per-load guards
+        const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t oh[4], og[4];
+        for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
+        if constexpr (LN) {
+          const float4* sp = reinterpret_cast<const float4*>(ep.colsum + col);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int e = 8 * j + 2 * q;
-          const float4 b4 = bv[e >> 2];
-          const f32x2 bb = (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
-          const f32x2 v = f2_add(f2_pack_u(r[e], r[e + 1]), bb);
-          oh[q] = pack_bf16_2(v);
-          og[q] = pack_bf16_2(quick_gelu2(v));
+          for (int i = 0; i < 8; ++i) sv[i] = __ldg(sp + i);
         }
-        *reinterpret_cast<uint4*>(uh + unit_slot(lane, j)) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-        *reinterpret_cast<uint4*>(ug + unit_slot(lane, j)) = make_uint4(og[0], og[1], og[2], og[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((has_bias || LN) && col + 4 * i < N) bv[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i);
+          if constexpr (LN) {
+            sv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col + 4 * i < N) sv[i] = __ldg(reinterpret_cast<const float4*>(ep.colsum + col) + i);
+          }
+        }
+      }
+      const f32x2 lna2 = f2_pack(ln_a, ln_a), lnb2 = f2_pack(ln_b, ln_b);
+      // fused value of the pair (e, e + 1)
+      auto value = [&](int e) {
+        f32x2 v = f2_pack_u(r[e], r[e + 1]);
+        const float4 b4 = bv[e >> 2];
+        const f32x2 bb = (e & 2) ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
+        if constexpr (LN) {
+          const float4 s4 = sv[e >> 2];
+          const f32x2 ss = (e & 2) ? f2_pack(s4.z, s4.w) : f2_pack(s4.x, s4.y);
+          v = f2_fma(lna2, v, f2_fma(lnb2, ss, bb));  // rstd * acc + (b' - rstd * mean * colsum)
+        } else if (has_bias) {  // (dgrad GEMMs have none: warp-uniform)
+          v = f2_add(v, bb);
+        }
+        return v;
+      };
+      if constexpr (Bf16Fwd<MODE>::value) {
+        uint8_t* u = units + (k & 1) * kUnitBytes;
+        if (lane == 0) bulk_wait_read<1>();  // the store issued from this unit two boxes ago has read it
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = pack_bf16_2(value(8 * j + 2 * q));
+          *reinterpret_cast<uint4*>(u + unit_slot(lane, j)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(mp.o0, u, col, row); bulk_commit(); }
+      } else {
+        // units {0,1} / {2,3} alternate per box: h and QuickGELU(h)
+        uint8_t* uh = units + (k & 1) * 2 * kUnitBytes;
+        uint8_t* ug = uh + kUnitBytes;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t oh[4], og[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const f32x2 v = value(8 * j + 2 * q);
+            oh[q] = pack_bf16_2(v);
+            og[q] = pack_bf16_2(quick_gelu2(v));
+          }
+          *reinterpret_cast<uint4*>(uh + unit_slot(lane, j)) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+          *reinterpret_cast<uint4*>(ug + unit_slot(lane, j)) = make_uint4(og[0], og[1], og[2], og[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (ep.out0 != nullptr) tma_store_2d(mp.o0, uh, col, row);
+          tma_store_2d(mp.o1, ug, col, row);
+          bulk_commit();  // both stores of the box form one group
+        }
+      }
+    } else if constexpr (DualEpi<MODE>::value) {
+      // fp32 box (residual in, out0 out: 32 rows x 128 B, 128B swizzle) + bf16 box (x2 in for the LN backward, out2 out)
+      uint8_t* u = units + (k & 1) * 2 * kUnitBytes;
+      uint8_t* ub = units + 4 * kUnitBytes + (k & 1) * kUnitBytes;
+      if (lane == 0) {
+        bulk_wait_read<0>();  // the other buffers' stores (previous box) have been read: refill them for the next box
+        prefetch_next(k + 1);
+      }
+      mbar_wait(&ex_bar[k & 1], (k >> 1) & 1);  // this box's operands have landed
+      uint4 rq8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        rq8[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (MODE == EPI_RESID_STATS || has_resid) rq8[j] = *reinterpret_cast<const uint4*>(u + lane * 128 + ((j ^ (lane & 7)) << 4));
+      }
+      if constexpr (MODE == EPI_RESID_STATS) {
+        // x = acc + bias + resid, or the spliced prompt row; statistics of x; x as fp32 and bf16
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f32x2 v0 = f2_pack_u(r[4 * j], r[4 * j + 1]), v1 = f2_pack_u(r[4 * j + 2], r[4 * j + 3]);
+          if (has_bias && col + 4 * j < N) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
+            v0 = f2_add(v0, f2_pack(b4.x, b4.y));
+            v1 = f2_add(v1, f2_pack(b4.z, b4.w));
+          }
+          v0 = f2_add(v0, f2_pack_u(rq8[j].x, rq8[j].y));
+          v1 = f2_add(v1, f2_pack_u(rq8[j].z, rq8[j].w));
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(r[4 * j]), "=r"(r[4 * j + 1]) : "l"(v0));
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(r[4 * j + 2]), "=r"(r[4 * j + 3]) : "l"(v1));
+        }
+        if (prow >= 0) {  // deep-prompt splice: the row is replaced verbatim (bit-exact)
+          const float4* pp = reinterpret_cast<const float4*>(ep.splice_prompt + static_cast<size_t>(prow) * N + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (col + 4 * j < N) {
+              const float4 t = __ldg(pp + j);
+              r[4 * j] = __float_as_uint(t.x); r[4 * j + 1] = __float_as_uint(t.y);
+              r[4 * j + 2] = __float_as_uint(t.z); r[4 * j + 3] = __float_as_uint(t.w);
+            }
+          }
+        }
+        f32x2 s2 = f2_pack(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s2 = f2_add(s2, f2_pack_u(r[2 * i], r[2 * i + 1]));
+        const float sum = f2_hsum(s2), mean = sum * (1.f / 32.f);
+        const f32x2 nm2 = f2_pack(-mean, -mean);
+        f32x2 q2 = f2_pack(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const f32x2 dlt = f2_add(f2_pack_u(r[2 * i], r[2 * i + 1]), nm2);
+          q2 = f2_fma(dlt, dlt, q2);
+        }
+        const float m2 = f2_hsum(q2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(u + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o[q] = pack_bf16(__uint_as_float(r[8 * j + 2 * q]), __uint_as_float(r[8 * j + 2 * q + 1]));
+          *reinterpret_cast<uint4*>(ub + unit_slot(lane, j)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (((col >> 5) & 1) == 0) {
+          g_sum = sum; g_m2 = m2; g_mean = mean;
+        } else if (trow < M) {  // second box of the 64-column granule: merge (32 + 32 values) and publish
+          const float dm = mean - g_mean;
+          ep.stats_out[static_cast<size_t>(trow) * (N / kStatSpan) + (col >> 6)] = make_float2(g_sum + sum, g_m2 + m2 + 16.f * dm * dm);
+        }
+      } else {  // EPI_LN_BWD: out = resid + rstd * acc + a1 * x + a0
+        uint4 xq4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xq4[j] = *reinterpret_cast<const uint4*>(ub + unit_slot(lane, j));
+        const f32x2 a2 = f2_pack(ln_a, ln_a), a1_2 = f2_pack(bw_a1, bw_a1), a0_2 = f2_pack(bw_a0, bw_a0);
+        uint32_t ob[4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t w0 = (j & 1) ? xq4[j >> 1].z : xq4[j >> 1].x, w1 = (j & 1) ? xq4[j >> 1].w : xq4[j >> 1].y;
+          const f32x2 x0 = f2_pack_u(w0 << 16, w0 & 0xffff0000u), x1 = f2_pack_u(w1 << 16, w1 & 0xffff0000u);
+          f32x2 v0 = f2_fma(a2, f2_pack_u(r[4 * j], r[4 * j + 1]), f2_pack_u(rq8[j].x, rq8[j].y));
+          f32x2 v1 = f2_fma(a2, f2_pack_u(r[4 * j + 2], r[4 * j + 3]), f2_pack_u(rq8[j].z, rq8[j].w));
+          v0 = f2_add(f2_fma(a1_2, x0, v0), a0_2);
+          v1 = f2_add(f2_fma(a1_2, x1, v1), a0_2);
+          uint4 o;
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(o.x), "=r"(o.y) : "l"(v0));
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(o.z), "=r"(o.w) : "l"(v1));
+          *reinterpret_cast<uint4*>(u + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+          ob[(j & 1) * 2] = pack_bf16_2(v0);
+          ob[(j & 1) * 2 + 1] = pack_bf16_2(v1);
+          if (j & 1) *reinterpret_cast<uint4*>(ub + unit_slot(lane, j >> 1)) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (ep.out0 != nullptr) tma_store_2d(tma_o0, uh, col, row);
-        tma_store_2d(tma_o1, ug, col, row);
-        bulk_commit();  // both stores of the box form one group
+        tma_store_2d(mp.o0, u, col, row);
+        if (ep.out2 != nullptr) tma_store_2d(mp.o2, ub, col, row);
+        bulk_commit();
       }
     } else if constexpr (F32Epi<MODE>::value) {
       // out0 (fp32) = acc + bias (+ residual): the box is 32 rows x 128 B (two units, 128B TMA swizzle); the residual
       // is TMA-loaded into it one box ahead and rewritten in place (out-proj / c_proj, clip/model.py:299-300)
-      constexpr uint32_t kBufMask = MODE == EPI_RESID_DEEP ? 0u : 1u;
-      uint8_t* u = units + (k & kBufMask) * 2 * kUnitBytes;
+      uint8_t* u = units + (k & 1) * 2 * kUnitBytes;
       if constexpr (ResidEpi<MODE>::value) {
         if (lane == 0) {
-          // double-buffered: the other buffer's stores (previous box) have been read, it is refilled for the next
-          // box; single-buffered (DEEP): this box's own residual is requested now
-          bulk_wait_read<0>();
-          prefetch_next();
+          bulk_wait_read<0>();  // the other buffer's stores (previous box) have been read: refill it for the next box
+          prefetch_next(k + 1);
         }
-        mbar_wait(&ex_bar[k & kBufMask], (MODE == EPI_RESID_DEEP ? k : (k >> 1)) & 1);  // this box's residual has landed
+        mbar_wait(&ex_bar[k & 1], (k >> 1) & 1);  // this box's residual has landed
       } else {
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
+      }
+      float4 bv[8];
+      if (has_bias && col + 32 <= N) {
+        const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bv[i] = __ldg(bp + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_bias && col + 4 * i < N) bv[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i);
+        }
       }
       uint4 rq8[ResidEpi<MODE>::value ? 8 : 1];
       if constexpr (ResidEpi<MODE>::value) {  // read the whole residual row first (see the GELU' branch)
@@ -353,12 +638,12 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) { tma_store_2d(tma_o0, u, col, row); bulk_commit(); }
-    } else {  // EPI_GELU_BWD
+      if (lane == 0) { tma_store_2d(mp.o0, u, col, row); bulk_commit(); }
+    } else {  // EPI_GELU_BWD / EPI_GELU_BWD_DOTS
       uint8_t* u = units + (k & 1) * kUnitBytes;
       if (lane == 0) {
         bulk_wait_read<0>();  // the other unit's store (previous box) has been read: it may be refilled
-        prefetch_next();
+        prefetch_next(k + 1);
       }
       mbar_wait(&ex_bar[k & 1], (k >> 1) & 1);  // this box's pre-activation has landed
       // all four 16 B groups of the row are read before anything is written back: with a load per group the
@@ -372,32 +657,74 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
         uint4* slot = reinterpret_cast<uint4*>(u + unit_slot(lane, j));
         const uint32_t hw[4] = {hq4[j].x, hq4[j].y, hq4[j].z, hq4[j].w};
         uint32_t o[4];
+        const bool in_n = col + 8 * j < N;  // (warp-uniform; N % 8 == 0)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = 8 * j + 2 * q;
           f32x2 v = f2_pack_u(r[e], r[e + 1]);
-          if (has_bias && col + 8 * j < N) {  // (dgrad GEMMs have none: warp-uniform)
+          if (has_bias && in_n) {  // (dgrad GEMMs have none: warp-uniform)
             const float2 b2 = __ldg(reinterpret_cast<const float2*>(ep.bias + col + e));
             v = f2_add(v, f2_pack(b2.x, b2.y));
           }
           const f32x2 h = f2_pack_u(hw[q] << 16, hw[q] & 0xffff0000u);  // bf16 pair -> fp32 pair
-          o[q] = pack_bf16_2(mul_quick_gelu_grad2(v, h));
+          const f32x2 res = mul_quick_gelu_grad2(v, h);
+          if constexpr (MODE == EPI_GELU_BWD_DOTS) {
+            if (in_n) {  // partial dots of the row for the fused LayerNorm backward of the next GEMM
+              const float4 sb4 = __ldg(reinterpret_cast<const float4*>(ep.sb + col + e));  // (colsum, b') of columns e, e + 1
+              dot1 = f2_fma(res, f2_pack(sb4.x, sb4.z), dot1);
+              dot2 = f2_fma(res, f2_add(h, f2_pack(-sb4.y, -sb4.w)), dot2);
+            }
+          }
+          o[q] = pack_bf16_2(res);
         }
         *slot = make_uint4(o[0], o[1], o[2], o[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) { tma_store_2d(tma_o0, u, col, row); bulk_commit(); }
+      if (lane == 0) { tma_store_2d(mp.o0, u, col, row); bulk_commit(); }
     }
     ++k;
   };
+  // after the last box of a finished tile
+  auto tile_end = [&](int col0) {
+    if constexpr (MODE == EPI_GELU_BWD_DOTS) {
+      if (trow < M) ep.dots_out[static_cast<size_t>(trow) * ((N + kCols - 1) / kCols) + col0 / kCols] = make_float2(f2_hsum(dot1), f2_hsum(dot2));
+      dot1 = f2_pack(0.f, 0.f);
+      dot2 = f2_pack(0.f, 0.f);
+    }
+  };
 
+  // stream-K hand-over of partial accumulators (see the header comment): warp `we` of CTA c owns
+  // floats [we * kBoxes * 1024, +kBoxes * 1024) of CTA c's slot; element (box b, 16 B group j, lane) is one uint4
+  const size_t slot_floats = static_cast<size_t>(BM) * BN;
+  auto slot_of = [&](int cta) { return sk.partials + static_cast<size_t>(cta) * slot_floats + static_cast<size_t>(we) * (kBoxes * kBoxFloats); };
+  auto sk_add = [&](uint32_t (&r)[32], int b, int n_contrib) {
+    for (int c = 1; c <= n_contrib; ++c) {
+      const int cta = TWO ? 2 * (unit - c) + static_cast<int>(rank) : unit - c;
+      const uint4* p = reinterpret_cast<const uint4*>(slot_of(cta) + b * kBoxFloats) + lane;
+      uint4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcg(p + j * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + __uint_as_float(v[j].x));
+        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + __uint_as_float(v[j].y));
+        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + __uint_as_float(v[j].z));
+        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + __uint_as_float(v[j].w));
+      }
+    }
+  };
+
+  SegIter it;
+  it.init(unit, num_kb, sk);
+  Seg sg;
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int tile = unit; tile < num_tiles; tile += unit_stride) {
+  while (it.next(sg, unit, unit_stride, num_kb, sk)) {
     int row, col0;
-    box_origin(tile, row, col0);
-    const int nb = boxes_of(tile);
+    box_origin(sg.tile, row, col0);
+    const int nb = boxes_of(sg.tile);
+    if (sg.finish) row_setup(row);  // the row's statistics are in flight while the accumulator is awaited
     mbar_wait(&tmem_full_bar[acc], acc_phase);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kCols);
@@ -409,7 +736,43 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
         else mbar_arrive(&tmem_empty_bar[acc]);
       }
     };
-    if constexpr (EpiWarps<MODE>::value > 8) {
+    if (!sg.finish) {
+      // contributor: the raw partial accumulator goes to this CTA's slot, then the warp's flag is raised
+      uint32_t ra[32];
+      uint4* p = reinterpret_cast<uint4*>(slot_of(static_cast<int>(blockIdx.x))) + lane;
+      if (nb == 0) release_acc();
+#pragma unroll 1
+      for (int b = 0; b < nb; ++b) {
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(b * 32), ra);
+        tmem_ld_wait_regs(ra);
+        if (b + 1 == nb) release_acc();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) __stcg(p + (b * 8 + j) * 32, make_uint4(ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]));
+      }
+      if (nb > 0) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) flag_release(sk.flags + blockIdx.x * 16 + we);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      continue;
+    }
+    const int n_contrib = nb > 0 ? sg.n_contrib : 0;
+    for (int c = 1; c <= n_contrib; ++c) {  // finisher: the same warp of the lower-numbered unit(s) has written its part
+      const int cta = TWO ? 2 * (unit - c) + static_cast<int>(rank) : unit - c;
+      unsigned* f = sk.flags + cta * 16 + we;
+      uint32_t spins = 0;
+      while (flag_acquire(f) == 0u) {
+        __nanosleep(64);
+        if (++spins > (1u << 22)) {
+          if (lane == 0) printf("mudpt: stream-K partial of CTA %d never arrived (block %d warp %d)\n", cta, blockIdx.x, warp);
+          __trap();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) *f = 0u;  // single consumer: leave the flag clear for the next launch
+    }
+    if constexpr (EW > 8) {
       // 4 warps per scheduler: one accumulator register set, no TMEM prefetch
       uint32_t ra[32];
       if (nb == 0) release_acc();
@@ -418,28 +781,34 @@ __device__ __forceinline__ void epilogue_rows(const CUtensorMap* tma_o0, const C
         tmem_ld_32x32(taddr + static_cast<uint32_t>(b * 32), ra);
         tmem_ld_wait_regs(ra);
         if (b + 1 == nb) release_acc();
+        if (n_contrib) sk_add(ra, b, n_contrib);
         process(ra, row, col0 + b * 32);
       }
+      if (nb > 0) tile_end(col0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       continue;
-    }
-    uint32_t ra[32], rb[32];
-    if (nb > 0) tmem_ld_32x32(taddr, ra);
-    else release_acc();
-#pragma unroll 1
-    for (int b = 0; b < nb; b += 2) {
-      tmem_ld_wait_regs(ra);
-      if (b + 1 < nb) tmem_ld_32x32(taddr + static_cast<uint32_t>((b + 1) * 32), rb);
+    } else {
+      uint32_t ra[32], rb[32];
+      if (nb > 0) tmem_ld_32x32(taddr, ra);
       else release_acc();
-      process(ra, row, col0 + b * 32);
-      if (b + 1 < nb) {
-        tmem_ld_wait_regs(rb);
-        if (b + 2 < nb) tmem_ld_32x32(taddr + static_cast<uint32_t>((b + 2) * 32), ra);
+#pragma unroll 1
+      for (int b = 0; b < nb; b += 2) {
+        tmem_ld_wait_regs(ra);
+        if (b + 1 < nb) tmem_ld_32x32(taddr + static_cast<uint32_t>((b + 1) * 32), rb);
         else release_acc();
-        process(rb, row, col0 + (b + 1) * 32);
+        if (n_contrib) sk_add(ra, b, n_contrib);
+        process(ra, row, col0 + b * 32);
+        if (b + 1 < nb) {
+          tmem_ld_wait_regs(rb);
+          if (b + 2 < nb) tmem_ld_32x32(taddr + static_cast<uint32_t>((b + 2) * 32), ra);
+          else release_acc();
+          if (n_contrib) sk_add(rb, b + 1, n_contrib);
+          process(rb, row, col0 + (b + 1) * 32);
+        }
       }
+      if (nb > 0) tile_end(col0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
   if (lane == 0) bulk_wait<0>();  // shared memory must outlive the last store's read; writes complete before exit
 }
@@ -451,8 +820,9 @@ template <int BN, int MODE, bool TWO>
 __global__ void __launch_bounds__(GemmThreads<MODE>::value, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                        const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_o1,
-                       const __grid_constant__ CUtensorMap tma_ex, const GemmEpilogue ep, const int M, const int N,
-                       const int K) {
+                       const __grid_constant__ CUtensorMap tma_ex, const __grid_constant__ CUtensorMap tma_x2,
+                       const __grid_constant__ CUtensorMap tma_o2, const GemmEpilogue ep, const SkArgs sk, const int M,
+                       const int N, const int K) {
   using Cfg = GemmCfg<BN, MODE, TWO>;
   // CTA pair: rank 0 is the leader (issues the MMAs, owns the "full" and "accumulator drained" barriers)
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;
@@ -473,14 +843,12 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   constexpr int EPI_WARPS = EpiWarps<MODE>::value;
-  uint64_t* extra_bar = tmem_empty_bar + 2;  // [EPI_WARPS][2]: pre-activation / residual boxes of the row epilogues
+  uint64_t* extra_bar = tmem_empty_bar + 2;  // [EPI_WARPS][2]: operand boxes of the row epilogues
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(extra_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + TM - 1) / TM;
   const int num_n = (N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -515,11 +883,14 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = unit; tile < num_tiles; tile += unit_stride) {
-        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      SegIter it;
+      it.init(unit, num_kb, sk);
+      Seg sg;
+      while (it.next(sg, unit, unit_stride, num_kb, sk)) {
+        const int m_blk = sg.tile / num_n, n_blk = sg.tile - m_blk * num_n;
         const int a_row = m_blk * TM + static_cast<int>(rank) * BM;               // this CTA's 128 rows of A
         const int b_row = n_blk * BN + static_cast<int>(rank) * Cfg::kBRows;     // this CTA's share of B
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if constexpr (TWO) {
             // both CTAs' loads are credited to the leader's barrier; only the leader arms it
@@ -543,11 +914,14 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = unit; tile < num_tiles; tile += unit_stride) {
+      SegIter it;
+      it.init(unit, num_kb, sk);
+      Seg sg;
+      while (it.next(sg, unit, unit_stride, num_kb, sk)) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
           tc_fence_after();
           const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
@@ -555,12 +929,11 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (start-address field is >>4)
+            const uint32_t accum = static_cast<uint32_t>(kb != sg.kb0 || k != 0);
             if constexpr (TWO)
-              umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                            static_cast<uint32_t>((kb | k) != 0));
+              umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, accum);
             else
-              umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                        static_cast<uint32_t>((kb | k) != 0));
+              umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, accum);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
           if constexpr (TWO) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
@@ -572,12 +945,13 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       }
     }
   } else if constexpr (RowEpi<MODE>::value) {
-    // ===================== epilogue (warps 2..9), row layout + TMA stores =====================
-    epilogue_rows<BN, MODE, TWO>(&tma_o0, &tma_o1, &tma_ex, ep, M, N, num_n, num_tiles, unit, unit_stride, rank, tmem_base,
+    // ===================== epilogue (warps 2..), row layout + TMA stores =====================
+    const EpiMaps mp{&tma_o0, &tma_o1, &tma_ex, &tma_x2, &tma_o2};
+    epilogue_rows<BN, MODE, TWO>(mp, ep, sk, M, N, num_n, num_kb, unit, unit_stride, rank, tmem_base,
                                  smem_stage + (warp - 2) * Cfg::kWarpStaging, extra_bar + (warp - 2) * 2, tmem_full_bar,
                                  tmem_empty_bar, warp, lane);
   } else {
-    // ===================== epilogue (warps 2..9), transposing =====================
+    // ===================== epilogue (warps 2..9), transposing (patch embedding; whole tiles only) =====================
     // Two warps per TMEM lane quadrant (quad = warp % 4); the pair splits the 32-column chunks of the
     // accumulator between them (even / odd), so every SM sub-partition has two epilogue warps to
     // overlap TMEM / shared / global latencies.
@@ -585,6 +959,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     //            (32 rows x 128 B, 16-byte chunks XOR-swizzled by row: conflict-free).
     //   Phase B: 8 lanes per row, lane j owns columns 4j..4j+3, so every global load/store
     //            instruction covers whole 128 B (fp32) / 64 B (bf16) row segments of 4 rows.
+    const int num_tiles = sk.dp_tiles;  // (the host never cuts tiles in this mode)
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     uint8_t* stage = smem_stage + (warp - 2) * Cfg::kWarpStaging;
@@ -595,22 +970,18 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     for (int tile = unit; tile < num_tiles; tile += unit_stride) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       const int m_row0 = m_blk * TM + static_cast<int>(rank) * BM;  // first row of this CTA's accumulator
-      constexpr int OM = (MODE == EPI_RESID_DEEP) ? EPI_RESID_F32 : MODE;  // epilogue math of the transposing path
-      typedef typename EpiExtra<OM>::type Ex;
-      constexpr bool kHasExtra = (OM == EPI_RESID_F32 || OM == EPI_GELU_BWD || OM == EPI_PATCH);
-      constexpr bool kDouble = (MODE == EPI_GELU_BWD);  // packed operand: cheap enough to prefetch a chunk ahead
+      typedef typename EpiExtra<MODE>::type Ex;
       const int ncol = N - n_blk * BN;  // valid columns in this tile (may exceed BN)
       const int row_base = m_row0 + quad * 32 + rr0;
       int c = half;
-      Ex ex[kHasExtra ? 8 : 1], exn[kDouble ? 8 : 1];
-      auto load_extra = [&](Ex(&dst)[kHasExtra ? 8 : 1], int chunk) {
+      Ex ex[8];
+      auto load_extra = [&](Ex(&dst)[8], int chunk) {
         const int col = min(n_blk * BN + chunk * 32 + 4 * j, N - 4);  // clamped: out-of-range lanes never use it
 #pragma unroll
-        for (int it = 0; it < (kHasExtra ? 8 : 1); ++it)
-          dst[it] = epilogue_prefetch<OM>(ep, min(row_base + it * 4, M - 1), col);
+        for (int it = 0; it < 8; ++it) dst[it] = epilogue_prefetch<MODE>(ep, min(row_base + it * 4, M - 1), col);
       };
       // the first chunk's operand loads are issued before waiting for the accumulator
-      if constexpr (kHasExtra) { if (c * 32 < ncol) load_extra(ex, c); }
+      if (c * 32 < ncol) load_extra(ex, c);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -620,7 +991,6 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       for (; c < kChunks && c * 32 < ncol; c += 2) {
         const int col = n_blk * BN + c * 32 + 4 * j;  // this lane's 4 columns in phase B
         const bool has_next = (c + 2 < kChunks) && ((c + 2) * 32 < ncol);
-        if constexpr (kDouble) { if (has_next) load_extra(exn, c + 2); }
         tmem_ld_wait_regs(r);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -638,16 +1008,11 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             const int row = m_row0 + quad * 32 + rr;
             float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + (((j ^ rr) & 7) << 4));
             v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-            if (row < M) epilogue4<OM>(ep, row, col, v, ex[kHasExtra ? it : 0]);
+            if (row < M) epilogue4<MODE>(ep, row, col, v, ex[it]);
           }
         }
         __syncwarp();
-        if constexpr (kDouble) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) ex[it] = exn[it];
-        } else if constexpr (kHasExtra) {
-          if (has_next) load_extra(ex, c + 2);
-        }
+        if (has_next) load_extra(ex, c + 2);
       }
       tc_fence_before();
       __syncwarp();
@@ -670,7 +1035,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 
 #ifdef MUDPT_BRINGUP
 // Bring-up diagnostic only (libmudpt_b200_bringup.so, never the shipped library): a plain
-// CUDA-core GEMM with the same epilogues, used to validate the rest of the pipeline
+// CUDA-core GEMM with the epilogues of modes 0-5, used to validate the rest of the pipeline
 // independently of the tcgen05 path.
 template <int MODE>
 __global__ void gemm_tn_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, const GemmEpilogue ep,
@@ -771,6 +1136,10 @@ void gemm_clear_tensor_map_cache() {
 }
 
 static bool g_enable_2cta = []{ const char* e = getenv("MUDPT_GEMM_2CTA"); return e ? atoi(e) != 0 : true; }();
+// MUDPT_GEMM_SK: 0 = whole tiles only, 1 = cut whenever the tile count is not a multiple of the units, unset = cost model
+static const int g_sk_default = []{ const char* e = getenv("MUDPT_GEMM_SK"); return e ? atoi(e) : -1; }();
+static int g_sk_mode = g_sk_default;
+void gemm_set_stream_k(int mode) { g_sk_mode = mode == -2 ? g_sk_default : mode; }
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -782,9 +1151,43 @@ static int num_sms() {
   return g_num_sms;
 }
 
+static constexpr int kMaxCtas = 160;  // slots / flags are indexed by CTA; 148 SMs on B200
+size_t gemm_workspace_partial_bytes() { return static_cast<size_t>(kMaxCtas) * BM * 256 * sizeof(float); }
+size_t gemm_workspace_flag_bytes() { return static_cast<size_t>(kMaxCtas) * 16 * sizeof(unsigned); }
+static int pick_bn(int N) { return N >= 256 ? 256 : 128; }
+int gemm_dots_span(int N) { return pick_bn(N) / (EpiWarps<EPI_GELU_BWD_DOTS>::value / 4); }
+
+// Stream-K plan for `tiles` tiles of `num_kb` k-blocks on `units` units (see the header comment).
+static SkArgs plan_sk(int tiles, int units, int num_kb, const GemmWorkspace* ws, bool allowed) {
+  SkArgs a;
+  a.dp_tiles = tiles; a.sk_tiles = 0; a.sk_units = 0;
+  a.partials = ws ? ws->partials : nullptr;
+  a.flags = ws ? ws->flags : nullptr;
+  if (!allowed || ws == nullptr || ws->partials == nullptr || ws->flags == nullptr || g_sk_mode == 0) return a;
+  const int rem = tiles % units;
+  if (rem == 0) return a;
+  const int waves = tiles / units;
+  const int sk_tiles = rem + (waves > 0 ? units : 0);
+  const long long q = static_cast<long long>(sk_tiles) * num_kb;
+  // at least 4 k-blocks per unit (a unit's range is one or two accumulator passes + at most one hand-over)
+  int sk_units = static_cast<int>(q / 4 < units ? q / 4 : units);
+  if (sk_units < 1) sk_units = 1;
+  if (g_sk_mode != 1) {
+    // whole tiles cost ceil(sk_tiles / units) tile-times for this part, the cut sk_tiles / sk_units plus the
+    // hand-over of one 128 x BN fp32 tile through L2 per unit (measured in tile-times: ~3 k-blocks' worth)
+    const float whole = static_cast<float>((sk_tiles + units - 1) / units);
+    const float cut = static_cast<float>(sk_tiles) / static_cast<float>(sk_units) + 3.0f / static_cast<float>(num_kb);
+    if (cut > 0.92f * whole) return a;
+  }
+  a.dp_tiles = tiles - sk_tiles;
+  a.sk_tiles = sk_tiles;
+  a.sk_units = sk_units;
+  return a;
+}
+
 template <int BN, int MODE, bool TWO>
-static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap (&te)[3], const GemmEpilogue& ep,
-                              int M, int N, int K, cudaStream_t stream) {
+static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap (&te)[5], const GemmEpilogue& ep,
+                              int M, int N, int K, cudaStream_t stream, const GemmWorkspace* ws) {
   using Cfg = GemmCfg<BN, MODE, TWO>;
   static bool attr_done = false;
   auto kern = gemm_tn_tcgen05_kernel<BN, MODE, TWO>;
@@ -795,8 +1198,11 @@ static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, cons
   }
   constexpr int TM = TWO ? 2 * BM : BM;
   const int tiles = ((M + TM - 1) / TM) * ((N + BN - 1) / BN);
-  const int units = TWO ? num_sms() / 2 : num_sms();
-  const int grid = (tiles < units ? tiles : units) * (TWO ? 2 : 1);
+  int units = TWO ? num_sms() / 2 : num_sms();
+  if (units * (TWO ? 2 : 1) > kMaxCtas) units = kMaxCtas / (TWO ? 2 : 1);
+  const SkArgs sk = plan_sk(tiles, units, (K + BK - 1) / BK, ws, RowEpi<MODE>::value);
+  const int used = sk.sk_tiles > 0 ? units : (tiles < units ? tiles : units);
+  const int grid = used * (TWO ? 2 : 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GemmThreads<MODE>::value);
@@ -811,73 +1217,91 @@ static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, cons
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, te[0], te[1], te[2], ep, M, N, K) != cudaSuccess) return launch_status("gemm kernel launch failed");
+  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, te[0], te[1], te[2], te[3], te[4], ep, sk, M, N, K) != cudaSuccess)
+    return launch_status("gemm kernel launch failed");
   count_launch();
   return launch_status("gemm kernel launch failed");
 }
 
 template <int MODE>
 static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, const GemmEpilogue& ep, int M, int N,
-                               int K, cudaStream_t stream) {
+                               int K, cudaStream_t stream, const GemmWorkspace* ws) {
 #ifdef MUDPT_BRINGUP
   if (g_simt) {
-    dim3 grid((N / 8 + 63) / 64, M);
-    gemm_tn_simt_kernel<(MODE == EPI_RESID_DEEP ? EPI_RESID_F32 : MODE)><<<grid, 64, 0, stream>>>(A, B, ep, M, N, K, lda, ldb);
-    count_launch();
-    return launch_status("simt gemm launch failed");
+    if constexpr (MODE <= EPI_PATCH) {
+      dim3 grid((N / 8 + 63) / 64, M);
+      gemm_tn_simt_kernel<MODE><<<grid, 64, 0, stream>>>(A, B, ep, M, N, K, lda, ldb);
+      count_launch();
+      return launch_status("simt gemm launch failed");
+    } else {
+      return "bring-up SIMT GEMM: mode not implemented";
+    }
   }
 #endif
-  // Tile-shape choice: 128x256 tiles halve the A re-reads; use them when they still fill the
-  // machine (>= one full wave of 148 CTAs), otherwise 128x128 (thin N = d GEMMs).
-  // The grid is persistent (one CTA per SM), so what counts is the number of tile "waves":
-  // e.g. M = 6368 (32 images x 199 tokens), N = 768 gives 150 tiles of 128x256 -- two waves with
-  // the second almost empty -- but 300 tiles of 128x128 in three half-cost waves.  Pick the shape
-  // with the smaller estimated makespan (a 128x128 tile costs ~0.7 of a 128x256 one: it moves
-  // 1/3 more operand bytes per FLOP through shared memory).
-  const int mb = (M + BM - 1) / BM, sms = num_sms();
-  const int t256 = mb * ((N + 255) / 256), t128 = mb * ((N + 127) / 128);
-  const float cost256 = static_cast<float>((t256 + sms - 1) / sms);          // padded tiles cost a full tile
-  const float cost128 = 0.72f * static_cast<float>((t128 + sms - 1) / sms);  // measured: a 128x128 wave costs ~0.7 of a 128x256 one
-  const bool wide = cost256 <= cost128 * 1.02f;
-  // CTA pairs (256 x 256 tiles) when the pair grid is still well filled: a pair tile is two 128 x 256
-  // tiles' worth of work done with ~2/3 of the shared-memory operand traffic (est. cost 0.8 per wave).
-  const int t2 = ((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256), pairs = sms / 2;
-  const float cost2 = 0.8f * static_cast<float>((t2 + pairs - 1) / pairs);
-  const bool two = g_enable_2cta && N >= 256 && cost2 < cost256 && cost2 < cost128;
+  // Tile shape: BN = 256 whenever the output is at least that wide (one A row block feeds 256 columns), CTA pairs
+  // (256 x 256 pair tiles: a pair tile is two 128 x 256 tiles' worth of work with ~2/3 of the shared-memory operand
+  // traffic) whenever there is more than one row block.  The shape is a function of N (and M > 128) only, so the
+  // column span of the per-row partials the fused-LayerNorm epilogues exchange is known to the caller; wave
+  // quantisation is the work decomposition's problem (stream-K), not the tile shape's.
+  const int bn = pick_bn(N);
+  const bool two = g_enable_2cta && bn == 256 && M > BM;
   CUtensorMap ta, tb;
   const char* e = get_tensor_map(A, M, K, lda, BM, BK, &ta);
   if (e) return e;
-  e = get_tensor_map(B, N, K, ldb, (two || !wide) ? 128 : 256, BK, &tb);
+  e = get_tensor_map(B, N, K, ldb, two ? 128 : bn, BK, &tb);
   if (e) return e;
-  // epilogue boxes (row-layout modes): out0, out1, saved pre-activation; unused slots repeat the A map
-  CUtensorMap te[3] = {ta, ta, ta};
+  // epilogue boxes (row-layout modes): out0, out1, operand (residual / saved pre-activation), LN input, out2;
+  // unused slots repeat the A map
+  CUtensorMap te[5] = {ta, ta, ta, ta, ta};
   if constexpr (F32Epi<MODE>::value) {
     if ((e = get_tensor_map(ep.out0, M, N, ep.ldc, 32, 32, &te[0], 4))) return e;
-    if (ResidEpi<MODE>::value && (e = get_tensor_map(ep.resid, M, N, ep.ldc, 32, 32, &te[2], 4))) return e;
+    if (ResidEpi<MODE>::value && ep.resid != nullptr && (e = get_tensor_map(ep.resid, M, N, ep.ldc, 32, 32, &te[2], 4))) return e;
+    if constexpr (DualEpi<MODE>::value) {
+      if (ep.out2 != nullptr && (e = get_tensor_map(ep.out2, M, N, ep.ldc, 32, 32, &te[4]))) return e;
+      if (MODE == EPI_LN_BWD && (e = get_tensor_map(ep.x2, M, N, ep.ldc, 32, 32, &te[3]))) return e;
+    }
   } else if constexpr (RowEpi<MODE>::value) {
     if (ep.out0 != nullptr && (e = get_tensor_map(ep.out0, M, N, ep.ldc, 32, 32, &te[0]))) return e;
-    if (MODE == EPI_GELU && (e = get_tensor_map(ep.out1, M, N, ep.ldc, 32, 32, &te[1]))) return e;
-    if (MODE == EPI_GELU_BWD && (e = get_tensor_map(ep.aux, M, N, ep.ldc, 32, 32, &te[2]))) return e;
+    if (GeluFwd<MODE>::value && (e = get_tensor_map(ep.out1, M, N, ep.ldc, 32, 32, &te[1]))) return e;
+    if (GeluBwd<MODE>::value && (e = get_tensor_map(ep.aux, M, N, ep.ldc, 32, 32, &te[2]))) return e;
   }
-  if (two) return launch_one<256, MODE, true>(ta, tb, te, ep, M, N, K, stream);
-  return wide ? launch_one<256, MODE, false>(ta, tb, te, ep, M, N, K, stream)
-              : launch_one<128, MODE, false>(ta, tb, te, ep, M, N, K, stream);
+  if (two) return launch_one<256, MODE, true>(ta, tb, te, ep, M, N, K, stream, ws);
+  return bn == 256 ? launch_one<256, MODE, false>(ta, tb, te, ep, M, N, K, stream, ws)
+                   : launch_one<128, MODE, false>(ta, tb, te, ep, M, N, K, stream, ws);
 }
 
 const char* gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, const GemmEpilogue& ep, int M, int N, int K,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const GemmWorkspace* ws) {
   if (M <= 0 || N <= 0 || K <= 0) return nullptr;
   if (N % 8 != 0 || K % 8 != 0) return "gemm: N and K must be multiples of 8";
   if (ep.ldc % 8 != 0) return "gemm: ldc must be a multiple of 8";
   switch (ep.mode) {
-    case EPI_BF16: return launch_mode<EPI_BF16>(A, lda, B, ldb, ep, M, N, K, stream);
-    case EPI_F32: return launch_mode<EPI_F32>(A, lda, B, ldb, ep, M, N, K, stream);
+    case EPI_BF16: return launch_mode<EPI_BF16>(A, lda, B, ldb, ep, M, N, K, stream, ws);
+    case EPI_F32: return launch_mode<EPI_F32>(A, lda, B, ldb, ep, M, N, K, stream, ws);
     case EPI_RESID_F32:
-      return K >= 1024 ? launch_mode<EPI_RESID_DEEP>(A, lda, B, ldb, ep, M, N, K, stream)
-                       : launch_mode<EPI_RESID_F32>(A, lda, B, ldb, ep, M, N, K, stream);
-    case EPI_GELU: return launch_mode<EPI_GELU>(A, lda, B, ldb, ep, M, N, K, stream);
-    case EPI_GELU_BWD: return launch_mode<EPI_GELU_BWD>(A, lda, B, ldb, ep, M, N, K, stream);
-    case EPI_PATCH: return launch_mode<EPI_PATCH>(A, lda, B, ldb, ep, M, N, K, stream);
+      if (ep.resid == nullptr) return "gemm: EPI_RESID_F32 needs a residual";
+      return launch_mode<EPI_RESID_F32>(A, lda, B, ldb, ep, M, N, K, stream, ws);
+    case EPI_GELU: return launch_mode<EPI_GELU>(A, lda, B, ldb, ep, M, N, K, stream, ws);
+    case EPI_GELU_BWD: return launch_mode<EPI_GELU_BWD>(A, lda, B, ldb, ep, M, N, K, stream, ws);
+    case EPI_PATCH: return launch_mode<EPI_PATCH>(A, lda, B, ldb, ep, M, N, K, stream, ws);
+    case EPI_LN_BF16:
+    case EPI_LN_GELU:
+      if (!ep.ln_stats || !ep.colsum || !ep.bias || ep.ln_parts <= 0 || ep.ln_width <= 0)
+        return "gemm: fused LayerNorm needs row statistics, column sums and the folded bias";
+      return ep.mode == EPI_LN_BF16 ? launch_mode<EPI_LN_BF16>(A, lda, B, ldb, ep, M, N, K, stream, ws)
+                                    : launch_mode<EPI_LN_GELU>(A, lda, B, ldb, ep, M, N, K, stream, ws);
+    case EPI_RESID_STATS:
+      if (!ep.resid || !ep.stats_out || !ep.out2) return "gemm: EPI_RESID_STATS needs resid, out2 and stats_out";
+      if (N % kStatSpan != 0) return "gemm: EPI_RESID_STATS needs N % 64 == 0";
+      if (ep.splice_n > 0 && (!ep.splice_prompt || ep.splice_L <= 0)) return "gemm: bad splice arguments";
+      return launch_mode<EPI_RESID_STATS>(A, lda, B, ldb, ep, M, N, K, stream, ws);
+    case EPI_LN_BWD:
+      if (!ep.ln_stats || !ep.x2 || !ep.dots || ep.ln_parts <= 0 || ep.dot_parts <= 0 || ep.ln_width != N)
+        return "gemm: EPI_LN_BWD needs row statistics, the bf16 LN input and the row dots (ln_width == N)";
+      return launch_mode<EPI_LN_BWD>(A, lda, B, ldb, ep, M, N, K, stream, ws);
+    case EPI_GELU_BWD_DOTS:
+      if (!ep.sb || !ep.dots_out) return "gemm: EPI_GELU_BWD_DOTS needs sb and dots_out";
+      return launch_mode<EPI_GELU_BWD_DOTS>(A, lda, B, ldb, ep, M, N, K, stream, ws);
     default: return "gemm: unknown epilogue mode";
   }
 }

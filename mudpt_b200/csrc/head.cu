@@ -240,8 +240,11 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
   for (int c = lane; c < C; c += 32) se += expf(lg[c] - mx);
   se = warp_sum(se);
   const float lse = mx + logf(se);
-  const int y = static_cast<int>(labels[b]);
-  if (lane == 0) loss_rows[b] = lse - lg[y];
+  // a label outside [0, C) never indexes the row: its loss is NaN, which the trainer's finiteness check reports
+  const long long yl = labels[b];
+  const bool y_ok = yl >= 0 && yl < C;
+  const int y = y_ok ? static_cast<int>(yl) : -1;
+  if (lane == 0) loss_rows[b] = y_ok ? lse - lg[y] : __int_as_float(0x7fc00000);
   for (int c = lane; c < C; c += 32)
     dlogits[static_cast<size_t>(b) * C + c] = (expf(lg[c] - lse) - (c == y ? 1.f : 0.f)) * grad_scale;
 }

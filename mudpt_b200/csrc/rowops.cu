@@ -293,6 +293,187 @@ const char* splice_bwd(float* dx, bf16* dx_bf16, float* dprompt, float* workspac
   return launch_status("splice bwd launch failed");
 }
 
+// ------------------------------------------------------------------ fused-LayerNorm plumbing
+// With LayerNorm folded into the GEMMs (gemm.h, EPI_LN_*), an LN input row lives as fp32 (residual stream),
+// a bf16 copy (the GEMM's A operand) and partial statistics (sum, M2 about the partial's own mean) per 64
+// columns.  The GEMM epilogues produce all three for the rows they write; these kernels do it for rows that do
+// not come out of a GEMM: the tower inputs and the layer-0 prompt rows.
+//
+// 16 lanes own one 64-column span (one float4 each): v = the lane's 4 values -> (sum, M2) of the span in all 16 lanes
+__device__ __forceinline__ float2 span_stats(const float4& v) {
+  float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float m = s * (1.f / 64.f);
+  const float a = v.x - m, b = v.y - m, c = v.z - m, e = v.w - m;
+  float q = (a * a + b * b) + (c * c + e * e);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  return make_float2(s, q);
+}
+
+// xb[row, :] = bf16(x[row, :]), stats[row, p] = (sum, M2) of columns [64p, 64p + 64).  One warp per row.
+__global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ x, bf16* __restrict__ xb,
+                                                       float2* __restrict__ stats, int M, int d) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
+  if (row >= M) return;
+  const int parts = d >> 6;
+  for (int p0 = 0; p0 < parts; p0 += 2) {  // (warp-uniform trip count; a trailing odd span leaves lanes 16..31 idle)
+    const int p = p0 + (lane >> 4);
+    const bool ok = p < parts;
+    const size_t off = static_cast<size_t>(row) * d + (ok ? p : p0) * 64 + (lane & 15) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + off);
+    const float2 st = span_stats(v);
+    if (ok) {
+      uint2 u;
+      u.x = pack_bf16(v.x, v.y);
+      u.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(xb + off) = u;
+      if ((lane & 15) == 0) stats[static_cast<size_t>(row) * parts + p] = st;
+    }
+  }
+}
+
+const char* rowstats(const float* x, bf16* xb, float2* stats, int M, int d, cudaStream_t stream) {
+  if (M <= 0) return nullptr;
+  if (d % 64 != 0) return "rowstats: width must be a multiple of 64";
+  launch_pdl(rowstats_kernel, dim3((M + 7) / 8), dim3(256), 0, stream, x, xb, stats, M, d);
+  count_launch(1);
+  return launch_status("rowstats launch failed");
+}
+
+// Splice with the bf16 copy and the statistics of the spliced rows (values copied verbatim into x: bit-exact).
+__global__ void __launch_bounds__(128) splice_fwd_stats_kernel(float* __restrict__ x, bf16* __restrict__ xb,
+                                                               float2* __restrict__ stats, const float* __restrict__ prompt,
+                                                               int L, int row0, int d) {
+  const int s = blockIdx.x, r = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
+  const int parts = d >> 6;
+  const size_t row = static_cast<size_t>(s) * L + row0 + r;
+  for (int p0 = 2 * warp; p0 < parts; p0 += 8) {
+    const int p = p0 + (lane >> 4);
+    const bool ok = p < parts;
+    const int c = (ok ? p : p0) * 64 + (lane & 15) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(prompt + static_cast<size_t>(r) * d + c);
+    const float2 st = span_stats(v);
+    if (ok) {
+      *reinterpret_cast<float4*>(x + row * d + c) = v;
+      uint2 u;
+      u.x = pack_bf16(v.x, v.y);
+      u.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(xb + row * d + c) = u;
+      if ((lane & 15) == 0) stats[row * parts + p] = st;
+    }
+  }
+}
+
+const char* splice_fwd_stats(float* x, bf16* xb, float2* stats, const float* prompt, int S, int L, int row0, int n, int d,
+                             cudaStream_t stream) {
+  if (S <= 0 || n <= 0) return nullptr;
+  if (d % 64 != 0 || row0 < 0 || row0 + n > L) return "splice: bad geometry";
+  launch_pdl(splice_fwd_stats_kernel, dim3(S, n), dim3(128), 0, stream, x, xb, stats, prompt, L, row0, d);
+  count_launch(1);
+  return launch_status("splice fwd (stats) launch failed");
+}
+
+// LayerNorm folded into the following Linear (weights frozen, done once at weight-load time):
+//   W'[n,k] = bf16(W[n,k] * gamma[k])  (+ the K-major transposed copy for the dgrad GEMM)
+//   colsum[n] = sum_k W'[n,k] (of the ROUNDED weight: it must cancel what the tensor cores compute for a constant row)
+//   bias'[n] = bias[n] + sum_k W[n,k] * beta[k],   sb[n] = (colsum[n], bias'[n])
+// One warp per output row n.
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      bf16* __restrict__ Wl, bf16* __restrict__ Wlt, float* __restrict__ bias_l,
+                                                      float* __restrict__ colsum, float2* __restrict__ sb, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, bd = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[static_cast<size_t>(n) * K + k];
+    const bf16 wl = __float2bfloat16(w * gamma[k]);
+    Wl[static_cast<size_t>(n) * K + k] = wl;
+    Wlt[static_cast<size_t>(k) * N + n] = wl;
+    cs += __bfloat162float(wl);
+    bd += w * beta[k];
+  }
+  cs = warp_sum(cs);
+  bd = warp_sum(bd);
+  if (lane == 0) {
+    const float b = bias[n] + bd;
+    bias_l[n] = b;
+    colsum[n] = cs;
+    sb[n] = make_float2(cs, b);
+  }
+}
+
+const char* fold_layernorm(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wl, bf16* Wlt,
+                           float* bias_l, float* colsum, float2* sb, int N, int K, cudaStream_t stream) {
+  if (N <= 0 || K <= 0) return nullptr;
+  fold_ln_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, gamma, beta, bias, Wl, Wlt, bias_l, colsum, sb, N, K);
+  count_launch(1);
+  return launch_status("fold_layernorm launch failed");
+}
+
+// x[rows[i], :] (+)= src[i, :] for S rows (fp32 + optional bf16 copy of the result): scatters the S live rows of a
+// pruned pass back into a full [M, d] buffer.
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ rows, int L, float* __restrict__ x,
+                                    bf16* __restrict__ xb, int d, int accumulate) {
+  const int s = blockIdx.x;
+  pdl_wait();
+  pdl_trigger();
+  const size_t row = static_cast<size_t>(s) * L + (rows ? rows[s] : 0);
+  for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(src + static_cast<size_t>(s) * d + c);
+    if (accumulate) {
+      const float4 o = *reinterpret_cast<const float4*>(x + row * d + c);
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    *reinterpret_cast<float4*>(x + row * d + c) = v;
+    if (xb != nullptr) {
+      uint2 u;
+      u.x = pack_bf16(v.x, v.y);
+      u.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(xb + row * d + c) = u;
+    }
+  }
+}
+const char* scatter_rows(const float* src, const int* rows, int S, int L, float* x, bf16* xb, int d, bool accumulate,
+                         cudaStream_t stream) {
+  if (S <= 0) return nullptr;
+  if (d % 4 != 0) return "scatter_rows: width must be a multiple of 4";
+  launch_pdl(scatter_rows_kernel, dim3(S), dim3(128), 0, stream, src, rows, L, x, xb, d, accumulate ? 1 : 0);
+  count_launch(1);
+  return launch_status("scatter_rows launch failed");
+}
+
+// dst[i, :] = src[s*L + rows[s], :] for S rows, fp32 and/or bf16 sources (either may be null): gathers the CLS / EOT
+// rows the last block still needs after attention.
+__global__ void gather_rows_kernel(const float* __restrict__ src_f, const bf16* __restrict__ src_b, const int* __restrict__ rows,
+                                   int L, float* __restrict__ dst_f, bf16* __restrict__ dst_b, int d) {
+  const int s = blockIdx.x;
+  pdl_wait();
+  pdl_trigger();
+  const size_t row = static_cast<size_t>(s) * L + (rows ? rows[s] : 0);
+  for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+    if (src_f != nullptr) *reinterpret_cast<float4*>(dst_f + static_cast<size_t>(s) * d + c) = *reinterpret_cast<const float4*>(src_f + row * d + c);
+    if (src_b != nullptr) *reinterpret_cast<uint2*>(dst_b + static_cast<size_t>(s) * d + c) = *reinterpret_cast<const uint2*>(src_b + row * d + c);
+  }
+}
+const char* gather_rows(const float* src_f, const bf16* src_b, const int* rows, int S, int L, float* dst_f, bf16* dst_b, int d,
+                        cudaStream_t stream) {
+  if (S <= 0) return nullptr;
+  if (d % 4 != 0) return "gather_rows: width must be a multiple of 4";
+  launch_pdl(gather_rows_kernel, dim3(S), dim3(128), 0, stream, src_f, src_b, rows, L, dst_f, dst_b, d);
+  count_launch(1);
+  return launch_status("gather_rows launch failed");
+}
+
 // ------------------------------------------------------------------ patch extraction
 // patches[(b*gh + py)*gw + px, (c*p + iy)*p + ix] = image[b, c, py*p + iy, px*p + ix]  (bf16),
 // row stride ldo >= 3*p*p (padding columns, if any, are zeroed once at allocation).

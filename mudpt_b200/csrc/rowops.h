@@ -13,6 +13,16 @@ const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, in
 size_t splice_bwd_workspace_floats(int n, int d);
 const char* splice_bwd(float* dx, __nv_bfloat16* dx_bf16, float* dprompt, float* workspace, int S, int L, int row0, int n,
                        int d, bool zero_rows, cudaStream_t stream);
+// fused-LayerNorm plumbing (see rowops.cu): bf16 copy + per-64-column partial statistics of fp32 rows
+const char* rowstats(const float* x, __nv_bfloat16* xb, float2* stats, int M, int d, cudaStream_t stream);
+const char* splice_fwd_stats(float* x, __nv_bfloat16* xb, float2* stats, const float* prompt, int S, int L, int row0, int n,
+                             int d, cudaStream_t stream);
+const char* fold_layernorm(const float* W, const float* gamma, const float* beta, const float* bias, __nv_bfloat16* Wl,
+                           __nv_bfloat16* Wlt, float* bias_l, float* colsum, float2* sb, int N, int K, cudaStream_t stream);
+const char* scatter_rows(const float* src, const int* rows, int S, int L, float* x, __nv_bfloat16* xb, int d, bool accumulate,
+                         cudaStream_t stream);
+const char* gather_rows(const float* src_f, const __nv_bfloat16* src_b, const int* rows, int S, int L, float* dst_f,
+                        __nv_bfloat16* dst_b, int d, cudaStream_t stream);
 const char* im2col_bf16(const float* img, __nv_bfloat16* out, int B, int R, int p, int ldo, cudaStream_t stream);
 const char* write_cls_rows(float* x, const float* cls, const float* pos, int S, int L, int d, cudaStream_t stream);
 const char* add_positional(float* x0, const float* emb, const float* pos, int S, int L, int Lsrc, int d, cudaStream_t stream);

@@ -20,7 +20,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["gemm", "rowops", "attention", "head", "model_tiny", "model_vitb16"]
+GROUPS = ["gemm", "gemm_fused", "rowops", "attention", "head", "model_tiny", "model_vitb16"]
 
 
 def _metrics(a, b):
@@ -158,6 +158,217 @@ def group_gemm(res):
         res[f"gemm_text_{tag}"] = {"ms": ms, "tflops": 2 * M * N * K / ms / 1e9, "gbs": nbytes / ms / 1e6,
                                    "hbm_bound_ms": nbytes / 6538.3e6, "mma_bound_ms": 2 * M * N * K / 1618.5e9}
         print(f"gemm_text_{tag}", res[f"gemm_text_{tag}"], flush=True)
+
+
+# ------------------------------------------------------------------------------------------ fused-LN GEMM modes, stream-K
+def _row_stats_ref(x):
+    """[M, d] fp32 -> [M, d/64, 2]: (sum, M2 about the span mean) per 64 columns, as rowstats / EPI_RESID_STATS emit."""
+    import torch
+    M, d = x.shape
+    xs = x.double().view(M, d // 64, 64)
+    return torch.stack([xs.sum(-1), ((xs - xs.mean(-1, keepdim=True)) ** 2).sum(-1)], -1).float().contiguous()
+
+
+def _gemm_fused(lib, st, A, B, M, N, K, **kw):
+    import ctypes as C
+    from mudpt_b200 import _lib
+    ep = _lib.GemmEpilogue()
+    ep.ldc = N
+    ep.ln_eps = 1e-5
+    ep.splice_L = 1
+    ep.stream_k = -1
+    for k, v in kw.items():
+        setattr(ep, k, v.data_ptr() if hasattr(v, "data_ptr") else v)
+    _lib.check(lib.mudpt_gemm_fused(A.data_ptr(), B.data_ptr(), M, N, K, C.byref(ep), st))
+
+
+def group_gemm_fused(res):
+    import torch
+    import torch.nn.functional as F
+    from mudpt_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    st = _lib.stream_ptr(dev)
+    torch.manual_seed(5)
+    bf = torch.bfloat16
+
+    def fold(W, gamma, beta, bias):
+        N, K = W.shape
+        Wl = torch.empty(N, K, device=dev, dtype=bf); Wlt = torch.empty(K, N, device=dev, dtype=bf)
+        bl = torch.empty(N, device=dev); cs = torch.empty(N, device=dev); sb = torch.empty(N, 2, device=dev)
+        _lib.check(lib.mudpt_fold_layernorm(W.data_ptr(), gamma.data_ptr(), beta.data_ptr(), bias.data_ptr(), Wl.data_ptr(),
+                                            Wlt.data_ptr(), bl.data_ptr(), cs.data_ptr(), sb.data_ptr(), N, K, st))
+        return Wl, Wlt, bl, cs, sb
+
+    def prep(x):
+        M, d = x.shape
+        xb = torch.empty(M, d, device=dev, dtype=bf); stats = torch.empty(M, d // 64, 2, device=dev)
+        _lib.check(lib.mudpt_rowstats(x.data_ptr(), xb.data_ptr(), stats.data_ptr(), M, d, st))
+        return xb, stats
+
+    # ---- fold + rowstats
+    W = torch.randn(384, 256, device=dev) * 0.06; gamma = 1 + 0.2 * torch.randn(256, device=dev)
+    beta = 0.3 * torch.randn(256, device=dev); bias = torch.randn(384, device=dev)
+    Wl, Wlt, bl, cs, sb = fold(W, gamma, beta, bias)
+    torch.cuda.synchronize()
+    res["fold"] = {"w_exact": bool(torch.equal(Wl, (W * gamma).to(bf))), "wt_exact": bool(torch.equal(Wlt, Wl.t().contiguous())),
+                   "bias": _metrics(bl, bias + W @ beta), "colsum": _metrics(cs, Wl.float().sum(1)),
+                   "sb_ok": bool(torch.equal(sb[:, 0], cs) and torch.equal(sb[:, 1], bl))}
+    print("fold", res["fold"], flush=True)
+    x = torch.randn(777, 768, device=dev) * 1.7 + 25.0  # a row mean far above the spread: M2 must not cancel
+    xb, stats = prep(x)
+    torch.cuda.synchronize()
+    ref = _row_stats_ref(x)
+    res["rowstats"] = {"xb_exact": bool(torch.equal(xb, x.to(bf))), "sum": _metrics(stats[..., 0], ref[..., 0]),
+                       "m2": _metrics(stats[..., 1], ref[..., 1])}
+    print("rowstats", res["rowstats"], flush=True)
+
+    # ---- modes 7 / 8: LayerNorm + Linear (+ QuickGELU) in one GEMM
+    for (M, N, K, shift, sk) in [(300, 384, 128, 0.0, -1), (6368, 2304, 768, 0.4, 1), (6368, 2304, 768, 0.4, 0),
+                                 (9625, 1536, 512, 0.2, 1), (2000, 2048, 512, 3.0, -1), (130, 128, 64, 0.1, 1)]:
+        x = torch.randn(M, K, device=dev) * 1.3 + shift
+        x[:, 5] *= 8.0  # an outlier channel
+        W = torch.randn(N, K, device=dev) * K ** -0.5; gamma = 1 + 0.2 * torch.randn(K, device=dev)
+        beta = 0.2 * torch.randn(K, device=dev); bias = 0.5 * torch.randn(N, device=dev)
+        Wl, Wlt, bl, cs, sb = fold(W, gamma, beta, bias)
+        xb, stats = prep(x)
+        exact = F.layer_norm(x.double(), (K,), gamma.double(), beta.double(), 1e-5) @ W.double().t() + bias.double()
+        unfused = (F.layer_norm(x, (K,), gamma, beta, 1e-5).to(bf).float() @ W.to(bf).float().t() + bias).to(bf)
+        out = torch.zeros(M, N, device=dev, dtype=bf)
+        _gemm_fused(lib, st, xb, Wl, M, N, K, mode=7, out0=out, bias=bl, colsum=cs, ln_stats=stats, ln_parts=K // 64, ln_width=K, stream_k=sk)
+        torch.cuda.synchronize()
+        key = f"gemmf_{M}x{N}x{K}_sk{sk}"
+        res[key + "_m7"] = dict(_metrics(out.float(), exact.float()), unfused_rel=_metrics(unfused.float(), exact.float())["rel"])
+        h = torch.zeros(M, N, device=dev, dtype=bf); g = torch.zeros(M, N, device=dev, dtype=bf)
+        _gemm_fused(lib, st, xb, Wl, M, N, K, mode=8, out0=h, out1=g, bias=bl, colsum=cs, ln_stats=stats, ln_parts=K // 64, ln_width=K, stream_k=sk)
+        torch.cuda.synchronize()
+        eg = exact * torch.sigmoid(1.702 * exact)
+        res[key + "_m8"] = dict(_metrics(h.float(), exact.float()), gelu_rel=_metrics(g.float(), eg.float())["rel"],
+                                unfused_rel=res[key + "_m7"]["unfused_rel"])
+        print(key, res[key + "_m7"], res[key + "_m8"], flush=True)
+
+    # ---- mode 9: residual + bf16 copy + statistics + splice
+    for (M, N, K, L, row0, n, sk) in [(6368, 768, 3072, 199, 197, 2, 1), (6368, 768, 768, 199, 197, 2, 1), (9625, 512, 2048, 77, 1, 2, 1),
+                                      (9625, 512, 512, 77, 1, 2, 0), (260, 128, 128, 13, 3, 4, 1), (1000, 1024, 256, 1, 0, 0, -1)]:
+        A = (torch.randn(M, K, device=dev) * 0.5).to(bf); B = (torch.randn(N, K, device=dev) * 0.5).to(bf)
+        bias = torch.randn(N, device=dev); resid = torch.randn(M, N, device=dev) * 3 + 1.5
+        prompt = torch.randn(max(n, 1), N, device=dev)
+        exp = A.float() @ B.float().t() + bias + resid
+        if n > 0:
+            rows = torch.arange(M, device=dev)
+            pos = rows % L - row0
+            sel = (pos >= 0) & (pos < n)
+            exp[sel] = prompt[pos[sel]]
+        out = torch.zeros(M, N, device=dev); out2 = torch.zeros(M, N, device=dev, dtype=bf)
+        stats = torch.zeros(M, N // 64, 2, device=dev)
+        _gemm_fused(lib, st, A, B, M, N, K, mode=9, out0=out, out2=out2, bias=bias, resid=resid, stats_out=stats,
+                    splice_prompt=prompt if n > 0 else 0, splice_row0=row0, splice_n=n, splice_L=L, stream_k=sk)
+        torch.cuda.synchronize()
+        sref = _row_stats_ref(out)
+        key = f"gemmf_{M}x{N}x{K}_sk{sk}_m9"
+        res[key] = dict(_metrics(out, exp), out2_exact=bool(torch.equal(out2, out.to(bf))),
+                        splice_exact=bool(n == 0 or torch.equal(out[sel], prompt[pos[sel]])),
+                        sum_rel=_metrics(stats[..., 0], sref[..., 0])["rel"], m2_rel=_metrics(stats[..., 1], sref[..., 1])["rel"])
+        print(key, res[key], flush=True)
+
+    # ---- mode 11 -> mode 10: GELU' with row dots, then the LayerNorm dgrad in the dgrad GEMM's epilogue
+    for (M, d, sk) in [(6368, 768, 1), (9625, 512, 1), (300, 128, 0), (2000, 512, -1)]:
+        x = torch.randn(M, d, device=dev) * 1.4 + 0.3
+        W = torch.randn(4 * d, d, device=dev) * d ** -0.5; gamma = 1 + 0.2 * torch.randn(d, device=dev)
+        beta = 0.2 * torch.randn(d, device=dev); bias = 0.3 * torch.randn(4 * d, device=dev)
+        Wl, Wlt, bl, cs, sb = fold(W, gamma, beta, bias)
+        xb, stats = prep(x)
+        # forward pre-activation h (bf16) as the fused forward saves it
+        hsave = torch.zeros(M, 4 * d, device=dev, dtype=bf); gsave = torch.zeros(M, 4 * d, device=dev, dtype=bf)
+        _gemm_fused(lib, st, xb, Wl, M, 4 * d, d, mode=8, out0=hsave, out1=gsave, bias=bl, colsum=cs, ln_stats=stats, ln_parts=d // 64, ln_width=d)
+        dxo = (torch.randn(M, d, device=dev) * 0.1).to(bf)                    # gradient of the block output (bf16 copy)
+        Wp_t = (torch.randn(4 * d, d, device=dev) * (4 * d) ** -0.5).to(bf)   # c_proj weight, transposed: [4d, d]
+        span = int(lib.mudpt_gemm_dots_span(4 * d)); P = (4 * d + span - 1) // span
+        dh = torch.zeros(M, 4 * d, device=dev, dtype=bf); dots = torch.zeros(M, P, 2, device=dev)
+        _gemm_fused(lib, st, dxo, Wp_t, M, 4 * d, d, mode=11, out0=dh, aux=hsave, sb=sb, dots_out=dots, stream_k=sk)
+        torch.cuda.synchronize()
+        hf = hsave.float(); sg = torch.sigmoid(1.702 * hf)
+        dh_ref = (dxo.float() @ Wp_t.float().t()) * (sg * (1 + 1.702 * hf * (1 - sg)))
+        d1_ref = (dh_ref * cs).sum(1); d2_ref = (dh_ref * (hf - bl)).sum(1)
+        key = f"gemmf_lnbwd_{M}x{d}_sk{sk}"
+        res[key + "_m11"] = dict(_metrics(dh.float(), dh_ref), dot1=_metrics(dots[..., 0].sum(1), d1_ref), dot2=_metrics(dots[..., 1].sum(1), d2_ref))
+        # mode 10 against autograd through LayerNorm + Linear with the SAME dh
+        for with_resid in (True, False):
+            resid = torch.randn(M, d, device=dev) if with_resid else None
+            dx = resid.clone() if with_resid else torch.zeros(M, d, device=dev)
+            dx16 = torch.zeros(M, d, device=dev, dtype=bf)
+            _gemm_fused(lib, st, dh, Wlt, M, d, 4 * d, mode=10, out0=dx, out2=dx16, resid=dx if with_resid else 0, x2=xb,
+                        ln_stats=stats, ln_parts=d // 64, ln_width=d, dots=dots, dot_parts=P, stream_k=sk)
+            torch.cuda.synchronize()
+            xr = x.double().clone().requires_grad_(True)
+            y = F.layer_norm(xr, (d,), gamma.double(), beta.double(), 1e-5) @ W.double().t()
+            y.backward(dh.double())
+            exp = xr.grad.float() + (resid if with_resid else 0)
+            res[key + f"_m10_r{int(with_resid)}"] = dict(_metrics(dx, exp), out2_exact=bool(torch.equal(dx16, dx.to(bf))))
+        print(key, res[key + "_m11"], res[key + "_m10_r1"], res[key + "_m10_r0"], flush=True)
+
+    # ---- attention backward with the row dots of dqkv
+    for (S, L, H, causal) in [(3, 199, 12, 0), (5, 77, 8, 1), (4, 9, 8, 1), (2, 130, 2, 1)]:
+        d = H * 64
+        qkv = torch.randn(S * L, 3 * d, device=dev).to(bf)
+        o = torch.zeros(S * L, d, device=dev, dtype=bf); lse = torch.zeros(S, H, L, device=dev)
+        _lib.check(lib.mudpt_attention_forward(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), S, L, H, causal, st))
+        do = torch.randn(S * L, d, device=dev).to(bf)
+        dqkv = torch.zeros(S * L, 3 * d, device=dev, dtype=bf); dsum = torch.zeros(S, H, L, device=dev)
+        sb = torch.randn(3 * d, 2, device=dev); dots = torch.zeros(S * L, 3 * H, 2, device=dev)
+        _lib.check(lib.mudpt_attention_backward_dots(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
+                                                     dqkv.data_ptr(), S, L, H, causal, sb.data_ptr(), dots.data_ptr(), st))
+        dqkv2 = torch.zeros_like(dqkv)
+        _lib.check(lib.mudpt_attention_backward(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
+                                                dqkv2.data_ptr(), S, L, H, causal, st))
+        torch.cuda.synchronize()
+        gq = dqkv.float().view(S * L, 3 * H, 64)
+        d1 = (gq * sb[:, 0].view(3 * H, 64)).sum(-1)
+        d2 = (gq * (qkv.float().view(S * L, 3 * H, 64) - sb[:, 1].view(3 * H, 64))).sum(-1)
+        key = f"attn_dots_S{S}_L{L}_H{H}_c{causal}"
+        res[key] = {"same_dqkv": bool(torch.equal(dqkv, dqkv2)), "dot1": _metrics(dots[..., 0], d1), "dot2": _metrics(dots[..., 1], d2)}
+        print(key, res[key], flush=True)
+
+    # ---- stream-K: equality with whole-tile scheduling + timing against cuBLAS on the shapes of the towers
+    table = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for (M, N, K) in [(6368, 2304, 768), (6368, 768, 768), (6368, 3072, 768), (6368, 768, 3072), (6368, 768, 2304),
+                      (9625, 1536, 512), (9625, 512, 512), (9625, 2048, 512), (9625, 512, 2048), (9625, 512, 1536),
+                      (77000, 1536, 512), (77000, 512, 2048), (250, 512, 2048), (2000, 512, 1536)]:
+        A = torch.randn(M, K, device=dev).to(bf); B = torch.randn(N, K, device=dev).to(bf)
+        outs, times = {}, {}
+        for sk in (0, 1, -1):
+            out = torch.zeros(M, N, device=dev, dtype=bf)
+            call = lambda: _gemm_fused(lib, st, A, B, M, N, K, mode=0, out0=out, stream_k=sk)
+            for _ in range(3):
+                call()
+            ts = []
+            for _ in range(8):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); call(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            outs[sk], times[sk] = out, sorted(ts)[len(ts) // 2]
+        c = torch.empty(M, N, device=dev, dtype=bf)
+        for _ in range(3):
+            torch.matmul(A, B.t(), out=c)
+        ts = []
+        for _ in range(8):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(A, B.t(), out=c); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t_cublas = sorted(ts)[len(ts) // 2]
+        ref = A.float() @ B.float().t()
+        fl = 2.0 * M * N * K / 1e9
+        table[f"{M}x{N}x{K}"] = {"us_whole": round(times[0] * 1e3, 1), "us_streamk": round(times[1] * 1e3, 1),
+                                 "us_auto": round(times[-1] * 1e3, 1), "us_cublas": round(t_cublas * 1e3, 1),
+                                 "tflops_whole": round(fl / times[0], 0), "tflops_streamk": round(fl / times[1], 0),
+                                 "tflops_auto": round(fl / times[-1], 0), "tflops_cublas": round(fl / t_cublas, 0),
+                                 "rel_streamk": _metrics(outs[1].float(), ref)["rel"],
+                                 "max_abs_sk_vs_whole": float((outs[1].float() - outs[0].float()).abs().max())}
+        print("gemm_time", f"{M}x{N}x{K}", table[f"{M}x{N}x{K}"], flush=True)
+    res["gemm_time_table"] = table
 
 
 # ------------------------------------------------------------------------------------------ rowops
