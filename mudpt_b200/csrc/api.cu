@@ -67,6 +67,16 @@ struct Tower {
   bf16 *a_buf = nullptr, *g_buf = nullptr, *dh_buf = nullptr, *do_buf = nullptr, *dqkv_buf = nullptr, *dx_bf16 = nullptr;
   float *dx = nullptr, *dsum = nullptr, *splice_ws = nullptr, *head_ws = nullptr;  // head_ws: feature_head_workspace_floats(S, d, e)
   size_t head_cap = 0;  // floats in head_ws (sized by the sequence count, which may grow while rows = S * L shrinks)
+  // exact work skipping: after the last block's attention only one row per sequence is consumed
+  // (CLS, clip/model.py:548; EOT, trainers/mudpt.py:154), so its out-proj / MLP run on S gathered rows
+  const int* sel_rows = nullptr;  // consumed row per sequence (null: row 0)
+  size_t pr_cap = 0;              // sequences the buffers below hold
+  std::vector<void*> pr_allocs;
+  bf16 *pr_o = nullptr, *pr_xmb = nullptr, *pr_h = nullptr, *pr_g = nullptr, *pr_a = nullptr, *pr_dxb = nullptr, *pr_dh = nullptr,
+       *pr_do = nullptr;
+  float *pr_x = nullptr, *pr_xm = nullptr, *pr_xo = nullptr, *pr_dx = nullptr;
+  float2 *pr_stm = nullptr, *pr_dots = nullptr;
+  bool fwd_pruned = false;
   std::vector<void*> ws_allocs;  // everything sized by cap_rows: released when the tower outgrows it
   GemmWorkspace gws;             // stream-K scratch of this tower's stream
   bool fwd_done = false;
@@ -182,6 +192,30 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
     CUDA_OK(h, dev_alloc(h, &t.gws.partials, gemm_workspace_partial_bytes() / sizeof(float)));
     CUDA_OK(h, dev_alloc(h, &t.gws.flags, gemm_workspace_flag_bytes() / sizeof(unsigned)));
     CUDA_OK(h, cudaMemset(t.gws.flags, 0, gemm_workspace_flag_bytes()));
+  }
+  if (static_cast<size_t>(S) > t.pr_cap) {
+    for (void* p : t.pr_allocs) cudaFree(p);
+    t.pr_allocs.clear();
+    gemm_clear_tensor_map_cache();
+    std::vector<void*>* g = &t.pr_allocs;
+    const size_t Ss = S, d = t.d;
+    const int dots_mlp = (4 * t.d + gemm_dots_span(4 * t.d) - 1) / gemm_dots_span(4 * t.d);
+    CUDA_OK(h, dev_alloc(h, &t.pr_o, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_xmb, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_h, Ss * 4 * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_g, Ss * 4 * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_a, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_dxb, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_dh, Ss * 4 * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_do, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_x, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_xm, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_xo, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_dx, Ss * d, g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_stm, Ss * (d / 64), g));
+    CUDA_OK(h, dev_alloc(h, &t.pr_dots, Ss * dots_mlp, g));
+    t.pr_cap = S;
+    t.fwd_done = false;
   }
   if (rows <= t.cap_rows) return 0;
   // grow: the outgrown buffers are released first (cudaFree waits for the device, so nothing in flight uses them);
@@ -334,6 +368,7 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
   const double Md = static_cast<double>(M), dd = d;
   const double attn_fl = 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // QK^T + PV, dense count
   const bool fused = h->ln_fused;
+  const bool pruned = h->prune;
   const int parts = d / 64;
   auto spliced = [&](int i) { return i < t.depth && i >= first_splice_layer && t.n_ctx > 0 && i < t.layers; };
   if (fused && ensure_folded(h, t, st)) return -1;
@@ -360,6 +395,31 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
           gemm_bf16_tn(t.a_buf, d, w.w_in, d, e1, M, 3 * d, d, st, &t.gws));
     }
     CKP(h, st, PC_ATTN_FWD, attn_fl, Md * dd * 2 * 4, attention_fwd(t.qkv[i], t.o[i], t.lse[i], t.S, t.L, t.H, d, t.causal, st));
+    if (pruned && i == t.layers - 1) {
+      // the block's output is consumed on one row per sequence: out-proj and the MLP on S gathered rows
+      const int S = t.S;
+      const double Sd = S;
+      CKP(h, st, PC_SPLICE, 0, Sd * dd * 12, gather_rows(t.x_in[i], t.o[i], t.sel_rows, S, t.L, t.pr_x, t.pr_o, d, st));
+      GemmEpilogue p2;
+      p2.out0 = t.pr_xm; p2.bias = w.b_out; p2.resid = t.pr_x; p2.ldc = d;
+      if (fused) { p2.mode = EPI_RESID_STATS; p2.out2 = t.pr_xmb; p2.stats_out = t.pr_stm; }
+      else p2.mode = EPI_RESID_F32;
+      CKP(h, st, PC_GEMM, 2.0 * Sd * dd * dd, 2 * (Sd * dd + dd * dd) + 10 * Sd * dd, gemm_bf16_tn(t.pr_o, d, w.w_out, d, p2, S, d, d, st, &t.gws));
+      GemmEpilogue p3;
+      p3.out0 = t.pr_h; p3.out1 = t.pr_g; p3.ldc = 4 * d;
+      if (fused) {
+        p3.mode = EPI_LN_GELU; p3.bias = w.b_fc_ln; p3.colsum = w.cs_fc; p3.ln_stats = t.pr_stm; p3.ln_parts = parts; p3.ln_width = d; p3.ln_eps = kLnEps;
+        CKP(h, st, PC_GEMM, 2.0 * Sd * 4 * dd * dd, 2 * (Sd * dd + 4 * dd * dd + 2 * Sd * 4 * dd), gemm_bf16_tn(t.pr_xmb, d, w.w_fc_ln, d, p3, S, 4 * d, d, st, &t.gws));
+      } else {
+        CKP(h, st, PC_LN_FWD, 0, Sd * dd * 6, layernorm_fwd(t.pr_xm, w.ln2_g, w.ln2_b, t.pr_a, true, S, d, kLnEps, st));
+        p3.mode = EPI_GELU; p3.bias = w.b_fc;
+        CKP(h, st, PC_GEMM, 2.0 * Sd * 4 * dd * dd, 2 * (Sd * dd + 4 * dd * dd + 2 * Sd * 4 * dd), gemm_bf16_tn(t.pr_a, d, w.w_fc, d, p3, S, 4 * d, d, st, &t.gws));
+      }
+      GemmEpilogue p4;
+      p4.mode = EPI_RESID_F32; p4.out0 = t.pr_xo; p4.bias = w.b_pr; p4.resid = t.pr_xm; p4.ldc = d;
+      CKP(h, st, PC_GEMM, 2.0 * Sd * 4 * dd * dd, 2 * (Sd * 4 * dd + 4 * dd * dd) + 8 * Sd * dd, gemm_bf16_tn(t.pr_g, 4 * d, w.w_pr, 4 * d, p4, S, d, 4 * d, st, &t.gws));
+      break;
+    }
     GemmEpilogue e2;
     e2.out0 = t.x_mid[i]; e2.bias = w.b_out; e2.resid = t.x_in[i]; e2.ldc = d;
     if (fused) { e2.mode = EPI_RESID_STATS; e2.out2 = t.xb_mid[i]; e2.stats_out = t.st_mid[i]; }
@@ -395,7 +455,15 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
   }
   t.fwd_done = true;
   t.fwd_fused = fused;
+  t.fwd_pruned = pruned;
   return 0;
+}
+
+// x (and the row stride) the feature head reads its one row per sequence from
+const float* tower_head_input(const Tower& t, const int** rows, int* L) {
+  if (t.fwd_pruned) { *rows = nullptr; *L = 1; return t.pr_xo; }
+  *rows = t.sel_rows; *L = t.L;
+  return t.x_in[t.layers];
 }
 
 // Precondition: t.dx / t.dx_bf16 hold the gradient w.r.t. the tower output x_in[layers].
@@ -413,6 +481,34 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
   const int dots_mlp = (4 * d + gemm_dots_span(4 * d) - 1) / gemm_dots_span(4 * d);
   for (int i = t.layers - 1; i >= 0; --i) {
     const Layer& w = t.lw[i];
+    const bool tail_pruned = t.fwd_pruned && i == t.layers - 1;
+    if (tail_pruned) {
+      // Precondition here: t.pr_dx / t.pr_dxb hold the gradient of the S consumed rows of the block output.
+      const int S = t.S;
+      const double Sd = S;
+      GemmEpilogue p1;
+      p1.out0 = t.pr_dh; p1.aux = t.pr_h; p1.ldc = 4 * d;
+      if (fused) { p1.mode = EPI_GELU_BWD_DOTS; p1.sb = w.sb_fc; p1.dots_out = t.pr_dots; }
+      else p1.mode = EPI_GELU_BWD;
+      CKP(h, st, PC_GEMM, 2.0 * Sd * 4 * dd * dd, 2 * (Sd * dd + 4 * dd * dd + 2 * Sd * 4 * dd), gemm_bf16_tn(t.pr_dxb, d, w.w_pr_t, d, p1, S, 4 * d, d, st, &t.gws));
+      GemmEpilogue p2;
+      p2.ldc = d;
+      if (fused) {
+        p2.mode = EPI_LN_BWD; p2.out0 = t.pr_dx; p2.resid = t.pr_dx; p2.out2 = t.pr_dxb; p2.x2 = t.pr_xmb;
+        p2.ln_stats = t.pr_stm; p2.ln_parts = parts; p2.ln_width = d; p2.ln_eps = kLnEps; p2.dots = t.pr_dots; p2.dot_parts = dots_mlp;
+        CKP(h, st, PC_GEMM, 2.0 * Sd * 4 * dd * dd, 2 * (Sd * 4 * dd + 4 * dd * dd) + 12 * Sd * dd, gemm_bf16_tn(t.pr_dh, 4 * d, w.w_fc_t_ln, 4 * d, p2, S, d, 4 * d, st, &t.gws));
+      } else {
+        p2.mode = EPI_BF16; p2.out0 = t.pr_a;
+        CKP(h, st, PC_GEMM, 2.0 * Sd * 4 * dd * dd, 2 * (Sd * 4 * dd + 4 * dd * dd) + 2 * Sd * dd, gemm_bf16_tn(t.pr_dh, 4 * d, w.w_fc_t, 4 * d, p2, S, d, 4 * d, st, &t.gws));
+        CKP(h, st, PC_LN_BWD, 0, Sd * dd * 16, layernorm_bwd(t.pr_a, true, t.pr_xm, w.ln2_g, t.pr_dx, t.pr_dx, t.pr_dxb, S, d, kLnEps, st));
+      }
+      GemmEpilogue p3;
+      p3.mode = EPI_BF16; p3.out0 = t.pr_do; p3.ldc = d;
+      CKP(h, st, PC_GEMM, 2.0 * Sd * dd * dd, 2 * (2 * Sd * dd + dd * dd), gemm_bf16_tn(t.pr_dxb, d, w.w_out_t, d, p3, S, d, d, st, &t.gws));
+      // dO of the whole block: zero but for the S consumed rows
+      CUDA_OK(h, cudaMemsetAsync(t.do_buf, 0, static_cast<size_t>(M) * d * sizeof(bf16), st));
+      CKP(h, st, PC_SPLICE, 0, Sd * dd * 4, scatter_rows_bf16(t.pr_do, t.sel_rows, S, t.L, t.do_buf, d, st));
+    } else {
     // MLP branch: dg = dx W_pr ; dh = dg * GELU'(h) ; dm = dh W_fc ; dx += LN2_bwd(dm)
     GemmEpilogue e1;
     e1.out0 = t.dh_buf; e1.aux = t.h[i]; e1.ldc = 4 * d;
@@ -437,13 +533,14 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
     GemmEpilogue e3;
     e3.mode = EPI_BF16; e3.out0 = t.do_buf; e3.ldc = d;
     CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (2 * Md * dd + dd * dd), gemm_bf16_tn(t.dx_bf16, d, w.w_out_t, d, e3, M, d, d, st, &t.gws));
+    }
     CKP(h, st, PC_ATTN_BWD, attn_fl, Md * dd * 2 * 8,
         attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st,
                       fused ? w.sb_in : nullptr, fused ? t.dots : nullptr));
     GemmEpilogue e4;
     e4.ldc = d;
     if (fused) {
-      e4.mode = EPI_LN_BWD; e4.out0 = t.dx; e4.resid = t.dx; e4.out2 = t.dx_bf16; e4.x2 = t.xb_in[i];
+      e4.mode = EPI_LN_BWD; e4.out0 = t.dx; e4.resid = tail_pruned ? nullptr : t.dx; e4.out2 = t.dx_bf16; e4.x2 = t.xb_in[i];
       e4.ln_stats = t.st_in[i]; e4.ln_parts = parts; e4.ln_width = d; e4.ln_eps = kLnEps; e4.dots = t.dots; e4.dot_parts = 3 * t.H;
       CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 12 * Md * dd,
           gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t_ln, 3 * d, e4, M, d, 3 * d, st, &t.gws));
@@ -451,14 +548,32 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
       e4.mode = EPI_BF16; e4.out0 = t.a_buf;
       CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 2 * Md * dd,
           gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st, &t.gws));
-      CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_in[i], w.ln1_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+      CKP(h, st, PC_LN_BWD, 0, Md * dd * 16,
+          layernorm_bwd(t.a_buf, true, t.x_in[i], w.ln1_g, tail_pruned ? nullptr : t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
     }
+    if (tail_pruned)  // the residual path of the S consumed rows (everything else of it is zero)
+      CKP(h, st, PC_SPLICE, 0, t.S * dd * 14, scatter_rows(t.pr_dx, t.sel_rows, t.S, t.L, t.dx, t.dx_bf16, d, true, st));
     // splice backward: the inserted prompt rows collect the batch-summed gradient; the rows
     // they overwrote get none (clip/model.py:281-297)
     if (i < t.depth && i >= first_splice_layer && t.n_ctx > 0)
       CKP(h, st, PC_SPLICE, 0, t.S * t.n_ctx * dd * 4,
           splice_bwd(t.dx, t.dx_bf16, d_prompts + static_cast<size_t>(i) * t.n_ctx * d, t.splice_ws, t.S, t.L, t.row0, t.n_ctx, d, i > 0, st));
   }
+  return 0;
+}
+
+// Gradient of the feature head into the tower output: the S consumed rows only (pruned: a dense [S, d] buffer;
+// otherwise scattered into the zeroed full gradient).
+int head_backward(mudpt_handle* h, Tower& t, const float* d_f, const float* gamma, const float* proj, cudaStream_t st) {
+  const int e = h->cfg.embed_dim;
+  if (t.fwd_pruned) {
+    CK(h, feature_head_bwd(d_f, t.pr_xo, nullptr, gamma, proj, t.pr_dx, t.pr_dxb, t.head_ws, t.S, 1, t.d, e, kLnEps, st));
+    return 0;
+  }
+  const size_t n = static_cast<size_t>(t.S) * t.L * t.d;
+  CUDA_OK(h, cudaMemsetAsync(t.dx, 0, n * sizeof(float), st));
+  CUDA_OK(h, cudaMemsetAsync(t.dx_bf16, 0, n * sizeof(bf16), st));
+  CK(h, feature_head_bwd(d_f, t.x_in[t.layers], t.sel_rows, gamma, proj, t.dx, t.dx_bf16, t.head_ws, t.S, t.L, t.d, e, kLnEps, st));
   return 0;
 }
 
@@ -516,8 +631,10 @@ void mudpt_destroy(mudpt_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
-  for (void* p : h->vis.ws_allocs) cudaFree(p);
-  for (void* p : h->txt.ws_allocs) cudaFree(p);
+  for (Tower* t : {&h->vis, &h->txt}) {
+    for (void* p : t->ws_allocs) cudaFree(p);
+    for (void* p : t->pr_allocs) cudaFree(p);
+  }
   for (ProfRec& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
   gemm_clear_tensor_map_cache();
@@ -613,8 +730,11 @@ int mudpt_vision_forward(mudpt_handle* h, const float* images, int32_t B, const 
   // prompts[0] = ln_pre(visual_ctx + shared_ctx), which is identical for every image
   CK(h, layernorm_fwd(t.x_in[0], h->ln_pre_g, h->ln_pre_b, t.x_in[0], false, B * t.L, t.d, kLnEps, st));
   if (h->ln_fused) CK(h, rowstats(t.x_in[0], t.xb_in[0], t.st_in[0], B * t.L, t.d, st));  // tower input as fp32 + bf16 + statistics
+  t.sel_rows = nullptr;  // CLS row (clip/model.py:548)
   if (tower_forward(h, t, prompts, 0, st)) return -1;
-  CK(h, feature_head_fwd(t.x_in[t.layers], nullptr, h->ln_post_g, h->ln_post_b, h->proj_v, f_img, t.head_ws, B, t.L, t.d, c.embed_dim, kLnEps, st));
+  const int* rows; int Lh;
+  const float* xh = tower_head_input(t, &rows, &Lh);
+  CK(h, feature_head_fwd(xh, rows, h->ln_post_g, h->ln_post_b, h->proj_v, f_img, t.head_ws, B, Lh, t.d, c.embed_dim, kLnEps, st));
   return 0;
 }
 
@@ -624,10 +744,7 @@ int mudpt_vision_backward(mudpt_handle* h, const float* d_f_img, float* d_prompt
   if (!t.fwd_done) return fail(h, "mudpt_vision_backward: no forward pass to differentiate");
   cudaSetDevice(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t n = static_cast<size_t>(t.S) * t.L * t.d;
-  CUDA_OK(h, cudaMemsetAsync(t.dx, 0, n * sizeof(float), st));
-  CUDA_OK(h, cudaMemsetAsync(t.dx_bf16, 0, n * sizeof(bf16), st));
-  CK(h, feature_head_bwd(d_f_img, t.x_in[t.layers], nullptr, h->ln_post_g, h->proj_v, t.dx, t.dx_bf16, t.head_ws, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  if (head_backward(h, t, d_f_img, h->ln_post_g, h->proj_v, st)) return -1;
   return tower_backward(h, t, d_prompts, 0, st);
 }
 
@@ -664,8 +781,11 @@ int mudpt_text_forward(mudpt_handle* h, const float* prompts, int32_t splice_lay
   if (t.cap_rows == 0 || t.S <= 0) return fail(h, "mudpt_text_forward: call mudpt_text_set_classes first");
   cudaSetDevice(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  t.sel_rows = h->eot;  // EOT row (trainers/mudpt.py:154)
   if (tower_forward(h, t, prompts, splice_layer0 ? 0 : 1, st)) return -1;
-  CK(h, feature_head_fwd(t.x_in[t.layers], h->eot, h->ln_final_g, h->ln_final_b, h->proj_t, f_txt, t.head_ws, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  const int* rows; int Lh;
+  const float* xh = tower_head_input(t, &rows, &Lh);
+  CK(h, feature_head_fwd(xh, rows, h->ln_final_g, h->ln_final_b, h->proj_t, f_txt, t.head_ws, t.S, Lh, t.d, h->cfg.embed_dim, kLnEps, st));
   t.first_splice = splice_layer0 ? 0 : 1;  // the backward must mirror the forward's splice set
   return 0;
 }
@@ -677,9 +797,7 @@ int mudpt_text_backward(mudpt_handle* h, const float* d_f_txt, float* d_prompts,
   cudaSetDevice(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = static_cast<size_t>(t.S) * t.L * t.d;
-  CUDA_OK(h, cudaMemsetAsync(t.dx, 0, n * sizeof(float), st));
-  CUDA_OK(h, cudaMemsetAsync(t.dx_bf16, 0, n * sizeof(bf16), st));
-  CK(h, feature_head_bwd(d_f_txt, t.x_in[t.layers], h->eot, h->ln_final_g, h->proj_t, t.dx, t.dx_bf16, t.head_ws, t.S, t.L, t.d, h->cfg.embed_dim, kLnEps, st));
+  if (head_backward(h, t, d_f_txt, h->ln_final_g, h->proj_t, st)) return -1;
   if (tower_backward(h, t, d_prompts, t.first_splice, st)) return -1;
   if (d_x0) CUDA_OK(h, cudaMemcpyAsync(d_x0, t.dx, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;

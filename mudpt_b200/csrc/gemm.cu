@@ -22,17 +22,21 @@
 // is launched with programmatic stream serialization: its prologue (barriers, TMEM allocation,
 // descriptor prefetch) overlaps the tail of the previous kernel (pdl_wait() in common.cuh).
 //
-// Work decomposition (stream-K hybrid).  Whole tiles are dealt round-robin to the units (CTAs or CTA pairs) for
-// as many full waves as there are; the tiles of the last full wave plus the remainder are cut into ONE contiguous
-// range of k-blocks per unit (75 pair tiles on 74 pairs: 1.014 tile-times instead of 2).  A unit walks its range
+// Work decomposition (grouped stream-K).  Whole tiles are dealt round-robin to the units (CTAs or CTA pairs); when
+// the tile count leaves a remainder of R tiles, the LAST g units give up their tile of the last full wave and share
+// those g tiles plus the R remainder tiles as ONE contiguous range of k-blocks each (75 pair tiles on 74 pairs with
+// g = 8: 67 units do one tile, 8 units do 9/8 of a tile -- 1.125 tile-times instead of 2).  A unit walks its range
 // from the high end down, so the part of a tile that ends at the tile's last k-block comes last in its range: that
 // unit ("finisher") runs the epilogue, after adding the fp32 partial accumulators that the lower-numbered
 // unit(s) holding the rest of the tile wrote to an L2-resident scratch slot at the START of their ranges (one slot per
 // CTA, one ready flag per epilogue warp: warp w of the finisher reads exactly what warp w of the contributor wrote,
 // so the hand-over is warp to warp).  A finisher only ever waits for lower-numbered units, which the hardware
-// dispatches first: no deadlock when another stream's kernel holds part of the machine.
+// dispatches first: no deadlock when another stream's kernel holds part of the machine.  g trades the imbalance
+// R/g against the L2 traffic of g hand-overs (measured: all 74 pairs handing over 256 KB each costs ~9 us, more than
+// a whole K = 768 tile), see plan_sk().
 #include "gemm.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -100,9 +104,10 @@ struct GemmCfg {
 // Work decomposition shared by the three warp roles
 // ---------------------------------------------------------------------------------------
 struct SkArgs {
-  int dp_tiles;   // tiles [0, dp_tiles) are dealt whole, round-robin (a multiple of the unit count, or all tiles)
-  int sk_tiles;   // tiles [dp_tiles, dp_tiles + sk_tiles) are cut into sk_units contiguous k-block ranges
-  int sk_units;
+  int dp_tiles;   // tiles [0, dp_tiles) are dealt whole, round-robin over all units
+  int sk_tiles;   // tiles [dp_tiles, dp_tiles + sk_tiles) are cut into sk_units contiguous k-block ranges ...
+  int sk_units;   // ... owned by the units [sk_first, sk_first + sk_units)
+  int sk_first;
   float* partials;  // one slot of 128 x BN floats per CTA
   unsigned* flags;  // [CTA][16]
 };
@@ -117,12 +122,13 @@ struct Seg {
 // constant bank) on each step -- three roles hold an iterator each and the 16-warp epilogues have 96 registers.
 struct SegIter {
   int dp_next, q;
-  __device__ __forceinline__ static int cut(int u, const SkArgs& a, int num_kb) {  // lower end of unit u's k-block range
-    return static_cast<int>(static_cast<long long>(u) * (a.sk_tiles * num_kb) / a.sk_units);
+  __device__ __forceinline__ static int cut(int v, const SkArgs& a, int num_kb) {  // lower end of the range of SK unit v
+    return static_cast<int>(static_cast<long long>(v) * (a.sk_tiles * num_kb) / a.sk_units);
   }
   __device__ __forceinline__ void init(int unit, int num_kb, const SkArgs& a) {
     dp_next = unit;
-    q = (a.sk_tiles > 0 && unit < a.sk_units) ? cut(unit + 1, a, num_kb) : 0;
+    const int v = unit - a.sk_first;
+    q = (a.sk_tiles > 0 && v >= 0 && v < a.sk_units) ? cut(v + 1, a, num_kb) : 0;
   }
   __device__ __forceinline__ bool next(Seg& s, int unit, int stride, int num_kb, const SkArgs& a) {
     if (dp_next < a.dp_tiles) {
@@ -131,13 +137,14 @@ struct SegIter {
       return true;
     }
     if (q > 0) {  // the unit's stream-K range, walked from the high end down (q == 0: none, or done)
-      const int q_lo = cut(unit, a, num_kb);
+      const int v = unit - a.sk_first;
+      const int q_lo = cut(v, a, num_kb);
       const int ts = (q - 1) / num_kb, t0 = ts * num_kb;
       const int lo = q_lo > t0 ? q_lo : t0;
       s.tile = a.dp_tiles + ts; s.kb0 = lo - t0; s.kb1 = q - t0; s.finish = (s.kb1 == num_kb); s.n_contrib = 0;
-      if (s.finish && s.kb0 > 0) {
-        int v = unit;
-        do { --v; ++s.n_contrib; } while (cut(v, a, num_kb) > t0);
+      if (s.finish && s.kb0 > 0) {  // the rest of the tile is held by the units just below
+        int w = v;
+        do { --w; ++s.n_contrib; } while (cut(w, a, num_kb) > t0);
       }
       q = lo > q_lo ? lo : 0;  // (lo == q_lo: range exhausted)
       return true;
@@ -1157,31 +1164,44 @@ size_t gemm_workspace_flag_bytes() { return static_cast<size_t>(kMaxCtas) * 16 *
 static int pick_bn(int N) { return N >= 256 ? 256 : 128; }
 int gemm_dots_span(int N) { return pick_bn(N) / (EpiWarps<EPI_GELU_BWD_DOTS>::value / 4); }
 
-// Stream-K plan for `tiles` tiles of `num_kb` k-blocks on `units` units (see the header comment).
-static SkArgs plan_sk(int tiles, int units, int num_kb, const GemmWorkspace* ws, bool allowed) {
+// Grouped stream-K plan for `tiles` tiles of `num_kb` k-blocks on `units` units (see the header comment).
+// Costs in k-block times (one 64-deep k-block of a tile = 0.46 us on one SM / SM pair at the sustained rate):
+//   whole tiles : the remainder costs one more tile-time for everyone: num_kb
+//   group of g  : rem * num_kb / g  (imbalance)  +  c * g  (g hand-overs share the L2: measured ~9 us for 74 pair
+//                 tiles of 256 KB, i.e. c = 0.29 per pair tile, half of that per single-CTA tile)  +  ~4 (dump, flag,
+//                 read-back on the last tile's critical path)
+static SkArgs plan_sk(int tiles, int units, int num_kb, bool pair, const GemmWorkspace* ws, bool allowed) {
   SkArgs a;
-  a.dp_tiles = tiles; a.sk_tiles = 0; a.sk_units = 0;
+  a.dp_tiles = tiles; a.sk_tiles = 0; a.sk_units = 0; a.sk_first = 0;
   a.partials = ws ? ws->partials : nullptr;
   a.flags = ws ? ws->flags : nullptr;
   if (!allowed || ws == nullptr || ws->partials == nullptr || ws->flags == nullptr || g_sk_mode == 0) return a;
   const int rem = tiles % units;
   if (rem == 0) return a;
   const int waves = tiles / units;
-  const int sk_tiles = rem + (waves > 0 ? units : 0);
-  const long long q = static_cast<long long>(sk_tiles) * num_kb;
-  // at least 4 k-blocks per unit (a unit's range is one or two accumulator passes + at most one hand-over)
-  int sk_units = static_cast<int>(q / 4 < units ? q / 4 : units);
-  if (sk_units < 1) sk_units = 1;
+  const float c = pair ? 0.29f : 0.145f;
+  int g = static_cast<int>(sqrtf(static_cast<float>(rem) * num_kb / c) + 0.5f);
+  if (g > units) g = units;
+  if (waves == 0) {            // fewer tiles than units: the group shares all of them
+    if (g <= rem) return a;    // (nothing to gain from cutting)
+    const long long q4 = static_cast<long long>(rem) * num_kb / 4;  // at least 4 k-blocks per unit
+    if (g > q4) g = static_cast<int>(q4);
+    if (g <= rem) return a;
+  } else if (g < 2) {
+    g = 2;
+  }
+  const int sk_tiles = rem + (waves > 0 ? g : 0);
   if (g_sk_mode != 1) {
-    // whole tiles cost ceil(sk_tiles / units) tile-times for this part, the cut sk_tiles / sk_units plus the
-    // hand-over of one 128 x BN fp32 tile through L2 per unit (measured in tile-times: ~3 k-blocks' worth)
-    const float whole = static_cast<float>((sk_tiles + units - 1) / units);
-    const float cut = static_cast<float>(sk_tiles) / static_cast<float>(sk_units) + 3.0f / static_cast<float>(num_kb);
-    if (cut > 0.92f * whole) return a;
+    // whole tiles: the remainder costs everyone one more tile-time (waves == 0: the one and only tile-time);
+    // cut: the group's makespan beyond the full waves
+    const float whole = static_cast<float>(num_kb);
+    const float cut = static_cast<float>(rem) * num_kb / g + c * g + 4.f;
+    if (cut > 0.9f * whole) return a;
   }
   a.dp_tiles = tiles - sk_tiles;
   a.sk_tiles = sk_tiles;
-  a.sk_units = sk_units;
+  a.sk_units = g;
+  a.sk_first = units - g;
   return a;
 }
 
@@ -1200,7 +1220,7 @@ static const char* launch_one(const CUtensorMap& ta, const CUtensorMap& tb, cons
   const int tiles = ((M + TM - 1) / TM) * ((N + BN - 1) / BN);
   int units = TWO ? num_sms() / 2 : num_sms();
   if (units * (TWO ? 2 : 1) > kMaxCtas) units = kMaxCtas / (TWO ? 2 : 1);
-  const SkArgs sk = plan_sk(tiles, units, (K + BK - 1) / BK, ws, RowEpi<MODE>::value);
+  const SkArgs sk = plan_sk(tiles, units, (K + BK - 1) / BK, TWO, ws, RowEpi<MODE>::value);
   const int used = sk.sk_tiles > 0 ? units : (tiles < units ? tiles : units);
   const int grid = used * (TWO ? 2 : 1);
   cudaLaunchConfig_t cfg = {};

@@ -452,6 +452,22 @@ const char* scatter_rows(const float* src, const int* rows, int S, int L, float*
   return launch_status("scatter_rows launch failed");
 }
 
+__global__ void scatter_rows_bf16_kernel(const bf16* __restrict__ src, const int* __restrict__ rows, int L, bf16* __restrict__ x, int d) {
+  const int s = blockIdx.x;
+  pdl_wait();
+  pdl_trigger();
+  const size_t row = static_cast<size_t>(s) * L + (rows ? rows[s] : 0);
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(x + row * d + c) = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(s) * d + c);
+}
+const char* scatter_rows_bf16(const bf16* src, const int* rows, int S, int L, bf16* x, int d, cudaStream_t stream) {
+  if (S <= 0) return nullptr;
+  if (d % 8 != 0) return "scatter_rows_bf16: width must be a multiple of 8";
+  launch_pdl(scatter_rows_bf16_kernel, dim3(S), dim3(128), 0, stream, src, rows, L, x, d);
+  count_launch(1);
+  return launch_status("scatter_rows_bf16 launch failed");
+}
+
 // dst[i, :] = src[s*L + rows[s], :] for S rows, fp32 and/or bf16 sources (either may be null): gathers the CLS / EOT
 // rows the last block still needs after attention.
 __global__ void gather_rows_kernel(const float* __restrict__ src_f, const bf16* __restrict__ src_b, const int* __restrict__ rows,

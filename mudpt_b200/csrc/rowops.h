@@ -21,6 +21,7 @@ const char* fold_layernorm(const float* W, const float* gamma, const float* beta
                            __nv_bfloat16* Wlt, float* bias_l, float* colsum, float2* sb, int N, int K, cudaStream_t stream);
 const char* scatter_rows(const float* src, const int* rows, int S, int L, float* x, __nv_bfloat16* xb, int d, bool accumulate,
                          cudaStream_t stream);
+const char* scatter_rows_bf16(const __nv_bfloat16* src, const int* rows, int S, int L, __nv_bfloat16* x, int d, cudaStream_t stream);
 const char* gather_rows(const float* src_f, const __nv_bfloat16* src_b, const int* rows, int S, int L, float* dst_f,
                         __nv_bfloat16* dst_b, int d, cudaStream_t stream);
 const char* im2col_bf16(const float* img, __nv_bfloat16* out, int B, int R, int p, int ldo, cudaStream_t stream);
