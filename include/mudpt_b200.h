@@ -66,6 +66,8 @@ void mudpt_destroy(mudpt_handle* h);
  *   "ln_fused"  1 (default; env MUDPT_LN_FUSED) LayerNorm folded into the GEMM epilogues, 0 stand-alone LN kernels
  *               (for checkpoints whose residual rows have |mean| >> std: the fused form feeds bf16(x), not
  *               bf16(LN(x)), to the tensor cores)
+ *   "ln_bwd_fused" 0 (default; env MUDPT_LN_BWD_FUSED) 1 = LayerNorm dgrad in the dgrad GEMMs' epilogues (needs
+ *               ln_fused; measured slower than the stand-alone kernel at the cfg-2 shapes, kept for narrow towers)
  *   "prune"     1 (default; env MUDPT_PRUNE) exact work skipping: the last block's out-proj / MLP (forward and
  *               dgrad) run on the CLS / EOT rows only (clip/model.py:548, trainers/mudpt.py:154), 0 = every row */
 int mudpt_set_option(mudpt_handle* h, const char* name, int32_t value);
@@ -227,7 +229,8 @@ int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t
 /* Per-kernel-class timing with CUDA events on the launch stream (bench.py's roofline leg).  Between
  * begin and end every tower launch is bracketed by an event pair.  end() blocks until the recorded
  * work has finished and fills out_host[cat*4 + {0,1,2,3}] = {total ms, launches, algorithmic FLOPs,
- * algorithmic bytes} for cat = gemm, attn_fwd, attn_bwd, ln_fwd, ln_bwd, splice, head, stem. */
+ * algorithmic bytes} for cat = gemm (other), attn_fwd, attn_bwd, ln_fwd, ln_bwd, splice, head, stem, then the eight
+ * GEMMs of a block: gemm_qkv, gemm_out, gemm_fc, gemm_proj, gemm_dproj, gemm_dfc, gemm_dout, gemm_dqkv (16 x 4 doubles). */
 int mudpt_profile_begin(mudpt_handle* h);
 int mudpt_profile_end(mudpt_handle* h, double* out_host, int32_t n_out);
 /* number of kernel launches issued by the library on this handle since creation */

@@ -87,7 +87,9 @@ struct Tower {
 }  // namespace
 
 // Optional per-kernel-class timing with CUDA events on the launch stream (bench.py's roofline leg).
-enum ProfCat { PC_GEMM = 0, PC_ATTN_FWD, PC_ATTN_BWD, PC_LN_FWD, PC_LN_BWD, PC_SPLICE, PC_HEAD, PC_STEM, PC_COUNT };
+enum ProfCat { PC_GEMM = 0, PC_ATTN_FWD, PC_ATTN_BWD, PC_LN_FWD, PC_LN_BWD, PC_SPLICE, PC_HEAD, PC_STEM,
+               // the eight GEMMs of a block, forward and dgrad (PC_GEMM: everything else -- patch embedding, pruned tail)
+               PC_GEMM_QKV, PC_GEMM_OUT, PC_GEMM_FC, PC_GEMM_PROJ, PC_GEMM_DPROJ, PC_GEMM_DFC, PC_GEMM_DOUT, PC_GEMM_DQKV, PC_COUNT };
 struct ProfRec { int cat; cudaEvent_t e0, e1; double flops, bytes; };
 struct Prof {
   bool on = false;
@@ -124,6 +126,10 @@ struct mudpt_handle {
   // fallback for checkpoints whose residual stream has a row mean far above its spread (bf16(x) instead of
   // bf16(LN(x)) as the GEMM operand would lose the signal there)
   bool ln_fused = true;
+  // LayerNorm dgrad in the dgrad GEMMs' epilogues (EPI_LN_BWD) instead of the stand-alone kernel.  Off by default:
+  // measured on B200 the row dots it needs cost more at their producers (GELU' epilogue +66 us, attention backward
+  // +82 us per block at the cfg-2 shapes) than the fused epilogue saves (60 us): profiles/r02_ln_fusion_ab.txt
+  bool ln_bwd_fused = false;
   // exact work skipping: the last block's out-proj / MLP on the CLS / EOT rows only
   bool prune = true;
 };
@@ -386,12 +392,12 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
     e1.out0 = t.qkv[i]; e1.ldc = 3 * d;
     if (fused) {
       e1.mode = EPI_LN_BF16; e1.bias = w.b_in_ln; e1.colsum = w.cs_in; e1.ln_stats = t.st_in[i]; e1.ln_parts = parts; e1.ln_width = d; e1.ln_eps = kLnEps;
-      CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
+      CKP(h, st, PC_GEMM_QKV, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
           gemm_bf16_tn(t.xb_in[i], d, w.w_in_ln, d, e1, M, 3 * d, d, st, &t.gws));
     } else {
       CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_in[i], w.ln1_g, w.ln1_b, t.a_buf, true, M, d, kLnEps, st));
       e1.mode = EPI_BF16; e1.bias = w.b_in;
-      CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
+      CKP(h, st, PC_GEMM_QKV, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
           gemm_bf16_tn(t.a_buf, d, w.w_in, d, e1, M, 3 * d, d, st, &t.gws));
     }
     CKP(h, st, PC_ATTN_FWD, attn_fl, Md * dd * 2 * 4, attention_fwd(t.qkv[i], t.o[i], t.lse[i], t.S, t.L, t.H, d, t.causal, st));
@@ -424,19 +430,19 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
     e2.out0 = t.x_mid[i]; e2.bias = w.b_out; e2.resid = t.x_in[i]; e2.ldc = d;
     if (fused) { e2.mode = EPI_RESID_STATS; e2.out2 = t.xb_mid[i]; e2.stats_out = t.st_mid[i]; }
     else e2.mode = EPI_RESID_F32;
-    CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (Md * dd + dd * dd) + (fused ? 10 : 8) * Md * dd,
+    CKP(h, st, PC_GEMM_OUT, 2.0 * Md * dd * dd, 2 * (Md * dd + dd * dd) + (fused ? 10 : 8) * Md * dd,
         gemm_bf16_tn(t.o[i], d, w.w_out, d, e2, M, d, d, st, &t.gws));
     // x + c_proj(QuickGELU(c_fc(ln_2(x))))   (clip/model.py:300)
     GemmEpilogue e3;
     e3.out0 = t.h[i]; e3.out1 = t.g_buf; e3.ldc = 4 * d;
     if (fused) {
       e3.mode = EPI_LN_GELU; e3.bias = w.b_fc_ln; e3.colsum = w.cs_fc; e3.ln_stats = t.st_mid[i]; e3.ln_parts = parts; e3.ln_width = d; e3.ln_eps = kLnEps;
-      CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
+      CKP(h, st, PC_GEMM_FC, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
           gemm_bf16_tn(t.xb_mid[i], d, w.w_fc_ln, d, e3, M, 4 * d, d, st, &t.gws));
     } else {
       CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_mid[i], w.ln2_g, w.ln2_b, t.a_buf, true, M, d, kLnEps, st));
       e3.mode = EPI_GELU; e3.bias = w.b_fc;
-      CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
+      CKP(h, st, PC_GEMM_FC, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
           gemm_bf16_tn(t.a_buf, d, w.w_fc, d, e3, M, 4 * d, d, st, &t.gws));
     }
     GemmEpilogue e4;
@@ -450,7 +456,7 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
     } else {
       e4.mode = EPI_RESID_F32;
     }
-    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + (fused ? 10 : 8) * Md * dd,
+    CKP(h, st, PC_GEMM_PROJ, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + (fused ? 10 : 8) * Md * dd,
         gemm_bf16_tn(t.g_buf, 4 * d, w.w_pr, 4 * d, e4, M, d, 4 * d, st, &t.gws));
   }
   t.fwd_done = true;
@@ -476,7 +482,7 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
   const int M = t.S * t.L, d = t.d;
   const double Md = static_cast<double>(M), dd = d;
   const double attn_fl = 2.5 * 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // 2.5x forward
-  const bool fused = t.fwd_fused;
+  const bool fused = t.fwd_fused && h->ln_bwd_fused;  // (the fused forward also keeps the fp32 LN inputs the kernel needs)
   const int parts = d / 64;
   const int dots_mlp = (4 * d + gemm_dots_span(4 * d) - 1) / gemm_dots_span(4 * d);
   for (int i = t.layers - 1; i >= 0; --i) {
@@ -514,25 +520,25 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
     e1.out0 = t.dh_buf; e1.aux = t.h[i]; e1.ldc = 4 * d;
     if (fused) { e1.mode = EPI_GELU_BWD_DOTS; e1.sb = w.sb_fc; e1.dots_out = t.dots; }
     else e1.mode = EPI_GELU_BWD;
-    CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
+    CKP(h, st, PC_GEMM_DPROJ, 2.0 * Md * 4 * dd * dd, 2 * (Md * dd + 4 * dd * dd + 2 * Md * 4 * dd),
         gemm_bf16_tn(t.dx_bf16, d, w.w_pr_t, d, e1, M, 4 * d, d, st, &t.gws));
     GemmEpilogue e2;
     e2.ldc = d;
     if (fused) {
       e2.mode = EPI_LN_BWD; e2.out0 = t.dx; e2.resid = t.dx; e2.out2 = t.dx_bf16; e2.x2 = t.xb_mid[i];
       e2.ln_stats = t.st_mid[i]; e2.ln_parts = parts; e2.ln_width = d; e2.ln_eps = kLnEps; e2.dots = t.dots; e2.dot_parts = dots_mlp;
-      CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 12 * Md * dd,
+      CKP(h, st, PC_GEMM_DFC, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 12 * Md * dd,
           gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t_ln, 4 * d, e2, M, d, 4 * d, st, &t.gws));
     } else {
       e2.mode = EPI_BF16; e2.out0 = t.a_buf;  // a_buf: forward transient, free during the backward
-      CKP(h, st, PC_GEMM, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 2 * Md * dd,
+      CKP(h, st, PC_GEMM_DFC, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 2 * Md * dd,
           gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st, &t.gws));
       CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
     }
     // attention branch: dO = dx W_out ; (dQ,dK,dV) ; da = dQKV W_in ; dx += LN1_bwd(da)
     GemmEpilogue e3;
     e3.mode = EPI_BF16; e3.out0 = t.do_buf; e3.ldc = d;
-    CKP(h, st, PC_GEMM, 2.0 * Md * dd * dd, 2 * (2 * Md * dd + dd * dd), gemm_bf16_tn(t.dx_bf16, d, w.w_out_t, d, e3, M, d, d, st, &t.gws));
+    CKP(h, st, PC_GEMM_DOUT, 2.0 * Md * dd * dd, 2 * (2 * Md * dd + dd * dd), gemm_bf16_tn(t.dx_bf16, d, w.w_out_t, d, e3, M, d, d, st, &t.gws));
     }
     CKP(h, st, PC_ATTN_BWD, attn_fl, Md * dd * 2 * 8,
         attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st,
@@ -542,11 +548,11 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
     if (fused) {
       e4.mode = EPI_LN_BWD; e4.out0 = t.dx; e4.resid = tail_pruned ? nullptr : t.dx; e4.out2 = t.dx_bf16; e4.x2 = t.xb_in[i];
       e4.ln_stats = t.st_in[i]; e4.ln_parts = parts; e4.ln_width = d; e4.ln_eps = kLnEps; e4.dots = t.dots; e4.dot_parts = 3 * t.H;
-      CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 12 * Md * dd,
+      CKP(h, st, PC_GEMM_DQKV, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 12 * Md * dd,
           gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t_ln, 3 * d, e4, M, d, 3 * d, st, &t.gws));
     } else {
       e4.mode = EPI_BF16; e4.out0 = t.a_buf;
-      CKP(h, st, PC_GEMM, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 2 * Md * dd,
+      CKP(h, st, PC_GEMM_DQKV, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 2 * Md * dd,
           gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st, &t.gws));
       CKP(h, st, PC_LN_BWD, 0, Md * dd * 16,
           layernorm_bwd(t.a_buf, true, t.x_in[i], w.ln1_g, tail_pruned ? nullptr : t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
@@ -622,6 +628,7 @@ int mudpt_create(const mudpt_config* cfg, mudpt_handle** out) {
   h->Kp = (3 * cfg->vision_patch_size * cfg->vision_patch_size + 7) & ~7;
   h->launches_at_create = g_launch_counter.load();
   h->ln_fused = env_flag("MUDPT_LN_FUSED", true);
+  h->ln_bwd_fused = env_flag("MUDPT_LN_BWD_FUSED", false);
   h->prune = env_flag("MUDPT_PRUNE", true);
   *out = h;
   return 0;
@@ -644,6 +651,7 @@ void mudpt_destroy(mudpt_handle* h) {
 int mudpt_set_option(mudpt_handle* h, const char* name, int32_t value) {
   if (!h || !name) return fail(h, "mudpt_set_option: null argument");
   if (!strcmp(name, "ln_fused")) h->ln_fused = value != 0;
+  else if (!strcmp(name, "ln_bwd_fused")) h->ln_bwd_fused = value != 0;
   else if (!strcmp(name, "prune")) h->prune = value != 0;
   else return fail(h, "mudpt_set_option: unknown option %s", name);
   h->vis.fwd_done = h->txt.fwd_done = false;  // saved activations belong to the previous formulation
@@ -998,7 +1006,8 @@ int mudpt_profile_begin(mudpt_handle* h) {
 }
 
 // out[cat*4 + {0,1,2,3}] = {total ms, launches, algorithmic FLOPs, algorithmic bytes}; cat order:
-// gemm, attn_fwd, attn_bwd, ln_fwd, ln_bwd, splice, head, stem.  Blocks until the recorded work is done.
+// gemm (other), attn_fwd, attn_bwd, ln_fwd, ln_bwd, splice, head, stem, gemm_qkv, gemm_out, gemm_fc, gemm_proj,
+// gemm_dproj, gemm_dfc, gemm_dout, gemm_dqkv.  Blocks until the recorded work is done.
 int mudpt_profile_end(mudpt_handle* h, double* out_host, int32_t n_out) {
   if (!h || !out_host) return fail(h, "mudpt_profile_end: null argument");
   if (n_out < PC_COUNT * 4) return fail(h, "mudpt_profile_end: output too small");

@@ -155,7 +155,8 @@ class Engine:
                                                   _lib.stream_ptr(self.device)), self.h)
         return d_i, d_t
 
-    PROFILE_CATEGORIES = ("gemm", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "splice", "head", "stem")
+    PROFILE_CATEGORIES = ("gemm_other", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "splice", "head", "stem", "gemm_qkv", "gemm_out",
+                          "gemm_fc", "gemm_proj", "gemm_dproj", "gemm_dfc", "gemm_dout", "gemm_dqkv")
 
     def profile_begin(self) -> None:
         _lib.check(self.lib.mudpt_profile_begin(self.h), self.h)
@@ -164,8 +165,11 @@ class Engine:
         n = len(self.PROFILE_CATEGORIES) * 4
         buf = (C.c_double * n)()
         _lib.check(self.lib.mudpt_profile_end(self.h, buf, n), self.h)
-        return {c: {"ms": buf[i * 4], "launches": int(buf[i * 4 + 1]), "flops": buf[i * 4 + 2], "bytes": buf[i * 4 + 3]}
-                for i, c in enumerate(self.PROFILE_CATEGORIES)}
+        out = {c: {"ms": buf[i * 4], "launches": int(buf[i * 4 + 1]), "flops": buf[i * 4 + 2], "bytes": buf[i * 4 + 3]}
+               for i, c in enumerate(self.PROFILE_CATEGORIES)}
+        # "gemm" = every launch of the tcgen05 GEMM kernel (the per-GEMM entries stay beside it)
+        out["gemm"] = {k: sum(v[k] for c, v in out.items() if c.startswith("gemm_")) for k in ("ms", "launches", "flops", "bytes")}
+        return out
 
     def launch_count(self) -> int:
         return int(self.lib.mudpt_launch_count(self.h))

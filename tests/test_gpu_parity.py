@@ -153,7 +153,7 @@ def test_full_size_properties_cfg2():
     (1) EOT-truncated and full 77-token text towers agree (exact under the causal mask up to bf16
     tile-order effects), (2) the step is deterministic (bitwise equal logits and gradients on
     repeat), (3) sharding the classes in two halves and concatenating equals the unsharded text
-    features (class independence, the multi-GPU partition), (4) sum of dlogits rows is 0
+    features to rounding level (class independence, the multi-GPU partition), (4) sum of dlogits rows is 0
     (softmax - onehot) so the all-class gradient of a constant logit shift vanishes: loss is
     finite and gradients are finite and non-zero."""
     from mudpt_b200 import synthetic as syn
@@ -198,7 +198,13 @@ def test_full_size_properties_cfg2():
                              pl.token_suffix[lo:hi]], dim=1)
             eng.text_set_classes(emb, eot[lo:hi], int(eot.max()) + 1)
             halves.append(eng.text_forward(P_t, True).clone())
-    assert torch.equal(torch.cat(halves), full)
+    # Not bitwise: the stream-K cut of a GEMM's tail wave depends on the row count, so a tile's k-blocks are summed
+    # in a different fp32 order for 500 and 1000 classes and bf16 roundings downstream may flip (MUDPT_GEMM_SK=0
+    # restores bit-identical shards).  Class independence itself is exact: bound the difference at rounding level.
+    cat = torch.cat(halves)
+    a, b = cat.flatten().double(), full.flatten().double()
+    assert float((a @ b) / (a.norm() * b.norm())) >= 0.99999
+    assert float((cat - full).abs().max()) <= 0.02 * float(full.abs().max())
 
 
 def _model_and_oracle_sd(arch_name, classnames, n_ctx, depth, ctx_init, seed=0):
@@ -266,13 +272,15 @@ def test_headline_full_shape_vs_oracle():
 
 
 def test_unfused_layernorm_fallback_matches_reference(bring):
-    """MUDPT option ln_fused = 0 (stand-alone LayerNorm kernels, bf16(LN(x)) operands) and prune = 0 stay
-    parity-green: the path for checkpoints whose residual rows have a mean far above their spread."""
+    """Every combination of the formulation options stays parity-green: ln_fused = 0 (stand-alone LayerNorm kernels,
+    bf16(LN(x)) operands: the path for checkpoints whose residual rows have a mean far above their spread),
+    ln_bwd_fused = 1 (LayerNorm dgrad in the dgrad GEMM epilogues), prune = 0 (every row of the last block)."""
     c = gu.load("tiny_a")
     model, _ = gu.build_model(c, "cuda")
     eng = model._clip_ref[0].engine()
     from mudpt_b200 import _lib
-    for opts in ({"ln_fused": 0, "prune": 0}, {"ln_fused": 1, "prune": 0}, {"ln_fused": 0, "prune": 1}):
+    for opts in ({"ln_fused": 0, "prune": 0}, {"ln_fused": 1, "prune": 0}, {"ln_fused": 0, "prune": 1},
+                 {"ln_fused": 1, "ln_bwd_fused": 1, "prune": 1}, {"ln_fused": 1, "ln_bwd_fused": 1, "prune": 0}):
         for k, v in opts.items():
             _lib.check(eng.lib.mudpt_set_option(eng.h, k.encode(), v), eng.h)
         model.zero_grad(set_to_none=True)
