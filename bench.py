@@ -43,6 +43,7 @@ UNIT = "imgs/s"
 BATCH_PER_GPU = 32
 N_CLASSES = 1000
 N_CTX, DEPTH = 2, 9
+ARCH = "ViT-B/16"   # --config 5 switches to ViT-L/14, prompt depth 12 (BASELINE configs[4])
 
 
 def _peaks():
@@ -55,14 +56,25 @@ def _peaks():
 
 
 def _gemm_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_gemm_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum averaged over the
-    captured text-tower GEMM launches); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    try:
-        return json.load(open(p))["avg_traffic_bytes_per_launch"]
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum averaged over EVERY
+    tcgen05 GEMM launch of one train step (the population `algorithmic_bytes_per_launch` is averaged over), from the
+    committed ncu capture of `bench.py --quick` (profiles/make_step_traffic.py).  The capture names the library build
+    it was taken from; a different build gives None (and says so) rather than a stale number."""
+    import glob
+    import hashlib
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_traffic.json")))
+    if not cands:
+        return None, "no capture committed"
+    d = json.load(open(cands[-1]))
+    lib = os.path.join(ROOT, "mudpt_b200", "lib", "libmudpt_b200.so")
+    src = hashlib.sha256()
+    csrc = os.path.join(ROOT, "mudpt_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        src.update(f.encode())
+        src.update(open(os.path.join(csrc, f), "rb").read())
+    if d.get("csrc_sha256") != src.hexdigest():
+        return None, f"{os.path.basename(cands[-1])} was captured from another build of csrc/ (re-run profiles/make_step_traffic.py)"
+    return d["avg_traffic_bytes_per_gemm_launch"], os.path.basename(cands[-1])
 
 
 class ClockSampler:
@@ -117,25 +129,26 @@ class ClockSampler:
 # CPU path (oracle port of the reference) -- cpu_baseline leg and --impl reference
 # ------------------------------------------------------------------------------------------------
 
-def cpu_sample_setup(frac_images: int = 1, frac_classes: int = 32):
-    """1/32 of the cfg-2 step: 1 image x 32 classes (vision cost is linear in images, text cost in
-    classes, so a full 32-image / 1000-class step costs 32 x (1 image + 31.25 classes))."""
-    import torch
+def cpu_setup(n_images: int, n_classes: int):
+    """Inputs of the oracle (fp32 CPU port of the reference path, pinned to the reference by tests/golden) for a step
+    of n_images x n_classes at the headline architecture."""
     from mudpt_b200 import synthetic as syn
     from oracle import mudpt_oracle as orc  # the checker; executed here only as the CPU baseline
     arch = syn.ARCHS["ViT-B/16"]
-    names = syn.synthetic_classnames(frac_classes)
+    names = syn.synthetic_classnames(n_classes)
     tok = syn.synthetic_tokenize(["a photo " + n + "." for n in names])
     ctx_tok = syn.synthetic_tokenize("a photo of a")[0]
     sd = syn.assemble_state_dict(arch, tok, N_CTX, DEPTH, ctx_tok, seed=0)
-    image = syn.synthetic_images(frac_images, 224, seed=1)
-    labels = syn.synthetic_labels(frac_images, frac_classes, seed=1)
+    image = syn.synthetic_images(n_images, 224, seed=1)
+    labels = syn.synthetic_labels(n_images, n_classes, seed=1)
     return orc, sd, image, tok, labels
 
 
 def cpu_time_steps(steps: int, warmup: int):
+    """cpu_baseline leg of the GPU arm: a bounded 1/32 sample of the step (1 image x 32 classes; vision cost is linear
+    in images, text cost in classes, so the full 32-image / 1000-class step costs 32 x (1 image + 31.25 classes))."""
     import torch
-    orc, sd, image, tok, labels = cpu_sample_setup()
+    orc, sd, image, tok, labels = cpu_setup(1, 32)
     threads = torch.get_num_threads()
     for _ in range(warmup):
         orc.forward_backward(sd, image, tok, labels)
@@ -152,23 +165,47 @@ def cpu_time_steps(steps: int, warmup: int):
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores.  The reference itself
+    (pure PyTorch + Dassl, no setup.py) cannot travel to the GPU box; the oracle port restates it (kind: "port").
+    With >= 48 GB of free host memory the step is the FULL configuration (32 images x 1000 classes, ~34 GB of fp32
+    activations, about a minute per step on 16 cores): 1 warm-up on the 1/32 sample (thread pool, allocator) + at most
+    2 timed full steps, so the run ends within a few minutes.  Otherwise the 1/32 sample is timed and scaled."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
+    import psutil
     import torch
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; use every host thread
-    # bound the run: each iteration is ~1-4 s on the box's host cores
-    steps = max(1, min(args.steps, 40))
-    warm = max(1, min(args.warmup, 3))
-    cb = cpu_time_steps(steps, warm)
+    threads = torch.get_num_threads()
+    full = psutil.virtual_memory().available >= 48 * 2 ** 30 and os.environ.get("MUDPT_REF_SAMPLE", "0") != "1"
+    if full:
+        orc, sd, image, tok, labels = cpu_setup(1, 32)
+        orc.forward_backward(sd, image, tok, labels)  # warm-up on the sample
+        del orc, sd, image, tok, labels
+        orc, sd, image, tok, labels = cpu_setup(BATCH_PER_GPU, N_CLASSES)
+        steps, warm = max(1, min(args.steps, 2)), 1
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.forward_backward(sd, image, tok, labels)
+        dt = (time.perf_counter() - t0) / steps
+        value, ms = BATCH_PER_GPU / dt, dt * 1e3
+        cb = {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+              "sample": f"the full step ({BATCH_PER_GPU} images x {N_CLASSES} classes, 77-token text, fp32 torch CPU oracle of the "
+                        f"reference path, {threads} threads of {os.cpu_count()} cpus): {steps} timed step(s) of {dt:.1f} s after a "
+                        f"warm-up on a 1/32 sample", "s_per_step": dt}
+    else:
+        steps, warm = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
+        cb = cpu_time_steps(steps, warm)
+        value, ms = cb["value"], cb["s_per_sample_step"] * 32 * 1e3
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": cb["s_per_sample_step"] * 32 * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MuDPT ViT-B/16 train step, batch {BATCH_PER_GPU}/GPU, {N_CLASSES} classes, n_ctx 2, depth 9 "
-                               "(CPU fp32 path, one process; does not scale with --gpus)", "text_seq_len": 77},
+        "config": {"workload": f"MuDPT ViT-B/16 16-shot-shaped train step (BASELINE configs[1]): batch {BATCH_PER_GPU}/GPU, "
+                               f"{N_CLASSES} classes, n_ctx {N_CTX}, prompt depth {DEPTH} (CPU fp32 path, one process; does not "
+                               "scale with --gpus)", "text_seq_len": 77, "full_configuration": bool(full)},
         "cpu_baseline": cb,
-        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -182,8 +219,8 @@ def build_trainer(device, truncate: bool, n_classes: int = N_CLASSES):
     import torch
     from mudpt_b200 import synthetic as syn
     from mudpt_b200.trainers import mudpt as M
-    cfg = syn.make_cfg(N_CTX, DEPTH, "a photo of a", 224, "ViT-B/16")
-    arch = syn.ARCHS["ViT-B/16"]
+    arch = syn.ARCHS[ARCH]
+    cfg = syn.make_cfg(N_CTX, DEPTH, "a photo of a", arch.image_resolution, ARCH)
     torch.manual_seed(0)  # prompt parameters are torch-initialised: identical replicas on every rank
     clip_model = M.clip.CLIP(*arch.astuple(), cfg).float()
     clip_model.load_state_dict(syn.synthetic_clip_state_dict(arch, 0), strict=False)
@@ -356,9 +393,10 @@ def run_ours(args):
         return out
 
     h2d = B * 3 * 224 * 224 * 4 + B * 8
-    cb = cpu_time_steps(3, 1) if world == 1 else None  # rank 0 at N=1 only (torchrun pins OMP threads to 1)
+    # rank 0 at N=1 only (torchrun pins OMP threads to 1); the oracle sample is the headline architecture's
+    cb = cpu_time_steps(3, 1) if (world == 1 and ARCH == "ViT-B/16") else None
     pipe = infer = None
-    if world == 1:
+    if world == 1 and ARCH == "ViT-B/16":
         try:
             pipe = input_pipeline_bench(device, peaks)
         except Exception as e:  # an aside to the contract line: never lose the headline over it
@@ -368,10 +406,11 @@ def run_ours(args):
         except Exception as e:
             infer = {"error": f"{type(e).__name__}: {e}"}
     line = {
-        "metric": METRIC, "value": gB / (full["ms"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC if ARCH == "ViT-B/16" else f"train imgs/s MuDPT {ARCH} 1000-cls depth {DEPTH}",
+        "value": gB / (full["ms"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": full["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"MuDPT ViT-B/16 16-shot-shaped train step (BASELINE configs[1]): batch {B}/GPU, "
+        "config": {"workload": f"MuDPT {ARCH} 16-shot-shaped train step (BASELINE configs[{1 if ARCH == 'ViT-B/16' else 4}]): batch {B}/GPU, "
                                f"{N_CLASSES} classes sharded by class over {world} rank(s), n_ctx {N_CTX}, prompt depth {DEPTH}, "
                                "fwd + CE + dgrad-only bwd + SGD step, random-init weights",
                    "global_batch": gB, "classes_per_gpu": -(-N_CLASSES // world), "text_seq_len": full["text_len"],
@@ -389,7 +428,8 @@ def run_ours(args):
                           "note": "text tower run on max(eot)+1 tokens: exact under the causal mask (tests), product default"},
         "roofline": {"bound": "tensor", "kernel": "gemm_tn_tcgen05_kernel (all GEMM launches of the step)",
                      "achieved": round(gemm_tflops, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": round(gemm_tflops / peaks["bf16_sustained"], 4), "traffic": _gemm_traffic(),
+                     "frac": round(gemm_tflops / peaks["bf16_sustained"], 4), "traffic": _gemm_traffic()[0],
+                     "traffic_source": _gemm_traffic()[1],
                      "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1),
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                      "launches_per_step": g["launches"] // full["nprof"],
@@ -482,6 +522,80 @@ def inference_bench(device, batch=256, reps=10):
     torch.cuda.empty_cache()
     return out
 
+def run_config3(args):
+    """BASELINE configs[2] as its own line: inference with cached text features, batch 256 per GPU."""
+    import torch
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    r = inference_bench(device, reps=max(args.steps, 5))
+    print(json.dumps({"metric": "inference imgs/s MuDPT ViT-B/16 1000-cls, cached text features", "value": r["imgs_per_s"],
+                      "unit": UNIT, "n_gpus": 1, "steps": max(args.steps, 5), "warmup": 3, "ms_per_step": r["ms_per_batch"],
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": r["workload"], "batch": r["batch"]}, "detail": r}), flush=True)
+
+
+def run_config4(args):
+    """BASELINE configs[3]: CoCoOp-style instance-conditioned prompts on the shared CLIP kernels -- one train step =
+    vision tower (no prompts) -> meta-net -> B x C text sequences in ONE native text-tower pass -> per-image cosine
+    logits -> CE -> dgrad through the dense text tower into ctx and the meta-net -> SGD (trainers/cocoop.py:178-198,
+    which loops over the images instead).  B = 4 images x 1000 classes per GPU = 4000 sequences of 77 tokens."""
+    import torch
+    import torch.distributed as dist
+    from mudpt_b200 import clip, synthetic as syn
+    from mudpt_b200.trainers.cocoop import CustomCLIP
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B, C = 4, N_CLASSES
+    arch = syn.ARCHS["ViT-B/16"]
+    cfg = syn.make_cfg(4, 1, "a photo of a", 224, "ViT-B/16")
+    cfg.TRAINER["NAME"] = "CoCoOp"
+    cfg.TRAINER["COCOOP"] = type(cfg)(N_CTX=4, CTX_INIT="a photo of a", PREC="fp32")
+    torch.manual_seed(0)
+    clip_model = clip.CLIP(*arch.astuple(), None).float()
+    clip_model.load_state_dict(syn.synthetic_clip_state_dict(arch, 0), strict=False)
+    model = CustomCLIP(cfg, syn.synthetic_classnames(C), clip_model, tokenizer=syn.synthetic_tokenize)
+    for n, p in model.named_parameters():
+        if "prompt_learner" not in n:
+            p.requires_grad_(False)
+    model = model.to(device).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    optim = torch.optim.SGD(params, lr=0.002, momentum=0.9, weight_decay=5e-4)
+    imgs = [syn.synthetic_images(B, 224, seed=300 + rank * 4 + i).to(device) for i in range(4)]
+    labs = [syn.synthetic_labels(B, C, seed=300 + rank * 4 + i).to(device) for i in range(4)]
+
+    def step(i):
+        optim.zero_grad(set_to_none=False)
+        loss = model(imgs[i % 4], labs[i % 4])
+        loss.backward()
+        if world > 1:
+            from mudpt_b200 import dist as mdist
+            mdist.all_reduce_grads(params)
+        optim.step()
+        return loss
+
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    ms, _, _ = timed_loop(step, K, W, device, world)
+    loss = float(step(0))
+    if rank == 0:
+        eng = clip_model.engine(device)
+        print(json.dumps({"metric": "train imgs/s CoCoOp ViT-B/16 1000-cls (B x C text sequences)", "value": B * world / (ms / K * 1e-3),
+                          "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"CoCoOp ViT-B/16 train step (BASELINE configs[3]): {B} images x {C} classes per GPU = "
+                                                 f"{B * C} text sequences of {eng.text_len} tokens in one text-tower pass, n_ctx 4, "
+                                                 "meta-net + ctx trainable, data-parallel over the images",
+                                     "text_sequences_per_s": B * C * world / (ms / K * 1e-3)},
+                          "loss": loss, "gpu_launches_per_step": None}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -491,7 +605,13 @@ def main():
     ap.add_argument("--quick", action="store_true", help="profiling aid: resident loop of the full-length variant only")
     ap.add_argument("--classes", type=int, default=N_CLASSES, help="--quick only: classes on this GPU")
     ap.add_argument("--no-overlap", action="store_true", help="--quick only: towers on one stream")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs (1-based): 2 = the headline (default), 3 = inference with cached text features, "
+                         "4 = CoCoOp-shaped step, 5 = ViT-L/14 prompt depth 12")
     args = ap.parse_args()
+    if args.config == 5:
+        global ARCH, DEPTH
+        ARCH, DEPTH = "ViT-L/14", 12
     # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version
     # banner to fd 1 at the first communicator): point fd 1 at stderr for the run and keep the real stdout
     # for the JSON line(s) this script prints itself.
@@ -501,6 +621,10 @@ def main():
     sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 3:
+        run_config3(args)
+    elif args.config == 4:
+        run_config4(args)
     else:
         run_ours(args)
     real_stdout.flush()

@@ -187,6 +187,9 @@ int mudpt_fold_layernorm(const float* W, const float* gamma, const float* beta, 
 int mudpt_attention_backward_dots(const uint16_t* qkv, const uint16_t* o, const uint16_t* d_o, const float* lse2,
                                   float* dsum_scratch, uint16_t* dqkv, int32_t S, int32_t L, int32_t H, int32_t causal,
                                   const float* ln_sb, float* ln_dots, void* stream);
+/* which sequences take the tcgen05 / TMEM attention kernels: 0 = none (warp-MMA kernels), 1 = default (non-causal,
+ * 129..256 tokens: the vision tower), 2 = every sequence of up to 256 tokens.  Process-wide (tests, A/B runs). */
+int mudpt_set_attention_tc(int32_t mode);
 int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream);
 int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream);
 

@@ -53,6 +53,7 @@ SIGNATURES = {
                                        C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_attention_backward_dots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int32,
                                                 C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
+    "mudpt_set_attention_tc": (C.c_int, [C.c_int32]),
     "mudpt_im2col": (C.c_int, [c_f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_cast_bf16": (C.c_int, [c_f32p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mudpt_sgd_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),

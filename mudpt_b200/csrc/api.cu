@@ -946,6 +946,10 @@ int mudpt_gemm_bf16(const uint16_t* A, const uint16_t* B, int32_t M, int32_t N, 
                    unit_workspace()));
   return 0;
 }
+int mudpt_set_attention_tc(int32_t mode) {
+  attention_tc_set_mode(mode);
+  return 0;
+}
 int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream) {
   CKG(im2col_bf16(images, reinterpret_cast<bf16*>(patches), B, R, patch, ld, static_cast<cudaStream_t>(stream)));
   return 0;

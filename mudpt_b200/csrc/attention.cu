@@ -890,6 +890,7 @@ const char* attention_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L, i
                           cudaStream_t stream) {
   if (S <= 0 || L <= 0) return nullptr;
   if (d != H * DH) return "attention: head width must be 64";
+  if (attention_tc_fwd_eligible(L, causal)) return attention_tc_fwd(qkv, o, lse2, S, L, H, d, causal, stream);
   const float sl2 = 0.125f * 1.4426950408889634f;
   if (use_short(L)) {
     const int tiles = (L + 15) / 16;

@@ -15,4 +15,10 @@ const char* attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* o, float* lse
 const char* attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
                           float* dsum, __nv_bfloat16* dqkv, int S, int L, int H, int d, bool causal, cudaStream_t stream,
                           const float2* ln_sb = nullptr, float2* ln_dots = nullptr);
+// tcgen05 / TMEM path (attention_tc.cu); attention_fwd dispatches to it when eligible.
+// mode: 0 = never, 1 = default (non-causal sequences of 129..256 tokens: the vision tower), 2 = every L <= 256
+void attention_tc_set_mode(int mode);
+bool attention_tc_fwd_eligible(int L, bool causal);
+const char* attention_tc_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* o, float* lse2, int S, int L, int H, int d, bool causal,
+                             cudaStream_t stream);
 }  // namespace mudpt

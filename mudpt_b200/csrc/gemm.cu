@@ -1137,6 +1137,33 @@ static const char* get_tensor_map(const void* ptr, int rows, int cols, int ld, i
   return nullptr;
 }
 
+// 3D bf16 tensor [d2][d1][d0] (d0 contiguous; strides in elements), box [1][box1][box0 = 64] with 128B swizzle:
+// one (sequence, head) slice of a token matrix for the attention kernels -- rows past d1 are zero-filled on load
+// and clipped on store, so a tile never touches the neighbouring sequence.
+const char* tensor_map_3d_bf16(const void* ptr, int d0, int d1, int d2, long long stride1, long long stride2, int box1,
+                               CUtensorMap* out) {
+  MapKey key{ptr, d1, d0, static_cast<int>(stride1), box1, d2, 3};
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return nullptr; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return "cuTensorMapEncodeTiled not available (no CUDA driver?)";
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride1 % 8) || (stride2 % 8)) return "TMA operand must be 16 B aligned";
+  CUtensorMap m;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(stride1) * 2, static_cast<cuuint64_t>(stride2) * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box1), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled (3D) failed";
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return nullptr;
+}
+
 void gemm_clear_tensor_map_cache() {
   std::lock_guard<std::mutex> lk(g_maps_mu);
   g_maps.clear();

@@ -1,5 +1,6 @@
 // Internal interface of the tcgen05 GEMM (see gemm.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -72,6 +73,9 @@ int gemm_dots_span(int N);
 // error string. Asynchronous on `stream`.  ws == nullptr: whole-tile scheduling only (no stream-K).
 const char* gemm_bf16_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, const GemmEpilogue& ep,
                          int M, int N, int K, cudaStream_t stream, const GemmWorkspace* ws = nullptr);
+// cached 3D TMA descriptor (bf16, 64-column boxes of box1 rows, 128B swizzle) for the attention kernels
+const char* tensor_map_3d_bf16(const void* ptr, int d0, int d1, int d2, long long stride1, long long stride2, int box1,
+                               CUtensorMap* out);
 void gemm_clear_tensor_map_cache();
 // 0 = whole tiles only, 1 = always cut, -1 = cost model, -2 = back to the process default (env MUDPT_GEMM_SK)
 void gemm_set_stream_k(int mode);

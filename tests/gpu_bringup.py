@@ -461,10 +461,20 @@ def group_attention(res):
         qkv = torch.randn(S * L, 3 * d, device=dev).bfloat16()
         o = torch.zeros(S * L, d, device=dev, dtype=torch.bfloat16)
         lse = torch.zeros(S, H, L, device=dev)
+        lib.mudpt_set_attention_tc(0)  # warp-MMA kernels
         _lib.check(lib.mudpt_attention_forward(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), S, L, H, causal, st))
         torch.cuda.synchronize()
         qr = qkv.float().clone().requires_grad_(True)
         oref = _attn_ref(qr, S, L, H, causal)
+        tc = None
+        if L <= 256:  # tcgen05 / TMEM kernels on the same input: output and log-sum-exp (the backward below uses them)
+            o_w, lse_w = o, lse
+            o = torch.zeros_like(o_w); lse = torch.zeros_like(lse_w)
+            lib.mudpt_set_attention_tc(2)
+            _lib.check(lib.mudpt_attention_forward(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), S, L, H, causal, st))
+            torch.cuda.synchronize()
+            tc = {"o_warp": _metrics(o_w.float(), oref.detach()), "lse_vs_warp": _metrics(lse, lse_w)}
+        lib.mudpt_set_attention_tc(1)
         do = torch.randn(S * L, d, device=dev).bfloat16()
         oref.backward(do.float())
         dqkv = torch.zeros(S * L, 3 * d, device=dev, dtype=torch.bfloat16)
@@ -476,10 +486,15 @@ def group_attention(res):
         key = f"attn_S{S}_L{L}_H{H}_c{causal}"
         res[key] = {"o": _metrics(o.float(), oref.detach()), "dq": _metrics(dqkv[:, :d].float(), g[:, :d]),
                     "dk": _metrics(dqkv[:, d:2 * d].float(), g[:, d:2 * d]), "dv": _metrics(dqkv[:, 2 * d:].float(), g[:, 2 * d:])}
+        if tc is not None:
+            res[key]["tc"] = tc
         print(key, res[key], flush=True)
     # timing at the cfg-2 shapes: vision, full-length text, EOT-truncated text
     for (S, L, H, causal, tag) in [(32, 199, 12, 0, "vision"), (1000, 77, 8, 1, "text77"), (1000, 9, 8, 1, "text9")]:
-        _time_attention(res, lib, st, dev, S, L, H, causal, tag)
+        for mode in (0, 2):
+            lib.mudpt_set_attention_tc(mode)
+            _time_attention(res, lib, st, dev, S, L, H, causal, tag + ("_tc" if mode else "_warp"))
+    lib.mudpt_set_attention_tc(1)
 
 
 def _time_attention(res, lib, st, dev, S, L, H, causal, tag):

@@ -94,6 +94,8 @@ def test_attention_forward_backward(bring):
         if k.startswith("attn_S"):
             for part in ("o", "dq", "dk", "dv"):
                 assert not v[part]["nan"] and v[part]["rel"] <= BF16_REL, (k, part, v[part])
+            if "tc" in v:  # "o" above came from the tcgen05 kernels, "o_warp" from the warp-MMA ones
+                assert v["tc"]["o_warp"]["rel"] <= BF16_REL and v["tc"]["lse_vs_warp"]["max_abs"] <= 2e-3, (k, v["tc"])
 
 
 def test_heads(bring):
