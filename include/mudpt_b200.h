@@ -63,9 +63,10 @@ const char* mudpt_global_last_error(void);
 int mudpt_create(const mudpt_config* cfg, mudpt_handle** out);
 void mudpt_destroy(mudpt_handle* h);
 /* Options (name, integer value):
- *   "ln_fused"  1 (default; env MUDPT_LN_FUSED) LayerNorm folded into the GEMM epilogues, 0 stand-alone LN kernels
- *               (for checkpoints whose residual rows have |mean| >> std: the fused form feeds bf16(x), not
- *               bf16(LN(x)), to the tensor cores)
+ *   "ln_fused"  -1 (default) by tower size: LayerNorm folded into the forward GEMM epilogues for towers of >= 32768
+ *               token rows, stand-alone LN kernels below (measured A/B); 1 always, 0 never (env MUDPT_LN_FUSED = 1 / 0).
+ *               0 is also the setting for checkpoints whose residual rows have |mean| >> std: the fused form feeds
+ *               bf16(x), not bf16(LN(x)), to the tensor cores
  *   "ln_bwd_fused" 0 (default; env MUDPT_LN_BWD_FUSED) 1 = LayerNorm dgrad in the dgrad GEMMs' epilogues (needs
  *               ln_fused; measured slower than the stand-alone kernel at the cfg-2 shapes, kept for narrow towers)
  *   "prune"     1 (default; env MUDPT_PRUNE) exact work skipping: the last block's out-proj / MLP (forward and

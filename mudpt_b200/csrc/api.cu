@@ -125,7 +125,7 @@ struct mudpt_handle {
   // options (mudpt_set_option): LayerNorm folded into the GEMMs (default) or the stand-alone LN kernels -- the
   // fallback for checkpoints whose residual stream has a row mean far above its spread (bf16(x) instead of
   // bf16(LN(x)) as the GEMM operand would lose the signal there)
-  bool ln_fused = true;
+  int ln_fused = -1;  // -1 = by tower size (see tower_forward), 0 = never, 1 = always
   // LayerNorm dgrad in the dgrad GEMMs' epilogues (EPI_LN_BWD) instead of the stand-alone kernel.  Off by default:
   // measured on B200 the row dots it needs cost more at their producers (GELU' epilogue +66 us, attention backward
   // +82 us per block at the cfg-2 shapes) than the fused epilogue saves (60 us): profiles/r02_ln_fusion_ab.txt
@@ -373,7 +373,11 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
   const int M = t.S * t.L, d = t.d;
   const double Md = static_cast<double>(M), dd = d;
   const double attn_fl = 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // QK^T + PV, dense count
-  const bool fused = h->ln_fused;
+  // Measured on B200 (profiles/r02_ln_fusion_ab.txt): folding the LayerNorm into the GEMMs saves its 4 B/element read
+  // but makes the four forward epilogues heavier (+2 B/element bf16 copy, statistics, rank-1 correction).  For the
+  // large HBM-bound tower (text, 77,000 rows) that is a gain; for ~6,000-row towers, whose 25-40 us GEMMs are
+  // launch / epilogue bound, the stand-alone LayerNorm kernels are faster: choose by row count unless told otherwise.
+  const bool fused = h->ln_fused == 1 || (h->ln_fused < 0 && M >= 32768);
   const bool pruned = h->prune;
   const int parts = d / 64;
   auto spliced = [&](int i) { return i < t.depth && i >= first_splice_layer && t.n_ctx > 0 && i < t.layers; };
@@ -627,7 +631,7 @@ int mudpt_create(const mudpt_config* cfg, mudpt_handle** out) {
   t.lw.resize(t.layers);
   h->Kp = (3 * cfg->vision_patch_size * cfg->vision_patch_size + 7) & ~7;
   h->launches_at_create = g_launch_counter.load();
-  h->ln_fused = env_flag("MUDPT_LN_FUSED", true);
+  h->ln_fused = getenv("MUDPT_LN_FUSED") ? (atoi(getenv("MUDPT_LN_FUSED")) != 0 ? 1 : 0) : -1;
   h->ln_bwd_fused = env_flag("MUDPT_LN_BWD_FUSED", false);
   h->prune = env_flag("MUDPT_PRUNE", true);
   *out = h;
@@ -650,7 +654,7 @@ void mudpt_destroy(mudpt_handle* h) {
 
 int mudpt_set_option(mudpt_handle* h, const char* name, int32_t value) {
   if (!h || !name) return fail(h, "mudpt_set_option: null argument");
-  if (!strcmp(name, "ln_fused")) h->ln_fused = value != 0;
+  if (!strcmp(name, "ln_fused")) h->ln_fused = value < 0 ? -1 : (value != 0 ? 1 : 0);
   else if (!strcmp(name, "ln_bwd_fused")) h->ln_bwd_fused = value != 0;
   else if (!strcmp(name, "prune")) h->prune = value != 0;
   else return fail(h, "mudpt_set_option: unknown option %s", name);
@@ -737,7 +741,8 @@ int mudpt_vision_forward(mudpt_handle* h, const float* images, int32_t B, const 
   // ln_pre in place (:541); the prompt rows are overwritten by the layer-0 splice with
   // prompts[0] = ln_pre(visual_ctx + shared_ctx), which is identical for every image
   CK(h, layernorm_fwd(t.x_in[0], h->ln_pre_g, h->ln_pre_b, t.x_in[0], false, B * t.L, t.d, kLnEps, st));
-  if (h->ln_fused) CK(h, rowstats(t.x_in[0], t.xb_in[0], t.st_in[0], B * t.L, t.d, st));  // tower input as fp32 + bf16 + statistics
+  if (h->ln_fused == 1 || (h->ln_fused < 0 && B * t.L >= 32768))  // (the rule of tower_forward)
+    CK(h, rowstats(t.x_in[0], t.xb_in[0], t.st_in[0], B * t.L, t.d, st));  // tower input as fp32 + bf16 + statistics
   t.sel_rows = nullptr;  // CLS row (clip/model.py:548)
   if (tower_forward(h, t, prompts, 0, st)) return -1;
   const int* rows; int Lh;

@@ -926,6 +926,8 @@ const char* attention_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const
                           int S, int L, int H, int d, bool causal, cudaStream_t stream, const float2* ln_sb, float2* ln_dots) {
   if (S <= 0 || L <= 0) return nullptr;
   if (d != H * DH) return "attention: head width must be 64";
+  if (ln_dots == nullptr && attention_tc_bwd_eligible(L, causal))  // (the row-dot by-product exists in the warp-MMA kernels only)
+    return attention_tc_bwd(qkv, o, d_o, lse2, dsum, dqkv, S, L, H, d, causal, stream);
   if (use_short(L)) {
     const int tiles = (L + 15) / 16;
     const size_t sm = short_bwd_smem(tiles * 16);

@@ -19,6 +19,9 @@ const char* attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, cons
 // mode: 0 = never, 1 = default (non-causal sequences of 129..256 tokens: the vision tower), 2 = every L <= 256
 void attention_tc_set_mode(int mode);
 bool attention_tc_fwd_eligible(int L, bool causal);
+bool attention_tc_bwd_eligible(int L, bool causal);
+const char* attention_tc_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
+                             float* dsum, __nv_bfloat16* dqkv, int S, int L, int H, int d, bool causal, cudaStream_t stream);
 const char* attention_tc_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* o, float* lse2, int S, int L, int H, int d, bool causal,
                              cudaStream_t stream);
 }  // namespace mudpt

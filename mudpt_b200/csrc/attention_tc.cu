@@ -204,6 +204,280 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
   }
 }
 
+// =======================================================================================
+// Backward on tcgen05.  Two launches of one kernel template, as in the warp-MMA path:
+//   KV = false  rows = 128 queries of the block:  S = Q K^T, dP = dO V^T, dS = P (dP - D),  dQ = scale dS K
+//   KV = true   rows = 128 keys of the block:     S^T = K Q^T, dP^T = V dO^T, P^T, dS^T,     dV = P^T dO, dK = scale dS^T Q
+// The other index runs in ROUNDS of 64 columns: per round two score MMAs (128 x 64 x 64) into TMEM columns [0, 64) /
+// [64, 128), the element-wise step by 8 warps (thread = row, each warp half takes 32 columns; P recomputed from the
+// saved log-sum-exp: no row reduction at all), the bf16 P / dS tiles into one 16 KB swizzled slab each, and the output
+// MMAs accumulating in TMEM columns [128, 192) / [192, 256) over the rounds, with the round's K / V (resp. Q / dO)
+// tile as the MN-major B operand.  256 TMEM columns and 96 KB of shared memory per CTA: two CTAs per SM.
+// D = rowsum(dO * O) is computed by the KV = false launch (thread-local: the thread owns the row) and handed to the
+// KV = true launch through `dsum`.  Without a mask nothing needs masking: padded key / query rows are zero-filled by
+// TMA, so their contributions vanish in the output MMAs whatever their (finite) P.
+// =======================================================================================
+static constexpr int TCB_THREADS = 288;  // 8 element-wise warps + 1 control warp
+static constexpr int TCB_TILE = 8192;    // 64 rows x 64 bf16
+
+__host__ __device__ inline int tcb_smem_bytes(int Lpad) {
+  return 2 * TC_SLAB /*A tiles*/ + 4 * TCB_TILE /*round tiles x2*/ + 2 * TC_SLAB /*slabs*/ + 2 * Lpad * 4 /*lse, D*/ + 2 * 128 * 4 /*exchange*/ +
+         256 /*barriers*/ + 1024;
+}
+
+template <bool KV, bool CAUSAL>
+__global__ void __launch_bounds__(TCB_THREADS) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv128,  // row blocks of qkv
+                                                                  const __grid_constant__ CUtensorMap map_qkv64,   // round tiles of qkv
+                                                                  const __grid_constant__ CUtensorMap map_do128,
+                                                                  const __grid_constant__ CUtensorMap map_do64,
+                                                                  const __grid_constant__ CUtensorMap map_dqkv,    // output, 128-row boxes
+                                                                  const bf16* __restrict__ o, const float* __restrict__ lse2,
+                                                                  float* __restrict__ dsum, const int L, const int H, const int d,
+                                                                  const float scale, const float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = blockIdx.x, sh = blockIdx.y, s = sh / H, h = sh - s * H;
+  const int Lpad = (L + 63) & ~63;
+  uint8_t* sA0 = smem;                 // KV ? K block : Q block
+  uint8_t* sA1 = sA0 + TC_SLAB;        // KV ? V block : dO block
+  uint8_t* sU = sA1 + TC_SLAB;         // [2] KV ? Q round : K round
+  uint8_t* sW = sU + 2 * TCB_TILE;     // [2] KV ? dO round : V round
+  uint8_t* slabP = sW + 2 * TCB_TILE;  // P^T of the round (KV only)
+  uint8_t* slabS = slabP + TC_SLAB;    // dS / dS^T of the round
+  float* sLse = reinterpret_cast<float*>(slabS + TC_SLAB);  // KV: per query column
+  float* sD = sLse + Lpad;
+  float* sX = sD + Lpad;               // [2][128] exchange between the two warp halves of a row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 256);
+  uint64_t* bar_a = bars;          // block tiles loaded
+  uint64_t* bar_t = bars + 1;      // [2] round tiles loaded
+  uint64_t* bar_s = bars + 3;      // scores of the round in TMEM
+  uint64_t* bar_c = bars + 4;      // scores consumed (256 arrivals)
+  uint64_t* bar_p = bars + 5;      // slabs written (256 arrivals)
+  uint64_t* bar_f = bars + 6;      // output MMAs of the round done: slabs and the round's tile buffer are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  // rounds: queries of the block see keys [0, kv_end), keys of the block are seen by queries [q_begin, L)
+  const int row_blk0 = blk * TC_ROWS;
+  int c_begin = 0, c_end = L;
+  if (CAUSAL) {
+    if (KV) c_begin = row_blk0 & ~63;                      // queries before the block's first key never see it
+    else c_end = min(L, row_blk0 + TC_ROWS);               // keys after the block's last query are invisible
+  }
+  const int r_begin = c_begin >> 6, r_end = (c_end + 63) >> 6;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_qkv128);
+      tma_prefetch_desc(&map_qkv64);
+      tma_prefetch_desc(&map_do128);
+      tma_prefetch_desc(&map_do64);
+      mbar_init(bar_a, 1);
+      mbar_init(&bar_t[0], 1);
+      mbar_init(&bar_t[1], 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_c, 256);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_f, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  const int colA0 = (KV ? d : 0) + h * 64, colU = (KV ? 0 : d) + h * 64;  // columns of qkv: A0 / U tiles
+  if (warp == 8) {
+    if (lane == 0) {
+      auto load_round = [&](int r) {
+        const int b = (r - r_begin) & 1;
+        mbar_expect_tx(&bar_t[b], 2 * TCB_TILE);
+        tma_load_3d(sU + b * TCB_TILE, &map_qkv64, &bar_t[b], colU, r * 64, s);
+        if (KV) tma_load_3d(sW + b * TCB_TILE, &map_do64, &bar_t[b], h * 64, r * 64, s);
+        else tma_load_3d(sW + b * TCB_TILE, &map_qkv64, &bar_t[b], 2 * d + h * 64, r * 64, s);
+      };
+      mbar_expect_tx(bar_a, 2 * TC_SLAB);
+      tma_load_3d(sA0, &map_qkv128, bar_a, colA0, row_blk0, s);
+      if (KV) tma_load_3d(sA1, &map_qkv128, bar_a, 2 * d + h * 64, row_blk0, s);
+      else tma_load_3d(sA1, &map_do128, bar_a, h * 64, row_blk0, s);
+      load_round(r_begin);
+      if (r_begin + 1 < r_end) load_round(r_begin + 1);
+      mbar_wait(bar_a, 0);
+      const uint64_t dA0 = make_smem_desc_sw128(smem_u32(sA0)), dA1 = make_smem_desc_sw128(smem_u32(sA1));
+      const uint64_t dP = make_smem_desc_sw128(smem_u32(slabP)), dS = make_smem_desc_sw128(smem_u32(slabS));
+      const uint32_t idesc_out = make_idesc_bf16(TC_ROWS, 64) | kIdescBMnMajor;
+      for (int r = r_begin; r < r_end; ++r) {
+        const int i = r - r_begin, b = i & 1;
+        const int nr = min(64, ((c_end + 15) & ~15) - r * 64);  // columns of this round (multiple of 16)
+        mbar_wait(&bar_t[b], (i >> 1) & 1);
+        if (i > 0) mbar_wait(bar_c, (i - 1) & 1);  // the previous round's scores have been read
+        tc_fence_after();
+        const uint64_t dU = make_smem_desc_sw128(smem_u32(sU + b * TCB_TILE)), dW = make_smem_desc_sw128(smem_u32(sW + b * TCB_TILE));
+        const uint32_t idesc_s = make_idesc_bf16(TC_ROWS, nr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dA0 + static_cast<uint64_t>(k * 2), dU + static_cast<uint64_t>(k * 2), idesc_s, static_cast<uint32_t>(k != 0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 64u, dA1 + static_cast<uint64_t>(k * 2), dW + static_cast<uint64_t>(k * 2), idesc_s, static_cast<uint32_t>(k != 0));
+        umma_commit(bar_s);
+        // the buffer of round r - 1 is free once its output MMAs are done: refill it with round r + 1
+        if (i >= 1 && r + 1 < r_end) {
+          mbar_wait(bar_f, (i - 1) & 1);
+          load_round(r + 1);
+        }
+        mbar_wait(bar_p, i & 1);  // the round's slabs are written
+        tc_fence_after();
+        const int nk = nr >> 4;
+        for (int k = 0; k < nk; ++k) {
+          const uint32_t acc = static_cast<uint32_t>(i != 0 || k != 0);
+          if (KV) {
+            umma_bf16(tmem_base + 128u, dP + static_cast<uint64_t>(k * 2), dW + static_cast<uint64_t>(k * 128), idesc_out, acc);  // dV += P^T dO
+            umma_bf16(tmem_base + 192u, dS + static_cast<uint64_t>(k * 2), dU + static_cast<uint64_t>(k * 128), idesc_out, acc);  // dK += dS^T Q
+          } else {
+            umma_bf16(tmem_base + 128u, dS + static_cast<uint64_t>(k * 2), dU + static_cast<uint64_t>(k * 128), idesc_out, acc);  // dQ += dS K
+          }
+        }
+        umma_commit(bar_f);
+      }
+    }
+  } else {
+    // ===================== element-wise warps: thread = row of the block, half = 32 of the round's 64 columns =====================
+    const int quad = warp & 3, half = warp >> 2;
+    const int t = quad * 32 + lane;
+    const int row = row_blk0 + t;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const size_t stat_base = (static_cast<size_t>(s) * H + h) * L;
+    float lse_r = 0.f, D_r = 0.f;  // KV = false: of this thread's query row
+    if (KV) {
+      for (int i = threadIdx.x; i < Lpad; i += 256) {
+        sLse[i] = i < L ? lse2[stat_base + i] : 0.f;
+        sD[i] = i < L ? dsum[stat_base + i] : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    } else {
+      // D = rowsum(dO * O): this half's 32 of the 64 head columns, exchanged through shared memory
+      mbar_wait(bar_a, 0);
+      float part = 0.f;
+      if (row < L) {
+        const bf16* orow = o + (static_cast<size_t>(s) * L + row) * d + h * 64 + half * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 a = *reinterpret_cast<const uint4*>(sA1 + t * 128 + (((half * 4 + c) ^ (t & 7)) << 4));
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(orow) + c);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 x = unpack_bf16(aw[q]), y = unpack_bf16(bw[q]);
+            part += x.x * y.x + x.y * y.y;
+          }
+        }
+        lse_r = lse2[stat_base + row];
+      }
+      sX[half * 128 + t] = part;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      D_r = part + sX[(half ^ 1) * 128 + t];
+      if (half == 0 && row < L) dsum[stat_base + row] = D_r;
+    }
+    const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
+    for (int r = r_begin; r < r_end; ++r) {
+      const int i = r - r_begin;
+      mbar_wait(bar_s, i & 1);
+      tc_fence_after();
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32(trow + static_cast<uint32_t>(half * 32), sv);
+      tmem_ld_32x32(trow + 64u + static_cast<uint32_t>(half * 32), dv);
+      tmem_ld_wait_regs(sv);
+      tmem_ld_wait_regs(dv);
+      tc_fence_before();
+      mbar_arrive(bar_c);  // the next round's score MMAs may overwrite the columns
+      const int col0 = r * 64 + half * 32;  // first column (key for KV = false, query for KV = true) of this thread's 32
+      uint32_t pp[16], ds[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        f32x2 nl, nD;
+        if (KV) {
+          const float2 l2 = *reinterpret_cast<const float2*>(sLse + col0 + 2 * e);
+          const float2 d2 = *reinterpret_cast<const float2*>(sD + col0 + 2 * e);
+          nl = f2_pack(-l2.x, -l2.y);
+          nD = f2_pack(-d2.x, -d2.y);
+        } else {
+          nl = f2_pack(-lse_r, -lse_r);
+          nD = f2_pack(-D_r, -D_r);
+        }
+        float a, b;
+        f2_unpack(f2_fma(f2_pack_u(sv[2 * e], sv[2 * e + 1]), c2, nl), a, b);
+        a = exp2f(a);
+        b = exp2f(b);
+        if (CAUSAL) {  // key <= query
+          const int c = col0 + 2 * e;
+          if (KV) { a = row <= c ? a : 0.f; b = row <= c + 1 ? b : 0.f; }
+          else { a = c <= row ? a : 0.f; b = c + 1 <= row ? b : 0.f; }
+        }
+        float x, y;
+        f2_unpack(f2_mul(f2_pack(a, b), f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), nD)), x, y);  // dS (unscaled)
+        pp[e] = pack_bf16(a, b);
+        ds[e] = pack_bf16(x, y);
+      }
+      if (i > 0) mbar_wait(bar_f, (i - 1) & 1);  // the previous round's output MMAs have read the slabs
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q) ^ (t & 7)) << 4));
+        if (KV) *reinterpret_cast<uint4*>(slabP + off) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
+        *reinterpret_cast<uint4*>(slabS + off) = make_uint4(ds[4 * q], ds[4 * q + 1], ds[4 * q + 2], ds[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_p);
+    }
+    // outputs: this half's 32 of the 64 head columns, scaled, as bf16 into the (dead) block tiles, then TMA stores
+    mbar_wait(bar_f, (r_end - r_begin - 1) & 1);
+    tc_fence_after();
+    {
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(trow + 128u + static_cast<uint32_t>(half * 32), o0);
+      if (KV) tmem_ld_32x32(trow + 192u + static_cast<uint32_t>(half * 32), o1);
+      tmem_ld_wait_regs(o0);
+      if (KV) tmem_ld_wait_regs(o1);
+      const float sc0 = KV ? 1.f : scale;  // dV unscaled; dQ, dK carry the softmax scale
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q) ^ (t & 7)) << 4));
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q + 2 * e]) * sc0, __uint_as_float(o0[8 * q + 2 * e + 1]) * sc0);
+        *reinterpret_cast<uint4*>(sA0 + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (KV) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q + 2 * e]) * scale, __uint_as_float(o1[8 * q + 2 * e + 1]) * scale);
+          *reinterpret_cast<uint4*>(sA1 + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x == 0) {
+      if (KV) {
+        tma_store_3d(&map_dqkv, sA0, 2 * d + h * 64, row_blk0, s);  // dV
+        tma_store_3d(&map_dqkv, sA1, d + h * 64, row_blk0, s);      // dK
+      } else {
+        tma_store_3d(&map_dqkv, sA0, h * 64, row_blk0, s);          // dQ
+      }
+      bulk_commit();
+      bulk_wait_read<0>();
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256u);
+  }
+}
+
 static int g_tc_mode = -1;
 static int tc_enabled() {
   if (g_tc_mode < 0) {
@@ -245,6 +519,43 @@ const char* attention_tc_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L
              Lk, tmem_cols, sl2);
   count_launch(1);
   return launch_status("attention fwd (tcgen05) launch failed");
+}
+
+bool attention_tc_bwd_eligible(int L, bool causal) {
+  const int en = tc_enabled();
+  if (en == 0 || L < 1) return false;
+  if (en == 2) return true;
+  return !causal && L > 128;
+}
+
+const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv,
+                             int S, int L, int H, int d, bool causal, cudaStream_t stream) {
+  CUtensorMap m128, m64, mdo128, mdo64, mout;
+  const char* e;
+  const long long ld = 3LL * d;
+  if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, TC_ROWS, &m128))) return e;
+  if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, 64, &m64))) return e;
+  if ((e = tensor_map_3d_bf16(d_o, d, L, S, d, static_cast<long long>(d) * L, TC_ROWS, &mdo128))) return e;
+  if ((e = tensor_map_3d_bf16(d_o, d, L, S, d, static_cast<long long>(d) * L, 64, &mdo64))) return e;
+  if ((e = tensor_map_3d_bf16(dqkv, 3 * d, L, S, ld, ld * L, TC_ROWS, &mout))) return e;
+  const int Lpad = (L + 63) & ~63;
+  const int smem = tcb_smem_bytes(Lpad);
+  if (smem > 227 * 1024) return "attention (tcgen05 backward): sequence too long";
+  const float scale = 0.125f, sl2 = 0.125f * 1.4426950408889634f;
+  const dim3 grid((L + TC_ROWS - 1) / TC_ROWS, S * H);
+#define MUDPT_TCB_LAUNCH(KVF, CF)                                                                                        \
+  do {                                                                                                                   \
+    auto kern = attn_tc_bwd_kernel<KVF, CF>;                                                                             \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)                    \
+      return "attention (tcgen05 backward): cudaFuncSetAttribute failed";                                                \
+    launch_pdl(kern, grid, dim3(TCB_THREADS), static_cast<size_t>(smem), stream, m128, m64, mdo128, mdo64, mout, o, lse2, dsum, L, \
+               H, d, scale, sl2);                                                                                        \
+  } while (0)
+  if (causal) { MUDPT_TCB_LAUNCH(false, true); MUDPT_TCB_LAUNCH(true, true); }
+  else { MUDPT_TCB_LAUNCH(false, false); MUDPT_TCB_LAUNCH(true, false); }
+#undef MUDPT_TCB_LAUNCH
+  count_launch(2);
+  return launch_status("attention bwd (tcgen05) launch failed");
 }
 
 }  // namespace mudpt

@@ -479,15 +479,27 @@ def group_attention(res):
         oref.backward(do.float())
         dqkv = torch.zeros(S * L, 3 * d, device=dev, dtype=torch.bfloat16)
         dsum = torch.zeros(S, H, L, device=dev)
+        lib.mudpt_set_attention_tc(0)
         _lib.check(lib.mudpt_attention_backward(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
                                                 dqkv.data_ptr(), S, L, H, causal, st))
         torch.cuda.synchronize()
+        lib.mudpt_set_attention_tc(1)
         g = qr.grad
         key = f"attn_S{S}_L{L}_H{H}_c{causal}"
         res[key] = {"o": _metrics(o.float(), oref.detach()), "dq": _metrics(dqkv[:, :d].float(), g[:, :d]),
                     "dk": _metrics(dqkv[:, d:2 * d].float(), g[:, d:2 * d]), "dv": _metrics(dqkv[:, 2 * d:].float(), g[:, 2 * d:])}
-        if tc is not None:
-            res[key]["tc"] = tc
+        # tcgen05 backward (both launches) on the same input, any length
+        dq2 = torch.zeros_like(dqkv); ds2 = torch.zeros(S, H, L, device=dev)
+        lib.mudpt_set_attention_tc(2)
+        _lib.check(lib.mudpt_attention_backward(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), ds2.data_ptr(),
+                                                dq2.data_ptr(), S, L, H, causal, st))
+        torch.cuda.synchronize()
+        lib.mudpt_set_attention_tc(1)
+        if tc is None:
+            tc = {}
+        tc.update({"dq": _metrics(dq2[:, :d].float(), g[:, :d]), "dk": _metrics(dq2[:, d:2 * d].float(), g[:, d:2 * d]),
+                   "dv": _metrics(dq2[:, 2 * d:].float(), g[:, 2 * d:])})
+        res[key]["tc"] = tc
         print(key, res[key], flush=True)
     # timing at the cfg-2 shapes: vision, full-length text, EOT-truncated text
     for (S, L, H, causal, tag) in [(32, 199, 12, 0, "vision"), (1000, 77, 8, 1, "text77"), (1000, 9, 8, 1, "text9")]:

@@ -94,8 +94,10 @@ def test_attention_forward_backward(bring):
         if k.startswith("attn_S"):
             for part in ("o", "dq", "dk", "dv"):
                 assert not v[part]["nan"] and v[part]["rel"] <= BF16_REL, (k, part, v[part])
-            if "tc" in v:  # "o" above came from the tcgen05 kernels, "o_warp" from the warp-MMA ones
+            if "o_warp" in v["tc"]:  # "o" above came from the tcgen05 kernels, "o_warp" from the warp-MMA ones
                 assert v["tc"]["o_warp"]["rel"] <= BF16_REL and v["tc"]["lse_vs_warp"]["max_abs"] <= 2e-3, (k, v["tc"])
+            for part in ("dq", "dk", "dv"):  # tcgen05 backward ("dq" etc. above: warp-MMA kernels)
+                assert not v["tc"][part]["nan"] and v["tc"][part]["rel"] <= BF16_REL, (k, part, v["tc"][part])
 
 
 def test_heads(bring):
