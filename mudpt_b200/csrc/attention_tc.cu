@@ -2,14 +2,15 @@
 // staged by TMA.  Replaces the scaled_dot_product_attention inside nn.MultiheadAttention (clip/model.py:271-273;
 // causal mask of the text tower :810-816) for sequences of up to 256 tokens, head width 64.
 //
-// Forward, one CTA per (sequence, head, block of 128 query rows), 160 threads:
-//   warp 4 (one elected lane)  TMA: Q block [128 x 64], K and V [Lk x 64] (3D descriptors over [S][L][3d]: rows past
+// Forward, one CTA per (sequence, head, block of 128 query rows), 288 threads:
+//   warp 8 (one elected lane)  TMA: Q block [128 x 64], K and V [Lk x 64] (3D descriptors over [S][L][3d]: rows past
 //                              the sequence end are zero-filled, never the next sequence's tokens)
 //                              S = Q K^T : tcgen05.mma 128 x Lk x 64, fp32 scores in TMEM columns [0, Lk)
 //                              O = P V   : tcgen05.mma 128 x 64 x Lk, V as the MN-major B operand (no transpose),
 //                                          P from shared memory, fp32 output in TMEM columns [0, 64) (S is dead)
-//   warps 0-3 (thread = row)   tcgen05.ld of the thread's own score row in 16-column pieces: row max, then
-//                              p = exp2(s c - m c), row sum -- no shuffles, no cross-thread reduction; P as bf16 into
+//   warps 0-7 (thread = row,   tcgen05.ld of the thread's own score row in 32-column pieces: row max, then
+//    two warps per row: each   p = exp2(s c - m c), row sum -- no shuffles; the two halves of a row exchange their
+//    half of the keys)         max / sum through 1 KB of shared memory; P as bf16 into
 //                              the 128B-swizzled K-major layout the second MMA reads; log-sum-exp (log2 domain) saved;
 //                              O / l -> bf16 -> TMA store (clipped at the sequence end)
 // Shared memory: Q 16 KB | K | V | extra; the P slabs (64 keys = 16 KB each) reuse the Q tile, then the K tile (both
@@ -33,11 +34,11 @@ __host__ __device__ inline int tc_smem_bytes(int Lk) {
   const int nslab = (Lk + 63) / 64;
   int extra = nslab - 1 - (kv >= TC_SLAB ? 1 : 0);  // slab 0 = Q tile, slab 1 = K tile when it is large enough
   if (extra < 0) extra = 0;
-  return TC_SLAB + 2 * kv + extra * TC_SLAB + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  return TC_SLAB + 2 * kv + extra * TC_SLAB + 1024 /*exchange*/ + 256 /*barriers*/ + 1024 /*alignment slack*/;
 }
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q,
+__global__ void __launch_bounds__(288) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q,
                                                           const __grid_constant__ CUtensorMap map_kv,
                                                           const __grid_constant__ CUtensorMap map_o, float* __restrict__ lse2,
                                                           const int L, const int H, const int d, const int Lk,
@@ -60,20 +61,21 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
   };
   int extra = nslab - 1 - (k_slab ? 1 : 0);
   if (extra < 0) extra = 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + extra * TC_SLAB);
+  float* sEx = reinterpret_cast<float*>(sX + extra * TC_SLAB);  // [2][128]: row max / row sum of the other column half
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEx + 256);
   uint64_t* bar_load = bars;      // TMA bytes
   uint64_t* bar_s = bars + 1;     // scores in TMEM
-  uint64_t* bar_p = bars + 2;     // P in shared memory (128 arrivals)
+  uint64_t* bar_p = bars + 2;     // P in shared memory (256 arrivals)
   uint64_t* bar_o = bars + 3;     // output in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&map_q);
       tma_prefetch_desc(&map_kv);
       mbar_init(bar_load, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, TC_ROWS);
+      mbar_init(bar_p, 256);
       mbar_init(bar_o, 1);
       fence_mbar_init();
     }
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
   pdl_wait();
   pdl_trigger();
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(bar_load, static_cast<uint32_t>(TC_SLAB + 2 * kv_bytes));
       tma_load_3d(sQ, &map_q, bar_load, h * 64, mb * TC_ROWS, s);
@@ -118,87 +120,98 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
       }
     }
   } else {
-    // ===================== softmax / epilogue: thread = query row =====================
-    const int t = warp * 32 + lane;           // row inside the block = TMEM lane
+    // ===================== softmax / epilogue: thread = query row, warp half = half of the key columns =====================
+    const int quad = warp & 3, half = warp >> 2;
+    const int t = quad * 32 + lane;           // row inside the block = TMEM lane
     const int row = mb * TC_ROWS + t;         // token index of the row
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     // keys this row sees (rows past the sequence end compute on zero-filled Q and are never stored)
     const int nvis = CAUSAL ? (row < L ? row + 1 : L) : L;
-    const int n16 = Lk >> 4;
+    const int n32 = (Lk + 31) >> 5, nh0 = (n32 + 1) >> 1;
+    const int j_lo = half ? nh0 : 0, j_hi = half ? n32 : nh0;  // this half's 32-column pieces
     mbar_wait(bar_s, 0);
     tc_fence_after();
     float mx = -INFINITY;
-    for (int j = 0; j < n16; ++j) {
-      uint32_t r[16];
-      tmem_ld_32x16(trow + static_cast<uint32_t>(j * 16), r);
-      tmem_ld_wait_regs16(r);
-      if (j * 16 + 16 <= nvis) {
+    for (int j = j_lo; j < j_hi; ++j) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + static_cast<uint32_t>(j * 32), r);
+      tmem_ld_wait_regs(r);
+      if (j * 32 + 32 <= nvis) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, j * 16 + i < nvis ? __uint_as_float(r[i]) : -INFINITY);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, j * 32 + i < nvis ? __uint_as_float(r[i]) : -INFINITY);
       }
     }
+    sEx[half * 128 + t] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(mx, sEx[(half ^ 1) * 128 + t]);
     const float m2 = mx * scale_log2e;  // scaled max, log2 domain (nvis >= 1: finite)
     float l = 0.f;
     const f32x2 sc2 = f2_pack(scale_log2e, scale_log2e), nm2 = f2_pack(-m2, -m2);
-    for (int j = 0; j < n16; ++j) {
-      uint32_t r[16];
-      tmem_ld_32x16(trow + static_cast<uint32_t>(j * 16), r);
-      tmem_ld_wait_regs16(r);
-      uint32_t pk[8];
-      const bool full = j * 16 + 16 <= nvis;
+    for (int j = j_lo; j < j_hi; ++j) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + static_cast<uint32_t>(j * 32), r);
+      tmem_ld_wait_regs(r);
+      uint32_t pk[16];
+      const bool full = j * 32 + 32 <= nvis;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 16; ++i) {
         float a, b;
         f2_unpack(f2_fma(f2_pack_u(r[2 * i], r[2 * i + 1]), sc2, nm2), a, b);
         a = exp2f(a);
         b = exp2f(b);
         if (!full) {
-          a = j * 16 + 2 * i < nvis ? a : 0.f;
-          b = j * 16 + 2 * i + 1 < nvis ? b : 0.f;
+          a = j * 32 + 2 * i < nvis ? a : 0.f;
+          b = j * 32 + 2 * i + 1 < nvis ? b : 0.f;
         }
         l += a + b;
         pk[i] = pack_bf16(a, b);
       }
-      // 16 keys = two 16 B chunks of this row in slab j / 4 (64 keys per slab)
-      uint8_t* ps = slab(j >> 2) + t * 128;
-      const int c = (j & 3) * 2;
-      *reinterpret_cast<uint4*>(ps + (((c) ^ (t & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(ps + (((c + 1) ^ (t & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      // 32 keys = four 16 B chunks of this row in slab j / 2 (64 keys per slab)
+      uint8_t* ps = slab(j >> 1) + t * 128;
+      const int c = (j & 1) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(ps + (((c + q) ^ (t & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     }
     tc_fence_before();          // every tcgen05.ld of the scores has completed: the MMA may overwrite them with O
     fence_proxy_async_smem();   // P is visible to the tensor core's shared-memory reads
     mbar_arrive(bar_p);
-    if (row < L) lse2[(static_cast<size_t>(s) * H + h) * L + row] = m2 + log2f(l);
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // (the max exchange has been read by everyone)
+    sEx[half * 128 + t] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += sEx[(half ^ 1) * 128 + t];
+    if (half == 0 && row < L) lse2[(static_cast<size_t>(s) * H + h) * L + row] = m2 + log2f(l);
     const float inv = 1.f / l;
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    // O / l as bf16 into the (dead) Q tile: 128 rows x 128 B, 128B swizzle, then one TMA store
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t r[16];
-      tmem_ld_32x16(trow + static_cast<uint32_t>(j * 16), r);
-      tmem_ld_wait_regs16(r);
-      uint32_t pk[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
+    // O / l as bf16 into the (dead) Q tile: 128 rows x 128 B, 128B swizzle; this half's 32 head columns
+    {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + static_cast<uint32_t>(half * 32), r);
+      tmem_ld_wait_regs(r);
       uint8_t* po = sQ + t * 128;
-      *reinterpret_cast<uint4*>(po + (((2 * j) ^ (t & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(po + (((2 * j + 1) ^ (t & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(r[8 * q + 2 * e]) * inv, __uint_as_float(r[8 * q + 2 * e + 1]) * inv);
+        *reinterpret_cast<uint4*>(po + (((half * 4 + q) ^ (t & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
     tc_fence_before();
     fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps
-    if (t == 0) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x == 0) {
       tma_store_3d(&map_o, sQ, h * 64, mb * TC_ROWS, s);
       bulk_commit();
-      bulk_wait<0>();
+      bulk_wait_read<0>();  // the tile has been read out of shared memory; the global writes complete on their own
     }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(tmem_cols));
   }
@@ -515,17 +528,18 @@ const char* attention_tc_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L
       return "attention (tcgen05): cudaFuncSetAttribute failed";
     attr_done[causal ? 1 : 0] = true;
   }
-  launch_pdl(kern, dim3((L + TC_ROWS - 1) / TC_ROWS, S * H), dim3(160), static_cast<size_t>(smem), stream, mq, mkv, mo, lse2, L, H, d,
+  launch_pdl(kern, dim3((L + TC_ROWS - 1) / TC_ROWS, S * H), dim3(288), static_cast<size_t>(smem), stream, mq, mkv, mo, lse2, L, H, d,
              Lk, tmem_cols, sl2);
   count_launch(1);
   return launch_status("attention fwd (tcgen05) launch failed");
 }
 
+// The tcgen05 backward is parity-tested on every shape but, at 199 tokens, bound by its per-round hand-over chain
+// (score MMA -> tcgen05.ld -> element-wise -> slab -> output MMA, two CTAs per SM by TMEM): 82 us per vision layer
+// against 75 us for the warp-MMA pair (profiles/r02_attention_tc.txt).  It runs only on request (mode 2).
 bool attention_tc_bwd_eligible(int L, bool causal) {
-  const int en = tc_enabled();
-  if (en == 0 || L < 1) return false;
-  if (en == 2) return true;
-  return !causal && L > 128;
+  (void)causal;
+  return tc_enabled() == 2 && L >= 1;
 }
 
 const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv,
