@@ -29,6 +29,12 @@ namespace mudpt {
 static constexpr int TC_ROWS = 128;      // query rows per CTA = TMEM lanes
 static constexpr int TC_SLAB = 16384;    // 128 rows x 64 bf16
 
+__device__ __forceinline__ float f2_hsum_tc(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return lo + hi;
+}
+
 __host__ __device__ inline int tc_smem_bytes(int Lk) {
   const int kv = Lk * 128;
   const int nslab = (Lk + 63) / 64;
@@ -491,6 +497,272 @@ __global__ void __launch_bounds__(TCB_THREADS) attn_tc_bwd_kernel(const __grid_c
   }
 }
 
+// =======================================================================================
+// Backward for single-block sequences (L <= 128: the text tower), PERSISTENT: one CTA per SM walks the (sequence, head)
+// problems; a TMA ring of 3 stages (Q, dO, K, V tiles of the problem, rows clipped to the sequence) keeps HBM busy while
+// the current problem computes.  Per problem, FIVE tcgen05 products and no recomputation:
+//     S = Q K^T, dP = dO V^T                       (TMEM columns [0,128) / [128,256))
+//     element-wise, thread = query row (8 warps, two per row): P = exp2(S c - lse), D = rowsum(P dP) (the halves of a
+//         row exchange through shared memory), dS = P (dP - D); P and dS as bf16 into 128B-swizzled slabs [query][key]
+//     dQ = dS K       A = dS slab K-major,               B = K tile MN-major      (columns [256,320))
+//     dK = dS^T Q     A = dS slab read MN-major (M = keys), B = Q tile MN-major   (columns [320,384))
+//     dV = P^T dO     A = P slab read MN-major,          B = dO tile MN-major     (columns [384,448))
+//   the transposes are free: the same slab serves as K-major and as MN-major operand.  Outputs leave through the
+//   problem's (dead) Q / K / V tiles and three TMA stores.
+// Padding needs no masks: rows past the sequence are zero-filled by TMA, so whatever (finite) P they get multiplies
+// zero dO / Q / K rows; the causal mask is an index compare.
+// =======================================================================================
+static constexpr int TCS_THREADS = 320;  // 8 element-wise warps + TMA warp + MMA warp
+static constexpr int TCS_STAGES = 3;
+
+__host__ __device__ inline int tcs_smem_bytes(int Lb) {
+  return TCS_STAGES * 4 * Lb * 128 + 4 * TC_SLAB + 2 * 128 * 4 + 256 + 1024;
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(TCS_THREADS, 1) attn_tc_bwd_short_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                                           const __grid_constant__ CUtensorMap map_do,
+                                                                           const __grid_constant__ CUtensorMap map_dqkv,
+                                                                           const float* __restrict__ lse2, const int L, const int H,
+                                                                           const int d, const int Lb, const int n_items,
+                                                                           const float scale, const float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_bytes = Lb * 128;           // Lb = sequence length rounded up to 16 rows (<= 128)
+  const int stage_bytes = 4 * tile_bytes;    // Q | dO | K | V
+  uint8_t* slabP = smem + TCS_STAGES * stage_bytes;  // 2 slabs: keys [0,64), [64,128); 128 query rows each
+  uint8_t* slabS = slabP + 2 * TC_SLAB;
+  float* sX = reinterpret_cast<float*>(slabS + 2 * TC_SLAB);  // [2][128]: partial D of the other column half
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 256);
+  uint64_t* bar_full = bars;                      // [3] stage loaded
+  uint64_t* bar_empty = bars + TCS_STAGES;        // [3] stage free again
+  uint64_t* bar_s = bars + 2 * TCS_STAGES;        // scores in TMEM
+  uint64_t* bar_sfree = bar_s + 1;                // scores consumed (256)
+  uint64_t* bar_p = bar_s + 2;                    // slabs written (256)
+  uint64_t* bar_o = bar_s + 3;                    // outputs in TMEM
+  uint64_t* bar_ofree = bar_s + 4;                // outputs drained (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
+
+  if (warp == 9) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_qkv);
+      tma_prefetch_desc(&map_do);
+      for (int i = 0; i < TCS_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+      mbar_init(bar_s, 1);
+      mbar_init(bar_sfree, 256);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_o, 1);
+      mbar_init(bar_ofree, 256);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int s = it / H, h = it - s * H;
+        mbar_wait(&bar_empty[st], ph ^ 1);
+        uint8_t* base = smem + st * stage_bytes;
+        mbar_expect_tx(&bar_full[st], static_cast<uint32_t>(stage_bytes));
+        tma_load_3d(base, &map_qkv, &bar_full[st], h * 64, 0, s);                       // Q
+        tma_load_3d(base + tile_bytes, &map_do, &bar_full[st], h * 64, 0, s);           // dO
+        tma_load_3d(base + 2 * tile_bytes, &map_qkv, &bar_full[st], d + h * 64, 0, s);  // K
+        tma_load_3d(base + 3 * tile_bytes, &map_qkv, &bar_full[st], 2 * d + h * 64, 0, s);  // V
+        if (++st == TCS_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(TC_ROWS, Lb);
+      const uint32_t idesc_dq = make_idesc_bf16(TC_ROWS, 64) | kIdescBMnMajor;
+      const uint32_t idesc_dkv = make_idesc_bf16(TC_ROWS, 64) | kIdescAMnMajor | kIdescBMnMajor;
+      // MN-major A over two 64-key slabs: leading-dimension byte offset = slab stride
+      const uint64_t lbo_slab = static_cast<uint64_t>(TC_SLAB >> 4) << 16;
+      const uint64_t dPk = make_smem_desc_sw128(smem_u32(slabP)), dSk = make_smem_desc_sw128(smem_u32(slabS));
+      const uint64_t dPm = (dPk & ~(static_cast<uint64_t>(0x3FFF) << 16)) | lbo_slab;
+      const uint64_t dSm = (dSk & ~(static_cast<uint64_t>(0x3FFF) << 16)) | lbo_slab;
+      const int nk = Lb >> 4;
+      int st = 0;
+      uint32_t ph = 0;
+      int k = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+        uint8_t* base = smem + st * stage_bytes;
+        const uint64_t dQt = make_smem_desc_sw128(smem_u32(base)), dOt = make_smem_desc_sw128(smem_u32(base + tile_bytes));
+        const uint64_t dKt = make_smem_desc_sw128(smem_u32(base + 2 * tile_bytes)), dVt = make_smem_desc_sw128(smem_u32(base + 3 * tile_bytes));
+        mbar_wait(&bar_full[st], ph);
+        if (k > 0) mbar_wait(bar_sfree, (k - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tmem_base, dQt + static_cast<uint64_t>(j * 2), dKt + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + 128u, dOt + static_cast<uint64_t>(j * 2), dVt + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
+        umma_commit(bar_s);
+        mbar_wait(bar_p, k & 1);
+        if (k > 0) mbar_wait(bar_ofree, (k - 1) & 1);
+        tc_fence_after();
+        for (int j = 0; j < nk; ++j) {  // contraction over keys (dQ) / queries (dK, dV), 16 per instruction
+          const uint32_t acc = static_cast<uint32_t>(j != 0);
+          // dQ: A = dS [query][key] K-major -- keys 16 j .. : slab j / 4, 32 B step inside the swizzle row
+          const uint64_t a_dq = dSk + static_cast<uint64_t>((j >> 2) * (TC_SLAB >> 4) + (j & 3) * 2);
+          umma_bf16(tmem_base + 256u, a_dq, dKt + static_cast<uint64_t>(j * 128), idesc_dq, acc);
+          // dK / dV: A = dS / P read MN-major (M = 128 keys over the two slabs), queries 16 j .. = 16 rows = 2048 B
+          umma_bf16(tmem_base + 320u, dSm + static_cast<uint64_t>(j * 128), dQt + static_cast<uint64_t>(j * 128), idesc_dkv, acc);
+          umma_bf16(tmem_base + 384u, dPm + static_cast<uint64_t>(j * 128), dOt + static_cast<uint64_t>(j * 128), idesc_dkv, acc);
+        }
+        umma_commit(bar_o);
+        if (++st == TCS_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== element-wise + epilogue: thread = row (query, then output row), 2 warps per row =====================
+    const int quad = warp & 3, half = warp >> 2;
+    const int t = quad * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const bool live = quad * 32 < Lb;                 // (warp-uniform) rows of this warp exist in the tiles
+    const int n32 = (Lb + 31) >> 5;                   // 32-column pieces of the scores
+    const int nh0 = (n32 + 1) >> 1;
+    const int j_lo = half ? nh0 : 0, j_hi = half ? n32 : nh0;
+    const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
+    int st = 0;
+    int k = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+      const int s = it / H, h = it - s * H;
+      uint8_t* base = smem + st * stage_bytes;
+      const float lse_r = (live && t < L) ? lse2[(static_cast<size_t>(s) * H + h) * L + t] : 0.f;
+      mbar_wait(bar_s, k & 1);
+      tc_fence_after();
+      // pass 1: P (kept as packed bf16) and this half's part of D = rowsum(P dP)
+      uint32_t pk[2][16];
+      float dpart = 0.f;
+      if (live) {
+        const f32x2 nl = f2_pack(-lse_r, -lse_r);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = j_lo + jj;
+          if (j < j_hi) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(trow + static_cast<uint32_t>(j * 32), sv);
+            tmem_ld_32x32(trow + 128u + static_cast<uint32_t>(j * 32), dv);
+            tmem_ld_wait_regs(sv);
+            tmem_ld_wait_regs(dv);
+            f32x2 acc2 = f2_pack(0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float a, b;
+              f2_unpack(f2_fma(f2_pack_u(sv[2 * e], sv[2 * e + 1]), c2, nl), a, b);
+              a = exp2f(a);
+              b = exp2f(b);
+              const int c = j * 32 + 2 * e;
+              if (CAUSAL) { a = c <= t ? a : 0.f; b = c + 1 <= t ? b : 0.f; }
+              if (c >= Lb) { a = 0.f; b = 0.f; }  // columns past the score tile hold stale TMEM
+              acc2 = f2_fma(f2_pack(a, b), f2_pack_u(dv[2 * e], dv[2 * e + 1]), acc2);
+              pk[jj][e] = pack_bf16(a, b);
+            }
+            dpart += f2_hsum_tc(acc2);
+          }
+        }
+      }
+      sX[half * 128 + t] = dpart;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float D_r = dpart + sX[(half ^ 1) * 128 + t];
+      // pass 2: dS = P (dP - D); both tiles into the slabs [query row][key]
+      if (live) {
+        const f32x2 nD = f2_pack(-D_r, -D_r);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = j_lo + jj;
+          if (j < j_hi) {
+            uint32_t dv[32];
+            tmem_ld_32x32(trow + 128u + static_cast<uint32_t>(j * 32), dv);
+            tmem_ld_wait_regs(dv);
+            uint32_t ds[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const uint32_t w = pk[jj][e];
+              const f32x2 p2 = f2_pack_u(w << 16, w & 0xffff0000u);
+              float x, y;
+              f2_unpack(f2_mul(p2, f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), nD)), x, y);
+              ds[e] = pack_bf16(x, y);
+            }
+            const uint32_t off = static_cast<uint32_t>((j >> 1) * TC_SLAB + t * 128);
+            const int cb = (j & 1) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t o2 = off + static_cast<uint32_t>(((cb + q) ^ (t & 7)) << 4);
+              *reinterpret_cast<uint4*>(slabP + o2) = make_uint4(pk[jj][4 * q], pk[jj][4 * q + 1], pk[jj][4 * q + 2], pk[jj][4 * q + 3]);
+              *reinterpret_cast<uint4*>(slabS + o2) = make_uint4(ds[4 * q], ds[4 * q + 1], ds[4 * q + 2], ds[4 * q + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_sfree);        // the next problem's score MMAs may overwrite S / dP
+      fence_proxy_async_smem();
+      mbar_arrive(bar_p);
+      // epilogue: dQ (row = query t), dK / dV (row = key t); this half's 32 head columns
+      mbar_wait(bar_o, k & 1);
+      tc_fence_after();
+      if (live) {
+        uint32_t o0[32], o1[32], o2[32];
+        tmem_ld_32x32(trow + 256u + static_cast<uint32_t>(half * 32), o0);
+        tmem_ld_32x32(trow + 320u + static_cast<uint32_t>(half * 32), o1);
+        tmem_ld_32x32(trow + 384u + static_cast<uint32_t>(half * 32), o2);
+        tmem_ld_wait_regs(o0);
+        tmem_ld_wait_regs(o1);
+        tmem_ld_wait_regs(o2);
+        if (t < Lb) {  // the problem's tiles hold Lb rows: Q <- dQ, K <- dK, V <- dV
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q) ^ (t & 7)) << 4));
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q + 2 * e]) * scale, __uint_as_float(o0[8 * q + 2 * e + 1]) * scale);
+            *reinterpret_cast<uint4*>(base + off) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q + 2 * e]) * scale, __uint_as_float(o1[8 * q + 2 * e + 1]) * scale);
+            *reinterpret_cast<uint4*>(base + 2 * tile_bytes + off) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o2[8 * q + 2 * e]), __uint_as_float(o2[8 * q + 2 * e + 1]));
+            *reinterpret_cast<uint4*>(base + 3 * tile_bytes + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_ofree);        // the next problem's output MMAs may overwrite dQ / dK / dV
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        tma_store_3d(&map_dqkv, base, h * 64, 0, s);
+        tma_store_3d(&map_dqkv, base + 2 * tile_bytes, d + h * 64, 0, s);
+        tma_store_3d(&map_dqkv, base + 3 * tile_bytes, 2 * d + h * 64, 0, s);
+        bulk_commit();
+        bulk_wait_read<0>();         // the tiles have been read: the stage may be refilled
+        mbar_arrive(&bar_empty[st]);
+      }
+      if (++st == TCS_STAGES) st = 0;
+    }
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 static int g_tc_mode = -1;
 static int tc_enabled() {
   if (g_tc_mode < 0) {
@@ -544,9 +816,34 @@ bool attention_tc_bwd_eligible(int L, bool causal) {
 
 const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv,
                              int S, int L, int H, int d, bool causal, cudaStream_t stream) {
-  CUtensorMap m128, m64, mdo128, mdo64, mout;
   const char* e;
   const long long ld = 3LL * d;
+  if (L <= TC_ROWS) {  // single-block sequences: the persistent kernel
+    const int Lb = (L + 15) & ~15;
+    CUtensorMap mq, mdo, mo;
+    if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, Lb, &mq))) return e;
+    if ((e = tensor_map_3d_bf16(d_o, d, L, S, d, static_cast<long long>(d) * L, Lb, &mdo))) return e;
+    if ((e = tensor_map_3d_bf16(dqkv, 3 * d, L, S, ld, ld * L, Lb, &mo))) return e;
+    const int smem = tcs_smem_bytes(Lb);
+    static int n_sms = 0;
+    if (n_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (n_sms <= 0) n_sms = 148;
+    }
+    const int n_items = S * H;
+    const int grid = n_items < n_sms ? n_items : n_sms;
+    const float scale_s = 0.125f, sl2_s = 0.125f * 1.4426950408889634f;
+    auto kern = causal ? attn_tc_bwd_short_kernel<true> : attn_tc_bwd_short_kernel<false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return "attention (tcgen05 backward, short): cudaFuncSetAttribute failed";
+    launch_pdl(kern, dim3(grid), dim3(TCS_THREADS), static_cast<size_t>(smem), stream, mq, mdo, mo, lse2, L, H, d, Lb, n_items, scale_s,
+               sl2_s);
+    count_launch(1);
+    return launch_status("attention bwd (tcgen05, short) launch failed");
+  }
+  CUtensorMap m128, m64, mdo128, mdo64, mout;
   if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, TC_ROWS, &m128))) return e;
   if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, 64, &m64))) return e;
   if ((e = tensor_map_3d_bf16(d_o, d, L, S, d, static_cast<long long>(d) * L, TC_ROWS, &mdo128))) return e;

@@ -11,6 +11,8 @@
 // in fp32 on the CUDA cores: a small strided SGEMM (64x64 tiles) plus row kernels (one warp per row).
 #include "head.h"
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch_count.h"
 
@@ -273,6 +275,10 @@ __global__ void sum_scale_kernel(const float* __restrict__ v, float* __restrict_
   if (threadIdx.x == 0) out[0] = s * scale;
 }
 
+static bool logits_head_fused(const float* f_img, const float* f_txt, const long long* labels, float scale, int B, int C, int e,
+                              float inv_global_batch, float* ws, float* logits, float* loss, float* d_f_img, float* d_f_txt,
+                              cudaStream_t stream);
+
 static size_t logits_head_fixed_floats(int B, int C, int e) {
   return static_cast<size_t>(B) * e + static_cast<size_t>(C) * e + B + C + B + static_cast<size_t>(B) * C;
 }
@@ -288,6 +294,8 @@ const char* logits_head(const float* f_img, const float* f_txt, const long long*
                         float inv_global_batch, float* ws, float* logits, float* loss, float* d_f_img, float* d_f_txt,
                         cudaStream_t stream) {
   if (B <= 0 || C <= 0) return nullptr;
+  if (logits_head_fused(f_img, f_txt, labels, scale, B, C, e, inv_global_batch, ws, logits, loss, d_f_img, d_f_txt, stream))
+    return launch_status("fused logits head launch failed");
   // workspace layout (floats): in_hat[B*e] tn_hat[C*e] inv_i[B] inv_t[C] loss_rows[B] dlogits[B*C]
   float* in_hat = ws;
   float* tn_hat = in_hat + static_cast<size_t>(B) * e;
@@ -316,6 +324,287 @@ const char* logits_head(const float* f_img, const float* f_txt, const long long*
     }
   }
   return launch_status("logits head launch failed");
+}
+
+// ------------------------------------------------------------------ fused logits / CE head (training)
+// L2-normalise, scaled cosine logits, cross-entropy and both feature gradients in TWO launches
+// (trainers/mudpt.py:178-182, :250; the serial section between the towers' forward and backward):
+//   head_rows_kernel   one thread-block CLUSTER of 8 CTAs per image row b; CTA r owns the classes [r C/8, (r+1) C/8).
+//                      One pass over its class features gives the dots with i_hat_b AND their norms (t_hat is never
+//                      materialised), the row's softmax statistics are combined through distributed shared memory,
+//                      a second pass accumulates this slice's part of d i_hat_b, which rank 0 sums over the cluster
+//                      (DSMEM again) and pushes through the normalisation backward.  Outputs: logits, dlogits,
+//                      loss per row, 1 / ||f_txt||, d f_img.
+//   head_cols_kernel   one warp per class: d t_hat_c = scale sum_b dlogits[b, c] i_hat_b, normalisation backward;
+//                      block 0 also adds the per-row losses in a fixed order.
+// Everything stays fp32 and every reduction has a fixed order: results are deterministic.
+static constexpr int HEAD_CL = 8;       // cluster size (portable maximum)
+static constexpr int HEAD_THREADS = 256;
+static constexpr int HEAD_MAX_E = 1024;
+
+struct HeadShared {
+  float ihat[HEAD_MAX_E];      // normalised image feature of the row
+  float part[HEAD_MAX_E];      // this CTA's part of d i_hat
+  float red[32];
+  float stat[2];               // (max, sum exp) of this CTA's logits slice
+  float lse;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (HEAD_THREADS >> 5); ++w) t += red[w];
+  return t;
+}
+
+__global__ void __cluster_dims__(HEAD_CL, 1, 1) __launch_bounds__(HEAD_THREADS)
+head_rows_kernel(const float* __restrict__ f_img, const float* __restrict__ f_txt, const long long* __restrict__ labels,
+                 float scale, int C, int e, float grad_scale, float* __restrict__ logits, float* __restrict__ dlogits,
+                 float* __restrict__ loss_rows, float* __restrict__ inv_t, float* __restrict__ d_f_img) {
+  extern __shared__ float head_dyn[];  // [per] logits (then dlogits) of this CTA's class slice, [per] 1 / ||f_txt||
+  __shared__ HeadShared sh;
+  const int b = blockIdx.x / HEAD_CL;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (C + HEAD_CL - 1) / HEAD_CL;
+  const int c_lo = static_cast<int>(rank) * per, c_hi = min(C, c_lo + per);
+  float* inv_s = head_dyn + per;
+  // 1. i_hat_b
+  float sq = 0.f;
+  for (int j = threadIdx.x; j < e; j += HEAD_THREADS) {
+    const float v = f_img[static_cast<size_t>(b) * e + j];
+    sh.ihat[j] = v;
+    sq += v * v;
+  }
+  const float inv_i = rsqrtf(block_sum(sq, sh.red));
+  for (int j = threadIdx.x; j < e; j += HEAD_THREADS) sh.ihat[j] *= inv_i;
+  __syncthreads();
+  // 2. logits of the slice: one warp per class, dot and squared norm in the same pass
+  for (int c = c_lo + warp; c < c_hi; c += (HEAD_THREADS >> 5)) {
+    const float* tr = f_txt + static_cast<size_t>(c) * e;
+    float dot = 0.f, nn = 0.f;
+    for (int j = lane * 4; j < e; j += 128) {
+      const float4 t4 = *reinterpret_cast<const float4*>(tr + j);
+      const float4 i4 = *reinterpret_cast<const float4*>(sh.ihat + j);
+      dot += t4.x * i4.x + t4.y * i4.y + t4.z * i4.z + t4.w * i4.w;
+      nn += t4.x * t4.x + t4.y * t4.y + t4.z * t4.z + t4.w * t4.w;
+    }
+    dot = warp_sum(dot);
+    nn = warp_sum(nn);
+    if (lane == 0) {
+      const float it = rsqrtf(nn);
+      const float lg = scale * dot * it;
+      head_dyn[c - c_lo] = lg;
+      inv_s[c - c_lo] = it;
+      logits[static_cast<size_t>(b) * C + c] = lg;
+      if (b == 0 && inv_t != nullptr) inv_t[c] = it;
+    }
+  }
+  __syncthreads();
+  if (labels == nullptr) return;  // logits only (every CTA of the cluster takes this branch together)
+  // 3. softmax statistics of the row: slice max / sum, combined over the cluster through DSMEM
+  float mx = -INFINITY;
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += HEAD_THREADS) mx = fmaxf(mx, head_dyn[c - c_lo]);
+  mx = warp_max(mx);
+  __syncthreads();
+  if (lane == 0) sh.red[warp] = mx;
+  __syncthreads();
+  mx = -INFINITY;
+  for (int w = 0; w < (HEAD_THREADS >> 5); ++w) mx = fmaxf(mx, sh.red[w]);
+  float se = 0.f;
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += HEAD_THREADS) se += expf(head_dyn[c - c_lo] - mx);
+  se = block_sum(se, sh.red);
+  if (threadIdx.x == 0) { sh.stat[0] = mx; sh.stat[1] = se; }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x == 0) {
+    float gm = -INFINITY, st[HEAD_CL][2];
+    for (uint32_t r = 0; r < HEAD_CL; ++r) {
+      uint32_t a;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(sh.stat)), "r"(r));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(st[r][0]) : "r"(a) : "memory");
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(st[r][1]) : "r"(a + 4) : "memory");
+      gm = fmaxf(gm, st[r][0]);
+    }
+    float gs = 0.f;
+    for (uint32_t r = 0; r < HEAD_CL; ++r) gs += st[r][1] > 0.f ? st[r][1] * expf(st[r][0] - gm) : 0.f;
+    sh.lse = gm + logf(gs);
+  }
+  __syncthreads();
+  const float lse = sh.lse;
+  // 4. loss of the row (the CTA owning the label's class; a label outside [0, C) gives NaN -- see ce_rows_kernel)
+  const long long yl = labels[b];
+  const bool y_ok = yl >= 0 && yl < C;
+  const int y = y_ok ? static_cast<int>(yl) : -1;
+  if (threadIdx.x == 0) {
+    if (y_ok && y >= c_lo && y < c_hi) loss_rows[b] = lse - head_dyn[y - c_lo];
+    else if (!y_ok && rank == 0) loss_rows[b] = __int_as_float(0x7fc00000);
+  }
+  // 5. dlogits of the slice (kept in shared memory as the weights of the second pass)
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += HEAD_THREADS) {
+    const float dl = (expf(head_dyn[c - c_lo] - lse) - (c == y ? 1.f : 0.f)) * grad_scale;
+    dlogits[static_cast<size_t>(b) * C + c] = dl;
+    head_dyn[c - c_lo] = dl;
+  }
+  __syncthreads();
+  if (d_f_img == nullptr) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    return;
+  }
+  // 6. this slice's part of d i_hat_b = scale sum_c dl_c t_hat_c  (thread j owns columns j, j + 256, ...)
+  float acc[HEAD_MAX_E / HEAD_THREADS];
+#pragma unroll
+  for (int k = 0; k < HEAD_MAX_E / HEAD_THREADS; ++k) acc[k] = 0.f;
+  for (int c = c_lo; c < c_hi; ++c) {
+    const float* tr = f_txt + static_cast<size_t>(c) * e;
+    const float w = head_dyn[c - c_lo] * inv_s[c - c_lo];  // dl_c / ||t_c||
+#pragma unroll
+    for (int k = 0; k < HEAD_MAX_E / HEAD_THREADS; ++k) {
+      const int j = threadIdx.x + k * HEAD_THREADS;
+      if (j < e) acc[k] += w * tr[j];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < HEAD_MAX_E / HEAD_THREADS; ++k) {
+    const int j = threadIdx.x + k * HEAD_THREADS;
+    if (j < e) sh.part[j] = acc[k] * scale;
+  }
+  // 7. rank 0 adds the eight parts (fixed order) and applies the normalisation backward of the image feature
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0) {
+    float g[HEAD_MAX_E / HEAD_THREADS], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < HEAD_MAX_E / HEAD_THREADS; ++k) {
+      const int j = threadIdx.x + k * HEAD_THREADS;
+      g[k] = 0.f;
+      if (j < e) {
+        for (uint32_t r = 0; r < HEAD_CL; ++r) {
+          uint32_t a;
+          float v;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(sh.part + j)), "r"(r));
+          asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+          g[k] += v;
+        }
+        dot += g[k] * sh.ihat[j];
+      }
+    }
+    dot = block_sum(dot, sh.red);
+#pragma unroll
+    for (int k = 0; k < HEAD_MAX_E / HEAD_THREADS; ++k) {
+      const int j = threadIdx.x + k * HEAD_THREADS;
+      if (j < e) d_f_img[static_cast<size_t>(b) * e + j] = (g[k] - sh.ihat[j] * dot) * inv_i;
+    }
+  }
+  // nobody leaves while rank 0 still reads its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// One warp per class c: d f_txt[c] = normalisation backward of scale * sum_b dlogits[b, c] i_hat_b.
+// Shared memory: i_hat [B, e] (B <= 64 images at e = 512 fit 128 KB; larger batches read f_img rows from L2).
+__global__ void __launch_bounds__(HEAD_THREADS) head_cols_kernel(const float* __restrict__ f_img, const float* __restrict__ f_txt,
+                                                               const float* __restrict__ dlogits, const float* __restrict__ inv_t,
+                                                               const float* __restrict__ loss_rows, float scale, int Bn, int C,
+                                                               int e, int b_smem, float loss_scale, float* __restrict__ loss,
+                                                               float* __restrict__ d_f_txt) {
+  extern __shared__ float cols_dyn[];  // [b_smem][e] normalised image features + [Bn] 1 / ||f_img||
+  float* inv_i = cols_dyn + static_cast<size_t>(b_smem) * e;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < Bn; b += (HEAD_THREADS >> 5)) {
+    float sq = 0.f;
+    for (int j = lane; j < e; j += 32) { const float v = f_img[static_cast<size_t>(b) * e + j]; sq += v * v; }
+    sq = warp_sum(sq);
+    if (lane == 0) inv_i[b] = rsqrtf(sq);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < b_smem * e; i += HEAD_THREADS) cols_dyn[i] = f_img[i] * inv_i[i / e];
+  __syncthreads();
+  if (blockIdx.x == 0 && warp == 0 && loss != nullptr) {  // mean loss: fixed-order sum of the rows
+    float sacc = 0.f;
+    for (int b = lane; b < Bn; b += 32) sacc += loss_rows[b];
+    sacc = warp_sum(sacc);
+    if (lane == 0) loss[0] = sacc * loss_scale;
+  }
+  const int c = blockIdx.x * (HEAD_THREADS >> 5) + warp;
+  if (c >= C) return;
+  const float it = inv_t[c];
+  const float* tr = f_txt + static_cast<size_t>(c) * e;
+  float dot = 0.f;
+  for (int j0 = lane * 4; j0 < e; j0 += 128) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < Bn; ++b) {
+      const float dl = dlogits[static_cast<size_t>(b) * C + c];
+      float4 i4;
+      if (b < b_smem) i4 = *reinterpret_cast<const float4*>(cols_dyn + static_cast<size_t>(b) * e + j0);
+      else {
+        i4 = *reinterpret_cast<const float4*>(f_img + static_cast<size_t>(b) * e + j0);
+        const float s = inv_i[b];
+        i4.x *= s; i4.y *= s; i4.z *= s; i4.w *= s;
+      }
+      g.x += dl * i4.x; g.y += dl * i4.y; g.z += dl * i4.z; g.w += dl * i4.w;
+    }
+    g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+    const float4 t4 = *reinterpret_cast<const float4*>(tr + j0);
+    dot += (g.x * t4.x + g.y * t4.y + g.z * t4.z + g.w * t4.w) * it;  // g . t_hat
+    *reinterpret_cast<float4*>(d_f_txt + static_cast<size_t>(c) * e + j0) = g;  // (finished below)
+  }
+  dot = warp_sum(dot);
+  for (int j0 = lane * 4; j0 < e; j0 += 128) {
+    float4 g = *reinterpret_cast<const float4*>(d_f_txt + static_cast<size_t>(c) * e + j0);
+    const float4 t4 = *reinterpret_cast<const float4*>(tr + j0);
+    g.x = (g.x - t4.x * it * dot) * it; g.y = (g.y - t4.y * it * dot) * it;
+    g.z = (g.z - t4.z * it * dot) * it; g.w = (g.w - t4.w * it * dot) * it;
+    *reinterpret_cast<float4*>(d_f_txt + static_cast<size_t>(c) * e + j0) = g;
+  }
+}
+
+static bool fused_head_enabled() {
+  static int en = -1;
+  if (en < 0) {
+    const char* v = getenv("MUDPT_FUSED_HEAD");
+    en = v ? (atoi(v) != 0) : 1;
+  }
+  return en != 0;
+}
+
+// Fused path of logits_head (same arguments); returns false when the shape is outside what the kernels take.
+static bool logits_head_fused(const float* f_img, const float* f_txt, const long long* labels, float scale, int B, int C, int e,
+                              float inv_global_batch, float* ws, float* logits, float* loss, float* d_f_img, float* d_f_txt,
+                              cudaStream_t stream) {
+  if (!fused_head_enabled() || e % 4 != 0 || e > HEAD_MAX_E) return false;
+  const int per = (C + HEAD_CL - 1) / HEAD_CL;
+  const size_t dyn_rows = 2 * static_cast<size_t>(per) * sizeof(float);
+  if (dyn_rows > 64 * 1024) return false;
+  // workspace (floats): inv_t[C] loss_rows[B] dlogits[B*C]   (laid out inside the fixed part of logits_head's workspace)
+  float* inv_t = ws;
+  float* loss_rows = inv_t + C;
+  float* dlogits = loss_rows + B;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(head_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  head_rows_kernel<<<B * HEAD_CL, HEAD_THREADS, dyn_rows, stream>>>(f_img, f_txt, labels, scale, C, e, inv_global_batch, logits, dlogits,
+                                                                  loss_rows, inv_t, labels ? d_f_img : nullptr);
+  count_launch(1);
+  if (labels != nullptr) {
+    int b_smem = B;
+    while (b_smem > 0 && (static_cast<size_t>(b_smem) * e + B) * sizeof(float) > 150 * 1024) --b_smem;
+    const size_t dyn_cols = (static_cast<size_t>(b_smem) * e + B) * sizeof(float);
+    if (d_f_txt != nullptr) {
+      head_cols_kernel<<<(C + 7) / 8, HEAD_THREADS, dyn_cols, stream>>>(f_img, f_txt, dlogits, inv_t, loss_rows, scale, B, C, e, b_smem,
+                                                                       inv_global_batch, loss, d_f_txt);
+      count_launch(1);
+    } else {
+      sum_scale_kernel<<<1, 32, 0, stream>>>(loss_rows, loss, B, inv_global_batch);
+      count_launch(1);
+    }
+  }
+  return true;
 }
 
 // Backward of the logits alone for the module-level autograd path (CustomCLIP.forward returns
