@@ -513,10 +513,11 @@ __global__ void __launch_bounds__(TCB_THREADS) attn_tc_bwd_kernel(const __grid_c
 // zero dO / Q / K rows; the causal mask is an index compare.
 // =======================================================================================
 static constexpr int TCS_THREADS = 320;  // 8 element-wise warps + TMA warp + MMA warp
-static constexpr int TCS_STAGES = 3;
-
+static constexpr int TCS_MAX_STAGES = 3;
+// stages of the TMA ring: 3 while they fit beside the four slabs (sequences of up to 96 tokens), else 2
+__host__ __device__ inline int tcs_stages(int Lb) { return Lb <= 96 ? 3 : 2; }
 __host__ __device__ inline int tcs_smem_bytes(int Lb) {
-  return TCS_STAGES * 4 * Lb * 128 + 4 * TC_SLAB + 2 * 128 * 4 + 256 + 1024;
+  return tcs_stages(Lb) * 4 * Lb * 128 + 4 * TC_SLAB + 2 * 128 * 4 + 256 + 1024;
 }
 
 template <bool CAUSAL>
@@ -531,13 +532,14 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) attn_tc_bwd_short_kernel(const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_bytes = Lb * 128;           // Lb = sequence length rounded up to 16 rows (<= 128)
   const int stage_bytes = 4 * tile_bytes;    // Q | dO | K | V
+  const int TCS_STAGES = tcs_stages(Lb);
   uint8_t* slabP = smem + TCS_STAGES * stage_bytes;  // 2 slabs: keys [0,64), [64,128); 128 query rows each
   uint8_t* slabS = slabP + 2 * TC_SLAB;
   float* sX = reinterpret_cast<float*>(slabS + 2 * TC_SLAB);  // [2][128]: partial D of the other column half
   uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 256);
   uint64_t* bar_full = bars;                      // [3] stage loaded
-  uint64_t* bar_empty = bars + TCS_STAGES;        // [3] stage free again
-  uint64_t* bar_s = bars + 2 * TCS_STAGES;        // scores in TMEM
+  uint64_t* bar_empty = bars + TCS_MAX_STAGES;        // [3] stage free again
+  uint64_t* bar_s = bars + 2 * TCS_MAX_STAGES;        // scores in TMEM
   uint64_t* bar_sfree = bar_s + 1;                // scores consumed (256)
   uint64_t* bar_p = bar_s + 2;                    // slabs written (256)
   uint64_t* bar_o = bar_s + 3;                    // outputs in TMEM

@@ -444,6 +444,7 @@ head_rows_kernel(const float* __restrict__ f_img, const float* __restrict__ f_tx
     if (y_ok && y >= c_lo && y < c_hi) loss_rows[b] = lse - head_dyn[y - c_lo];
     else if (!y_ok && rank == 0) loss_rows[b] = __int_as_float(0x7fc00000);
   }
+  __syncthreads();  // (the label's logit is read before step 5 turns the slice into dlogits)
   // 5. dlogits of the slice (kept in shared memory as the weights of the second pass)
   for (int c = c_lo + threadIdx.x; c < c_hi; c += HEAD_THREADS) {
     const float dl = (expf(head_dyn[c - c_lo] - lse) - (c == y ? 1.f : 0.f)) * grad_scale;
