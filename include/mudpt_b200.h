@@ -194,6 +194,27 @@ int mudpt_set_attention_tc(int32_t mode);
 int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream);
 int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream);
 
+/* ---- trainable prompt algebra of MuDPT (trainers/mudpt.py:117-130, 143, 175; clip/model.py:534-541) --------------
+ * The three trainable Linear layers, ln_pre on the shallow vision prompt and the stacking that turn the 10 trainable
+ * tensors into the two prompt stacks the towers splice, and the backward into those tensors: 2 + 2 launches.
+ * All pointers fp32, contiguous; n = n_ctx, depth = DEEP_PROMPT_DEPTH, dt / dv = text / vision width.
+ *   forward : reads ctx [n,dt], deep [depth-1,n,dt], We [dv,dt], be [dv], Wd [dv,dt], bd [dv], vctx [n,dv],
+ *             vdeep [depth-1,n,dv], Wv [dt,dv], bv [dt], ln_g / ln_b [dv] (ln_pre), pos [n,dt];
+ *             writes P_v [depth,n,dv], P_t [depth,n,dt], ln_in [n,dv] (saved for the backward)
+ *   backward: reads the above + dP_v, dP_t; u [n,dv] is scratch; writes the d_* gradients of the 10 tensors */
+typedef struct mudpt_prompt_args {
+  int32_t n, depth, dt, dv;
+  float eps;
+  const float *ctx, *deep, *We, *be, *Wd, *bd, *vctx, *vdeep, *Wv, *bv;
+  const float *ln_g, *ln_b, *pos;
+  float *P_v, *P_t, *ln_in;
+  const float *dP_v, *dP_t;
+  float* u;
+  float *d_ctx, *d_deep, *d_We, *d_be, *d_Wd, *d_bd, *d_vctx, *d_vdeep, *d_Wv, *d_bv;
+} mudpt_prompt_args;
+int mudpt_prompt_forward(const mudpt_prompt_args* args, void* stream);
+int mudpt_prompt_backward(const mudpt_prompt_args* args, void* stream);
+
 /* ---- fused SGD step over the (small) trainable tensors -----------------------------------------
  * One launch for all tensors, torch.optim.SGD semantics (what Dassl's build_optimizer creates for
  * the yaml's OPTIM.NAME = "sgd", configs/trainers/MuDPT/*.yaml:15-22; called from

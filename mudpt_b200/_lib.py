@@ -56,6 +56,8 @@ SIGNATURES = {
     "mudpt_set_attention_tc": (C.c_int, [C.c_int32]),
     "mudpt_im2col": (C.c_int, [c_f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_cast_bf16": (C.c_int, [c_f32p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mudpt_prompt_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mudpt_prompt_backward": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mudpt_sgd_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                  C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_augment_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
@@ -84,6 +86,14 @@ class GemmEpilogue(C.Structure):
                 ("colsum", C.c_void_p), ("stats_out", C.c_void_p), ("splice_prompt", C.c_void_p),
                 ("splice_row0", C.c_int32), ("splice_n", C.c_int32), ("splice_L", C.c_int32), ("stream_k", C.c_int32),
                 ("x2", C.c_void_p), ("dots", C.c_void_p), ("sb", C.c_void_p), ("dots_out", C.c_void_p)]
+
+
+class PromptArgs(C.Structure):
+    """mudpt_prompt_args (include/mudpt_b200.h)."""
+    _fields_ = ([(k, C.c_int32) for k in ("n", "depth", "dt", "dv")] + [("eps", C.c_float)] +
+                [(k, C.c_void_p) for k in ("ctx", "deep", "We", "be", "Wd", "bd", "vctx", "vdeep", "Wv", "bv", "ln_g", "ln_b", "pos",
+                                           "P_v", "P_t", "ln_in", "dP_v", "dP_t", "u", "d_ctx", "d_deep", "d_We", "d_be", "d_Wd",
+                                           "d_bd", "d_vctx", "d_vdeep", "d_Wv", "d_bv")])
 
 
 def library_path() -> str:

@@ -16,6 +16,7 @@
 #include "gemm.h"
 #include "head.h"
 #include "launch_count.h"
+#include "prompt.h"
 #include "rowops.h"
 
 namespace mudpt {
@@ -961,6 +962,26 @@ int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, i
 }
 int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream) {
   CKG(cast_to_bf16(in, reinterpret_cast<bf16*>(out), static_cast<size_t>(numel), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+static PromptArgs to_prompt_args(const mudpt_prompt_args* p) {
+  PromptArgs a;
+  a.n = p->n; a.depth = p->depth; a.dt = p->dt; a.dv = p->dv; a.eps = p->eps;
+  a.ctx = p->ctx; a.deep = p->deep; a.We = p->We; a.be = p->be; a.Wd = p->Wd; a.bd = p->bd; a.vctx = p->vctx; a.vdeep = p->vdeep;
+  a.Wv = p->Wv; a.bv = p->bv; a.ln_g = p->ln_g; a.ln_b = p->ln_b; a.pos = p->pos; a.P_v = p->P_v; a.P_t = p->P_t; a.ln_in = p->ln_in;
+  a.dP_v = p->dP_v; a.dP_t = p->dP_t; a.u = p->u; a.d_ctx = p->d_ctx; a.d_deep = p->d_deep; a.d_We = p->d_We; a.d_be = p->d_be;
+  a.d_Wd = p->d_Wd; a.d_bd = p->d_bd; a.d_vctx = p->d_vctx; a.d_vdeep = p->d_vdeep; a.d_Wv = p->d_Wv; a.d_bv = p->d_bv;
+  return a;
+}
+int mudpt_prompt_forward(const mudpt_prompt_args* args, void* stream) {
+  if (!args) return fail(nullptr, "mudpt_prompt_forward: null argument");
+  CKG(prompt_forward(to_prompt_args(args), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_prompt_backward(const mudpt_prompt_args* args, void* stream) {
+  if (!args) return fail(nullptr, "mudpt_prompt_backward: null argument");
+  CKG(prompt_backward(to_prompt_args(args), static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -765,6 +765,271 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) attn_tc_bwd_short_kernel(const
   }
 }
 
+// =======================================================================================
+// The same backward with TWO problems in flight per SM (sequences of up to 80 tokens: the 77-token text tower).
+// One problem's chain has ~10 barrier hops (MMA commit -> tcgen05.ld -> element-wise -> slab -> MMA -> epilogue -> TMA
+// store), ~3 us that a single problem in flight leaves exposed (176 us per layer, no better than the warp-MMA kernel).
+// Here two groups of 4 warps (thread = query row, the whole row: no exchange between halves) each own a TMEM slot
+// (256 columns: S at +0, dP at +96; the outputs dQ / dK / dV at +0 / +64 / +128 reuse the score columns once the group
+// has consumed them) and a set of P / dS slabs (Lb rows each -- the 128-row reads of the dQ product run into the
+// following tile and only produce rows that are never stored), and the MMA warp serves both, so one problem's hops
+// hide behind the other's work.  3-stage TMA ring as above.
+// =======================================================================================
+static constexpr int TCP_THREADS = 320;
+static constexpr int TCP_STAGES = 3;
+
+__host__ __device__ inline int tcp_smem_bytes(int Lb) {
+  return 2 * 4 * Lb * 128 /*slabs of both slots*/ + TCP_STAGES * 4 * Lb * 128 + 256 + 1024;
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(TCP_THREADS, 1) attn_tc_bwd_pp_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                                        const __grid_constant__ CUtensorMap map_do,
+                                                                        const __grid_constant__ CUtensorMap map_dqkv,
+                                                                        const float* __restrict__ lse2, const int L, const int H,
+                                                                        const int d, const int Lb, const int n_items,
+                                                                        const float scale, const float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_bytes = Lb * 128;           // Lb <= 80 rows
+  const int stage_bytes = 4 * tile_bytes;    // Q | dO | K | V
+  // slabs first (their 128-row over-reads land in the stages): slot g: P[2] then dS[2], each Lb rows x 128 B
+  uint8_t* slabs = smem;
+  uint8_t* stages = smem + 2 * 4 * tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + TCP_STAGES * stage_bytes);
+  uint64_t* bar_full = bars;                 // [3]
+  uint64_t* bar_empty = bars + 3;            // [3]
+  uint64_t* bar_s = bars + 6;                // [2] scores of the slot in TMEM
+  uint64_t* bar_p = bars + 8;                // [2] slabs of the slot written (128)
+  uint64_t* bar_o = bars + 10;               // [2] outputs of the slot in TMEM
+  uint64_t* bar_ofree = bars + 12;           // [2] outputs drained (128)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  if (warp == 9) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_qkv);
+      tma_prefetch_desc(&map_do);
+      for (int i = 0; i < TCP_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+      for (int g = 0; g < 2; ++g) {
+        mbar_init(&bar_s[g], 1);
+        mbar_init(&bar_p[g], 128);
+        mbar_init(&bar_o[g], 1);
+        mbar_init(&bar_ofree[g], 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+  const int n_local = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int k = 0; k < n_local; ++k) {
+        const int it = blockIdx.x + k * gridDim.x;
+        const int s = it / H, h = it - s * H;
+        const int st = k % TCP_STAGES;
+        mbar_wait(&bar_empty[st], ((k / TCP_STAGES) & 1) ^ 1);
+        uint8_t* base = stages + st * stage_bytes;
+        mbar_expect_tx(&bar_full[st], static_cast<uint32_t>(stage_bytes));
+        tma_load_3d(base, &map_qkv, &bar_full[st], h * 64, 0, s);                          // Q
+        tma_load_3d(base + tile_bytes, &map_do, &bar_full[st], h * 64, 0, s);              // dO
+        tma_load_3d(base + 2 * tile_bytes, &map_qkv, &bar_full[st], d + h * 64, 0, s);     // K
+        tma_load_3d(base + 3 * tile_bytes, &map_qkv, &bar_full[st], 2 * d + h * 64, 0, s); // V
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer: scores of two problems, then their outputs =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(TC_ROWS, Lb);
+      const uint32_t idesc_dq = make_idesc_bf16(TC_ROWS, 64) | kIdescBMnMajor;
+      const uint32_t idesc_dkv = make_idesc_bf16(TC_ROWS, 64) | kIdescAMnMajor | kIdescBMnMajor;
+      const uint64_t lbo_mask = ~(static_cast<uint64_t>(0x3FFF) << 16);
+      const uint64_t lbo_slab = static_cast<uint64_t>(tile_bytes >> 4) << 16;  // MN-major A: the second 64 keys = next slab
+      const int nk = Lb >> 4;
+      auto scores = [&](int k) {
+        const int g = k & 1, kk = k >> 1, st = k % TCP_STAGES;
+        uint8_t* base = stages + st * stage_bytes;
+        const uint64_t dQt = make_smem_desc_sw128(smem_u32(base)), dOt = make_smem_desc_sw128(smem_u32(base + tile_bytes));
+        const uint64_t dKt = make_smem_desc_sw128(smem_u32(base + 2 * tile_bytes)), dVt = make_smem_desc_sw128(smem_u32(base + 3 * tile_bytes));
+        const uint32_t tb = tmem_base + static_cast<uint32_t>(g * 256);
+        mbar_wait(&bar_full[st], (k / TCP_STAGES) & 1);
+        if (kk > 0) mbar_wait(&bar_ofree[g], (kk - 1) & 1);  // the slot's previous outputs (same columns) are drained
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tb, dQt + static_cast<uint64_t>(j * 2), dKt + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tb + 96u, dOt + static_cast<uint64_t>(j * 2), dVt + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
+        umma_commit(&bar_s[g]);
+      };
+      auto outputs = [&](int k) {
+        const int g = k & 1, kk = k >> 1, st = k % TCP_STAGES;
+        uint8_t* base = stages + st * stage_bytes;
+        const uint64_t dQt = make_smem_desc_sw128(smem_u32(base)), dOt = make_smem_desc_sw128(smem_u32(base + tile_bytes));
+        const uint64_t dKt = make_smem_desc_sw128(smem_u32(base + 2 * tile_bytes));
+        uint8_t* sp = slabs + g * 4 * tile_bytes;  // P[0], P[1], dS[0], dS[1]
+        const uint64_t dPm = (make_smem_desc_sw128(smem_u32(sp)) & lbo_mask) | lbo_slab;
+        const uint64_t dSk = make_smem_desc_sw128(smem_u32(sp + 2 * tile_bytes));
+        const uint64_t dSm = (dSk & lbo_mask) | lbo_slab;
+        const uint32_t tb = tmem_base + static_cast<uint32_t>(g * 256);
+        mbar_wait(&bar_p[g], kk & 1);
+        tc_fence_after();
+        for (int j = 0; j < nk; ++j) {
+          const uint32_t acc = static_cast<uint32_t>(j != 0);
+          const uint64_t a_dq = dSk + static_cast<uint64_t>((j >> 2) * (tile_bytes >> 4) + (j & 3) * 2);
+          umma_bf16(tb, a_dq, dKt + static_cast<uint64_t>(j * 128), idesc_dq, acc);                                          // dQ += dS K
+          umma_bf16(tb + 64u, dSm + static_cast<uint64_t>(j * 128), dQt + static_cast<uint64_t>(j * 128), idesc_dkv, acc);   // dK += dS^T Q
+          umma_bf16(tb + 128u, dPm + static_cast<uint64_t>(j * 128), dOt + static_cast<uint64_t>(j * 128), idesc_dkv, acc);  // dV += P^T dO
+        }
+        umma_commit(&bar_o[g]);
+      };
+      for (int k0 = 0; k0 < n_local; k0 += 2) {
+        scores(k0);
+        if (k0 + 1 < n_local) scores(k0 + 1);
+        outputs(k0);
+        if (k0 + 1 < n_local) outputs(k0 + 1);
+      }
+    }
+  } else {
+    // ===================== group g = warp / 4: problems k = g, g + 2, ...; thread = row =====================
+    const int g = warp >> 2, quad = warp & 3;
+    const int t = quad * 32 + lane;
+    const uint32_t trow = tmem_base + static_cast<uint32_t>(g * 256) + (static_cast<uint32_t>(quad * 32) << 16);
+    const bool live = quad * 32 < Lb;   // (warp-uniform)
+    const bool mine = t < Lb;           // the row exists in the tiles / slabs
+    const int n32 = (Lb + 31) >> 5;     // <= 3
+    uint8_t* sp = slabs + g * 4 * tile_bytes;
+    const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
+    for (int k = g; k < n_local; k += 2) {
+      const int kk = k >> 1, st = k % TCP_STAGES;
+      const int it = blockIdx.x + k * gridDim.x;
+      const int s = it / H, h = it - s * H;
+      uint8_t* base = stages + st * stage_bytes;
+      const float lse_r = (live && t < L) ? lse2[(static_cast<size_t>(s) * H + h) * L + t] : 0.f;
+      mbar_wait(&bar_s[g], kk & 1);
+      tc_fence_after();
+      if (live) {
+        // pass 1: P (packed bf16) and D = rowsum(P dP)
+        uint32_t pk[3][16];
+        const f32x2 nl = f2_pack(-lse_r, -lse_r);
+        f32x2 acc2 = f2_pack(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (j < n32) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(trow + static_cast<uint32_t>(j * 32), sv);
+            tmem_ld_32x32(trow + 96u + static_cast<uint32_t>(j * 32), dv);
+            tmem_ld_wait_regs(sv);
+            tmem_ld_wait_regs(dv);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float a, b;
+              f2_unpack(f2_fma(f2_pack_u(sv[2 * e], sv[2 * e + 1]), c2, nl), a, b);
+              a = exp2f(a);
+              b = exp2f(b);
+              const int c = j * 32 + 2 * e;
+              if (CAUSAL) { a = c <= t ? a : 0.f; b = c + 1 <= t ? b : 0.f; }
+              if (c >= Lb) { a = 0.f; b = 0.f; }  // columns past the score tile hold other data
+              acc2 = f2_fma(f2_pack(a, b), f2_pack_u(dv[2 * e], dv[2 * e + 1]), acc2);
+              pk[j][e] = pack_bf16(a, b);
+            }
+          }
+        }
+        const float D_r = f2_hsum_tc(acc2);
+        const f32x2 nD = f2_pack(-D_r, -D_r);
+        // pass 2: dS = P (dP - D); rows of the slabs that exist (t < Lb)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (j < n32) {
+            uint32_t dv[32];
+            tmem_ld_32x32(trow + 96u + static_cast<uint32_t>(j * 32), dv);
+            tmem_ld_wait_regs(dv);
+            uint32_t ds[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const uint32_t w = pk[j][e];
+              float x, y;
+              f2_unpack(f2_mul(f2_pack_u(w << 16, w & 0xffff0000u), f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), nD)), x, y);
+              ds[e] = pack_bf16(x, y);
+            }
+            if (mine) {
+              const uint32_t off = static_cast<uint32_t>((j >> 1) * tile_bytes + t * 128);
+              const int cb = (j & 1) * 4;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t o2 = off + static_cast<uint32_t>(((cb + q) ^ (t & 7)) << 4);
+                *reinterpret_cast<uint4*>(sp + o2) = make_uint4(pk[j][4 * q], pk[j][4 * q + 1], pk[j][4 * q + 2], pk[j][4 * q + 3]);
+                *reinterpret_cast<uint4*>(sp + 2 * tile_bytes + o2) = make_uint4(ds[4 * q], ds[4 * q + 1], ds[4 * q + 2], ds[4 * q + 3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_p[g]);
+      // epilogue: dQ (row = query t), dK / dV (row = key t): 64 head columns each, in two halves
+      mbar_wait(&bar_o[g], kk & 1);
+      tc_fence_after();
+      if (live) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t o0[32], o1[32], o2[32];
+          tmem_ld_32x32(trow + static_cast<uint32_t>(hh * 32), o0);
+          tmem_ld_32x32(trow + 64u + static_cast<uint32_t>(hh * 32), o1);
+          tmem_ld_32x32(trow + 128u + static_cast<uint32_t>(hh * 32), o2);
+          tmem_ld_wait_regs(o0);
+          tmem_ld_wait_regs(o1);
+          tmem_ld_wait_regs(o2);
+          if (mine) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t off = static_cast<uint32_t>(t * 128 + (((hh * 4 + q) ^ (t & 7)) << 4));
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q + 2 * e]) * scale, __uint_as_float(o0[8 * q + 2 * e + 1]) * scale);
+              *reinterpret_cast<uint4*>(base + off) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q + 2 * e]) * scale, __uint_as_float(o1[8 * q + 2 * e + 1]) * scale);
+              *reinterpret_cast<uint4*>(base + 2 * tile_bytes + off) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o2[8 * q + 2 * e]), __uint_as_float(o2[8 * q + 2 * e + 1]));
+              *reinterpret_cast<uint4*>(base + 3 * tile_bytes + off) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_ofree[g]);
+      fence_proxy_async_smem();
+      if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (quad == 0 && lane == 0) {
+        tma_store_3d(&map_dqkv, base, h * 64, 0, s);
+        tma_store_3d(&map_dqkv, base + 2 * tile_bytes, d + h * 64, 0, s);
+        tma_store_3d(&map_dqkv, base + 3 * tile_bytes, 2 * d + h * 64, 0, s);
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(&bar_empty[st]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 static int g_tc_mode = -1;
 static int tc_enabled() {
   if (g_tc_mode < 0) {
@@ -826,7 +1091,8 @@ const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, co
     if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, Lb, &mq))) return e;
     if ((e = tensor_map_3d_bf16(d_o, d, L, S, d, static_cast<long long>(d) * L, Lb, &mdo))) return e;
     if ((e = tensor_map_3d_bf16(dqkv, 3 * d, L, S, ld, ld * L, Lb, &mo))) return e;
-    const int smem = tcs_smem_bytes(Lb);
+    const bool pp = Lb <= 80;  // two problems in flight per SM
+    const int smem = pp ? tcp_smem_bytes(Lb) : tcs_smem_bytes(Lb);
     static int n_sms = 0;
     if (n_sms == 0) {
       int dev = 0;
@@ -837,11 +1103,12 @@ const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, co
     const int n_items = S * H;
     const int grid = n_items < n_sms ? n_items : n_sms;
     const float scale_s = 0.125f, sl2_s = 0.125f * 1.4426950408889634f;
-    auto kern = causal ? attn_tc_bwd_short_kernel<true> : attn_tc_bwd_short_kernel<false>;
+    auto kern = pp ? (causal ? attn_tc_bwd_pp_kernel<true> : attn_tc_bwd_pp_kernel<false>)
+                   : (causal ? attn_tc_bwd_short_kernel<true> : attn_tc_bwd_short_kernel<false>);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return "attention (tcgen05 backward, short): cudaFuncSetAttribute failed";
-    launch_pdl(kern, dim3(grid), dim3(TCS_THREADS), static_cast<size_t>(smem), stream, mq, mdo, mo, lse2, L, H, d, Lb, n_items, scale_s,
-               sl2_s);
+    launch_pdl(kern, dim3(grid), dim3(pp ? TCP_THREADS : TCS_THREADS), static_cast<size_t>(smem), stream, mq, mdo, mo, lse2, L, H, d, Lb,
+               n_items, scale_s, sl2_s);
     count_launch(1);
     return launch_status("attention bwd (tcgen05, short) launch failed");
   }

@@ -27,7 +27,7 @@ import torch.nn.functional as F
 
 from .. import clip
 from .. import dist as mdist
-from ..engine import LogitsFn, TextTowerDenseFn, TextTowerFn, VisionTowerFn
+from ..engine import LogitsFn, PromptAlgebraFn, TextTowerDenseFn, TextTowerFn, VisionTowerFn
 
 try:  # the Dassl engine is not in the reference tree nor in this image
     from dassl.engine import TRAINER_REGISTRY, TrainerX
@@ -320,6 +320,15 @@ class CustomCLIP(nn.Module):
         """The two [depth, n_ctx, width] prompt stacks the towers splice in, as differentiable
         functions of the 10 trainable tensors (trainers/mudpt.py:127-128, :175; clip/model.py:534-539)."""
         pl, ve = self.mudpt_prompt_learner, self.image_encoder
+        if (type(self) is CustomCLIP and pl.ctx.is_cuda and pl.ctx.dtype == torch.float32 and pl.deep_prompts.shape[0] > 0
+                and os.environ.get("MUDPT_NATIVE_PROMPTS", "1") == "1"):
+            # the same algebra as below in 2 (+2 backward) native launches
+            from .. import _lib
+            return PromptAlgebraFn.apply(
+                _lib.load(), ve.ln_pre.eps, ve.ln_pre.weight, ve.ln_pre.bias, self.text_encoder.positional_embedding[1:1 + pl.n_ctx],
+                pl.ctx, pl.deep_prompts, pl.embed_projection.weight, pl.embed_projection.bias, pl.deep_projections.weight,
+                pl.deep_projections.bias, ve.visual_ctx, ve.visual_ctx_deep_prompts, ve.visual_ctx_deep_projections.weight,
+                ve.visual_ctx_deep_projections.bias)
         visual_prompts = pl.deep_projections(pl.deep_prompts)                 # t2v deep
         shared_ctx = pl.embed_projection(pl.ctx.unsqueeze(0))                 # t2v shallow
         P_v = ve.prompt_stack(shared_ctx, visual_prompts)

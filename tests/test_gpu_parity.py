@@ -301,6 +301,31 @@ def test_unfused_layernorm_fallback_matches_reference(bring):
                 assert m["cos"] >= 0.999 and m["rel_l2"] <= 0.05, (opts, k, m)
 
 
+def test_native_prompt_algebra_matches_torch():
+    """mudpt_prompt_forward / _backward (2 + 2 launches) against the torch autograd version of the same algebra
+    (trainers/mudpt.py:117-130, 143, 175; clip/model.py:534-541): both prompt stacks and the 10 gradients."""
+    import os
+    for name in ("tiny_a", "tiny_c", "vitb16_cfg1"):
+        c = gu.load(name)
+        model, _ = gu.build_model(c, "cuda")
+        outs = {}
+        for native in ("1", "0"):
+            os.environ["MUDPT_NATIVE_PROMPTS"] = native
+            model.zero_grad(set_to_none=True)
+            P_v, P_t = model.prompt_stacks()
+            torch.manual_seed(0)
+            gv, gt = torch.randn_like(P_v), torch.randn_like(P_t)
+            torch.autograd.backward([P_v, P_t], [gv, gt])
+            outs[native] = (P_v.detach().clone(), P_t.detach().clone(),
+                            {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad})
+        os.environ["MUDPT_NATIVE_PROMPTS"] = "1"
+        for a, b in zip(outs["1"][:2], outs["0"][:2]):
+            assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max())), name
+        for n, g in outs["0"][2].items():
+            m = (outs["1"][2][n] - g).norm() / (g.norm() + 1e-30)
+            assert float(m) <= 1e-4, (name, n, float(m))
+
+
 def test_vit_l14_depth12_vs_oracle():
     """BASELINE config 5 architecture (ViT-L/14, prompt depth 12; patch 14 -> padded K = 592, 24 vision
     layers of width 1024, text width 768) at a size the CPU oracle finishes in seconds."""
