@@ -131,6 +131,7 @@ struct mudpt_handle {
   // measured on B200 the row dots it needs cost more at their producers (GELU' epilogue +66 us, attention backward
   // +82 us per block at the cfg-2 shapes) than the fused epilogue saves (60 us): profiles/r02_ln_fusion_ab.txt
   bool ln_bwd_fused = false;
+  bool ln_bwd_bf16x = true;  // env MUDPT_LN_BWD_BF16X
   // exact work skipping: the last block's out-proj / MLP on the CLS / EOT rows only
   bool prune = true;
 };
@@ -488,6 +489,9 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
   const double Md = static_cast<double>(M), dd = d;
   const double attn_fl = 2.5 * 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // 2.5x forward
   const bool fused = t.fwd_fused && h->ln_bwd_fused;  // (the fused forward also keeps the fp32 LN inputs the kernel needs)
+  // stand-alone LayerNorm backward after a fused forward: the bf16 row + its exact statistics instead of the fp32 row
+  // (14 instead of 16 B/element on an HBM-bound kernel; xhat from bf16(x) -- the operand precision of every GEMM here)
+  const bool xstats = t.fwd_fused && !fused && h->ln_bwd_bf16x;
   const int parts = d / 64;
   const int dots_mlp = (4 * d + gemm_dots_span(4 * d) - 1) / gemm_dots_span(4 * d);
   for (int i = t.layers - 1; i >= 0; --i) {
@@ -511,7 +515,7 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
       } else {
         p2.mode = EPI_BF16; p2.out0 = t.pr_a;
         CKP(h, st, PC_GEMM, 2.0 * Sd * 4 * dd * dd, 2 * (Sd * 4 * dd + 4 * dd * dd) + 2 * Sd * dd, gemm_bf16_tn(t.pr_dh, 4 * d, w.w_fc_t, 4 * d, p2, S, d, 4 * d, st, &t.gws));
-        CKP(h, st, PC_LN_BWD, 0, Sd * dd * 16, layernorm_bwd(t.pr_a, true, t.pr_xm, w.ln2_g, t.pr_dx, t.pr_dx, t.pr_dxb, S, d, kLnEps, st));
+        CKP(h, st, PC_LN_BWD, 0, Sd * dd * 16, layernorm_bwd(t.pr_a, true, t.pr_xm, nullptr, w.ln2_g, t.pr_dx, t.pr_dx, t.pr_dxb, S, d, kLnEps, st));
       }
       GemmEpilogue p3;
       p3.mode = EPI_BF16; p3.out0 = t.pr_do; p3.ldc = d;
@@ -538,7 +542,8 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
       e2.mode = EPI_BF16; e2.out0 = t.a_buf;  // a_buf: forward transient, free during the backward
       CKP(h, st, PC_GEMM_DFC, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 2 * Md * dd,
           gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st, &t.gws));
-      CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, t.x_mid[i], w.ln2_g, t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+      CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, xstats ? static_cast<const void*>(t.xb_mid[i]) : t.x_mid[i], xstats ? t.st_mid[i] : nullptr, w.ln2_g, t.dx,
+                                                            t.dx, t.dx_bf16, M, d, kLnEps, st));
     }
     // attention branch: dO = dx W_out ; (dQ,dK,dV) ; da = dQKV W_in ; dx += LN1_bwd(da)
     GemmEpilogue e3;
@@ -560,7 +565,8 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
       CKP(h, st, PC_GEMM_DQKV, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 2 * Md * dd,
           gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st, &t.gws));
       CKP(h, st, PC_LN_BWD, 0, Md * dd * 16,
-          layernorm_bwd(t.a_buf, true, t.x_in[i], w.ln1_g, tail_pruned ? nullptr : t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+          layernorm_bwd(t.a_buf, true, xstats ? static_cast<const void*>(t.xb_in[i]) : t.x_in[i], xstats ? t.st_in[i] : nullptr, w.ln1_g,
+                        tail_pruned ? nullptr : t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
     }
     if (tail_pruned)  // the residual path of the S consumed rows (everything else of it is zero)
       CKP(h, st, PC_SPLICE, 0, t.S * dd * 14, scatter_rows(t.pr_dx, t.sel_rows, t.S, t.L, t.dx, t.dx_bf16, d, true, st));
@@ -634,6 +640,7 @@ int mudpt_create(const mudpt_config* cfg, mudpt_handle** out) {
   h->launches_at_create = g_launch_counter.load();
   h->ln_fused = getenv("MUDPT_LN_FUSED") ? (atoi(getenv("MUDPT_LN_FUSED")) != 0 ? 1 : 0) : -1;
   h->ln_bwd_fused = env_flag("MUDPT_LN_BWD_FUSED", false);
+  h->ln_bwd_bf16x = env_flag("MUDPT_LN_BWD_BF16X", true);
   h->prune = env_flag("MUDPT_PRUNE", true);
   *out = h;
   return 0;
@@ -863,7 +870,7 @@ int mudpt_layernorm_forward(const float* x, const float* gamma, const float* bet
 }
 int mudpt_layernorm_backward(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
                              uint16_t* dx_bf16, int32_t rows, int32_t width, void* stream) {
-  CKG(layernorm_bwd(dy, false, x, gamma, resid, dx, reinterpret_cast<bf16*>(dx_bf16), rows, width, kLnEps, static_cast<cudaStream_t>(stream)));
+  CKG(layernorm_bwd(dy, false, x, nullptr, gamma, resid, dx, reinterpret_cast<bf16*>(dx_bf16), rows, width, kLnEps, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 int mudpt_splice_forward(float* x, const float* prompt, int32_t S, int32_t L, int32_t row0, int32_t n, int32_t width, void* stream) {

@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) attn_tc_bwd_short_kernel(const
               b = exp2f(b);
               const int c = j * 32 + 2 * e;
               if (CAUSAL) { a = c <= t ? a : 0.f; b = c + 1 <= t ? b : 0.f; }
-              if (c >= Lb) { a = 0.f; b = 0.f; }  // columns past the score tile hold stale TMEM
+              if (c >= Lb) { a = 0.f; b = 0.f; dv[2 * e] = 0u; dv[2 * e + 1] = 0u; }  // columns past the score tile hold stale TMEM (0 * Inf = NaN)
               acc2 = f2_fma(f2_pack(a, b), f2_pack_u(dv[2 * e], dv[2 * e + 1]), acc2);
               pk[jj][e] = pack_bf16(a, b);
             }
@@ -697,6 +697,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) attn_tc_bwd_short_kernel(const
               const uint32_t w = pk[jj][e];
               const f32x2 p2 = f2_pack_u(w << 16, w & 0xffff0000u);
               float x, y;
+              if (j * 32 + 2 * e >= Lb) { dv[2 * e] = 0u; dv[2 * e + 1] = 0u; }
               f2_unpack(f2_mul(p2, f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), nD)), x, y);
               ds[e] = pack_bf16(x, y);
             }
@@ -779,7 +780,8 @@ static constexpr int TCP_THREADS = 320;
 static constexpr int TCP_STAGES = 3;
 
 __host__ __device__ inline int tcp_smem_bytes(int Lb) {
-  return 2 * 4 * Lb * 128 /*slabs of both slots*/ + TCP_STAGES * 4 * Lb * 128 + 256 + 1024;
+  // (+16 KB: the 128-row A reads of the score products start inside the last stage's Q / dO tiles and run past short ones)
+  return 2 * 4 * Lb * 128 /*slabs of both slots*/ + TCP_STAGES * 4 * Lb * 128 + 256 + 1024 + TC_SLAB;
 }
 
 template <bool CAUSAL>
@@ -938,7 +940,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) attn_tc_bwd_pp_kernel(const __
               b = exp2f(b);
               const int c = j * 32 + 2 * e;
               if (CAUSAL) { a = c <= t ? a : 0.f; b = c + 1 <= t ? b : 0.f; }
-              if (c >= Lb) { a = 0.f; b = 0.f; }  // columns past the score tile hold other data
+              if (c >= Lb) { a = 0.f; b = 0.f; dv[2 * e] = 0u; dv[2 * e + 1] = 0u; }  // columns past the score tile hold other data (0 * Inf = NaN)
               acc2 = f2_fma(f2_pack(a, b), f2_pack_u(dv[2 * e], dv[2 * e + 1]), acc2);
               pk[j][e] = pack_bf16(a, b);
             }
@@ -958,6 +960,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) attn_tc_bwd_pp_kernel(const __
             for (int e = 0; e < 16; ++e) {
               const uint32_t w = pk[j][e];
               float x, y;
+              if (j * 32 + 2 * e >= Lb) { dv[2 * e] = 0u; dv[2 * e + 1] = 0u; }
               f2_unpack(f2_mul(f2_pack_u(w << 16, w & 0xffff0000u), f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), nD)), x, y);
               ds[e] = pack_bf16(x, y);
             }
@@ -1073,12 +1076,17 @@ const char* attention_tc_fwd(const bf16* qkv, bf16* o, float* lse2, int S, int L
   return launch_status("attention fwd (tcgen05) launch failed");
 }
 
-// The tcgen05 backward is parity-tested on every shape but, at 199 tokens, bound by its per-round hand-over chain
-// (score MMA -> tcgen05.ld -> element-wise -> slab -> output MMA, two CTAs per SM by TMEM): 82 us per vision layer
-// against 75 us for the warp-MMA pair (profiles/r02_attention_tc.txt).  It runs only on request (mode 2).
+// The round-based tcgen05 backward for longer sequences is parity-tested on every shape but, at 199 tokens, bound by its
+// per-round hand-over chain (score MMA -> tcgen05.ld -> element-wise -> slab -> output MMA, two CTAs per SM by TMEM):
+// 82 us per vision layer against 75 us for the warp-MMA pair (profiles/r02_attention_tc.txt): on request only (mode 2).
 bool attention_tc_bwd_eligible(int L, bool causal) {
   (void)causal;
-  return tc_enabled() == 2 && L >= 1;
+  const int en = tc_enabled();
+  if (en == 0 || L < 1) return false;
+  if (en == 2) return true;
+  // default: the two-problems-in-flight persistent kernel where it wins -- 65..80-token sequences (the 77-token text
+  // tower: 141 us per layer against 171 us for the warp-MMA kernel, 96 us of Q / K / V / dO / dQKV traffic)
+  return L > 64 && L <= 80;
 }
 
 const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv,

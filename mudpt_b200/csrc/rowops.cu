@@ -105,16 +105,20 @@ const char* layernorm_fwd(const float* x, const float* gamma, const float* beta,
 // gamma/beta are frozen (trainers/mudpt.py:205-212): no dgamma/dbeta. Statistics are
 // recomputed from the saved fp32 input row. dx may alias resid. Also emits the bf16 copy of dx
 // that feeds the next dgrad GEMM.  DY_BF16: dy comes from a bf16 GEMM epilogue.
-template <int NV, bool DY_BF16>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
-                                                     const float* __restrict__ gamma, const float* resid, float* dx,
-                                                     bf16* __restrict__ dx_bf16, int M, int d, float eps) {
+// X_STATS: the row comes as its bf16 copy + per-64-column partial statistics (the form the fused-LayerNorm forward
+// keeps, rowops.cu "fused-LayerNorm plumbing"): 2 B instead of 4 B per element read, exact fp32 mean / rstd.
+template <int NV, bool DY_BF16, bool X_STATS>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ xv,
+                                                     const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                     const float* resid, float* dx, bf16* __restrict__ dx_bf16, int M, int d,
+                                                     float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_wait();
   pdl_trigger();
   if (row >= M) return;
   const size_t off = static_cast<size_t>(row) * d;
+  const float* x = reinterpret_cast<const float*>(xv);
   float4 v[NV], g[NV];
   float sum = 0.f;
   // issue every load of the row up front (x, dy, residual gradient): 3 streams in flight per lane
@@ -122,7 +126,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
-      v[i] = *reinterpret_cast<const float4*>(x + off + c);
+      if constexpr (X_STATS) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(xv) + off + c);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        v[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        v[i] = *reinterpret_cast<const float4*>(x + off + c);
+      }
       if constexpr (DY_BF16) {
         const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy) + off + c);
         const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
@@ -133,17 +143,35 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
-  const float mean = warp_sum(sum) / d;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < d) {
-      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  float mean, rstd;
+  if constexpr (X_STATS) {
+    // lane p holds the partial of columns [64 p, 64 p + 64): exact pairwise combination (no cancellation)
+    const int parts = (d + 63) >> 6;
+    float2 st = make_float2(0.f, 0.f);
+    float np = 0.f;
+    if (lane < parts) {
+      st = stats[static_cast<size_t>(row) * parts + lane];
+      const int rem = d - lane * 64;
+      np = static_cast<float>(rem < 64 ? rem : 64);
     }
+    mean = warp_sum(st.x) / d;
+    const float dm = np > 0.f ? st.x / np - mean : 0.f;
+    rstd = rsqrtf(warp_sum(st.y + np * dm * dm) / d + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean; }
+  } else {
+    mean = warp_sum(sum) / d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    }
+    rstd = rsqrtf(warp_sum(sq) / d + eps);
   }
-  const float rstd = rsqrtf(warp_sum(sq) / d + eps);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -181,23 +209,30 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
 }
 
 template <int NV>
-static void launch_ln_bwd(const void* dy, bool dy_bf16, const float* x, const float* gamma, const float* resid, float* dx,
-                          bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
+static void launch_ln_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
+                          float* dx, bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
   const int grid = (M + 7) / 8;
-  if (dy_bf16) launch_pdl(ln_bwd_kernel<NV, true>, dim3(grid), dim3(256), 0, stream, dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
-  else launch_pdl(ln_bwd_kernel<NV, false>, dim3(grid), dim3(256), 0, stream, dy, x, gamma, resid, dx, dx_bf16, M, d, eps);
+  if (stats != nullptr) {  // (bf16 dy only: the dgrad GEMM's output)
+    launch_pdl(ln_bwd_kernel<NV, true, true>, dim3(grid), dim3(256), 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+  } else if (dy_bf16) {
+    launch_pdl(ln_bwd_kernel<NV, true, false>, dim3(grid), dim3(256), 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+  } else {
+    launch_pdl(ln_bwd_kernel<NV, false, false>, dim3(grid), dim3(256), 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+  }
 }
 
-const char* layernorm_bwd(const void* dy, bool dy_bf16, const float* x, const float* gamma, const float* resid, float* dx,
-                          bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
+// x: fp32 rows, or (stats != nullptr) their bf16 copy with the per-64-column partial statistics
+const char* layernorm_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
+                          float* dx, bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
   if (M <= 0) return nullptr;
   if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
+  if (stats != nullptr && (!dy_bf16 || d % 64 != 0)) return "layernorm: the bf16-input form needs bf16 dy and width % 64 == 0";
   switch (pick_nv(d)) {
-    case 1: launch_ln_bwd<1>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-    case 2: launch_ln_bwd<2>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-    case 4: launch_ln_bwd<4>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-    case 6: launch_ln_bwd<6>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-    default: launch_ln_bwd<8>(dy, dy_bf16, x, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    case 1: launch_ln_bwd<1>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    case 2: launch_ln_bwd<2>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    case 4: launch_ln_bwd<4>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    case 6: launch_ln_bwd<6>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
+    default: launch_ln_bwd<8>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
   }
   count_launch(1);
   return launch_status("layernorm bwd launch failed");

@@ -7,8 +7,9 @@
 namespace mudpt {
 const char* layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
                           float eps, cudaStream_t stream);
-const char* layernorm_bwd(const void* dy, bool dy_bf16, const float* x, const float* gamma, const float* resid, float* dx,
-                          __nv_bfloat16* dx_bf16, int M, int d, float eps, cudaStream_t stream);
+// x: fp32 rows, or (stats != nullptr) their bf16 copy + per-64-column partial statistics (fused-LayerNorm towers)
+const char* layernorm_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
+                          float* dx, __nv_bfloat16* dx_bf16, int M, int d, float eps, cudaStream_t stream);
 const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, int n, int d, cudaStream_t stream);
 size_t splice_bwd_workspace_floats(int n, int d);
 const char* splice_bwd(float* dx, __nv_bfloat16* dx_bf16, float* dprompt, float* workspace, int S, int L, int row0, int n,
