@@ -316,12 +316,14 @@ def group_gemm_fused(res):
         do = torch.randn(S * L, d, device=dev).to(bf)
         dqkv = torch.zeros(S * L, 3 * d, device=dev, dtype=bf); dsum = torch.zeros(S, H, L, device=dev)
         sb = torch.randn(3 * d, 2, device=dev); dots = torch.zeros(S * L, 3 * H, 2, device=dev)
+        lib.mudpt_set_attention_tc(0)  # the row dots are a by-product of the warp-MMA kernels: compare like with like
         _lib.check(lib.mudpt_attention_backward_dots(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
                                                      dqkv.data_ptr(), S, L, H, causal, sb.data_ptr(), dots.data_ptr(), st))
         dqkv2 = torch.zeros_like(dqkv)
         _lib.check(lib.mudpt_attention_backward(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
                                                 dqkv2.data_ptr(), S, L, H, causal, st))
         torch.cuda.synchronize()
+        lib.mudpt_set_attention_tc(1)
         gq = dqkv.float().view(S * L, 3 * H, 64)
         d1 = (gq * sb[:, 0].view(3 * H, 64)).sum(-1)
         d2 = (gq * (qkv.float().view(S * L, 3 * H, 64) - sb[:, 1].view(3 * H, 64))).sum(-1)
