@@ -365,6 +365,10 @@ def run_ours(args):
         del trainer, model, eng
         torch.cuda.empty_cache()
 
+    dist_check = collectives = None
+    if world > 1:
+        dist_check = sharded_equivalence_check(device, imgs_dev[0], labs_dev[0], world)
+        collectives = collective_timings(device, world)
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -437,19 +441,117 @@ def run_ours(args):
                      "flops_per_launch": g["flops"] / max(g["launches"], 1),
                      "share_of_step": shares},
         "kernels": cat_table(full["prof"], full["nprof"]),
-        "step_flops_reference_formulation_T": round((g["flops"] + full["prof"]["attn_fwd"]["flops"] +
-                                                     full["prof"]["attn_bwd"]["flops"]) / full["nprof"] / 1e12, 3),
+        # reference formulation = every row of every block, forward + dgrad; executed = what the
+        # launches of the step actually compute after the exact work skipping of the last block (CLS / EOT rows only)
+        "step_flops_reference_formulation_T": round(reference_step_flops(B, -(-N_CLASSES // world), full["text_len"]) / 1e12, 3),
+        "step_flops_executed_T": round((g["flops"] + full["prof"]["attn_fwd"]["flops"] +
+                                        full["prof"]["attn_bwd"]["flops"]) / full["nprof"] / 1e12, 3),
         "loss": full["loss"], "loss_eot_truncated": tr["loss"],
         "clocks": clocks,
         "cpu_baseline": cb,
         "input_pipeline": pipe,
         "inference_cfg3": infer,
+        "sharded_vs_unsharded": dist_check,
+        "collectives_us": collectives,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
+
+
+def reference_step_flops(batch, classes, text_len):
+    """Per-rank FLOPs of one train step in the reference formulation: 12 d^2 MACs per token and block forward, the same
+    again for the dgrad (no wgrad: frozen weights), attention 4 L^2 64 per head forward and 2.5 x that backward."""
+    from mudpt_b200 import synthetic as syn
+    a = syn.ARCHS[ARCH]
+    fl = 0.0
+    for (S, L, d, layers) in ((batch, (a.image_resolution // a.vision_patch_size) ** 2 + 1 + N_CTX, a.vision_width, a.vision_layers),
+                              (classes, text_len, a.transformer_width, a.transformer_layers)):
+        M, H = S * L, d // 64
+        fl += layers * (2 * 24.0 * M * d * d + 3.5 * 4.0 * S * H * L * L * 64)
+    return fl
+
+
+def sharded_equivalence_check(device, image, label, world):
+    """N > 1: the class-sharded step (text tower over C / N classes per rank, all-gather of the text features,
+    reduce-scatter of their gradient, all-reduce of the prompt gradients) against the UNSHARDED step on the same
+    images (every rank runs all classes; gradients summed over ranks by hand): logits max-abs / cosine, loss and
+    the worst gradient cosine.  Not bitwise: the stream-K cut of a GEMM depends on its row count."""
+    import torch
+    import torch.distributed as dist
+    trainer = build_trainer(device, True)
+    model = trainer.model
+    out = {}
+    res = {}
+    for mode in ("sharded", "unsharded"):
+        model.shard_classes = mode == "sharded"
+        model._clip_ref[0].engine(device).class_key = None
+        model.zero_grad(set_to_none=True)
+        loss, logits = model.forward_backward(image, label)
+        grads = [p.grad.detach().clone() for p in model.parameters() if p.requires_grad]
+        if mode == "unsharded":  # local-batch mean -> global-batch mean, summed over the ranks
+            loss = loss.detach().clone() / world
+            dist.all_reduce(loss)
+            for g in grads:
+                g.div_(world)
+                dist.all_reduce(g)
+        res[mode] = (float(loss), logits.detach().clone(), grads)
+    a, b = res["sharded"], res["unsharded"]
+    la, lb = a[1].flatten().double(), b[1].flatten().double()
+    out["logits_max_abs"] = float((a[1] - b[1]).abs().max())
+    out["logits_cos"] = float((la @ lb) / (la.norm() * lb.norm()))
+    out["loss"] = [a[0], b[0]]
+    cos = []
+    for ga, gb in zip(a[2], b[2]):
+        x, y = ga.flatten().double(), gb.flatten().double()
+        cos.append(float((x @ y) / (x.norm() * y.norm() + 1e-300)))
+    out["grad_cos_min"] = min(cos)
+    t = torch.tensor([out["logits_max_abs"], -out["logits_cos"], -out["grad_cos_min"]], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # worst over the ranks
+    out["logits_max_abs"], out["logits_cos"], out["grad_cos_min"] = float(t[0]), -float(t[1]), -float(t[2])
+    out["ranks"] = world
+    del trainer, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def collective_timings(device, world, reps=20):
+    """Device time (CUDA events, max over ranks) of each collective of the step at its real size: all-gather of the
+    text features [C / N, 512] -> [C, 512], reduce-scatter of their gradient, all-reduce of the 1.2 M prompt-gradient
+    floats in one bucket, all-reduce of the loss scalar."""
+    import torch
+    import torch.distributed as dist
+    from mudpt_b200 import dist as mdist
+    C, e = N_CLASSES, 512
+    lo, hi = mdist.shard_bounds(C, dist.get_rank(), world)
+    f_loc = torch.randn(hi - lo, e, device=device)
+    d_full = torch.randn(C, e, device=device)
+    grads = [torch.nn.Parameter(torch.randn(n, device=device)) for n in (1024, 8 * 1024, 393216, 768, 393216, 768, 1536, 12288, 393216, 512)]
+    for p in grads:
+        p.grad = torch.randn_like(p)
+    loss = torch.zeros((), device=device)
+    ops = {"all_gather_text_features": lambda: mdist.all_gather_rows(f_loc, C),
+           "reduce_scatter_d_text_features": lambda: mdist.reduce_scatter_rows(d_full, C),
+           "all_reduce_prompt_grads": lambda: mdist.all_reduce_grads(grads),
+           "all_reduce_loss": lambda: mdist.all_reduce_sum(loss)}
+    out = {}
+    for name, fn in ops.items():
+        for _ in range(3):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = round(float(t), 1)
+    return out
 
 
 def input_pipeline_bench(device, peaks, batch=BATCH_PER_GPU, reps=20):
