@@ -1195,8 +1195,9 @@ int gemm_dots_span(int N) { return pick_bn(N) / (EpiWarps<EPI_GELU_BWD_DOTS>::va
 // Costs in k-block times (one 64-deep k-block of a tile = 0.46 us on one SM / SM pair at the sustained rate):
 //   whole tiles : the remainder costs one more tile-time for everyone: num_kb
 //   group of g  : rem * num_kb / g  (imbalance)  +  c * g  (g hand-overs share the L2: measured ~9 us for 74 pair
-//                 tiles of 256 KB, i.e. c = 0.29 per pair tile, half of that per single-CTA tile)  +  ~4 (dump, flag,
-//                 read-back on the last tile's critical path)
+//                 tiles of 256 KB, i.e. c = 0.29 per pair tile, half of that per single-CTA tile)  +  ~14 (dump, fence,
+//                 flag, read-back and the two extra accumulator passes on the last tile's critical path: measured
+//                 ~6-8 us whatever g, profiles/r02_gemm_time.txt -- the cut pays for K >= 1536 only)
 static SkArgs plan_sk(int tiles, int units, int num_kb, bool pair, const GemmWorkspace* ws, bool allowed) {
   SkArgs a;
   a.dp_tiles = tiles; a.sk_tiles = 0; a.sk_units = 0; a.sk_first = 0;
@@ -1209,7 +1210,10 @@ static SkArgs plan_sk(int tiles, int units, int num_kb, bool pair, const GemmWor
   const float c = pair ? 0.29f : 0.145f;
   int g = static_cast<int>(sqrtf(static_cast<float>(rem) * num_kb / c) + 0.5f);
   if (g > units) g = units;
-  if (waves == 0) {            // fewer tiles than units: the group shares all of them
+  if (waves == 0) {            // fewer tiles than units: the group would share all of them ...
+    // ... with several contributors per tile, read back one after the other by the finisher: measured slower than
+    // whole tiles (250 x 512 x 2048: 30.6 against 20.2 us), so only when explicitly forced
+    if (g_sk_mode != 1) return a;
     if (g <= rem) return a;    // (nothing to gain from cutting)
     const long long q4 = static_cast<long long>(rem) * num_kb / 4;  // at least 4 k-blocks per unit
     if (g > q4) g = static_cast<int>(q4);
@@ -1222,7 +1226,7 @@ static SkArgs plan_sk(int tiles, int units, int num_kb, bool pair, const GemmWor
     // whole tiles: the remainder costs everyone one more tile-time (waves == 0: the one and only tile-time);
     // cut: the group's makespan beyond the full waves
     const float whole = static_cast<float>(num_kb);
-    const float cut = static_cast<float>(rem) * num_kb / g + c * g + 4.f;
+    const float cut = static_cast<float>(rem) * num_kb / g + c * g + 14.f;
     if (cut > 0.9f * whole) return a;
   }
   a.dp_tiles = tiles - sk_tiles;
@@ -1290,8 +1294,15 @@ static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, c
   // traffic) whenever there is more than one row block.  The shape is a function of N (and M > 128) only, so the
   // column span of the per-row partials the fused-LayerNorm epilogues exchange is known to the caller; wave
   // quantisation is the work decomposition's problem (stream-K), not the tile shape's.
-  const int bn = pick_bn(N);
-  const bool two = g_enable_2cta && bn == 256 && M > BM;
+  int bn = pick_bn(N);
+  bool two = g_enable_2cta && bn == 256 && M > BM;
+  // Few-row problems (the S gathered CLS / EOT rows of the pruned last block): 256 x 256 pair tiles would leave most
+  // of the machine idle while a handful of CTAs walk K alone, so they take 128 x 128 single-CTA tiles (4x the tiles).
+  // (Not for EPI_GELU_BWD_DOTS, whose partial-dot span is a function of N alone.)
+  if (MODE != EPI_GELU_BWD_DOTS && ((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256) * 4 < num_sms() / 2) {
+    bn = 128;
+    two = false;
+  }
   CUtensorMap ta, tb;
   const char* e = get_tensor_map(A, M, K, lda, BM, BK, &ta);
   if (e) return e;
