@@ -532,9 +532,11 @@ def collective_timings(device, world, reps=20):
     for p in grads:
         p.grad = torch.randn_like(p)
     loss = torch.zeros((), device=device)
+    bucket = mdist.FlatGrads(grads)   # what the fused step does: the gradients live in one flat bucket
+    bucket.attach(zero=False)
     ops = {"all_gather_text_features": lambda: mdist.all_gather_rows(f_loc, C),
            "reduce_scatter_d_text_features": lambda: mdist.reduce_scatter_rows(d_full, C),
-           "all_reduce_prompt_grads": lambda: mdist.all_reduce_grads(grads),
+           "all_reduce_prompt_grads": bucket.all_reduce,
            "all_reduce_loss": lambda: mdist.all_reduce_sum(loss)}
     out = {}
     for name, fn in ops.items():

@@ -412,9 +412,16 @@ class CustomCLIP(nn.Module):
             dP_t, _ = eng.text_backward(d_t_loc)
             main.wait_stream(side)
             dP_v.record_stream(main)
+        # the gradients of the trainable tensors live in one flat bucket (views): one all-reduce, no cat / copy-backs
+        trainable = [p for p in self.parameters() if p.requires_grad]
+        fg = self.__dict__.get("_flat_grads")
+        if fg is None or not fg.matches(trainable):
+            fg = mdist.FlatGrads(trainable)
+            self.__dict__["_flat_grads"] = fg
+        fg.attach(zero=True)
         torch.autograd.backward([P_v, P_t], [dP_v, dP_t])
         if world > 1:
-            mdist.all_reduce_grads([p for p in self.parameters() if p.requires_grad])
+            fg.all_reduce()
         return loss, logits
 
     def _publish_loss(self, loss, world):
