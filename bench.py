@@ -533,7 +533,6 @@ def collective_timings(device, world, reps=20):
         p.grad = torch.randn_like(p)
     loss = torch.zeros((), device=device)
     bucket = mdist.FlatGrads(grads)   # what the fused step does: the gradients live in one flat bucket
-    bucket.attach(zero=False)
     ops = {"all_gather_text_features": lambda: mdist.all_gather_rows(f_loc, C),
            "reduce_scatter_d_text_features": lambda: mdist.reduce_scatter_rows(d_full, C),
            "all_reduce_prompt_grads": bucket.all_reduce,

@@ -99,37 +99,28 @@ def all_reduce_grads(params: List[torch.nn.Parameter]) -> None:
 
 
 class FlatGrads:
-    """One flat fp32 bucket holding the gradients of the (small, replicated) trainable tensors: `.grad` of every
-    parameter is a view into it, so zeroing is one memset and the cross-rank sum is ONE all-reduce on the bucket itself --
-    no concatenation before and no copies back after (measured at 8 ranks: 282 us per step for the cat / all-reduce /
+    """One flat fp32 bucket holding the gradients of the (small, replicated) trainable tensors: the native prompt
+    backward writes into its views, `.grad` of every parameter is such a view, and the cross-rank sum is ONE all-reduce on
+    the bucket itself -- no concatenation before and no copies back after (measured at 8 ranks: 282 us per step for the cat / all-reduce /
     10 copy-backs of the 1.2 M prompt gradients, against ~50 us for the bare all-reduce)."""
+
+    ALIGN = 64  # floats: every view starts on a 256-byte boundary (vector loads of the native kernels)
 
     def __init__(self, params: List[torch.nn.Parameter]):
         self.params = list(params)
-        n = sum(p.numel() for p in self.params)
+        pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         p0 = self.params[0]
-        self.flat = torch.zeros(n, device=p0.device, dtype=p0.dtype)
+        self.flat = torch.zeros(sum(pad(p.numel()) for p in self.params), device=p0.device, dtype=torch.float32)
         self.views = []
         off = 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            off += pad(p.numel())
 
     def matches(self, params) -> bool:
         params = list(params)
         return len(params) == len(self.params) and all(a is b for a, b in zip(params, self.params)) and \
             all(p.device == self.flat.device for p in params)
-
-    def attach(self, zero: bool = True) -> None:
-        """(Re)point every `.grad` at its view (an optimizer's zero_grad(set_to_none=True) drops them); gradients that
-        were already accumulated elsewhere are carried over."""
-        carry = [(v, p.grad) for p, v in zip(self.params, self.views) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
-        if zero:
-            self.flat.zero_()
-        for v, g in carry:
-            v.add_(g)
-        for p, v in zip(self.params, self.views):
-            p.grad = v
 
     def all_reduce(self) -> None:
         if world_size() > 1:

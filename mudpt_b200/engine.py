@@ -204,57 +204,77 @@ def _from_ptr(ptr: int, numel: int, dtype: torch.dtype, device: torch.device) ->
 # autograd plumbing
 # ------------------------------------------------------------------------------------------------
 
-class PromptAlgebraFn(torch.autograd.Function):
-    """(P_v, P_t) = the two prompt stacks of MuDPT as functions of its 10 trainable tensors
-    (trainers/mudpt.py:117-130, 143, 175; clip/model.py:534-541) -- mudpt_prompt_forward / _backward: 2 + 2 native
-    launches instead of ~48 framework ops at the very start and end of the step.  `frozen` = (ln_pre.weight,
-    ln_pre.bias, positional_embedding[1:1+n])."""
+PROMPT_NAMES = ("ctx", "deep", "We", "be", "Wd", "bd", "vctx", "vdeep", "Wv", "bv")
 
-    NAMES = ("ctx", "deep", "We", "be", "Wd", "bd", "vctx", "vdeep", "Wv", "bv")
+
+def prompt_algebra_forward(lib, eps, ln_g, ln_b, pos, train):
+    """(P_v, P_t, saved) = the two prompt stacks of MuDPT as functions of its 10 trainable tensors `train` (in
+    PROMPT_NAMES order) -- trainers/mudpt.py:117-130, 143, 175; clip/model.py:534-541 -- in 2 native launches
+    (mudpt_prompt_forward).  `saved` is what prompt_algebra_backward needs."""
+    t = [x.detach().contiguous() for x in train]
+    ctx, deep, vctx = t[0], t[1], t[6]
+    n, dt = ctx.shape
+    dv = vctx.shape[1]
+    depth = deep.shape[0] + 1
+    dev = ctx.device
+    a = _lib.PromptArgs()
+    a.n, a.depth, a.dt, a.dv, a.eps = n, depth, dt, dv, float(eps)
+    frozen = [ln_g.detach().float().contiguous(), ln_b.detach().float().contiguous(), pos.detach().float().contiguous()]
+    for k, x in zip(PROMPT_NAMES, t):
+        setattr(a, k, x.data_ptr())
+    a.ln_g, a.ln_b, a.pos = (x.data_ptr() for x in frozen)
+    P_v = torch.empty(depth, n, dv, device=dev, dtype=torch.float32)
+    P_t = torch.empty(depth, n, dt, device=dev, dtype=torch.float32)
+    ln_in = torch.empty(n, dv, device=dev, dtype=torch.float32)
+    a.P_v, a.P_t, a.ln_in = P_v.data_ptr(), P_t.data_ptr(), ln_in.data_ptr()
+    _lib.check(lib.mudpt_prompt_forward(C.byref(a), _lib.stream_ptr(dev)))
+    return P_v, P_t, (t, frozen, ln_in, float(eps))
+
+
+def prompt_algebra_backward(lib, saved, dP_v, dP_t, grads=None):
+    """Gradients of the 10 trainable tensors from (dP_v, dP_t) in 2 native launches (mudpt_prompt_backward).  Every
+    element of every gradient is written (no accumulation): `grads` may be the views of a flat all-reduce bucket."""
+    t, frozen, ln_in, eps = saved
+    ctx, deep, vctx = t[0], t[1], t[6]
+    n, dt = ctx.shape
+    dv = vctx.shape[1]
+    dev = ctx.device
+    a = _lib.PromptArgs()
+    a.n, a.depth, a.dt, a.dv, a.eps = n, deep.shape[0] + 1, dt, dv, eps
+    for k, x in zip(PROMPT_NAMES, t):
+        setattr(a, k, x.data_ptr())
+    a.ln_g, a.ln_b, a.pos = (x.data_ptr() for x in frozen)
+    a.ln_in = ln_in.data_ptr()
+    dP_v, dP_t = dP_v.float().contiguous(), dP_t.float().contiguous()
+    a.dP_v, a.dP_t = dP_v.data_ptr(), dP_t.data_ptr()
+    u = torch.empty(n, dv, device=dev, dtype=torch.float32)
+    if grads is None:
+        grads = [torch.empty_like(x, dtype=torch.float32) for x in t]
+    for g, x in zip(grads, t):
+        if g.shape != x.shape or g.dtype != torch.float32 or not g.is_contiguous() or g.device != x.device:
+            raise ValueError("mudpt_b200: prompt gradient buffer does not match its parameter")
+    a.u = u.data_ptr()
+    for k, g in zip(PROMPT_NAMES, grads):
+        setattr(a, "d_" + k, g.data_ptr())
+    _lib.check(lib.mudpt_prompt_backward(C.byref(a), _lib.stream_ptr(dev)))
+    return grads
+
+
+class PromptAlgebraFn(torch.autograd.Function):
+    """prompt_algebra_forward / _backward behind autograd: 2 + 2 native launches instead of ~48 framework ops at the
+    very start and end of the step.  `frozen` = (ln_pre.weight, ln_pre.bias, positional_embedding[1:1+n])."""
+
+    NAMES = PROMPT_NAMES
 
     @staticmethod
     def forward(ctx_, lib, eps, ln_g, ln_b, pos, *train):
-        t = [x.detach().contiguous() for x in train]
-        ctx, deep, We, be, Wd, bd, vctx, vdeep, Wv, bv = t
-        n, dt = ctx.shape
-        dv = vctx.shape[1]
-        depth = deep.shape[0] + 1
-        dev = ctx.device
-        a = _lib.PromptArgs()
-        a.n, a.depth, a.dt, a.dv, a.eps = n, depth, dt, dv, float(eps)
-        frozen = [ln_g.detach().float().contiguous(), ln_b.detach().float().contiguous(), pos.detach().float().contiguous()]
-        for k, x in zip(PromptAlgebraFn.NAMES, t):
-            setattr(a, k, x.data_ptr())
-        a.ln_g, a.ln_b, a.pos = (x.data_ptr() for x in frozen)
-        P_v = torch.empty(depth, n, dv, device=dev, dtype=torch.float32)
-        P_t = torch.empty(depth, n, dt, device=dev, dtype=torch.float32)
-        ln_in = torch.empty(n, dv, device=dev, dtype=torch.float32)
-        a.P_v, a.P_t, a.ln_in = P_v.data_ptr(), P_t.data_ptr(), ln_in.data_ptr()
-        _lib.check(lib.mudpt_prompt_forward(C.byref(a), _lib.stream_ptr(dev)))
-        ctx_.lib, ctx_.saved = lib, (t, frozen, ln_in, float(eps))
+        P_v, P_t, saved = prompt_algebra_forward(lib, eps, ln_g, ln_b, pos, train)
+        ctx_.lib, ctx_.saved = lib, saved
         return P_v, P_t
 
     @staticmethod
     def backward(ctx_, dP_v, dP_t):
-        t, frozen, ln_in, eps = ctx_.saved
-        ctx, deep, We, be, Wd, bd, vctx, vdeep, Wv, bv = t
-        n, dt = ctx.shape
-        dv = vctx.shape[1]
-        dev = ctx.device
-        a = _lib.PromptArgs()
-        a.n, a.depth, a.dt, a.dv, a.eps = n, deep.shape[0] + 1, dt, dv, eps
-        for k, x in zip(PromptAlgebraFn.NAMES, t):
-            setattr(a, k, x.data_ptr())
-        a.ln_g, a.ln_b, a.pos = (x.data_ptr() for x in frozen)
-        a.ln_in = ln_in.data_ptr()
-        dP_v, dP_t = dP_v.float().contiguous(), dP_t.float().contiguous()
-        a.dP_v, a.dP_t = dP_v.data_ptr(), dP_t.data_ptr()
-        u = torch.empty(n, dv, device=dev, dtype=torch.float32)
-        grads = [torch.empty_like(x, dtype=torch.float32) for x in t]
-        a.u = u.data_ptr()
-        for k, g in zip(PromptAlgebraFn.NAMES, grads):
-            setattr(a, "d_" + k, g.data_ptr())
-        _lib.check(ctx_.lib.mudpt_prompt_backward(C.byref(a), _lib.stream_ptr(dev)))
+        grads = prompt_algebra_backward(ctx_.lib, ctx_.saved, dP_v, dP_t)
         return (None, None, None, None, None, *grads)
 
 

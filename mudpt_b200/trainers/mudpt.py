@@ -27,7 +27,7 @@ import torch.nn.functional as F
 
 from .. import clip
 from .. import dist as mdist
-from ..engine import LogitsFn, PromptAlgebraFn, TextTowerDenseFn, TextTowerFn, VisionTowerFn
+from ..engine import prompt_algebra_forward, prompt_algebra_backward, LogitsFn, PromptAlgebraFn, TextTowerDenseFn, TextTowerFn, VisionTowerFn
 
 try:  # the Dassl engine is not in the reference tree nor in this image
     from dassl.engine import TRAINER_REGISTRY, TrainerX
@@ -316,19 +316,28 @@ class CustomCLIP(nn.Module):
         eng.text_set_classes(emb.float(), eot_all[lo:hi], seq_len)
         eng.class_key = key
 
+    def _native_prompt_args(self):
+        """(frozen inputs, the 10 trainable tensors in engine.PROMPT_NAMES order) of the native prompt algebra, or None
+        where it does not apply (variants with extra mixing layers, CPU stand-in engine, no deep prompts)."""
+        pl, ve = self.mudpt_prompt_learner, self.image_encoder
+        if not (type(self) is CustomCLIP and pl.ctx.is_cuda and pl.ctx.dtype == torch.float32 and pl.deep_prompts.shape[0] > 0
+                and os.environ.get("MUDPT_NATIVE_PROMPTS", "1") == "1"):
+            return None
+        frozen = (ve.ln_pre.eps, ve.ln_pre.weight, ve.ln_pre.bias, self.text_encoder.positional_embedding[1:1 + pl.n_ctx])
+        train = [pl.ctx, pl.deep_prompts, pl.embed_projection.weight, pl.embed_projection.bias, pl.deep_projections.weight,
+                 pl.deep_projections.bias, ve.visual_ctx, ve.visual_ctx_deep_prompts, ve.visual_ctx_deep_projections.weight,
+                 ve.visual_ctx_deep_projections.bias]
+        return frozen, train
+
     def prompt_stacks(self):
         """The two [depth, n_ctx, width] prompt stacks the towers splice in, as differentiable
         functions of the 10 trainable tensors (trainers/mudpt.py:127-128, :175; clip/model.py:534-539)."""
         pl, ve = self.mudpt_prompt_learner, self.image_encoder
-        if (type(self) is CustomCLIP and pl.ctx.is_cuda and pl.ctx.dtype == torch.float32 and pl.deep_prompts.shape[0] > 0
-                and os.environ.get("MUDPT_NATIVE_PROMPTS", "1") == "1"):
+        native = self._native_prompt_args()
+        if native is not None:
             # the same algebra as below in 2 (+2 backward) native launches
             from .. import _lib
-            return PromptAlgebraFn.apply(
-                _lib.load(), ve.ln_pre.eps, ve.ln_pre.weight, ve.ln_pre.bias, self.text_encoder.positional_embedding[1:1 + pl.n_ctx],
-                pl.ctx, pl.deep_prompts, pl.embed_projection.weight, pl.embed_projection.bias, pl.deep_projections.weight,
-                pl.deep_projections.bias, ve.visual_ctx, ve.visual_ctx_deep_prompts, ve.visual_ctx_deep_projections.weight,
-                ve.visual_ctx_deep_projections.bias)
+            return PromptAlgebraFn.apply(_lib.load(), *native[0], *native[1])
         visual_prompts = pl.deep_projections(pl.deep_prompts)                 # t2v deep
         shared_ctx = pl.embed_projection(pl.ctx.unsqueeze(0))                 # t2v shallow
         P_v = ve.prompt_stack(shared_ctx, visual_prompts)
@@ -364,7 +373,18 @@ class CustomCLIP(nn.Module):
         self._register_classes(device)
         self._cached_text_features = None  # the parameters are about to change: evaluation recomputes them
         world = mdist.world_size() if self.shard_classes else 1
-        P_v, P_t = self.prompt_stacks()
+        # Native prompt algebra without autograd when the trainable set is exactly its 10 tensors and none of them
+        # carries a gradient yet (the trainer zeroes them to None): the backward kernels write straight into one flat
+        # bucket whose views become the .grad tensors, and that bucket is what the ranks all-reduce.
+        native = self._native_prompt_args()
+        trainable = [p for p in self.parameters() if p.requires_grad]
+        direct = (native is not None and len(trainable) == len(native[1]) and {id(p) for p in trainable} == {id(p) for p in native[1]}
+                  and all(p.grad is None for p in trainable))
+        if direct:
+            from .. import _lib
+            P_v, P_t, prompt_saved = prompt_algebra_forward(_lib.load(), *native[0], native[1])
+        else:
+            P_v, P_t = self.prompt_stacks()
         n_cls = self.mudpt_prompt_learner.n_cls
         if host_batch and not self.overlap_towers:
             image, label = image.to(device), label.to(device)
@@ -412,16 +432,20 @@ class CustomCLIP(nn.Module):
             dP_t, _ = eng.text_backward(d_t_loc)
             main.wait_stream(side)
             dP_v.record_stream(main)
-        # the gradients of the trainable tensors live in one flat bucket (views): one all-reduce, no cat / copy-backs
-        trainable = [p for p in self.parameters() if p.requires_grad]
-        fg = self.__dict__.get("_flat_grads")
-        if fg is None or not fg.matches(trainable):
-            fg = mdist.FlatGrads(trainable)
-            self.__dict__["_flat_grads"] = fg
-        fg.attach(zero=True)
-        torch.autograd.backward([P_v, P_t], [dP_v, dP_t])
-        if world > 1:
-            fg.all_reduce()
+        if direct:
+            fg = self.__dict__.get("_flat_grads")
+            if fg is None or not fg.matches(native[1]):
+                fg = mdist.FlatGrads(native[1])
+                self.__dict__["_flat_grads"] = fg
+            prompt_algebra_backward(_lib.load(), prompt_saved, dP_v, dP_t, fg.views)
+            for p, v in zip(fg.params, fg.views):
+                p.grad = v
+            if world > 1:
+                fg.all_reduce()  # one collective on the bucket itself: no concatenation, no copies back
+        else:
+            torch.autograd.backward([P_v, P_t], [dP_v, dP_t])
+            if world > 1:
+                mdist.all_reduce_grads(trainable)
         return loss, logits
 
     def _publish_loss(self, loss, world):
