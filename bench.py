@@ -69,7 +69,7 @@ def _gemm_traffic():
     lib = os.path.join(ROOT, "mudpt_b200", "lib", "libmudpt_b200.so")
     src = hashlib.sha256()
     csrc = os.path.join(ROOT, "mudpt_b200", "csrc")
-    for f in sorted(os.listdir(csrc)):
+    for f in ("api.cu", "common.cuh", "gemm.cu", "gemm.h"):  # what decides the step's GEMM launches and their traffic
         src.update(f.encode())
         src.update(open(os.path.join(csrc, f), "rb").read())
     if d.get("csrc_sha256") != src.hexdigest():

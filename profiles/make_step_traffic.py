@@ -14,7 +14,7 @@ Here (no GPU needed):
 
 Every step of `bench.py --quick` (warm-ups, timed, instrumented) launches the same GEMMs, so the mean over all captured
 launches is the mean over the launches of one step -- the population bench.py averages the algorithmic bytes over.
-The output names the build (sha256 of csrc/) it was captured from; bench.py reports `traffic: null` for any other build.
+The output names the build (sha256 of the GEMM-relevant sources: api.cu, common.cuh, gemm.cu, gemm.h) it was captured from; bench.py reports `traffic: null` for any other build.
 """
 import csv
 import hashlib
@@ -26,10 +26,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+# the sources that decide what the GEMM launches of a step are and how they move data: the kernel, its helpers, and the
+# tower orchestration that chooses the launches (attention / head / row kernels do not change GEMM traffic)
+GEMM_SOURCES = ("api.cu", "common.cuh", "gemm.cu", "gemm.h")
+
+
 def csrc_digest():
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "mudpt_b200", "csrc")
-    for f in sorted(os.listdir(csrc)):
+    for f in GEMM_SOURCES:
         h.update(f.encode())
         h.update(open(os.path.join(csrc, f), "rb").read())
     return h.hexdigest()
