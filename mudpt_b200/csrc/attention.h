@@ -16,7 +16,8 @@ const char* attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, cons
                           float* dsum, __nv_bfloat16* dqkv, int S, int L, int H, int d, bool causal, cudaStream_t stream,
                           const float2* ln_sb = nullptr, float2* ln_dots = nullptr);
 // tcgen05 / TMEM path (attention_tc.cu); attention_fwd dispatches to it when eligible.
-// mode: 0 = never, 1 = default (non-causal sequences of 129..256 tokens: the vision tower), 2 = every L <= 256
+// mode: 0 = never, 1 = default (forward: non-causal sequences of 129..256 tokens; backward: 65..80 and 129..256 tokens),
+//       2 = every length the kernels support
 void attention_tc_set_mode(int mode);
 bool attention_tc_fwd_eligible(int L, bool causal);
 bool attention_tc_bwd_eligible(int L, bool causal);

@@ -1033,6 +1033,327 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) attn_tc_bwd_pp_kernel(const __
   }
 }
 
+// =======================================================================================
+// Backward for two-block sequences (128 < L <= 256: the vision tower, 199 tokens) in ONE launch, PERSISTENT: one CTA per
+// SM walks the (sequence, head) problems with the whole problem resident -- Q, dO, K, V tiles [Lb x 64] in shared
+// memory, every accumulator in the 512 TMEM columns -- and nothing is recomputed (the two-launch kernel above computes
+// every score and every exp twice).  Rows of the score tiles are KEYS (two blocks kb of up to 128), columns are QUERIES
+// in chunks qc of 64; one step = (kb, qc):
+//     S^T = K_kb Q_qc^T, dP^T = V_kb dO_qc^T        128 x 64 each, TMEM columns [128 b, +64) / [128 b + 64, +64), b = step & 1
+//     element-wise, thread = key row, 8 warps (each half of the CTA takes 32 of the 64 query columns):
+//         P^T = exp2(S^T c - lse_q), dS^T = P^T (dP^T - D_q)   -> bf16 slabs [key][query] (128B swizzle)
+//     dV_kb += P^T dO_qc, dK_kb += dS^T Q_qc         A = slab K-major, B = dO / Q chunk MN-major       (columns 320 / 256)
+//     after the second chunk of a query block qb:  dQ_qb += dS K_kb   A = the two dS^T slabs read MN-major (M = 128
+//         queries: the transpose is free), B = K_kb MN-major                                        (columns 384 + 64 qb)
+// The score buffers are double: the MMA thread issues the scores of step i + 2 as soon as step i's slabs are written, so
+// the element-wise warps -- the bottleneck -- never wait for a product.  dK / dV leave after the key block's last step,
+// dQ at the end, through the problem's own (dead) K / V / Q tiles and three TMA stores.
+// D_q = rowsum(dO_q * O_q) is computed per problem by thread q from the dO tile and the O row in global memory.
+// Padding: TMA zero-fills rows past the sequence; key rows >= L and query columns >= L are forced to P = dS = 0 by a
+// select (the 128-row A operands of the second key block run past the tiles into whatever follows: finite or not, those
+// rows never reach an output that is stored).
+// =======================================================================================
+static constexpr int TCL_THREADS = 320;  // 8 element-wise warps + TMA warp + MMA warp
+__host__ __device__ inline int tcl_smem_bytes(int Lb) { return 4 * Lb * 128 + 3 * TC_SLAB + 2 * 256 * 4 + 256 + 1024; }
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                                          const __grid_constant__ CUtensorMap map_do,
+                                                                          const __grid_constant__ CUtensorMap map_dqkv,
+                                                                          const bf16* __restrict__ o, const float* __restrict__ lse2,
+                                                                          const int L, const int H, const int d, const int Lb,
+                                                                          const int n_items, const float scale, const float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_bytes = Lb * 128;  // Lb = sequence length rounded up to 16 rows (129..256): a multiple of 2048 B
+  uint8_t* tQ = smem;
+  uint8_t* tdO = tQ + tile_bytes;
+  uint8_t* tK = tdO + tile_bytes;
+  uint8_t* tV = tK + tile_bytes;
+  uint8_t* slabP = tV + tile_bytes;   // P^T of the step          [128 keys][64 queries]
+  uint8_t* slabS = slabP + TC_SLAB;   // dS^T, slot = qc & 1: the two slabs are the 128 queries of a query block
+  float* sLse = reinterpret_cast<float*>(slabS + 2 * TC_SLAB);  // [256] per query
+  float* sD = sLse + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  uint64_t* bar_full = bars;        // tiles of the problem loaded
+  uint64_t* bar_empty = bars + 1;   // outputs stored: the tiles may be refilled
+  uint64_t* bar_s = bars + 2;       // [2] scores of a step in TMEM
+  uint64_t* bar_p = bars + 4;       // slabs of the step written (256)
+  uint64_t* bar_f = bars + 5;       // output MMAs of the step done
+  uint64_t* bar_kv = bars + 6;      // dK / dV of the key block complete
+  uint64_t* bar_kvfree = bars + 7;  // ... and drained (256)
+  uint64_t* bar_qfree = bars + 8;   // dQ drained (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int nq = (Lb + 63) >> 6;  // query chunks (3 or 4)
+  const int n_steps = 2 * nq;
+
+  if (warp == 9) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_qkv);
+      tma_prefetch_desc(&map_do);
+      tma_prefetch_desc(&map_dqkv);
+      mbar_init(bar_full, 1);
+      mbar_init(bar_empty, 1);
+      mbar_init(&bar_s[0], 1);
+      mbar_init(&bar_s[1], 1);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_f, 1);
+      mbar_init(bar_kv, 1);
+      mbar_init(bar_kvfree, 256);
+      mbar_init(bar_qfree, 256);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int k = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+        const int s = it / H, h = it - s * H;
+        if (k > 0) mbar_wait(bar_empty, (k - 1) & 1);
+        mbar_expect_tx(bar_full, static_cast<uint32_t>(4 * tile_bytes));
+        tma_load_3d(tK, &map_qkv, bar_full, d + h * 64, 0, s);
+        tma_load_3d(tQ, &map_qkv, bar_full, h * 64, 0, s);
+        tma_load_3d(tV, &map_qkv, bar_full, 2 * d + h * 64, 0, s);
+        tma_load_3d(tdO, &map_do, bar_full, h * 64, 0, s);
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_out = make_idesc_bf16(TC_ROWS, 64) | kIdescBMnMajor;
+      const uint32_t idesc_dq = make_idesc_bf16(TC_ROWS, 64) | kIdescAMnMajor | kIdescBMnMajor;
+      const uint64_t dQt = make_smem_desc_sw128(smem_u32(tQ)), dOt = make_smem_desc_sw128(smem_u32(tdO));
+      const uint64_t dKt = make_smem_desc_sw128(smem_u32(tK)), dVt = make_smem_desc_sw128(smem_u32(tV));
+      const uint64_t dPk = make_smem_desc_sw128(smem_u32(slabP)), dSk = make_smem_desc_sw128(smem_u32(slabS));
+      // MN-major A over the two dS^T slabs (M = 128 queries): leading-dimension byte offset = slab stride
+      const uint64_t dSm = (dSk & ~(static_cast<uint64_t>(0x3FFF) << 16)) | (static_cast<uint64_t>(TC_SLAB >> 4) << 16);
+      auto issue_scores = [&](int i) {
+        const int kb = i >= nq ? 1 : 0, qc = i - kb * nq, b = i & 1;
+        const int nr = min(64, Lb - qc * 64);
+        const uint32_t idesc_s = make_idesc_bf16(TC_ROWS, nr);
+        const uint64_t aK = dKt + static_cast<uint64_t>(kb * (TC_SLAB >> 4)), aV = dVt + static_cast<uint64_t>(kb * (TC_SLAB >> 4));
+        const uint64_t bQ = dQt + static_cast<uint64_t>(qc * 512), bO = dOt + static_cast<uint64_t>(qc * 512);
+        const uint32_t col = tmem_base + static_cast<uint32_t>(b * 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(col, aK + static_cast<uint64_t>(j * 2), bQ + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(col + 64u, aV + static_cast<uint64_t>(j * 2), bO + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
+        umma_commit(&bar_s[b]);
+      };
+      uint32_t g = 0;  // steps issued so far (all problems)
+      int k = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+        mbar_wait(bar_full, k & 1);
+        tc_fence_after();
+        issue_scores(0);
+        issue_scores(1);
+        for (int i = 0; i < n_steps; ++i, ++g) {
+          const int kb = i >= nq ? 1 : 0, qc = i - kb * nq;
+          const int nr = min(64, Lb - qc * 64);
+          mbar_wait(bar_p, g & 1);  // the step's slabs are written (and its score columns read)
+          if (qc == 0) {
+            const int m = 2 * k + kb;
+            if (m > 0) mbar_wait(bar_kvfree, (m - 1) & 1);  // the previous key block's dK / dV have left TMEM
+          }
+          tc_fence_after();
+          const uint64_t bQ = dQt + static_cast<uint64_t>(qc * 512), bO = dOt + static_cast<uint64_t>(qc * 512);
+          const uint64_t aS = dSk + static_cast<uint64_t>((qc & 1) * (TC_SLAB >> 4));
+          const int nj = nr >> 4;
+          for (int j = 0; j < nj; ++j) {  // contraction over the chunk's queries, 16 per instruction
+            const uint32_t acc = static_cast<uint32_t>(qc != 0 || j != 0);
+            umma_bf16(tmem_base + 256u, aS + static_cast<uint64_t>(j * 2), bQ + static_cast<uint64_t>(j * 128), idesc_out, acc);   // dK += dS^T Q
+            umma_bf16(tmem_base + 320u, dPk + static_cast<uint64_t>(j * 2), bO + static_cast<uint64_t>(j * 128), idesc_out, acc);  // dV += P^T dO
+          }
+          if ((qc & 1) || qc == nq - 1) {  // both chunks of the query block are in the slabs: dQ_qb += dS K_kb
+            const int qb = qc >> 1;
+            if (kb == 0 && qb == 0 && k > 0) {
+              mbar_wait(bar_qfree, (k - 1) & 1);  // the previous problem's dQ has left TMEM
+              tc_fence_after();
+            }
+            const int nkk = (kb ? Lb - TC_ROWS : TC_ROWS) >> 4;
+            const uint64_t bK = dKt + static_cast<uint64_t>(kb * (TC_SLAB >> 4));
+            for (int j = 0; j < nkk; ++j)  // contraction over the block's keys
+              umma_bf16(tmem_base + 384u + static_cast<uint32_t>(qb * 64), dSm + static_cast<uint64_t>(j * 128), bK + static_cast<uint64_t>(j * 128), idesc_dq,
+                        static_cast<uint32_t>(kb != 0 || j != 0));
+          }
+          umma_commit(bar_f);
+          if (qc == nq - 1) umma_commit(bar_kv);
+          if (i + 2 < n_steps) issue_scores(i + 2);
+        }
+      }
+    }
+  } else {
+    // ===================== element-wise + epilogue: thread = key row of the block; half = 32 of the chunk's 64 query columns =====================
+    const int quad = warp & 3, half = warp >> 2;
+    const int t = quad * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
+    uint32_t g = 0;
+    int k = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+      const int s = it / H, h = it - s * H;
+      {  // lse and D = rowsum(dO * O) of query q = threadIdx.x
+        const int q = threadIdx.x;
+        uint4 ov[8];
+        float lse = 0.f;
+        if (q < L) {
+          const uint4* op = reinterpret_cast<const uint4*>(o + (static_cast<size_t>(s) * L + q) * d + h * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) ov[c] = __ldg(op + c);
+          lse = lse2[(static_cast<size_t>(s) * H + h) * L + q];
+        }
+        mbar_wait(bar_full, k & 1);
+        float D = 0.f;
+        if (q < L) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 a = *reinterpret_cast<const uint4*>(tdO + q * 128 + ((c ^ (q & 7)) << 4));
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16(aw[e]), y = unpack_bf16(bw[e]);
+              D += x.x * y.x + x.y * y.y;
+            }
+          }
+        }
+        sLse[q] = lse;
+        sD[q] = D;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      for (int i = 0; i < n_steps; ++i, ++g) {
+        const int kb = i >= nq ? 1 : 0, qc = i - kb * nq, b = i & 1;
+        const int key = kb * TC_ROWS + t;
+        const int col0 = qc * 64 + half * 32;   // first query of this thread's 32 columns
+        const bool active = col0 < Lb;          // (warp-uniform) the chunk has columns for this half
+        mbar_wait(&bar_s[b], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t pp[16], ds[16];
+        if (active) {
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32(trow + static_cast<uint32_t>(b * 128 + half * 32), sv);
+          tmem_ld_32x32(trow + static_cast<uint32_t>(b * 128 + 64 + half * 32), dv);
+          tmem_ld_wait_regs(sv);
+          tmem_ld_wait_regs(dv);
+          const bool key_ok = key < L;
+          const bool tail = col0 + 32 > L;  // (warp-uniform) some of the 32 queries do not exist
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int c = col0 + 2 * e;
+            const float2 l2 = *reinterpret_cast<const float2*>(sLse + c);
+            const float2 d2 = *reinterpret_cast<const float2*>(sD + c);
+            float p0, p1;
+            f2_unpack(f2_fma(f2_pack_u(sv[2 * e], sv[2 * e + 1]), c2, f2_pack(-l2.x, -l2.y)), p0, p1);
+            p0 = exp2f(p0);
+            p1 = exp2f(p1);
+            float x, y;
+            f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), f2_pack(-d2.x, -d2.y))), x, y);  // dS (unscaled)
+            bool ok0 = key_ok, ok1 = key_ok;
+            if (CAUSAL) { ok0 = ok0 && key <= c; ok1 = ok1 && key <= c + 1; }
+            if (tail) { ok0 = ok0 && c < L; ok1 = ok1 && c + 1 < L; }
+            // selects, not products: masked positions may hold stale TMEM / out-of-tile operands (Inf, NaN)
+            pp[e] = pack_bf16(ok0 ? p0 : 0.f, ok1 ? p1 : 0.f);
+            ds[e] = pack_bf16(ok0 ? x : 0.f, ok1 ? y : 0.f);
+          }
+        }
+        if (g > 0) mbar_wait(bar_f, (g - 1) & 1);  // the previous step's output MMAs have read the slabs
+        if (active) {
+          uint8_t* sS = slabS + (qc & 1) * TC_SLAB;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q4) ^ (t & 7)) << 4));
+            *reinterpret_cast<uint4*>(slabP + off) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+            *reinterpret_cast<uint4*>(sS + off) = make_uint4(ds[4 * q4], ds[4 * q4 + 1], ds[4 * q4 + 2], ds[4 * q4 + 3]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(bar_p);
+        if (qc == nq - 1) {
+          // the key block is complete: dK, dV (row = key, this half's 32 head columns) into the block's dead K / V rows
+          mbar_wait(bar_kv, (2 * k + kb) & 1);
+          tc_fence_after();
+          uint32_t o0[32], o1[32];
+          tmem_ld_32x32(trow + 256u + static_cast<uint32_t>(half * 32), o0);
+          tmem_ld_32x32(trow + 320u + static_cast<uint32_t>(half * 32), o1);
+          tmem_ld_wait_regs(o0);
+          tmem_ld_wait_regs(o1);
+          tc_fence_before();
+          mbar_arrive(bar_kvfree);
+          if (key < Lb) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint32_t off = static_cast<uint32_t>(key * 128 + (((half * 4 + q4) ^ (key & 7)) << 4));
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q4 + 2 * e]) * scale, __uint_as_float(o0[8 * q4 + 2 * e + 1]) * scale);
+              *reinterpret_cast<uint4*>(tK + off) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q4 + 2 * e]), __uint_as_float(o1[8 * q4 + 2 * e + 1]));
+              *reinterpret_cast<uint4*>(tV + off) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+      // dQ of both query blocks (row = query t and 128 + t) into the dead Q tile
+      mbar_wait(bar_f, (g - 1) & 1);
+      tc_fence_after();
+      {
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(trow + 384u + static_cast<uint32_t>(half * 32), o0);
+        tmem_ld_32x32(trow + 448u + static_cast<uint32_t>(half * 32), o1);
+        tmem_ld_wait_regs(o0);
+        tmem_ld_wait_regs(o1);
+        tc_fence_before();
+        mbar_arrive(bar_qfree);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q4) ^ (t & 7)) << 4));
+          uint32_t w[4];
+          if (t < Lb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q4 + 2 * e]) * scale, __uint_as_float(o0[8 * q4 + 2 * e + 1]) * scale);
+            *reinterpret_cast<uint4*>(tQ + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          if (TC_ROWS + t < Lb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q4 + 2 * e]) * scale, __uint_as_float(o1[8 * q4 + 2 * e + 1]) * scale);
+            *reinterpret_cast<uint4*>(tQ + TC_SLAB + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        tma_store_3d(&map_dqkv, tQ, h * 64, 0, s);
+        tma_store_3d(&map_dqkv, tK, d + h * 64, 0, s);
+        tma_store_3d(&map_dqkv, tV, 2 * d + h * 64, 0, s);
+        bulk_commit();
+        bulk_wait_read<0>();  // the tiles have been read: the next problem may be loaded over them
+        mbar_arrive(bar_empty);
+      }
+    }
+    if (threadIdx.x == 0) bulk_wait<0>();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 static int g_tc_mode = -1;
 static int tc_enabled() {
   if (g_tc_mode < 0) {
@@ -1086,7 +1407,8 @@ bool attention_tc_bwd_eligible(int L, bool causal) {
   if (en == 2) return true;
   // default: the two-problems-in-flight persistent kernel where it wins -- 65..80-token sequences (the 77-token text
   // tower: 141 us per layer against 171 us for the warp-MMA kernel, 96 us of Q / K / V / dO / dQKV traffic)
-  return L > 64 && L <= 80;
+  // ... and the resident-problem kernel for two-block sequences (the 199-token vision tower)
+  return (L > 64 && L <= 80) || (L > TC_ROWS && L <= 2 * TC_ROWS);
 }
 
 const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv,
@@ -1119,6 +1441,34 @@ const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, co
                n_items, scale_s, sl2_s);
     count_launch(1);
     return launch_status("attention bwd (tcgen05, short) launch failed");
+  }
+  if (L <= 2 * TC_ROWS) {  // two-block sequences: the whole problem resident, one launch
+    const int Lb = (L + 15) & ~15;
+    CUtensorMap mq, mdo, mo;
+    if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, Lb, &mq))) return e;
+    if ((e = tensor_map_3d_bf16(d_o, d, L, S, d, static_cast<long long>(d) * L, Lb, &mdo))) return e;
+    if ((e = tensor_map_3d_bf16(dqkv, 3 * d, L, S, ld, ld * L, Lb, &mo))) return e;
+    const int smem = tcl_smem_bytes(Lb);
+    static int n_sms_l = 0;
+    if (n_sms_l == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sms_l, cudaDevAttrMultiProcessorCount, dev);
+      if (n_sms_l <= 0) n_sms_l = 148;
+    }
+    const int n_items = S * H;
+    const int grid = n_items < n_sms_l ? n_items : n_sms_l;
+    auto kern = causal ? attn_tc_bwd_long_kernel<true> : attn_tc_bwd_long_kernel<false>;
+    static bool attr_long[2] = {false, false};
+    if (!attr_long[causal ? 1 : 0]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl_smem_bytes(256)) != cudaSuccess)
+        return "attention (tcgen05 backward, resident): cudaFuncSetAttribute failed";
+      attr_long[causal ? 1 : 0] = true;
+    }
+    launch_pdl(kern, dim3(grid), dim3(TCL_THREADS), static_cast<size_t>(smem), stream, mq, mdo, mo, o, lse2, L, H, d, Lb, n_items, 0.125f,
+               0.125f * 1.4426950408889634f);
+    count_launch(1);
+    return launch_status("attention bwd (tcgen05, resident) launch failed");
   }
   CUtensorMap m128, m64, mdo128, mdo64, mout;
   if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, TC_ROWS, &m128))) return e;

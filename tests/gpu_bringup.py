@@ -458,6 +458,9 @@ def group_attention(res):
     # tile-boundary lengths of the short-sequence kernels (1 / 2 / 5 / 8 tiles, both masks) and the first
     # lengths that fall back to the generic ones
     shapes += [(2, L, 2, c) for L in (2, 15, 17, 31, 32, 33, 48, 79, 80, 81, 96, 127, 128, 129, 144) for c in (0, 1)]
+    # the resident two-block tcgen05 backward: 3 / 4 query chunks, every tail width, more problems than SMs
+    shapes += [(2, L, 2, c) for L in (145, 160, 176, 192, 193, 208, 224, 241, 255, 256) for c in (0, 1)]
+    shapes += [(16, 199, 12, 0), (9, 197, 20, 0)]
     for (S, L, H, causal) in shapes:
         d = H * 64
         qkv = torch.randn(S * L, 3 * d, device=dev).bfloat16()
