@@ -1073,8 +1073,8 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
   uint8_t* tV = tK + tile_bytes;
   uint8_t* slabP = tV + tile_bytes;   // P^T of the step          [128 keys][64 queries]
   uint8_t* slabS = slabP + TC_SLAB;   // dS^T, slot = qc & 1: the two slabs are the 128 queries of a query block
-  float* sLse = reinterpret_cast<float*>(slabS + 2 * TC_SLAB);  // [256] per query
-  float* sD = sLse + 256;
+  float* sLse = reinterpret_cast<float*>(slabS + 2 * TC_SLAB);  // [256] per query: -lse
+  float* sD = sLse + 256;                                       //                  -D
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
   uint64_t* bar_full = bars;        // tiles of the problem loaded
   uint64_t* bar_empty = bars + 1;   // outputs stored: the tiles may be refilled
@@ -1229,44 +1229,95 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
             }
           }
         }
-        sLse[q] = lse;
-        sD[q] = D;
+        sLse[q] = -lse;  // both are only ever subtracted
+        sD[q] = -D;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      // dK, dV of a complete key block (row = key, this half's 32 head columns) into the block's dead K / V rows
+      auto drain_kv = [&](int kb) {
+        const int key = kb * TC_ROWS + t;
+        mbar_wait(bar_kv, (2 * k + kb) & 1);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(trow + 256u + static_cast<uint32_t>(half * 32), o0);
+        tmem_ld_32x32(trow + 320u + static_cast<uint32_t>(half * 32), o1);
+        tmem_ld_wait_regs(o0);
+        tmem_ld_wait_regs(o1);
+        tc_fence_before();
+        mbar_arrive(bar_kvfree);
+        if (key < Lb) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t off = static_cast<uint32_t>(key * 128 + (((half * 4 + q4) ^ (key & 7)) << 4));
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q4 + 2 * e]) * scale, __uint_as_float(o0[8 * q4 + 2 * e + 1]) * scale);
+            *reinterpret_cast<uint4*>(tK + off) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q4 + 2 * e]), __uint_as_float(o1[8 * q4 + 2 * e + 1]));
+            *reinterpret_cast<uint4*>(tV + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      };
       for (int i = 0; i < n_steps; ++i, ++g) {
         const int kb = i >= nq ? 1 : 0, qc = i - kb * nq, b = i & 1;
         const int key = kb * TC_ROWS + t;
-        const int col0 = qc * 64 + half * 32;   // first query of this thread's 32 columns
-        const bool active = col0 < Lb;          // (warp-uniform) the chunk has columns for this half
+        const int key0 = kb * TC_ROWS + quad * 32;  // first key of the warp
+        const int col0 = qc * 64 + half * 32;       // first query of this thread's 32 columns
+        const bool active = col0 < Lb;              // (warp-uniform) the chunk has columns for this half
+        // (warp-uniform) every (key, query) of the warp's 32 x 32 piece is live / none is: no masks, or no math at all
+        const bool all_live = key0 + 32 <= L && col0 + 32 <= L && (!CAUSAL || key0 + 31 <= col0);
+        const bool none_live = key0 >= L || col0 >= L || (CAUSAL && key0 > col0 + 31);
         mbar_wait(&bar_s[b], (g >> 1) & 1);
         tc_fence_after();
         uint32_t pp[16], ds[16];
-        if (active) {
+        if (active && !none_live) {
           uint32_t sv[32], dv[32];
           tmem_ld_32x32(trow + static_cast<uint32_t>(b * 128 + half * 32), sv);
           tmem_ld_32x32(trow + static_cast<uint32_t>(b * 128 + 64 + half * 32), dv);
           tmem_ld_wait_regs(sv);
           tmem_ld_wait_regs(dv);
-          const bool key_ok = key < L;
-          const bool tail = col0 + 32 > L;  // (warp-uniform) some of the 32 queries do not exist
+          if (all_live) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int c = col0 + 2 * e;
-            const float2 l2 = *reinterpret_cast<const float2*>(sLse + c);
-            const float2 d2 = *reinterpret_cast<const float2*>(sD + c);
-            float p0, p1;
-            f2_unpack(f2_fma(f2_pack_u(sv[2 * e], sv[2 * e + 1]), c2, f2_pack(-l2.x, -l2.y)), p0, p1);
-            p0 = exp2f(p0);
-            p1 = exp2f(p1);
-            float x, y;
-            f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), f2_pack(-d2.x, -d2.y))), x, y);  // dS (unscaled)
-            bool ok0 = key_ok, ok1 = key_ok;
-            if (CAUSAL) { ok0 = ok0 && key <= c; ok1 = ok1 && key <= c + 1; }
-            if (tail) { ok0 = ok0 && c < L; ok1 = ok1 && c + 1 < L; }
-            // selects, not products: masked positions may hold stale TMEM / out-of-tile operands (Inf, NaN)
-            pp[e] = pack_bf16(ok0 ? p0 : 0.f, ok1 ? p1 : 0.f);
-            ds[e] = pack_bf16(ok0 ? x : 0.f, ok1 ? y : 0.f);
+            for (int e4 = 0; e4 < 8; ++e4) {  // 4 queries per iteration
+              const float4 nl = *reinterpret_cast<const float4*>(sLse + col0 + 4 * e4);  // -lse
+              const float4 nD = *reinterpret_cast<const float4*>(sD + col0 + 4 * e4);    // -D
+              float p0, p1, p2, p3;
+              f2_unpack(f2_fma(f2_pack_u(sv[4 * e4], sv[4 * e4 + 1]), c2, f2_pack(nl.x, nl.y)), p0, p1);
+              f2_unpack(f2_fma(f2_pack_u(sv[4 * e4 + 2], sv[4 * e4 + 3]), c2, f2_pack(nl.z, nl.w)), p2, p3);
+              p0 = exp2f(p0); p1 = exp2f(p1); p2 = exp2f(p2); p3 = exp2f(p3);
+              float x0, x1, x2, x3;
+              f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack_u(dv[4 * e4], dv[4 * e4 + 1]), f2_pack(nD.x, nD.y))), x0, x1);
+              f2_unpack(f2_mul(f2_pack(p2, p3), f2_add(f2_pack_u(dv[4 * e4 + 2], dv[4 * e4 + 3]), f2_pack(nD.z, nD.w))), x2, x3);
+              pp[2 * e4] = pack_bf16(p0, p1);
+              pp[2 * e4 + 1] = pack_bf16(p2, p3);
+              ds[2 * e4] = pack_bf16(x0, x1);
+              ds[2 * e4 + 1] = pack_bf16(x2, x3);
+            }
+          } else {
+            // live columns of this thread's key: [c_lo, c_hi)
+            const int c_hi = key < L ? L : 0;
+            const int c_lo = CAUSAL ? key : 0;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int c = col0 + 2 * e;
+              const float2 nl = *reinterpret_cast<const float2*>(sLse + c);
+              const float2 nD = *reinterpret_cast<const float2*>(sD + c);
+              float p0, p1;
+              f2_unpack(f2_fma(f2_pack_u(sv[2 * e], sv[2 * e + 1]), c2, f2_pack(nl.x, nl.y)), p0, p1);
+              p0 = exp2f(p0);
+              p1 = exp2f(p1);
+              float x, y;
+              f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), f2_pack(nD.x, nD.y))), x, y);  // dS (unscaled)
+              // selects, not products: masked positions may hold stale TMEM / out-of-tile operands (Inf, NaN)
+              const bool ok0 = c >= c_lo && c < c_hi, ok1 = c + 1 >= c_lo && c + 1 < c_hi;
+              pp[e] = pack_bf16(ok0 ? p0 : 0.f, ok1 ? p1 : 0.f);
+              ds[e] = pack_bf16(ok0 ? x : 0.f, ok1 ? y : 0.f);
+            }
           }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { pp[e] = 0u; ds[e] = 0u; }
         }
         if (g > 0) mbar_wait(bar_f, (g - 1) & 1);  // the previous step's output MMAs have read the slabs
         if (active) {
@@ -1281,32 +1332,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(bar_p);
-        if (qc == nq - 1) {
-          // the key block is complete: dK, dV (row = key, this half's 32 head columns) into the block's dead K / V rows
-          mbar_wait(bar_kv, (2 * k + kb) & 1);
-          tc_fence_after();
-          uint32_t o0[32], o1[32];
-          tmem_ld_32x32(trow + 256u + static_cast<uint32_t>(half * 32), o0);
-          tmem_ld_32x32(trow + 320u + static_cast<uint32_t>(half * 32), o1);
-          tmem_ld_wait_regs(o0);
-          tmem_ld_wait_regs(o1);
-          tc_fence_before();
-          mbar_arrive(bar_kvfree);
-          if (key < Lb) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const uint32_t off = static_cast<uint32_t>(key * 128 + (((half * 4 + q4) ^ (key & 7)) << 4));
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q4 + 2 * e]) * scale, __uint_as_float(o0[8 * q4 + 2 * e + 1]) * scale);
-              *reinterpret_cast<uint4*>(tK + off) = make_uint4(w[0], w[1], w[2], w[3]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q4 + 2 * e]), __uint_as_float(o1[8 * q4 + 2 * e + 1]));
-              *reinterpret_cast<uint4*>(tV + off) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-        }
+        // the first key block's dK / dV leave one step late: its last output MMAs run under this step's math
+        if (kb == 1 && qc == 0) drain_kv(0);
       }
+      drain_kv(1);
       // dQ of both query blocks (row = query t and 128 + t) into the dead Q tile
       mbar_wait(bar_f, (g - 1) & 1);
       tc_fence_after();
