@@ -1035,10 +1035,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) attn_tc_bwd_pp_kernel(const __
 
 // =======================================================================================
 // Backward for two-block sequences (128 < L <= 256: the vision tower, 199 tokens) in ONE launch, PERSISTENT: one CTA per
-// SM walks the (sequence, head) problems with the whole problem resident -- Q, dO, K, V tiles [Lb x 64] in shared
-// memory, every accumulator in the 512 TMEM columns -- and nothing is recomputed (the two-launch kernel above computes
-// every score and every exp twice).  Rows of the score tiles are KEYS (two blocks kb of up to 128), columns are QUERIES
-// in chunks qc of 64; one step = (kb, qc):
+// SM walks the (sequence, head) problems with the whole problem resident -- Q and dO tiles [Lb x 64], the K / V rows of
+// the current key block in shared memory, every accumulator in the 512 TMEM columns -- and nothing is recomputed (the
+// two-launch kernel above computes every score and every exp twice).  Rows of the score tiles are KEYS (two blocks kb of
+// up to 128), columns are QUERIES in chunks qc of 64; one step = (kb, qc):
 //     S^T = K_kb Q_qc^T, dP^T = V_kb dO_qc^T        128 x 64 each, TMEM columns [128 b, +64) / [128 b + 64, +64), b = step & 1
 //     element-wise, thread = key row, 8 warps (each half of the CTA takes 32 of the 64 query columns):
 //         P^T = exp2(S^T c - lse_q), dS^T = P^T (dP^T - D_q)   -> bf16 slabs [key][query] (128B swizzle)
@@ -1046,58 +1046,72 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) attn_tc_bwd_pp_kernel(const __
 //     after the second chunk of a query block qb:  dQ_qb += dS K_kb   A = the two dS^T slabs read MN-major (M = 128
 //         queries: the transpose is free), B = K_kb MN-major                                        (columns 384 + 64 qb)
 // The score buffers are double: the MMA thread issues the scores of step i + 2 as soon as step i's slabs are written, so
-// the element-wise warps -- the bottleneck -- never wait for a product.  dK / dV leave after the key block's last step,
-// dQ at the end, through the problem's own (dead) K / V / Q tiles and three TMA stores.
-// D_q = rowsum(dO_q * O_q) is computed per problem by thread q from the dO tile and the O row in global memory.
-// Padding: TMA zero-fills rows past the sequence; key rows >= L and query columns >= L are forced to P = dS = 0 by a
-// select (the 128-row A operands of the second key block run past the tiles into whatever follows: finite or not, those
-// rows never reach an output that is stored).
+// the element-wise warps -- the bottleneck -- never wait for a product.  dK / dV leave one step after the key block's last
+// step, dQ at the end, through the problem's own (dead) K / V / Q tiles and TMA stores.
+// Loads never sit on the critical path when the tiles fit twice (Lb <= 208): the Q / dO tiles are double-buffered over
+// problems, the two K / V slots are a ring over key blocks (the next problem's first block is loaded while the second
+// block of this one computes), and D_q = rowsum(dO_q * O_q) of the NEXT problem is computed in the middle of this one
+// (thread q; O row loaded from global memory a step earlier) into a second copy of the per-query arrays.
+// Padding: TMA zero-fills rows past the sequence; (key, query) pairs outside it are forced to P = dS = 0 by a select
+// wherever a warp's 32 x 32 piece is not entirely inside.
 // =======================================================================================
-static constexpr int TCL_THREADS = 320;  // 8 element-wise warps + TMA warp + MMA warp
-__host__ __device__ inline int tcl_smem_bytes(int Lb) { return 4 * Lb * 128 + 3 * TC_SLAB + 2 * 256 * 4 + 256 + 1024; }
+static constexpr int TCL_THREADS = 320;          // 8 element-wise warps + TMA warp + MMA warp
+static constexpr int TCL_KV_SLOT = 2 * TC_SLAB;  // K block | V block, 128 rows each
+__host__ __device__ inline int tcl_fixed_bytes() { return 2 * TCL_KV_SLOT + 3 * TC_SLAB + 2 * 2 * 256 * 4 + 256 + 1024; }
+__host__ __device__ inline int tcl_qdo_stages(int Lb) { return 2 * 2 * Lb * 128 + tcl_fixed_bytes() <= 227 * 1024 ? 2 : 1; }
+__host__ __device__ inline int tcl_smem_bytes(int Lb) { return tcl_qdo_stages(Lb) * 2 * Lb * 128 + tcl_fixed_bytes(); }
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv,
-                                                                          const __grid_constant__ CUtensorMap map_do,
-                                                                          const __grid_constant__ CUtensorMap map_dqkv,
+__global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap map_q,    // qkv, Lb-row boxes
+                                                                          const __grid_constant__ CUtensorMap map_do,   // d_o, Lb-row boxes
+                                                                          const __grid_constant__ CUtensorMap map_kv,   // qkv, 128-row boxes
+                                                                          const __grid_constant__ CUtensorMap map_dq,   // dqkv, Lb-row boxes
+                                                                          const __grid_constant__ CUtensorMap map_dkv,  // dqkv, 128-row boxes
                                                                           const bf16* __restrict__ o, const float* __restrict__ lse2,
                                                                           const int L, const int H, const int d, const int Lb,
                                                                           const int n_items, const float scale, const float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_bytes = Lb * 128;  // Lb = sequence length rounded up to 16 rows (129..256): a multiple of 2048 B
-  uint8_t* tQ = smem;
-  uint8_t* tdO = tQ + tile_bytes;
-  uint8_t* tK = tdO + tile_bytes;
-  uint8_t* tV = tK + tile_bytes;
-  uint8_t* slabP = tV + tile_bytes;   // P^T of the step          [128 keys][64 queries]
-  uint8_t* slabS = slabP + TC_SLAB;   // dS^T, slot = qc & 1: the two slabs are the 128 queries of a query block
-  float* sLse = reinterpret_cast<float*>(slabS + 2 * TC_SLAB);  // [256] per query: -lse
-  float* sD = sLse + 256;                                       //                  -D
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
-  uint64_t* bar_full = bars;        // tiles of the problem loaded
-  uint64_t* bar_empty = bars + 1;   // outputs stored: the tiles may be refilled
-  uint64_t* bar_s = bars + 2;       // [2] scores of a step in TMEM
-  uint64_t* bar_p = bars + 4;       // slabs of the step written (256)
-  uint64_t* bar_f = bars + 5;       // output MMAs of the step done
-  uint64_t* bar_kv = bars + 6;      // dK / dV of the key block complete
-  uint64_t* bar_kvfree = bars + 7;  // ... and drained (256)
-  uint64_t* bar_qfree = bars + 8;   // dQ drained (256)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int tile_bytes = Lb * 128;  // Lb = sequence length rounded up to 16 rows (144..256): a multiple of 2048 B
+  const int QS = tcl_qdo_stages(Lb);
+  const bool PF = QS == 2;          // the next problem is prefetched while this one computes
+  uint8_t* qdo = smem;                             // [QS][Q tile | dO tile]
+  uint8_t* kv = qdo + QS * 2 * tile_bytes;         // [2 key blocks][K rows | V rows]
+  uint8_t* slabP = kv + 2 * TCL_KV_SLOT;           // P^T of the step          [128 keys][64 queries]
+  uint8_t* slabS = slabP + TC_SLAB;                // dS^T, slot = qc & 1: the two slabs are the 128 queries of a query block
+  float* sLse = reinterpret_cast<float*>(slabS + 2 * TC_SLAB);  // [2][256] per query: -lse
+  float* sD = sLse + 512;                                       // [2][256]            -D
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 512);
+  uint64_t* bar_qfull = bars;         // [2] Q / dO tiles of a problem loaded
+  uint64_t* bar_qempty = bars + 2;    // [2] ... and free again (dQ stored)
+  uint64_t* bar_kvfull = bars + 4;    // [2] K / V rows of key block kb loaded
+  uint64_t* bar_kvempty = bars + 6;   // [2] ... and free again (dK / dV stored)
+  uint64_t* bar_s = bars + 8;         // [2] scores of a step in TMEM
+  uint64_t* bar_p = bars + 10;        // slabs of the step written (256)
+  uint64_t* bar_f = bars + 11;        // output MMAs of the step done
+  uint64_t* bar_kv = bars + 12;       // dK / dV of the key block complete
+  uint64_t* bar_kvfree = bars + 13;   // ... and drained from TMEM (256)
+  uint64_t* bar_qfree = bars + 14;    // dQ drained from TMEM (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int nq = (Lb + 63) >> 6;  // query chunks (3 or 4)
   const int n_steps = 2 * nq;
 
   if (warp == 9) {
     if (lane == 0) {
-      tma_prefetch_desc(&map_qkv);
+      tma_prefetch_desc(&map_q);
       tma_prefetch_desc(&map_do);
-      tma_prefetch_desc(&map_dqkv);
-      mbar_init(bar_full, 1);
-      mbar_init(bar_empty, 1);
-      mbar_init(&bar_s[0], 1);
-      mbar_init(&bar_s[1], 1);
+      tma_prefetch_desc(&map_kv);
+      tma_prefetch_desc(&map_dq);
+      tma_prefetch_desc(&map_dkv);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_qfull[i], 1);
+        mbar_init(&bar_qempty[i], 1);
+        mbar_init(&bar_kvfull[i], 1);
+        mbar_init(&bar_kvempty[i], 1);
+        mbar_init(&bar_s[i], 1);
+      }
       mbar_init(bar_p, 256);
       mbar_init(bar_f, 1);
       mbar_init(bar_kv, 1);
@@ -1122,12 +1136,19 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
       int k = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
         const int s = it / H, h = it - s * H;
-        if (k > 0) mbar_wait(bar_empty, (k - 1) & 1);
-        mbar_expect_tx(bar_full, static_cast<uint32_t>(4 * tile_bytes));
-        tma_load_3d(tK, &map_qkv, bar_full, d + h * 64, 0, s);
-        tma_load_3d(tQ, &map_qkv, bar_full, h * 64, 0, s);
-        tma_load_3d(tV, &map_qkv, bar_full, 2 * d + h * 64, 0, s);
-        tma_load_3d(tdO, &map_do, bar_full, h * 64, 0, s);
+        const int qs = PF ? (k & 1) : 0, u = PF ? (k >> 1) : k;  // Q / dO stage and how often it has been used
+        if (u > 0) mbar_wait(&bar_qempty[qs], (u - 1) & 1);
+        uint8_t* tQ = qdo + qs * 2 * tile_bytes;
+        mbar_expect_tx(&bar_qfull[qs], static_cast<uint32_t>(2 * tile_bytes));
+        tma_load_3d(tQ, &map_q, &bar_qfull[qs], h * 64, 0, s);
+        tma_load_3d(tQ + tile_bytes, &map_do, &bar_qfull[qs], h * 64, 0, s);
+        for (int kb = 0; kb < 2; ++kb) {
+          if (k > 0) mbar_wait(&bar_kvempty[kb], (k - 1) & 1);
+          uint8_t* tK = kv + kb * TCL_KV_SLOT;
+          mbar_expect_tx(&bar_kvfull[kb], static_cast<uint32_t>(TCL_KV_SLOT));
+          tma_load_3d(tK, &map_kv, &bar_kvfull[kb], d + h * 64, kb * TC_ROWS, s);
+          tma_load_3d(tK + TC_SLAB, &map_kv, &bar_kvfull[kb], 2 * d + h * 64, kb * TC_ROWS, s);
+        }
       }
     }
   } else if (warp == 9) {
@@ -1135,29 +1156,34 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
     if (lane == 0) {
       const uint32_t idesc_out = make_idesc_bf16(TC_ROWS, 64) | kIdescBMnMajor;
       const uint32_t idesc_dq = make_idesc_bf16(TC_ROWS, 64) | kIdescAMnMajor | kIdescBMnMajor;
-      const uint64_t dQt = make_smem_desc_sw128(smem_u32(tQ)), dOt = make_smem_desc_sw128(smem_u32(tdO));
-      const uint64_t dKt = make_smem_desc_sw128(smem_u32(tK)), dVt = make_smem_desc_sw128(smem_u32(tV));
+      const uint64_t dK0 = make_smem_desc_sw128(smem_u32(kv));  // K rows of key block 0; V: + TC_SLAB, block 1: + TCL_KV_SLOT
       const uint64_t dPk = make_smem_desc_sw128(smem_u32(slabP)), dSk = make_smem_desc_sw128(smem_u32(slabS));
       // MN-major A over the two dS^T slabs (M = 128 queries): leading-dimension byte offset = slab stride
       const uint64_t dSm = (dSk & ~(static_cast<uint64_t>(0x3FFF) << 16)) | (static_cast<uint64_t>(TC_SLAB >> 4) << 16);
-      auto issue_scores = [&](int i) {
-        const int kb = i >= nq ? 1 : 0, qc = i - kb * nq, b = i & 1;
-        const int nr = min(64, Lb - qc * 64);
-        const uint32_t idesc_s = make_idesc_bf16(TC_ROWS, nr);
-        const uint64_t aK = dKt + static_cast<uint64_t>(kb * (TC_SLAB >> 4)), aV = dVt + static_cast<uint64_t>(kb * (TC_SLAB >> 4));
-        const uint64_t bQ = dQt + static_cast<uint64_t>(qc * 512), bO = dOt + static_cast<uint64_t>(qc * 512);
-        const uint32_t col = tmem_base + static_cast<uint32_t>(b * 128);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(col, aK + static_cast<uint64_t>(j * 2), bQ + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(col + 64u, aV + static_cast<uint64_t>(j * 2), bO + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
-        umma_commit(&bar_s[b]);
-      };
       uint32_t g = 0;  // steps issued so far (all problems)
       int k = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
-        mbar_wait(bar_full, k & 1);
-        tc_fence_after();
+        const int qs = PF ? (k & 1) : 0, u = PF ? (k >> 1) : k;
+        const uint64_t dQt = make_smem_desc_sw128(smem_u32(qdo + qs * 2 * tile_bytes));
+        const uint64_t dOt = dQt + static_cast<uint64_t>(tile_bytes >> 4);
+        auto issue_scores = [&](int i) {
+          const int kb = i >= nq ? 1 : 0, qc = i - kb * nq, b = i & 1;
+          if (qc == 0) {
+            mbar_wait(&bar_kvfull[kb], k & 1);
+            tc_fence_after();
+          }
+          const int nr = min(64, Lb - qc * 64);
+          const uint32_t idesc_s = make_idesc_bf16(TC_ROWS, nr);
+          const uint64_t aK = dK0 + static_cast<uint64_t>(kb * (TCL_KV_SLOT >> 4)), aV = aK + static_cast<uint64_t>(TC_SLAB >> 4);
+          const uint64_t bQ = dQt + static_cast<uint64_t>(qc * 512), bO = dOt + static_cast<uint64_t>(qc * 512);
+          const uint32_t col = tmem_base + static_cast<uint32_t>(b * 128);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16(col, aK + static_cast<uint64_t>(j * 2), bQ + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16(col + 64u, aV + static_cast<uint64_t>(j * 2), bO + static_cast<uint64_t>(j * 2), idesc_s, static_cast<uint32_t>(j != 0));
+          umma_commit(&bar_s[b]);
+        };
+        mbar_wait(&bar_qfull[qs], u & 1);
         issue_scores(0);
         issue_scores(1);
         for (int i = 0; i < n_steps; ++i, ++g) {
@@ -1184,7 +1210,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
               tc_fence_after();
             }
             const int nkk = (kb ? Lb - TC_ROWS : TC_ROWS) >> 4;
-            const uint64_t bK = dKt + static_cast<uint64_t>(kb * (TC_SLAB >> 4));
+            const uint64_t bK = dK0 + static_cast<uint64_t>(kb * (TCL_KV_SLOT >> 4));
             for (int j = 0; j < nkk; ++j)  // contraction over the block's keys
               umma_bf16(tmem_base + 384u + static_cast<uint32_t>(qb * 64), dSm + static_cast<uint64_t>(j * 128), bK + static_cast<uint64_t>(j * 128), idesc_dq,
                         static_cast<uint32_t>(kb != 0 || j != 0));
@@ -1201,41 +1227,64 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
     const int t = quad * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
-    uint32_t g = 0;
-    int k = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
-      const int s = it / H, h = it - s * H;
-      {  // lse and D = rowsum(dO * O) of query q = threadIdx.x
-        const int q = threadIdx.x;
-        uint4 ov[8];
-        float lse = 0.f;
-        if (q < L) {
-          const uint4* op = reinterpret_cast<const uint4*>(o + (static_cast<size_t>(s) * L + q) * d + h * 64);
+    // lse and D = rowsum(dO * O) of query q = threadIdx.x of problem `item`, in two halves: the O row is fetched from global
+    // memory first, the products with the dO tile (shared memory) come later
+    uint4 ov[8];
+    float lse_q = 0.f;
+    auto d_fetch = [&](int item) {
+      const int s = item / H, h = item - s * H, q = threadIdx.x;
+      lse_q = 0.f;
+      if (q < L) {
+        const uint4* op = reinterpret_cast<const uint4*>(o + (static_cast<size_t>(s) * L + q) * d + h * 64);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) ov[c] = __ldg(op + c);
-          lse = lse2[(static_cast<size_t>(s) * H + h) * L + q];
-        }
-        mbar_wait(bar_full, k & 1);
-        float D = 0.f;
-        if (q < L) {
+        for (int c = 0; c < 8; ++c) ov[c] = __ldg(op + c);
+        lse_q = lse2[(static_cast<size_t>(s) * H + h) * L + q];
+      }
+    };
+    auto d_finish = [&](int kk) {  // kk = per-CTA index of the problem
+      const int qs = PF ? (kk & 1) : 0, u = PF ? (kk >> 1) : kk, q = threadIdx.x;
+      mbar_wait(&bar_qfull[qs], u & 1);
+      const uint8_t* tdO = qdo + qs * 2 * tile_bytes + tile_bytes;
+      float D = 0.f;
+      if (q < L) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 a = *reinterpret_cast<const uint4*>(tdO + q * 128 + ((c ^ (q & 7)) << 4));
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w};
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = *reinterpret_cast<const uint4*>(tdO + q * 128 + ((c ^ (q & 7)) << 4));
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 x = unpack_bf16(aw[e]), y = unpack_bf16(bw[e]);
-              D += x.x * y.x + x.y * y.y;
-            }
+          for (int e = 0; e < 4; ++e) {
+            const float2 x = unpack_bf16(aw[e]), y = unpack_bf16(bw[e]);
+            D += x.x * y.x + x.y * y.y;
           }
         }
-        sLse[q] = -lse;  // both are only ever subtracted
-        sD[q] = -D;
+      }
+      sLse[(kk & 1) * 256 + q] = -lse_q;  // both are only ever subtracted
+      sD[(kk & 1) * 256 + q] = -D;
+    };
+    uint32_t g = 0;
+    int k = 0;
+    bool release_pending = false;  // (thread 0) the previous problem's last stores have not been waited for yet
+    int prev_qs = 0;
+    if (blockIdx.x < n_items) {
+      d_fetch(blockIdx.x);
+      d_finish(0);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+      const int s = it / H, h = it - s * H;
+      const int qs = PF ? (k & 1) : 0;
+      uint8_t* tQ = qdo + qs * 2 * tile_bytes;
+      const float* nLse = sLse + (k & 1) * 256;
+      const float* nDs = sD + (k & 1) * 256;
+      const bool has_next = it + static_cast<int>(gridDim.x) < n_items;
+      if (!PF && k > 0) {  // single-buffered tiles: this problem's per-query arrays can only be built now
+        d_fetch(it);
+        d_finish(k);
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       // dK, dV of a complete key block (row = key, this half's 32 head columns) into the block's dead K / V rows
       auto drain_kv = [&](int kb) {
-        const int key = kb * TC_ROWS + t;
+        uint8_t* tK = kv + kb * TCL_KV_SLOT;
         mbar_wait(bar_kv, (2 * k + kb) & 1);
         tc_fence_after();
         uint32_t o0[32], o1[32];
@@ -1245,18 +1294,16 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
         tmem_ld_wait_regs(o1);
         tc_fence_before();
         mbar_arrive(bar_kvfree);
-        if (key < Lb) {
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint32_t off = static_cast<uint32_t>(key * 128 + (((half * 4 + q4) ^ (key & 7)) << 4));
-            uint32_t w[4];
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q4) ^ (t & 7)) << 4));
+          uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q4 + 2 * e]) * scale, __uint_as_float(o0[8 * q4 + 2 * e + 1]) * scale);
-            *reinterpret_cast<uint4*>(tK + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q4 + 2 * e]) * scale, __uint_as_float(o0[8 * q4 + 2 * e + 1]) * scale);
+          *reinterpret_cast<uint4*>(tK + off) = make_uint4(w[0], w[1], w[2], w[3]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q4 + 2 * e]), __uint_as_float(o1[8 * q4 + 2 * e + 1]));
-            *reinterpret_cast<uint4*>(tV + off) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
+          for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o1[8 * q4 + 2 * e]), __uint_as_float(o1[8 * q4 + 2 * e + 1]));
+          *reinterpret_cast<uint4*>(tK + TC_SLAB + off) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       };
       for (int i = 0; i < n_steps; ++i, ++g) {
@@ -1268,6 +1315,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
         // (warp-uniform) every (key, query) of the warp's 32 x 32 piece is live / none is: no masks, or no math at all
         const bool all_live = key0 + 32 <= L && col0 + 32 <= L && (!CAUSAL || key0 + 31 <= col0);
         const bool none_live = key0 >= L || col0 >= L || (CAUSAL && key0 > col0 + 31);
+        if (PF && i == nq && has_next) d_fetch(it + gridDim.x);  // the next problem's O row: in flight during this step
         mbar_wait(&bar_s[b], (g >> 1) & 1);
         tc_fence_after();
         uint32_t pp[16], ds[16];
@@ -1280,8 +1328,8 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
           if (all_live) {
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {  // 4 queries per iteration
-              const float4 nl = *reinterpret_cast<const float4*>(sLse + col0 + 4 * e4);  // -lse
-              const float4 nD = *reinterpret_cast<const float4*>(sD + col0 + 4 * e4);    // -D
+              const float4 nl = *reinterpret_cast<const float4*>(nLse + col0 + 4 * e4);
+              const float4 nD = *reinterpret_cast<const float4*>(nDs + col0 + 4 * e4);
               float p0, p1, p2, p3;
               f2_unpack(f2_fma(f2_pack_u(sv[4 * e4], sv[4 * e4 + 1]), c2, f2_pack(nl.x, nl.y)), p0, p1);
               f2_unpack(f2_fma(f2_pack_u(sv[4 * e4 + 2], sv[4 * e4 + 3]), c2, f2_pack(nl.z, nl.w)), p2, p3);
@@ -1301,15 +1349,15 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const int c = col0 + 2 * e;
-              const float2 nl = *reinterpret_cast<const float2*>(sLse + c);
-              const float2 nD = *reinterpret_cast<const float2*>(sD + c);
+              const float2 nl = *reinterpret_cast<const float2*>(nLse + c);
+              const float2 nD = *reinterpret_cast<const float2*>(nDs + c);
               float p0, p1;
               f2_unpack(f2_fma(f2_pack_u(sv[2 * e], sv[2 * e + 1]), c2, f2_pack(nl.x, nl.y)), p0, p1);
               p0 = exp2f(p0);
               p1 = exp2f(p1);
               float x, y;
               f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack_u(dv[2 * e], dv[2 * e + 1]), f2_pack(nD.x, nD.y))), x, y);  // dS (unscaled)
-              // selects, not products: masked positions may hold stale TMEM / out-of-tile operands (Inf, NaN)
+              // selects, not products: masked positions may hold stale TMEM columns (Inf, NaN)
               const bool ok0 = c >= c_lo && c < c_hi, ok1 = c + 1 >= c_lo && c + 1 < c_hi;
               pp[e] = pack_bf16(ok0 ? p0 : 0.f, ok1 ? p1 : 0.f);
               ds[e] = pack_bf16(ok0 ? x : 0.f, ok1 ? y : 0.f);
@@ -1332,8 +1380,32 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(bar_p);
-        // the first key block's dK / dV leave one step late: its last output MMAs run under this step's math
-        if (kb == 1 && qc == 0) drain_kv(0);
+        if (i == 0 && threadIdx.x == 0 && release_pending) {
+          // the previous problem's last stores have been read by now: its second K / V slot and its Q / dO stage are free
+          bulk_wait_read<0>();
+          mbar_arrive(&bar_kvempty[1]);
+          mbar_arrive(&bar_qempty[prev_qs]);
+          release_pending = false;
+        }
+        if (i == nq) {
+          // the first key block's dK / dV leave one step late (its last output MMAs ran under this step's math) ...
+          drain_kv(0);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (threadIdx.x == 0) {
+            tma_store_3d(&map_dkv, kv, d + h * 64, 0, s);
+            tma_store_3d(&map_dkv, kv + TC_SLAB, 2 * d + h * 64, 0, s);
+            bulk_commit();
+          }
+        }
+        if (i == nq + 1) {
+          // ... and one step after that the slot is free for the next problem's first key block
+          if (threadIdx.x == 0) {
+            bulk_wait_read<0>();
+            mbar_arrive(&bar_kvempty[0]);
+          }
+          if (PF && has_next) d_finish(k + 1);  // ordered before its readers by the barrier at the end of this problem
+        }
       }
       drain_kv(1);
       // dQ of both query blocks (row = query t and 128 + t) into the dead Q tile
@@ -1366,12 +1438,18 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) {
-        tma_store_3d(&map_dqkv, tQ, h * 64, 0, s);
-        tma_store_3d(&map_dqkv, tK, d + h * 64, 0, s);
-        tma_store_3d(&map_dqkv, tV, 2 * d + h * 64, 0, s);
+        tma_store_3d(&map_dq, tQ, h * 64, 0, s);
+        tma_store_3d(&map_dkv, kv + TCL_KV_SLOT, d + h * 64, TC_ROWS, s);
+        tma_store_3d(&map_dkv, kv + TCL_KV_SLOT + TC_SLAB, 2 * d + h * 64, TC_ROWS, s);
         bulk_commit();
-        bulk_wait_read<0>();  // the tiles have been read: the next problem may be loaded over them
-        mbar_arrive(bar_empty);
+        if (PF) {
+          release_pending = true;  // waited for after the next problem's first step
+          prev_qs = qs;
+        } else {
+          bulk_wait_read<0>();     // the tiles have been read: the next problem may be loaded over them
+          mbar_arrive(&bar_kvempty[1]);
+          mbar_arrive(&bar_qempty[0]);
+        }
       }
     }
     if (threadIdx.x == 0) bulk_wait<0>();
@@ -1473,10 +1551,12 @@ const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, co
   }
   if (L <= 2 * TC_ROWS) {  // two-block sequences: the whole problem resident, one launch
     const int Lb = (L + 15) & ~15;
-    CUtensorMap mq, mdo, mo;
+    CUtensorMap mq, mdo, mkv, mdq, mdkv;
     if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, Lb, &mq))) return e;
     if ((e = tensor_map_3d_bf16(d_o, d, L, S, d, static_cast<long long>(d) * L, Lb, &mdo))) return e;
-    if ((e = tensor_map_3d_bf16(dqkv, 3 * d, L, S, ld, ld * L, Lb, &mo))) return e;
+    if ((e = tensor_map_3d_bf16(qkv, 3 * d, L, S, ld, ld * L, TC_ROWS, &mkv))) return e;
+    if ((e = tensor_map_3d_bf16(dqkv, 3 * d, L, S, ld, ld * L, Lb, &mdq))) return e;
+    if ((e = tensor_map_3d_bf16(dqkv, 3 * d, L, S, ld, ld * L, TC_ROWS, &mdkv))) return e;
     const int smem = tcl_smem_bytes(Lb);
     static int n_sms_l = 0;
     if (n_sms_l == 0) {
@@ -1490,12 +1570,12 @@ const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, co
     auto kern = causal ? attn_tc_bwd_long_kernel<true> : attn_tc_bwd_long_kernel<false>;
     static bool attr_long[2] = {false, false};
     if (!attr_long[causal ? 1 : 0]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl_smem_bytes(256)) != cudaSuccess)
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         return "attention (tcgen05 backward, resident): cudaFuncSetAttribute failed";
       attr_long[causal ? 1 : 0] = true;
     }
-    launch_pdl(kern, dim3(grid), dim3(TCL_THREADS), static_cast<size_t>(smem), stream, mq, mdo, mo, o, lse2, L, H, d, Lb, n_items, 0.125f,
-               0.125f * 1.4426950408889634f);
+    launch_pdl(kern, dim3(grid), dim3(TCL_THREADS), static_cast<size_t>(smem), stream, mq, mdo, mkv, mdq, mdkv, o, lse2, L, H, d, Lb, n_items,
+               0.125f, 0.125f * 1.4426950408889634f);
     count_launch(1);
     return launch_status("attention bwd (tcgen05, resident) launch failed");
   }
