@@ -78,6 +78,15 @@ struct Tower {
   float *pr_x = nullptr, *pr_xm = nullptr, *pr_xo = nullptr, *pr_dx = nullptr;
   float2 *pr_stm = nullptr, *pr_dots = nullptr;
   bool fwd_pruned = false;
+  // ... and below block 0 only the spliced prompt rows carry a gradient anyone reads (everything else of the tower input
+  // is frozen: patch / token embeddings, cls, positional embeddings), so block 0's d in-proj and LN1 backward run on
+  // the S * n_ctx gathered prompt rows
+  int* p0_rows = nullptr;  // absolute row of prompt token j of sequence s: s * L + row0 + j
+  int p0_S = 0, p0_L = 0;  // shape p0_rows was built for
+  size_t p0_cap = 0;       // rows the buffers below hold
+  std::vector<void*> p0_allocs;
+  bf16 *p0_dqkv = nullptr, *p0_a = nullptr, *p0_dxb = nullptr;
+  float *p0_x = nullptr, *p0_dx = nullptr;
   std::vector<void*> ws_allocs;  // everything sized by cap_rows: released when the tower outgrows it
   GemmWorkspace gws;             // stream-K scratch of this tower's stream
   bool fwd_done = false;
@@ -224,6 +233,29 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
     CUDA_OK(h, dev_alloc(h, &t.pr_dots, Ss * dots_mlp, g));
     t.pr_cap = S;
     t.fwd_done = false;
+  }
+  const size_t R0 = static_cast<size_t>(S) * t.n_ctx;
+  if (R0 > t.p0_cap) {
+    for (void* p : t.p0_allocs) cudaFree(p);
+    t.p0_allocs.clear();
+    gemm_clear_tensor_map_cache();
+    std::vector<void*>* g = &t.p0_allocs;
+    CUDA_OK(h, dev_alloc(h, &t.p0_rows, R0, g));
+    CUDA_OK(h, dev_alloc(h, &t.p0_dqkv, R0 * 3 * t.d, g));
+    CUDA_OK(h, dev_alloc(h, &t.p0_a, R0 * t.d, g));
+    CUDA_OK(h, dev_alloc(h, &t.p0_dxb, R0 * t.d, g));
+    CUDA_OK(h, dev_alloc(h, &t.p0_x, R0 * t.d, g));
+    CUDA_OK(h, dev_alloc(h, &t.p0_dx, R0 * t.d, g));
+    t.p0_cap = R0;
+    t.p0_S = 0;
+  }
+  if (R0 > 0 && (t.p0_S != S || t.p0_L != L)) {
+    std::vector<int> r(R0);
+    for (int q = 0; q < S; ++q)
+      for (int j = 0; j < t.n_ctx; ++j) r[static_cast<size_t>(q) * t.n_ctx + j] = q * L + t.row0 + j;
+    CUDA_OK(h, cudaMemcpy(t.p0_rows, r.data(), R0 * sizeof(int), cudaMemcpyHostToDevice));  // (set-up: shapes change rarely)
+    t.p0_S = S;
+    t.p0_L = L;
   }
   if (rows <= t.cap_rows) return 0;
   // grow: the outgrown buffers are released first (cudaFree waits for the device, so nothing in flight uses them);
@@ -484,7 +516,7 @@ const float* tower_head_input(const Tower& t, const int** rows, int* L) {
 // epilogue of the dgrad GEMM that produces g (through the gamma-folded weight).  Its two row means do not need g:
 //   mean(g) = (1/d) dout . colsum,   mean(g xhat) = (1/d) dout . (y - b')      (dout = the GEMM's A operand, y = the
 // saved output of the forward LN-GEMM), so the PRODUCER of dout (GELU' epilogue, attention backward) emits them.
-int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice_layer, cudaStream_t st) {
+int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice_layer, cudaStream_t st, bool need_dx0 = false) {
   const int M = t.S * t.L, d = t.d;
   const double Md = static_cast<double>(M), dd = d;
   const double attn_fl = 2.5 * 4.0 * t.S * t.H * static_cast<double>(t.L) * t.L * 64.0;  // 2.5x forward
@@ -553,6 +585,24 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
     CKP(h, st, PC_ATTN_BWD, attn_fl, Md * dd * 2 * 8,
         attention_bwd(t.qkv[i], t.o[i], t.do_buf, t.lse[i], t.dsum, t.dqkv_buf, t.S, t.L, t.H, d, t.causal, st,
                       fused ? w.sb_in : nullptr, fused ? t.dots : nullptr));
+    // exact work skipping below block 0: only the prompt rows of its input gradient are ever read (by the splice backward)
+    const bool head_pruned = i == 0 && h->prune && !fused && !tail_pruned && !need_dx0 && first_splice_layer == 0 && t.depth > 0 &&
+                             t.n_ctx > 0 && t.S * t.n_ctx < M;
+    if (head_pruned) {
+      const int R = t.S * t.n_ctx;
+      const double Rd = R;
+      CKP(h, st, PC_SPLICE, 0, Rd * dd * 12, gather_rows(nullptr, t.dqkv_buf, t.p0_rows, R, 0, nullptr, t.p0_dqkv, 3 * d, st));
+      GemmEpilogue q4;
+      q4.mode = EPI_BF16; q4.out0 = t.p0_a; q4.ldc = d;
+      CKP(h, st, PC_GEMM, 2.0 * Rd * 3 * dd * dd, 2 * (Rd * 3 * dd + 3 * dd * dd) + 2 * Rd * dd,
+          gemm_bf16_tn(t.p0_dqkv, 3 * d, w.w_in_t, 3 * d, q4, R, d, 3 * d, st, &t.gws));
+      CKP(h, st, PC_SPLICE, 0, Rd * dd * 8, gather_rows(t.x_in[0], nullptr, t.p0_rows, R, 0, t.p0_x, nullptr, d, st));
+      CKP(h, st, PC_SPLICE, 0, Rd * dd * 8, gather_rows(t.dx, nullptr, t.p0_rows, R, 0, t.p0_dx, nullptr, d, st));
+      CKP(h, st, PC_LN_BWD, 0, Rd * dd * 16, layernorm_bwd(t.p0_a, true, t.p0_x, nullptr, w.ln1_g, t.p0_dx, t.p0_dx, t.p0_dxb, R, d, kLnEps, st));
+      CKP(h, st, PC_SPLICE, 0, Rd * dd * 8, scatter_rows(t.p0_dx, t.p0_rows, R, 0, t.dx, nullptr, d, false, st));
+      CKP(h, st, PC_SPLICE, 0, t.S * t.n_ctx * dd * 4, splice_bwd(t.dx, t.dx_bf16, d_prompts, t.splice_ws, t.S, t.L, t.row0, t.n_ctx, d, false, st));
+      continue;
+    }
     GemmEpilogue e4;
     e4.ldc = d;
     if (fused) {
@@ -653,6 +703,7 @@ void mudpt_destroy(mudpt_handle* h) {
   for (Tower* t : {&h->vis, &h->txt}) {
     for (void* p : t->ws_allocs) cudaFree(p);
     for (void* p : t->pr_allocs) cudaFree(p);
+    for (void* p : t->p0_allocs) cudaFree(p);
   }
   for (ProfRec& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
@@ -819,7 +870,7 @@ int mudpt_text_backward(mudpt_handle* h, const float* d_f_txt, float* d_prompts,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = static_cast<size_t>(t.S) * t.L * t.d;
   if (head_backward(h, t, d_f_txt, h->ln_final_g, h->proj_t, st)) return -1;
-  if (tower_backward(h, t, d_prompts, t.first_splice, st)) return -1;
+  if (tower_backward(h, t, d_prompts, t.first_splice, st, d_x0 != nullptr)) return -1;
   if (d_x0) CUDA_OK(h, cudaMemcpyAsync(d_x0, t.dx, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }

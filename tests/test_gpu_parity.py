@@ -518,14 +518,16 @@ def test_umudpt_variants_vs_reference_golden(name):
         torch.cuda.synchronize()
         # semantics are pinned on the CPU (tests/test_host_logic.py::test_variant_prompt_algebra_matches_reference:
         # host algebra + fp32 oracle towers == reference to 2e-6); what is checked here is kernel numerics.  The
-        # synthetic LightTransformer weights give O(1)-norm prompts and logits up to |5|: tolerance 0.1 = 0.7 % of
-        # the logit scale (exp(logit_scale) = 14.3), i.e. a cosine error of 0.007 on 128-wide 3-layer towers
-        assert abs(float(loss) - float(g["loss"])) <= 0.03, mode
-        assert float((logits.detach().cpu() - torch.from_numpy(g["logits"])).abs().max()) <= 0.1, mode
+        # synthetic LightTransformer weights give O(1)-norm prompts and logits up to |4.9| (UMuDPT) / |3.0| (UUMuDPT).
+        # Measured on B200 (round 2): |dloss| 0.014 / 0.005, logit max-abs 0.054 / 0.008, worst gradient cosine
+        # 0.99994 / 0.99983 (rel-L2 1.2 % / 1.9 %).  The MuDPT bound of 0.05 holds for UUMuDPT; UMuDPT's larger logits
+        # (cosine x 14.3 with bf16 features: 0.054 = 1.1 % of its largest logit) get 0.07.
+        assert abs(float(loss) - float(g["loss"])) <= 0.02, mode
+        assert float((logits.detach().cpu() - torch.from_numpy(g["logits"])).abs().max()) <= (0.07 if name.startswith("umudpt") else 0.05), mode
         for n, p in model.named_parameters():
             if p.requires_grad:
                 ref = torch.from_numpy(g["grad/" + n])
                 m = orc.metrics(p.grad.cpu(), ref)
                 # tensors whose reference gradient is tiny relative to the loss scale carry bf16 noise: compare by
                 # absolute error against the largest gradient entry as well
-                assert (m["cos"] >= 0.999 and m["rel_l2"] <= 0.05) or m["max_abs"] <= 2e-3 * float(ref.abs().max() + 1e-6) + 1e-6, (mode, n, m)
+                assert (m["cos"] >= 0.9995 and m["rel_l2"] <= 0.04) or m["max_abs"] <= 2e-3 * float(ref.abs().max() + 1e-6) + 1e-6, (mode, n, m)
