@@ -528,12 +528,51 @@ class MuDPT(TrainerX):
         self.register_model("MultimodalDeepPromptTuning", self.model, self.optim, self.sched)
         self.scaler = None  # "amp" needs no loss scaling here: bf16 operands, fp32 accumulation and master state
 
+    def prefetch(self, batch):
+        """Start the host -> device copy of a FUTURE batch (what a pinned-memory data loader with non_blocking copies
+        does): call it with batch i + 1 before forward_backward(batch i); the upload then runs on a copy stream under
+        step i and forward_backward(batch i + 1) finds the images resident.  Two device slots, reused alternately; a slot
+        is only overwritten after the step that read it has finished (event-ordered, no host synchronisation)."""
+        if "img" not in batch or self.device.type != "cuda" or batch["img"].device.type != "cpu":
+            return
+        st = self.__dict__.setdefault("_pf", {"slot": 0, "bufs": [None, None], "free": [None, None], "ready": {}, "stream": torch.cuda.Stream(self.device)})
+        k = st["slot"]
+        st["slot"] ^= 1
+        img, lab = batch["img"], batch["label"]
+        buf = st["bufs"][k]
+        if buf is None or buf[0].shape != img.shape or buf[0].dtype != img.dtype or buf[1].shape != lab.shape:
+            buf = (torch.empty(img.shape, dtype=img.dtype, device=self.device), torch.empty(lab.shape, dtype=lab.dtype, device=self.device))
+            st["bufs"][k] = buf
+        cs = st["stream"]
+        if st["free"][k] is None:
+            cs.wait_stream(torch.cuda.current_stream(self.device))  # first use of the slot: its allocation is ordered there
+        else:
+            cs.wait_event(st["free"][k])                            # the step that read the slot last has finished
+        with torch.cuda.stream(cs):
+            buf[0].copy_(img, non_blocking=True)
+            buf[1].copy_(lab, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        st["ready"] = {"key": id(img), "slot": k, "event": ev}
+
+    def _prefetched(self, batch):
+        st = self.__dict__.get("_pf")
+        if not st or st["ready"].get("key") != id(batch.get("img")):
+            return None
+        r = st["ready"]
+        st["ready"] = {}
+        torch.cuda.current_stream(self.device).wait_event(r["event"])
+        return r["slot"], st["bufs"][r["slot"]]
+
     def forward_backward(self, batch):
         if os.environ.get("MUDPT_FUSED_STEP", "1") == "1":
             # fused loss + backward in the native head; same update as model_backward_and_update(loss).
             # Host batches go in as they are: the fused step uploads them on its vision stream
             # (parse_batch_train's blocking .to(device) would put the PCIe copy on the critical path).
-            if "img" not in batch:
+            pf = self._prefetched(batch) if "img" in batch else None
+            if pf is not None:
+                image, label = pf[1]  # uploaded by prefetch() under the previous step
+            elif "img" not in batch:
                 image, label = self.parse_batch_train(batch)  # raw 8-bit images: GPU input pipeline
             else:
                 image, label = batch["img"], batch["label"]
@@ -541,6 +580,10 @@ class MuDPT(TrainerX):
                     image, label = self.parse_batch_train(batch)
             self.optim.zero_grad()
             loss, _ = self.model.forward_backward(image, label)
+            if pf is not None:  # the slot may be refilled once this step (both streams joined on the current one) is done
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self._pf["free"][pf[0]] = ev
             # the loss value is on the host as soon as the head has run (the backward is still in flight):
             # same check-before-update order as model_backward_and_update, without draining the stream
             loss_value = self.model.loss_value() if loss.is_cuda else float(loss)

@@ -256,6 +256,44 @@ def test_gpu_trainer_takes_raw_images():
 
 
 @pytest.mark.gpu
+def test_gpu_trainer_prefetch_matches_plain_steps():
+    """MuDPT.prefetch(next batch) + forward_backward(batch): three optimizer steps over pinned host batches give the
+    same losses and bit-identical parameters as the same steps without prefetch (the upload moves to a copy stream
+    under the previous step; event-ordered slot reuse with more batches than slots)."""
+    from mudpt_b200.trainers import mudpt as M
+    from tests import golden_util as gu
+    case = gu.load("tiny_a")
+
+    def make_trainer():
+        model, cfg = gu.build_model(case, "cuda")
+        t = M.MuDPT.__new__(M.MuDPT)
+        M.TrainerX.__init__(t, None, None, torch.device("cuda"))
+        t.cfg, t.model = cfg, model
+        t.optim = M.build_optimizer(model, cfg.OPTIM)
+        t.sched = M.build_lr_scheduler(t.optim, cfg.OPTIM)
+        t.register_model("MultimodalDeepPromptTuning", model, t.optim, t.sched)
+        t.batch_idx, t.num_batches = 0, 10 ** 9
+        return t
+
+    g = torch.Generator().manual_seed(5)
+    batches = [{"img": (case["image"] + 0.1 * i * torch.randn(case["image"].shape, generator=g)).pin_memory(),
+                "label": case["labels"].roll(i).pin_memory()} for i in range(5)]
+    t1, t2 = make_trainer(), make_trainer()
+    l1, l2 = [], []
+    t1.prefetch(batches[0])
+    for i, b in enumerate(batches):
+        if i + 1 < len(batches):
+            t1.prefetch(batches[i + 1])
+        l1.append(t1.forward_backward(b)["loss"])
+        l2.append(t2.forward_backward(b)["loss"])
+    assert t1.__dict__["_pf"]["ready"] == {}  # every prefetched batch was consumed by its own step
+    assert l1 == l2 and all(np.isfinite(l1)), (l1, l2)
+    for (n1, p1), (_, p2) in zip(t1.model.named_parameters(), t2.model.named_parameters()):
+        if p1.requires_grad:
+            assert torch.equal(p1, p2), n1
+
+
+@pytest.mark.gpu
 def test_gpu_trainer_evaluates_raw_images():
     """test() over raw 8-bit images: evaluation transform on the GPU (bit-identical to the oracle), logits from the
     cached text features, accuracy accumulated on the device."""
