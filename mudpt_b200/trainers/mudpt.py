@@ -553,14 +553,15 @@ class MuDPT(TrainerX):
             buf[1].copy_(lab, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
-        st["ready"] = {"key": id(img), "slot": k, "event": ev}
+        # (a batch prefetched into this slot earlier and never consumed is forgotten: its step uploads in the call)
+        st["ready"] = {key: r for key, r in st["ready"].items() if r["slot"] != k}
+        st["ready"][id(img)] = {"slot": k, "event": ev}
 
     def _prefetched(self, batch):
         st = self.__dict__.get("_pf")
-        if not st or st["ready"].get("key") != id(batch.get("img")):
+        r = st["ready"].pop(id(batch.get("img")), None) if st else None
+        if r is None:
             return None
-        r = st["ready"]
-        st["ready"] = {}
         torch.cuda.current_stream(self.device).wait_event(r["event"])
         return r["slot"], st["bufs"][r["slot"]]
 
