@@ -555,7 +555,7 @@ class MuDPT(TrainerX):
             ev.record(cs)
         # (a batch prefetched into this slot earlier and never consumed is forgotten: its step uploads in the call)
         st["ready"] = {key: r for key, r in st["ready"].items() if r["slot"] != k}
-        st["ready"][id(img)] = {"slot": k, "event": ev}
+        st["ready"][id(img)] = {"slot": k, "event": ev, "host": img}  # (the reference keeps the id from being reused)
 
     def _prefetched(self, batch):
         st = self.__dict__.get("_pf")
