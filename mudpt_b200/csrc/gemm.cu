@@ -1303,10 +1303,21 @@ static const char* launch_mode(const bf16* A, int lda, const bf16* B, int ldb, c
     bn = 128;
     two = false;
   }
+  {  // experiment hook (MUDPT_GEMM_TILE = 1: 128 x 128 single-CTA tiles, 2: 128 x 256 single-CTA, for problems of at most
+     // MUDPT_GEMM_TILE_ROWS rows and MUDPT_GEMM_TILE_N columns).  Measured, with 256 x 128 pair tiles as a third variant:
+     // every alternative to the 256 x 256 pair tile is slower at the per-rank shapes (profiles/r02_gemm_tile_ab.txt)
+    static const int force = getenv("MUDPT_GEMM_TILE") ? atoi(getenv("MUDPT_GEMM_TILE")) : 0;
+    static const int force_rows = getenv("MUDPT_GEMM_TILE_ROWS") ? atoi(getenv("MUDPT_GEMM_TILE_ROWS")) : (1 << 30);
+    static const int force_n = getenv("MUDPT_GEMM_TILE_N") ? atoi(getenv("MUDPT_GEMM_TILE_N")) : (1 << 30);
+    if (force && MODE != EPI_GELU_BWD_DOTS && M <= force_rows && N <= force_n) {
+      two = false;
+      bn = (force == 1 || N < 256) ? 128 : 256;
+    }
+  }
   CUtensorMap ta, tb;
   const char* e = get_tensor_map(A, M, K, lda, BM, BK, &ta);
   if (e) return e;
-  e = get_tensor_map(B, N, K, ldb, two ? 128 : bn, BK, &tb);
+  e = get_tensor_map(B, N, K, ldb, two ? bn / 2 : bn, BK, &tb);
   if (e) return e;
   // epilogue boxes (row-layout modes): out0, out1, operand (residual / saved pre-activation), LN input, out2;
   // unused slots repeat the A map
