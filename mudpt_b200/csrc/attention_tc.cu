@@ -1055,14 +1055,22 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) attn_tc_bwd_pp_kernel(const __
 // Padding: TMA zero-fills rows past the sequence; (key, query) pairs outside it are forced to P = dS = 0 by a select
 // wherever a warp's 32 x 32 piece is not entirely inside.
 // =======================================================================================
-static constexpr int TCL_THREADS = 320;          // 8 element-wise warps + TMA warp + MMA warp
+// EW element-wise warps (8 or 16) + TMA warp + MMA warp.  16 warps (4 per scheduler, <= 112 registers, 16 query columns per
+// thread and step) hide the tcgen05.ld / MUFU / shared-memory latencies of the per-element chain that 8 warps leave exposed.
+__host__ __device__ constexpr int tcl_threads(int EW) { return EW * 32 + 64; }
+template <int NC> __device__ __forceinline__ void tcl_ld(uint32_t taddr, uint32_t (&r)[NC]);
+template <> __device__ __forceinline__ void tcl_ld<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+template <> __device__ __forceinline__ void tcl_ld<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x16(taddr, r); }
+template <int NC> __device__ __forceinline__ void tcl_wait(uint32_t (&r)[NC]);
+template <> __device__ __forceinline__ void tcl_wait<32>(uint32_t (&r)[32]) { tmem_ld_wait_regs(r); }
+template <> __device__ __forceinline__ void tcl_wait<16>(uint32_t (&r)[16]) { tmem_ld_wait_regs16(r); }
 static constexpr int TCL_KV_SLOT = 2 * TC_SLAB;  // K block | V block, 128 rows each
 __host__ __device__ inline int tcl_fixed_bytes() { return 2 * TCL_KV_SLOT + 3 * TC_SLAB + 2 * 2 * 256 * 4 + 256 + 1024; }
 __host__ __device__ inline int tcl_qdo_stages(int Lb) { return 2 * 2 * Lb * 128 + tcl_fixed_bytes() <= 227 * 1024 ? 2 : 1; }
 __host__ __device__ inline int tcl_smem_bytes(int Lb) { return tcl_qdo_stages(Lb) * 2 * Lb * 128 + tcl_fixed_bytes(); }
 
-template <bool CAUSAL>
-__global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap map_q,    // qkv, Lb-row boxes
+template <bool CAUSAL, int EW>
+__global__ void __launch_bounds__(tcl_threads(EW), 1) attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap map_q,    // qkv, Lb-row boxes
                                                                           const __grid_constant__ CUtensorMap map_do,   // d_o, Lb-row boxes
                                                                           const __grid_constant__ CUtensorMap map_kv,   // qkv, 128-row boxes
                                                                           const __grid_constant__ CUtensorMap map_dq,   // dqkv, Lb-row boxes
@@ -1097,8 +1105,11 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
 
   const int nq = (Lb + 63) >> 6;  // query chunks (3 or 4)
   const int n_steps = 2 * nq;
+  constexpr int NEW = EW * 32;         // element-wise threads
+  constexpr int NC = 64 / (EW / 4);    // query columns per thread and step (32 or 16)
+  constexpr int TPQ = NEW / 256;       // threads per query in the D computation
 
-  if (warp == 9) {
+  if (warp == EW + 1) {
     if (lane == 0) {
       tma_prefetch_desc(&map_q);
       tma_prefetch_desc(&map_do);
@@ -1112,11 +1123,11 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
         mbar_init(&bar_kvempty[i], 1);
         mbar_init(&bar_s[i], 1);
       }
-      mbar_init(bar_p, 256);
+      mbar_init(bar_p, NEW);
       mbar_init(bar_f, 1);
       mbar_init(bar_kv, 1);
-      mbar_init(bar_kvfree, 256);
-      mbar_init(bar_qfree, 256);
+      mbar_init(bar_kvfree, NEW);
+      mbar_init(bar_qfree, NEW);
       fence_mbar_init();
     }
     __syncwarp();
@@ -1130,7 +1141,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
   pdl_wait();
   pdl_trigger();
 
-  if (warp == 8) {
+  if (warp == EW) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int k = 0;
@@ -1151,7 +1162,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == EW + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_out = make_idesc_bf16(TC_ROWS, 64) | kIdescBMnMajor;
@@ -1222,34 +1233,37 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
       }
     }
   } else {
-    // ===================== element-wise + epilogue: thread = key row of the block; half = 32 of the chunk's 64 query columns =====================
-    const int quad = warp & 3, half = warp >> 2;
+    // ===================== element-wise + epilogue: thread = key row of the block; part = NC of the chunk's 64 query columns =====================
+    const int quad = warp & 3, half = warp >> 2;  // ("half": which NC-column part of a 64-column chunk / of the 64 head columns)
     const int t = quad * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const f32x2 c2 = f2_pack(scale_log2e, scale_log2e);
     // lse and D = rowsum(dO * O) of query q = threadIdx.x of problem `item`, in two halves: the O row is fetched from global
     // memory first, the products with the dO tile (shared memory) come later
-    uint4 ov[8];
+    // (TPQ threads per query, adjacent lanes: each takes 8 / TPQ of the row's eight 16-byte pieces)
+    constexpr int OV = 8 / TPQ;
+    uint4 ov[OV];
     float lse_q = 0.f;
+    const int dq_q = threadIdx.x / TPQ, dq_h = threadIdx.x % TPQ;
     auto d_fetch = [&](int item) {
-      const int s = item / H, h = item - s * H, q = threadIdx.x;
+      const int s = item / H, h = item - s * H, q = dq_q;
       lse_q = 0.f;
       if (q < L) {
-        const uint4* op = reinterpret_cast<const uint4*>(o + (static_cast<size_t>(s) * L + q) * d + h * 64);
+        const uint4* op = reinterpret_cast<const uint4*>(o + (static_cast<size_t>(s) * L + q) * d + h * 64) + dq_h * OV;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) ov[c] = __ldg(op + c);
+        for (int c = 0; c < OV; ++c) ov[c] = __ldg(op + c);
         lse_q = lse2[(static_cast<size_t>(s) * H + h) * L + q];
       }
     };
     auto d_finish = [&](int kk) {  // kk = per-CTA index of the problem
-      const int qs = PF ? (kk & 1) : 0, u = PF ? (kk >> 1) : kk, q = threadIdx.x;
+      const int qs = PF ? (kk & 1) : 0, u = PF ? (kk >> 1) : kk, q = dq_q;
       mbar_wait(&bar_qfull[qs], u & 1);
       const uint8_t* tdO = qdo + qs * 2 * tile_bytes + tile_bytes;
       float D = 0.f;
       if (q < L) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 a = *reinterpret_cast<const uint4*>(tdO + q * 128 + ((c ^ (q & 7)) << 4));
+        for (int c = 0; c < OV; ++c) {
+          const uint4 a = *reinterpret_cast<const uint4*>(tdO + q * 128 + (((dq_h * OV + c) ^ (q & 7)) << 4));
           const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -1258,8 +1272,11 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
           }
         }
       }
-      sLse[(kk & 1) * 256 + q] = -lse_q;  // both are only ever subtracted
-      sD[(kk & 1) * 256 + q] = -D;
+      if (TPQ == 2) D += __shfl_xor_sync(0xffffffffu, D, 1);
+      if (dq_h == 0) {
+        sLse[(kk & 1) * 256 + q] = -lse_q;  // both are only ever subtracted
+        sD[(kk & 1) * 256 + q] = -D;
+      }
     };
     uint32_t g = 0;
     int k = 0;
@@ -1268,7 +1285,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
     if (blockIdx.x < n_items) {
       d_fetch(blockIdx.x);
       d_finish(0);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NEW) : "memory");
     }
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
       const int s = it / H, h = it - s * H;
@@ -1280,23 +1297,23 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
       if (!PF && k > 0) {  // single-buffered tiles: this problem's per-query arrays can only be built now
         d_fetch(it);
         d_finish(k);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NEW) : "memory");
       }
       // dK, dV of a complete key block (row = key, this half's 32 head columns) into the block's dead K / V rows
       auto drain_kv = [&](int kb) {
         uint8_t* tK = kv + kb * TCL_KV_SLOT;
         mbar_wait(bar_kv, (2 * k + kb) & 1);
         tc_fence_after();
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32(trow + 256u + static_cast<uint32_t>(half * 32), o0);
-        tmem_ld_32x32(trow + 320u + static_cast<uint32_t>(half * 32), o1);
-        tmem_ld_wait_regs(o0);
-        tmem_ld_wait_regs(o1);
+        uint32_t o0[NC], o1[NC];
+        tcl_ld<NC>(trow + 256u + static_cast<uint32_t>(half * NC), o0);
+        tcl_ld<NC>(trow + 320u + static_cast<uint32_t>(half * NC), o1);
+        tcl_wait<NC>(o0);
+        tcl_wait<NC>(o1);
         tc_fence_before();
         mbar_arrive(bar_kvfree);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q4) ^ (t & 7)) << 4));
+        for (int q4 = 0; q4 < NC / 8; ++q4) {
+          const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * (NC / 8) + q4) ^ (t & 7)) << 4));
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(o0[8 * q4 + 2 * e]) * scale, __uint_as_float(o0[8 * q4 + 2 * e + 1]) * scale);
@@ -1310,24 +1327,24 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
         const int kb = i >= nq ? 1 : 0, qc = i - kb * nq, b = i & 1;
         const int key = kb * TC_ROWS + t;
         const int key0 = kb * TC_ROWS + quad * 32;  // first key of the warp
-        const int col0 = qc * 64 + half * 32;       // first query of this thread's 32 columns
-        const bool active = col0 < Lb;              // (warp-uniform) the chunk has columns for this half
-        // (warp-uniform) every (key, query) of the warp's 32 x 32 piece is live / none is: no masks, or no math at all
-        const bool all_live = key0 + 32 <= L && col0 + 32 <= L && (!CAUSAL || key0 + 31 <= col0);
-        const bool none_live = key0 >= L || col0 >= L || (CAUSAL && key0 > col0 + 31);
+        const int col0 = qc * 64 + half * NC;       // first query of this thread's NC columns
+        const bool active = col0 < Lb;              // (warp-uniform) the chunk has columns for this part
+        // (warp-uniform) every (key, query) of the warp's 32 x NC piece is live / none is: no masks, or no math at all
+        const bool all_live = key0 + 32 <= L && col0 + NC <= L && (!CAUSAL || key0 + 31 <= col0);
+        const bool none_live = key0 >= L || col0 >= L || (CAUSAL && key0 > col0 + NC - 1);
         if (PF && i == nq && has_next) d_fetch(it + gridDim.x);  // the next problem's O row: in flight during this step
         mbar_wait(&bar_s[b], (g >> 1) & 1);
         tc_fence_after();
-        uint32_t pp[16], ds[16];
+        uint32_t pp[NC / 2], ds[NC / 2];
         if (active && !none_live) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32(trow + static_cast<uint32_t>(b * 128 + half * 32), sv);
-          tmem_ld_32x32(trow + static_cast<uint32_t>(b * 128 + 64 + half * 32), dv);
-          tmem_ld_wait_regs(sv);
-          tmem_ld_wait_regs(dv);
+          uint32_t sv[NC], dv[NC];
+          tcl_ld<NC>(trow + static_cast<uint32_t>(b * 128 + half * NC), sv);
+          tcl_ld<NC>(trow + static_cast<uint32_t>(b * 128 + 64 + half * NC), dv);
+          tcl_wait<NC>(sv);
+          tcl_wait<NC>(dv);
           if (all_live) {
 #pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {  // 4 queries per iteration
+            for (int e4 = 0; e4 < NC / 4; ++e4) {  // 4 queries per iteration
               const float4 nl = *reinterpret_cast<const float4*>(nLse + col0 + 4 * e4);
               const float4 nD = *reinterpret_cast<const float4*>(nDs + col0 + 4 * e4);
               float p0, p1, p2, p3;
@@ -1347,7 +1364,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
             const int c_hi = key < L ? L : 0;
             const int c_lo = CAUSAL ? key : 0;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
+            for (int e = 0; e < NC / 2; ++e) {
               const int c = col0 + 2 * e;
               const float2 nl = *reinterpret_cast<const float2*>(nLse + c);
               const float2 nD = *reinterpret_cast<const float2*>(nDs + c);
@@ -1365,14 +1382,14 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) { pp[e] = 0u; ds[e] = 0u; }
+          for (int e = 0; e < NC / 2; ++e) { pp[e] = 0u; ds[e] = 0u; }
         }
         if (g > 0) mbar_wait(bar_f, (g - 1) & 1);  // the previous step's output MMAs have read the slabs
         if (active) {
           uint8_t* sS = slabS + (qc & 1) * TC_SLAB;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q4) ^ (t & 7)) << 4));
+          for (int q4 = 0; q4 < NC / 8; ++q4) {
+            const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * (NC / 8) + q4) ^ (t & 7)) << 4));
             *reinterpret_cast<uint4*>(slabP + off) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
             *reinterpret_cast<uint4*>(sS + off) = make_uint4(ds[4 * q4], ds[4 * q4 + 1], ds[4 * q4 + 2], ds[4 * q4 + 3]);
           }
@@ -1391,7 +1408,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
           // the first key block's dK / dV leave one step late (its last output MMAs ran under this step's math) ...
           drain_kv(0);
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(NEW) : "memory");
           if (threadIdx.x == 0) {
             tma_store_3d(&map_dkv, kv, d + h * 64, 0, s);
             tma_store_3d(&map_dkv, kv + TC_SLAB, 2 * d + h * 64, 0, s);
@@ -1412,16 +1429,16 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
       mbar_wait(bar_f, (g - 1) & 1);
       tc_fence_after();
       {
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32(trow + 384u + static_cast<uint32_t>(half * 32), o0);
-        tmem_ld_32x32(trow + 448u + static_cast<uint32_t>(half * 32), o1);
-        tmem_ld_wait_regs(o0);
-        tmem_ld_wait_regs(o1);
+        uint32_t o0[NC], o1[NC];
+        tcl_ld<NC>(trow + 384u + static_cast<uint32_t>(half * NC), o0);
+        tcl_ld<NC>(trow + 448u + static_cast<uint32_t>(half * NC), o1);
+        tcl_wait<NC>(o0);
+        tcl_wait<NC>(o1);
         tc_fence_before();
         mbar_arrive(bar_qfree);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * 4 + q4) ^ (t & 7)) << 4));
+        for (int q4 = 0; q4 < NC / 8; ++q4) {
+          const uint32_t off = static_cast<uint32_t>(t * 128 + (((half * (NC / 8) + q4) ^ (t & 7)) << 4));
           uint32_t w[4];
           if (t < Lb) {
 #pragma unroll
@@ -1436,7 +1453,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
         }
       }
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NEW) : "memory");
       if (threadIdx.x == 0) {
         tma_store_3d(&map_dq, tQ, h * 64, 0, s);
         tma_store_3d(&map_dkv, kv + TCL_KV_SLOT, d + h * 64, TC_ROWS, s);
@@ -1455,7 +1472,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) attn_tc_bwd_long_kernel(const 
     if (threadIdx.x == 0) bulk_wait<0>();
   }
   __syncthreads();
-  if (warp == 9) {
+  if (warp == EW + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
@@ -1567,15 +1584,17 @@ const char* attention_tc_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, co
     }
     const int n_items = S * H;
     const int grid = n_items < n_sms_l ? n_items : n_sms_l;
-    auto kern = causal ? attn_tc_bwd_long_kernel<true> : attn_tc_bwd_long_kernel<false>;
+    static const int ew = getenv("MUDPT_ATTN_TCL_WARPS") ? atoi(getenv("MUDPT_ATTN_TCL_WARPS")) : 16;
+    auto kern = ew == 8 ? (causal ? attn_tc_bwd_long_kernel<true, 8> : attn_tc_bwd_long_kernel<false, 8>)
+                        : (causal ? attn_tc_bwd_long_kernel<true, 16> : attn_tc_bwd_long_kernel<false, 16>);
     static bool attr_long[2] = {false, false};
     if (!attr_long[causal ? 1 : 0]) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         return "attention (tcgen05 backward, resident): cudaFuncSetAttribute failed";
       attr_long[causal ? 1 : 0] = true;
     }
-    launch_pdl(kern, dim3(grid), dim3(TCL_THREADS), static_cast<size_t>(smem), stream, mq, mdo, mkv, mdq, mdkv, o, lse2, L, H, d, Lb, n_items,
-               0.125f, 0.125f * 1.4426950408889634f);
+    launch_pdl(kern, dim3(grid), dim3(tcl_threads(ew == 8 ? 8 : 16)), static_cast<size_t>(smem), stream, mq, mdo, mkv, mdq, mdkv, o, lse2, L, H, d, Lb,
+               n_items, 0.125f, 0.125f * 1.4426950408889634f);
     count_launch(1);
     return launch_status("attention bwd (tcgen05, resident) launch failed");
   }
