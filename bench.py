@@ -305,7 +305,7 @@ def run_ours(args):
             trainer.model.overlap_towers = False
 
         def step_q(i):
-            trainer.optim.zero_grad(set_to_none=False)
+            trainer.optim.zero_grad()
             trainer.model.forward_backward(imgs_dev[i % NBUF], labs_dev[i % NBUF])
             trainer.optim.step()
 
