@@ -258,6 +258,9 @@ int mudpt_debug_buffer(mudpt_handle* h, int32_t tower, const char* name, int32_t
  * GEMMs of a block: gemm_qkv, gemm_out, gemm_fc, gemm_proj, gemm_dproj, gemm_dfc, gemm_dout, gemm_dqkv (16 x 4 doubles). */
 int mudpt_profile_begin(mudpt_handle* h);
 int mudpt_profile_end(mudpt_handle* h, double* out_host, int32_t n_out);
+/* The same with a fifth value per class: sum over its launches of max(FLOPs / peak_tflops, bytes / hbm_gbs) in ms -- the
+ * time the class would take if every launch ran at the bound that applies to it (n_out >= 5 * classes). */
+int mudpt_profile_end_bound(mudpt_handle* h, double* out_host, int32_t n_out, double peak_tflops, double hbm_gbs);
 /* number of kernel launches issued by the library on this handle since creation */
 int64_t mudpt_launch_count(mudpt_handle* h);
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mudpt_debug_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mudpt_profile_begin": (C.c_int, [C.c_void_p]),
     "mudpt_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
+    "mudpt_profile_end_bound": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_double, C.c_double]),
     "mudpt_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

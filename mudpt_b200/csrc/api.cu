@@ -1096,24 +1096,41 @@ int mudpt_profile_begin(mudpt_handle* h) {
 // out[cat*4 + {0,1,2,3}] = {total ms, launches, algorithmic FLOPs, algorithmic bytes}; cat order:
 // gemm (other), attn_fwd, attn_bwd, ln_fwd, ln_bwd, splice, head, stem, gemm_qkv, gemm_out, gemm_fc, gemm_proj,
 // gemm_dproj, gemm_dfc, gemm_dout, gemm_dqkv.  Blocks until the recorded work is done.
-int mudpt_profile_end(mudpt_handle* h, double* out_host, int32_t n_out) {
-  if (!h || !out_host) return fail(h, "mudpt_profile_end: null argument");
-  if (n_out < PC_COUNT * 4) return fail(h, "mudpt_profile_end: output too small");
+// With peaks (TFLOP/s, GB/s) > 0 a fifth value per class: the sum over its launches of the time the launch would take at
+// the bound that applies to it, max(FLOPs / peak, algorithmic bytes / hbm) -- per launch, so a class that mixes
+// tensor-bound and HBM-bound launches is measured against the right one each time.
+static int profile_collect(mudpt_handle* h, double* out_host, int stride, double peak_tflops, double hbm_gbs) {
   h->prof.on = false;
-  for (int i = 0; i < PC_COUNT * 4; ++i) out_host[i] = 0.0;
+  for (int i = 0; i < PC_COUNT * stride; ++i) out_host[i] = 0.0;
   for (ProfRec& r : h->prof.recs) {
     CUDA_OK(h, cudaEventSynchronize(r.e1));
     float ms = 0.f;
     CUDA_OK(h, cudaEventElapsedTime(&ms, r.e0, r.e1));
-    out_host[r.cat * 4 + 0] += ms;
-    out_host[r.cat * 4 + 1] += 1.0;
-    out_host[r.cat * 4 + 2] += r.flops;
-    out_host[r.cat * 4 + 3] += r.bytes;
+    out_host[r.cat * stride + 0] += ms;
+    out_host[r.cat * stride + 1] += 1.0;
+    out_host[r.cat * stride + 2] += r.flops;
+    out_host[r.cat * stride + 3] += r.bytes;
+    if (stride > 4 && peak_tflops > 0 && hbm_gbs > 0) {
+      const double t_fl = r.flops / (peak_tflops * 1e12), t_by = r.bytes / (hbm_gbs * 1e9);
+      out_host[r.cat * stride + 4] += 1e3 * (t_fl > t_by ? t_fl : t_by);
+    }
     h->prof.pool.push_back(r.e0);
     h->prof.pool.push_back(r.e1);
   }
   h->prof.recs.clear();
   return 0;
+}
+
+int mudpt_profile_end(mudpt_handle* h, double* out_host, int32_t n_out) {
+  if (!h || !out_host) return fail(h, "mudpt_profile_end: null argument");
+  if (n_out < PC_COUNT * 4) return fail(h, "mudpt_profile_end: output too small");
+  return profile_collect(h, out_host, 4, 0.0, 0.0);
+}
+
+int mudpt_profile_end_bound(mudpt_handle* h, double* out_host, int32_t n_out, double peak_tflops, double hbm_gbs) {
+  if (!h || !out_host) return fail(h, "mudpt_profile_end_bound: null argument");
+  if (n_out < PC_COUNT * 5) return fail(h, "mudpt_profile_end_bound: output too small");
+  return profile_collect(h, out_host, 5, peak_tflops, hbm_gbs);
 }
 
 int64_t mudpt_launch_count(mudpt_handle* h) { return h ? g_launch_counter.load() - h->launches_at_create : 0; }

@@ -165,14 +165,16 @@ class Engine:
     def profile_begin(self) -> None:
         _lib.check(self.lib.mudpt_profile_begin(self.h), self.h)
 
-    def profile_end(self) -> dict:
-        n = len(self.PROFILE_CATEGORIES) * 4
+    def profile_end(self, peak_tflops: float = 0.0, hbm_gbs: float = 0.0) -> dict:
+        """Per kernel class: ms, launches, algorithmic FLOPs and bytes -- and, with the two peaks given, `bound_ms`: the
+        sum over the launches of max(FLOPs / peak, bytes / hbm), the time at the bound that applies to each launch."""
+        n = len(self.PROFILE_CATEGORIES) * 5
         buf = (C.c_double * n)()
-        _lib.check(self.lib.mudpt_profile_end(self.h, buf, n), self.h)
-        out = {c: {"ms": buf[i * 4], "launches": int(buf[i * 4 + 1]), "flops": buf[i * 4 + 2], "bytes": buf[i * 4 + 3]}
-               for i, c in enumerate(self.PROFILE_CATEGORIES)}
+        _lib.check(self.lib.mudpt_profile_end_bound(self.h, buf, n, float(peak_tflops), float(hbm_gbs)), self.h)
+        out = {c: {"ms": buf[i * 5], "launches": int(buf[i * 5 + 1]), "flops": buf[i * 5 + 2], "bytes": buf[i * 5 + 3],
+                   "bound_ms": buf[i * 5 + 4]} for i, c in enumerate(self.PROFILE_CATEGORIES)}
         # "gemm" = every launch of the tcgen05 GEMM kernel (the per-GEMM entries stay beside it)
-        out["gemm"] = {k: sum(v[k] for c, v in out.items() if c.startswith("gemm_")) for k in ("ms", "launches", "flops", "bytes")}
+        out["gemm"] = {k: sum(v[k] for c, v in out.items() if c.startswith("gemm_")) for k in ("ms", "launches", "flops", "bytes", "bound_ms")}
         return out
 
     def launch_count(self) -> int:
