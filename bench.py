@@ -550,8 +550,8 @@ def collective_timings(device, world, reps=20):
     bucket = mdist.FlatGrads(grads)   # what the fused step does: the gradients live in one flat bucket
     ops = {"all_gather_text_features": lambda: mdist.all_gather_rows(f_loc, C),
            "reduce_scatter_d_text_features": lambda: mdist.reduce_scatter_rows(d_full, C),
-           "all_reduce_prompt_grads": bucket.all_reduce,  # what the step does: reduce-scatter + all-gather of the flat bucket
-           "all_reduce_prompt_grads_ncclAllReduce": lambda: bucket.all_reduce(two_phase=False),
+           "all_reduce_prompt_grads": bucket.all_reduce,  # what the step does: one all-reduce of the flat bucket
+           "all_reduce_prompt_grads_rs_ag": lambda: bucket.all_reduce(two_phase=True),
            "all_reduce_loss": lambda: mdist.all_reduce_sum(loss)}
     out = {}
     for name, fn in ops.items():
