@@ -119,13 +119,17 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   if (row >= M) return;
   const size_t off = static_cast<size_t>(row) * d;
   const float* x = reinterpret_cast<const float*>(xv);
-  float4 v[NV], g[NV];
+  float4 v[NV], g[NV], rs[NV];
   float sum = 0.f;
-  // issue every load of the row up front (x, dy, residual gradient): 3 streams in flight per lane
+  // issue every load of the row up front (x, dy, residual gradient): 3 streams in flight per lane.  The residual must be
+  // in registers before the first store: dx may alias it, so a load placed after a store of the row is ordered behind it
+  // and every 16-byte piece pays its own memory round trip (measured on the single-wave launches of 6-10 thousand rows)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
+    rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < d) {
+      if (resid != nullptr) rs[i] = *reinterpret_cast<const float4*>(resid + off + c);
       if constexpr (X_STATS) {
         const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(xv) + off + c);
         const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
@@ -190,8 +194,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (resid != nullptr) r = *reinterpret_cast<const float4*>(resid + off + c);
+      const float4 r = rs[i];
       float4 o;
       o.x = r.x + rstd * (g[i].x - s1 - v[i].x * s2);
       o.y = r.y + rstd * (g[i].y - s1 - v[i].y * s2);
