@@ -7,6 +7,8 @@
 //   patch extraction .. clip/model.py:527-529 (conv1 with stride == kernel == patch)
 #include "rowops.h"
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch_count.h"
 
@@ -77,12 +79,19 @@ static int pick_nv(int d) {
   return nv <= 1 ? 1 : nv <= 2 ? 2 : nv <= 4 ? 4 : nv <= 6 ? 6 : 8;
 }
 
+// rows (= warps) per CTA of the LayerNorm kernels: experiment hook MUDPT_LN_WARPS (1..8)
+static int ln_warps() {
+  static const int w = getenv("MUDPT_LN_WARPS") ? atoi(getenv("MUDPT_LN_WARPS")) : 8;
+  return w < 1 ? 1 : (w > 8 ? 8 : w);
+}
+
 template <int NV>
 static void launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
                           float eps, cudaStream_t stream) {
-  const int grid = (M + 7) / 8;
-  if (out_bf16) launch_pdl(ln_fwd_kernel<NV, true>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, out, M, d, eps);
-  else launch_pdl(ln_fwd_kernel<NV, false>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, out, M, d, eps);
+  const int wpc = ln_warps();
+  const int grid = (M + wpc - 1) / wpc;
+  if (out_bf16) launch_pdl(ln_fwd_kernel<NV, true>, dim3(grid), dim3(32 * wpc), 0, stream, x, gamma, beta, out, M, d, eps);
+  else launch_pdl(ln_fwd_kernel<NV, false>, dim3(grid), dim3(32 * wpc), 0, stream, x, gamma, beta, out, M, d, eps);
 }
 
 const char* layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
@@ -214,13 +223,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
 template <int NV>
 static void launch_ln_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
                           float* dx, bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
-  const int grid = (M + 7) / 8;
+  const int wpc = ln_warps();
+  const int grid = (M + wpc - 1) / wpc;
+  const dim3 blk(32 * wpc);
   if (stats != nullptr) {  // (bf16 dy only: the dgrad GEMM's output)
-    launch_pdl(ln_bwd_kernel<NV, true, true>, dim3(grid), dim3(256), 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+    launch_pdl(ln_bwd_kernel<NV, true, true>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
   } else if (dy_bf16) {
-    launch_pdl(ln_bwd_kernel<NV, true, false>, dim3(grid), dim3(256), 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+    launch_pdl(ln_bwd_kernel<NV, true, false>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
   } else {
-    launch_pdl(ln_bwd_kernel<NV, false, false>, dim3(grid), dim3(256), 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+    launch_pdl(ln_bwd_kernel<NV, false, false>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
   }
 }
 

@@ -408,6 +408,15 @@ class CustomCLIP(nn.Module):
             # all-gather / reduce-scatter hide behind the vision tower.
             main = torch.cuda.current_stream(device)
             side = eng.side_stream()
+            tl = self.__dict__.get("_timeline")  # diagnostic (tests/gpu_step_timeline.py): timed events at the phase boundaries
+
+            def mark(name, stream):
+                if tl is not None:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(stream)
+                    tl.append((name, ev))
+
+            mark("start", main)
             side.wait_stream(main)  # P_v, image are ready
             with torch.cuda.stream(side):
                 if host_batch:
@@ -416,20 +425,25 @@ class CustomCLIP(nn.Module):
                     image = image.to(device, non_blocking=True).type(self.dtype)
                     label = label.to(device, non_blocking=True)
                 f_img = eng.vision_forward(image, P_v.detach())
+            mark("vision_fwd_end", side)
             f_txt_loc = eng.text_forward(P_t.detach(), True)
             f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
+            mark("text_fwd_end", main)
             main.wait_stream(side)
             f_img.record_stream(main)
             if host_batch:
                 label.record_stream(main)
             logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True)
             loss = self._publish_loss(loss, world)
+            mark("head_end", main)
             side.wait_stream(main)  # d_i
             with torch.cuda.stream(side):
                 dP_v = eng.vision_backward(d_i)
+            mark("vision_bwd_end", side)
             d_i.record_stream(side)
             d_t_loc = mdist.reduce_scatter_rows(d_t, n_cls) if world > 1 else d_t
             dP_t, _ = eng.text_backward(d_t_loc)
+            mark("text_bwd_end", main)
             main.wait_stream(side)
             dP_v.record_stream(main)
         if direct:
@@ -442,6 +456,10 @@ class CustomCLIP(nn.Module):
                 p.grad = v
             if world > 1:
                 fg.all_reduce()  # one collective on the bucket itself: no concatenation, no copies back
+            if self.__dict__.get("_timeline") is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream(device))
+                self.__dict__["_timeline"].append(("grads_end", ev))
         else:
             torch.autograd.backward([P_v, P_t], [dP_v, dP_t])
             if world > 1:
