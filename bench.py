@@ -367,7 +367,7 @@ def run_ours(args):
         prof = eng.profile_end(pk["bf16_sustained"], pk["hbm"])
         model.overlap_towers = overlap
         nprof = min(K, 5)
-        results[variant] = {"ms": ms / K, "ms_e2e": ms_e2e / K, "launches": launches, "prof": prof, "nprof": nprof,
+        results[variant] = {"model_dict": model.__dict__, "ms": ms / K, "ms_e2e": ms_e2e / K, "launches": launches, "prof": prof, "nprof": nprof,
                             "text_len": eng.text_len, "loss": float(trainer.forward_backward(
                                 {"img": imgs_host[0], "label": labs_host[0]})["loss"])}
         del trainer, model, eng
@@ -468,6 +468,10 @@ def run_ours(args):
         "inference_cfg3": infer,
         "sharded_vs_unsharded": dist_check,
         "collectives_us": collectives,
+        # how the head's text-feature exchange ran in the timed step (mudpt_b200/dist.py:PeerExchange)
+        "head_exchange": (None if world == 1 else
+                          "peer memory over NVLink (own pull kernels after a symmetric-memory barrier)"
+                          if full["model_dict"].get("peer_exchange") is not None else "NCCL all_gather / reduce_scatter"),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -553,6 +557,10 @@ def collective_timings(device, world, reps=20):
            "all_reduce_prompt_grads": bucket.all_reduce,  # what the step does: one all-reduce of the flat bucket
            "all_reduce_prompt_grads_rs_ag": lambda: bucket.all_reduce(two_phase=True),
            "all_reduce_loss": lambda: mdist.all_reduce_sum(loss)}
+    px = mdist.peer_exchange({}, C, e, device)
+    if px is not None:  # the head's exchange as the step does it where the ranks share a node: barrier + own pull kernel
+        ops["peer_all_gather_text_features"] = lambda: px.all_gather(0)
+        ops["peer_reduce_scatter_d_text_features"] = lambda: px.reduce_scatter(0)
     out = {}
     for name, fn in ops.items():
         for _ in range(3):

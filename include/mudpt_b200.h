@@ -194,6 +194,17 @@ int mudpt_set_attention_tc(int32_t mode);
 int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream);
 int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream);
 
+/* ---- own collectives over NVLink peer memory for the head's exchange (replaces the all_gather / reduce_scatter that
+ * nn.DataParallel's gather / scatter of trainers/mudpt.py:230-233 become under class sharding).  peers_dev: DEVICE array of
+ * `world` base pointers, one per rank of the node, to fp32 row matrices of `width` columns in memory every GPU maps
+ * (symmetric allocation); row shards as in mudpt_b200/dist.py:shard_bounds.  The caller orders each call after a barrier
+ * that makes the peers' writes visible, and before the next overwrite of the buffers.
+ *   all_gather:      peers[r] = rank r's shard [rows(r), width];  out [n_total, width]
+ *   reduce_scatter:  peers[r] = rank r's full matrix [n_total, width];  out [rows(rank), width] = sum over r, fixed order */
+int mudpt_peer_all_gather_rows(const void* peers_dev, int32_t world, int32_t n_total, int32_t width, float* out, void* stream);
+int mudpt_peer_reduce_scatter_rows(const void* peers_dev, int32_t world, int32_t rank, int32_t n_total, int32_t width, float* out,
+                                   void* stream);
+
 /* ---- trainable prompt algebra of MuDPT (trainers/mudpt.py:117-130, 143, 175; clip/model.py:534-541) --------------
  * The three trainable Linear layers, ln_pre on the shallow vision prompt and the stacking that turn the 10 trainable
  * tensors into the two prompt stacks the towers splice, and the backward into those tensors: 2 + 2 launches.

@@ -65,6 +65,8 @@ SIGNATURES = {
                                        C.POINTER(C.c_float), C.c_void_p, C.c_int64, c_f32p, C.c_void_p]),
     "mudpt_debug_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mudpt_profile_begin": (C.c_int, [C.c_void_p]),
+    "mudpt_peer_all_gather_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mudpt_peer_reduce_scatter_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mudpt_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
     "mudpt_profile_end_bound": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_double, C.c_double]),
     "mudpt_launch_count": (C.c_int64, [C.c_void_p]),

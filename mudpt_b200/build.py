@@ -17,7 +17,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "head.cu", "prompt.cu", "augment.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "head.cu", "prompt.cu", "augment.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
 # --use_fast_math only affects the QuickGELU sigmoid / softmax exponentials inside epilogues whose

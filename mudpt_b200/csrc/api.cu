@@ -17,6 +17,7 @@
 #include "head.h"
 #include "launch_count.h"
 #include "prompt.h"
+#include "peer.h"
 #include "rowops.h"
 
 namespace mudpt {
@@ -1016,6 +1017,18 @@ int mudpt_set_attention_tc(int32_t mode) {
 }
 int mudpt_im2col(const float* images, uint16_t* patches, int32_t B, int32_t R, int32_t patch, int32_t ld, void* stream) {
   CKG(im2col_bf16(images, reinterpret_cast<bf16*>(patches), B, R, patch, ld, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_peer_all_gather_rows(const void* peers_dev, int32_t world, int32_t n_total, int32_t width, float* out, void* stream) {
+  if (!peers_dev || !out) return fail(nullptr, "mudpt_peer_all_gather_rows: null argument");
+  CKG(peer_gather_rows(reinterpret_cast<const float* const*>(peers_dev), world, n_total, width, out, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_peer_reduce_scatter_rows(const void* peers_dev, int32_t world, int32_t rank, int32_t n_total, int32_t width, float* out,
+                                   void* stream) {
+  if (!peers_dev || !out) return fail(nullptr, "mudpt_peer_reduce_scatter_rows: null argument");
+  CKG(peer_reduce_scatter_rows(reinterpret_cast<const float* const*>(peers_dev), world, rank, n_total, width, out,
+                               static_cast<cudaStream_t>(stream)));
   return 0;
 }
 int mudpt_cast_bf16(const float* in, uint16_t* out, int64_t numel, void* stream) {

@@ -141,6 +141,91 @@ class FlatGrads:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
 
+class PeerExchange:
+    """The logits head's exchange over NVLink peer memory instead of NCCL launches: every rank's
+    text-feature shard [C / G, e] and its full text-feature gradient [C, e] live in symmetric allocations that all GPUs of
+    the node map (torch.distributed._symmetric_memory: allocation, rendezvous, stream-ordered barrier); after a barrier each
+    rank PULLS what it needs with the library's own kernels (mudpt_peer_all_gather_rows / mudpt_peer_reduce_scatter_rows:
+    plain loads over NVLink, fixed summation order).  Two slots, used alternately: a rank can only be one barrier ahead of the
+    slowest one, so a slot is never overwritten while a peer still reads it.  Single node, NCCL process group only."""
+
+    def __init__(self, n_total: int, width: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        self.n_total, self.width, self.device = n_total, width, device
+        self.world, self.rank = world_size(), rank()
+        self.lo, self.hi = shard_bounds(n_total, self.rank, self.world)
+        cap = -(-n_total // self.world)
+        group = dist.group.WORLD
+        self.f, self.d, self.fh, self.dh = [], [], [], []
+        for _ in range(2):
+            f = symm.empty(cap, width, dtype=torch.float32, device=device)
+            d = symm.empty(n_total, width, dtype=torch.float32, device=device)
+            f.zero_()
+            d.zero_()
+            self.fh.append(symm.rendezvous(f, group))
+            self.dh.append(symm.rendezvous(d, group))
+            self.f.append(f)
+            self.d.append(d)
+        self.slot = 1
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+
+    def matches(self, n_total: int, width: int, device: torch.device) -> bool:
+        return (n_total, width, device) == (self.n_total, self.width, self.device) and self.world == world_size()
+
+    def next_slot(self) -> int:
+        self.slot ^= 1
+        return self.slot
+
+    def shard_out(self, slot: int) -> torch.Tensor:
+        """Where this rank's text features of the step go: its rows of the symmetric buffer."""
+        return self.f[slot][:self.hi - self.lo]
+
+    def grad_out(self, slot: int) -> torch.Tensor:
+        return self.d[slot]
+
+    def all_gather(self, slot: int) -> torch.Tensor:
+        """[C, e] text features of all ranks; to be called on the stream that wrote shard_out(slot)."""
+        self.fh[slot].barrier(channel=0)  # every rank's shard of this step is written and visible
+        out = torch.empty(self.n_total, self.width, device=self.device, dtype=torch.float32)
+        self._lib.check(self.lib.mudpt_peer_all_gather_rows(self.fh[slot].buffer_ptrs_dev, self.world, self.n_total, self.width,
+                                                            out.data_ptr(), self._lib.stream_ptr(self.device)))
+        return out
+
+    def reduce_scatter(self, slot: int) -> torch.Tensor:
+        """This rank's rows of the rank-summed [C, e] gradient; after grad_out(slot) was written on the same stream."""
+        self.dh[slot].barrier(channel=0)
+        out = torch.empty(self.hi - self.lo, self.width, device=self.device, dtype=torch.float32)
+        self._lib.check(self.lib.mudpt_peer_reduce_scatter_rows(self.dh[slot].buffer_ptrs_dev, self.world, self.rank, self.n_total,
+                                                                self.width, out.data_ptr(), self._lib.stream_ptr(self.device)))
+        return out
+
+
+_peer_exchange_failed = False
+
+
+def peer_exchange(cache: dict, n_total: int, width: int, device: torch.device):
+    """The PeerExchange of (n_total, width) kept in `cache`, or None where it does not apply (one rank, not NCCL, switched
+    off with MUDPT_PEER_EXCHANGE=0, or symmetric memory unavailable -- said once on stderr; NCCL collectives then)."""
+    import os
+    import sys
+    global _peer_exchange_failed
+    if world_size() == 1 or not _is_nccl() or device.type != "cuda" or _peer_exchange_failed or os.environ.get("MUDPT_PEER_EXCHANGE", "1") != "1":
+        return None
+    px = cache.get("peer_exchange")
+    if px is not None and px.matches(n_total, width, device):
+        return px
+    try:
+        px = PeerExchange(n_total, width, device)
+    except Exception as e:  # collective set-up: it fails (or not) on every rank alike
+        _peer_exchange_failed = True
+        print(f"mudpt_b200: peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL collectives", file=sys.stderr)
+        return None
+    cache["peer_exchange"] = px
+    return px
+
+
 def broadcast_params(params: List[torch.nn.Parameter], src: int = 0) -> None:
     """Make the replicated trainable tensors identical on every rank (one flat bucket)."""
     if world_size() == 1 or not params:

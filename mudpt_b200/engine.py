@@ -113,10 +113,13 @@ class Engine:
         self.n_classes, self.text_len = Cn, int(seq_len)
         self.class_key = None
 
-    def text_forward(self, prompts: torch.Tensor, splice_layer0: bool = True) -> torch.Tensor:
+    def text_forward(self, prompts: torch.Tensor, splice_layer0: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         prompts = prompts.contiguous()
         self._check_f32(prompts, (self.depth, self.n_ctx, self.arch["transformer_width"]))
-        out = torch.empty(self.n_classes, self.arch["embed_dim"], device=self.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(self.n_classes, self.arch["embed_dim"], device=self.device, dtype=torch.float32)
+        else:  # caller-owned destination (e.g. a peer-mapped buffer of the head's exchange)
+            self._check_f32(out, (self.n_classes, self.arch["embed_dim"]))
         _lib.check(self.lib.mudpt_text_forward(self.h, prompts.data_ptr(), 1 if splice_layer0 else 0, out.data_ptr(),
                                                _lib.stream_ptr(self.device)), self.h)
         self.text_gen += 1
@@ -135,13 +138,20 @@ class Engine:
                                                 _lib.stream_ptr(self.device)), self.h)
         return dP, dx0
 
-    def logits_head(self, f_img, f_txt, labels: Optional[torch.Tensor], inv_global_batch: float, want_grads: bool):
+    def logits_head(self, f_img, f_txt, labels: Optional[torch.Tensor], inv_global_batch: float, want_grads: bool,
+                    d_t_out: Optional[torch.Tensor] = None):
         f_img, f_txt = f_img.contiguous(), f_txt.contiguous()
         B, Cn = f_img.shape[0], f_txt.shape[0]
         logits = torch.empty(B, Cn, device=self.device, dtype=torch.float32)
         loss = torch.zeros((), device=self.device, dtype=torch.float32)
         d_i = torch.empty_like(f_img) if want_grads else None
-        d_t = torch.empty_like(f_txt) if want_grads else None
+        d_t = None
+        if want_grads:
+            if d_t_out is not None:  # caller-owned destination (peer-mapped buffer)
+                self._check_f32(d_t_out, tuple(f_txt.shape))
+                d_t = d_t_out
+            else:
+                d_t = torch.empty_like(f_txt)
         if labels is not None:
             labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
         _lib.check(self.lib.mudpt_logits_head(

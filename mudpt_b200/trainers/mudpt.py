@@ -426,14 +426,23 @@ class CustomCLIP(nn.Module):
                     label = label.to(device, non_blocking=True)
                 f_img = eng.vision_forward(image, P_v.detach())
             mark("vision_fwd_end", side)
-            f_txt_loc = eng.text_forward(P_t.detach(), True)
-            f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
+            # the head's exchange: over NVLink peer memory with the library's own kernels where the ranks share a node,
+            # else NCCL collectives
+            px = mdist.peer_exchange(self.__dict__, n_cls, eng.arch["embed_dim"], device) if world > 1 else None
+            if px is not None:
+                slot = px.next_slot()
+                eng.text_forward(P_t.detach(), True, out=px.shard_out(slot))
+                f_txt = px.all_gather(slot)
+            else:
+                f_txt_loc = eng.text_forward(P_t.detach(), True)
+                f_txt = mdist.all_gather_rows(f_txt_loc, n_cls) if world > 1 else f_txt_loc
             mark("text_fwd_end", main)
             main.wait_stream(side)
             f_img.record_stream(main)
             if host_batch:
                 label.record_stream(main)
-            logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True)
+            logits, loss, d_i, d_t = eng.logits_head(f_img, f_txt, label, 1.0 / (image.shape[0] * world), True,
+                                                     d_t_out=px.grad_out(slot) if px is not None else None)
             loss = self._publish_loss(loss, world)
             mark("head_end", main)
             side.wait_stream(main)  # d_i
@@ -441,7 +450,10 @@ class CustomCLIP(nn.Module):
                 dP_v = eng.vision_backward(d_i)
             mark("vision_bwd_end", side)
             d_i.record_stream(side)
-            d_t_loc = mdist.reduce_scatter_rows(d_t, n_cls) if world > 1 else d_t
+            if px is not None:
+                d_t_loc = px.reduce_scatter(slot)
+            else:
+                d_t_loc = mdist.reduce_scatter_rows(d_t, n_cls) if world > 1 else d_t
             dP_t, _ = eng.text_backward(d_t_loc)
             mark("text_bwd_end", main)
             main.wait_stream(side)
