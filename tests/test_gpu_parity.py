@@ -301,6 +301,44 @@ def test_unfused_layernorm_fallback_matches_reference(bring):
                 assert m["cos"] >= 0.999 and m["rel_l2"] <= 0.05, (opts, k, m)
 
 
+@pytest.mark.parametrize("world,n_total,width", [(8, 1000, 512), (4, 1001, 512), (3, 10, 64), (2, 1000, 768), (1, 5, 512)])
+def test_peer_collectives_on_one_device(world, n_total, width):
+    """mudpt_peer_all_gather_rows / mudpt_peer_reduce_scatter_rows with the `world` ranks' buffers emulated on one GPU (the
+    kernels only see a device array of base pointers): row shards as mudpt_b200.dist.shard_bounds, even and uneven splits;
+    gather bit-exact, reduce-scatter equal to the rank-ordered fp32 sum."""
+    import ctypes as C
+    from mudpt_b200 import _lib
+    from mudpt_b200 import dist as mdist
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    st = _lib.stream_ptr(dev)
+    g = torch.Generator(device="cpu").manual_seed(world * 1000 + n_total)
+    full = torch.randn(n_total, width, generator=g).to(dev)
+    cap = -(-n_total // world)
+    shards = []
+    for r in range(world):
+        lo, hi = mdist.shard_bounds(n_total, r, world)
+        b = torch.full((cap, width), float("nan"), device=dev)
+        b[:hi - lo] = full[lo:hi]
+        shards.append(b)
+    ptrs = torch.tensor([b.data_ptr() for b in shards], dtype=torch.int64, device=dev)
+    out = torch.empty(n_total, width, device=dev)
+    _lib.check(lib.mudpt_peer_all_gather_rows(ptrs.data_ptr(), world, n_total, width, out.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(out, full)
+    grads = [torch.randn(n_total, width, generator=g).to(dev) for _ in range(world)]
+    gptrs = torch.tensor([b.data_ptr() for b in grads], dtype=torch.int64, device=dev)
+    ref = grads[0].clone()
+    for b in grads[1:]:
+        ref += b  # rank order, fp32: the kernel's summation order
+    for r in range(world):
+        lo, hi = mdist.shard_bounds(n_total, r, world)
+        o = torch.empty(hi - lo, width, device=dev)
+        _lib.check(lib.mudpt_peer_reduce_scatter_rows(gptrs.data_ptr(), world, r, n_total, width, o.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert torch.equal(o, ref[lo:hi]), r
+
+
 def test_native_prompt_algebra_matches_torch():
     """mudpt_prompt_forward / _backward (2 + 2 launches) against the torch autograd version of the same algebra
     (trainers/mudpt.py:117-130, 143, 175; clip/model.py:534-541): both prompt stacks and the 10 gradients."""
