@@ -302,7 +302,11 @@ int ensure_tower(mudpt_handle* h, Tower& t, int S, int L) {
   CUDA_OK(h, dev_alloc(h, &t.dx_bf16, rows * d, g));
   CUDA_OK(h, dev_alloc(h, &t.dx, rows * d, g));
   CUDA_OK(h, dev_alloc(h, &t.dsum, rows * t.H, g));
-  if (!t.splice_ws) CUDA_OK(h, dev_alloc(h, &t.splice_ws, splice_bwd_workspace_floats(t.n_ctx > 0 ? t.n_ctx : 1, t.d)));
+  if (!t.splice_ws) {
+    const size_t nws = splice_bwd_workspace_floats(t.n_ctx > 0 ? t.n_ctx : 1, t.d);
+    CUDA_OK(h, dev_alloc(h, &t.splice_ws, nws));
+    CUDA_OK(h, cudaMemset(t.splice_ws, 0, nws * sizeof(float)));  // (the kernel's tickets start at zero and are left at zero)
+  }
   t.cap_rows = rows;
   t.fwd_done = false;
   return 0;
@@ -419,12 +423,11 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
   if (fused && ensure_folded(h, t, st)) return -1;
   for (int i = 0; i < t.layers; ++i) {
     const Layer& w = t.lw[i];
-    if (spliced(i) && (!fused || i == 0)) {
+    // the stand-alone LayerNorm does the block's splice in the same pass; the fused form splices in the previous block's
+    // residual epilogue (layer 0: a kernel of its own, with the statistics of the spliced rows)
+    if (spliced(i) && fused && i == 0) {
       const float* pr = prompts + static_cast<size_t>(i) * t.n_ctx * d;
-      if (fused)
-        CKP(h, st, PC_SPLICE, 0, 2.0 * t.S * t.n_ctx * dd * 4, splice_fwd_stats(t.x_in[i], t.xb_in[i], t.st_in[i], pr, t.S, t.L, t.row0, t.n_ctx, d, st));
-      else
-        CKP(h, st, PC_SPLICE, 0, 2.0 * t.S * t.n_ctx * dd * 4, splice_fwd(t.x_in[i], pr, t.S, t.L, t.row0, t.n_ctx, d, st));
+      CKP(h, st, PC_SPLICE, 0, 2.0 * t.S * t.n_ctx * dd * 4, splice_fwd_stats(t.x_in[i], t.xb_in[i], t.st_in[i], pr, t.S, t.L, t.row0, t.n_ctx, d, st));
     }
     // x + attn(ln_1(x))   (clip/model.py:299)
     GemmEpilogue e1;
@@ -434,7 +437,9 @@ int tower_forward(mudpt_handle* h, Tower& t, const float* prompts, int first_spl
       CKP(h, st, PC_GEMM_QKV, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
           gemm_bf16_tn(t.xb_in[i], d, w.w_in_ln, d, e1, M, 3 * d, d, st, &t.gws));
     } else {
-      CKP(h, st, PC_LN_FWD, 0, Md * dd * 6, layernorm_fwd(t.x_in[i], w.ln1_g, w.ln1_b, t.a_buf, true, M, d, kLnEps, st));
+      CKP(h, st, PC_LN_FWD, 0, Md * dd * 6,
+          layernorm_fwd_splice(t.x_in[i], spliced(i) ? prompts + static_cast<size_t>(i) * t.n_ctx * d : nullptr, t.L, t.row0,
+                               spliced(i) ? t.n_ctx : 0, w.ln1_g, w.ln1_b, t.a_buf, true, M, d, kLnEps, st));
       e1.mode = EPI_BF16; e1.bias = w.b_in;
       CKP(h, st, PC_GEMM_QKV, 2.0 * Md * 3 * dd * dd, 2 * (Md * dd + 3 * dd * dd + Md * 3 * dd),
           gemm_bf16_tn(t.a_buf, d, w.w_in, d, e1, M, 3 * d, d, st, &t.gws));
@@ -935,6 +940,7 @@ int mudpt_splice_backward(float* dx, uint16_t* dx_bf16, float* d_prompt, int32_t
   float* ws = nullptr;  // unit entry point: stream-ordered scratch (the towers own a persistent one)
   if (cudaMallocAsync(reinterpret_cast<void**>(&ws), splice_bwd_workspace_floats(n, width) * sizeof(float), st) != cudaSuccess)
     return fail(nullptr, "mudpt_splice_backward: scratch allocation failed");
+  cudaMemsetAsync(ws, 0, splice_bwd_workspace_floats(n, width) * sizeof(float), st);
   const char* e = splice_bwd(dx, reinterpret_cast<bf16*>(dx_bf16), d_prompt, ws, S, L, row0, n, width, zero_rows != 0, st);
   cudaFreeAsync(ws, st);
   if (e) return fail(nullptr, "%s", e);

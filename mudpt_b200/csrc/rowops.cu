@@ -21,22 +21,36 @@ static constexpr int LN_MAXV = 8;  // float4 per lane -> width <= 1024
 // do not pay registers for wide ones). OUT_BF16: normalized row as bf16 (GEMM A operand); else fp32
 // (may alias x).
 template <int NV, bool OUT_BF16>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, void* __restrict__ out, int M, int d,
-                                                     float eps) {
+// sp_prompt != nullptr: the deep-prompt splice of the block is done here too -- rows (row % sp_L) in [sp_row0, sp_row0 + sp_n)
+// take their values from sp_prompt (copied verbatim into x: bit-exact, clip/model.py:281-297) before being normalised.
+// (x is read through the read-only path; x_w is the same buffer, written for spliced rows only -- rows that are never read)
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, float* __restrict__ x_w,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     void* __restrict__ out, int M, int d, float eps,
+                                                     const float* __restrict__ sp_prompt, int sp_L, int sp_row0, int sp_n) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_wait();
   pdl_trigger();
   if (row >= M) return;
-  const float* xr = x + static_cast<size_t>(row) * d;
+  float* xr = x_w + static_cast<size_t>(row) * d;
+  const float* src = x + static_cast<size_t>(row) * d;
+  bool spliced = false;
+  if (sp_prompt != nullptr) {
+    const int pos = row % sp_L - sp_row0;
+    if (pos >= 0 && pos < sp_n) {
+      src = sp_prompt + static_cast<size_t>(pos) * d;
+      spliced = true;
+    }
+  }
   float4 v[NV];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
-      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      v[i] = *reinterpret_cast<const float4*>(src + c);
+      if (spliced) *reinterpret_cast<float4*>(xr + c) = v[i];
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
@@ -86,27 +100,42 @@ static int ln_warps() {
 }
 
 template <int NV>
-static void launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
-                          float eps, cudaStream_t stream) {
+static void launch_ln_fwd(float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d, float eps,
+                          const float* sp_prompt, int sp_L, int sp_row0, int sp_n, cudaStream_t stream) {
   const int wpc = ln_warps();
   const int grid = (M + wpc - 1) / wpc;
-  if (out_bf16) launch_pdl(ln_fwd_kernel<NV, true>, dim3(grid), dim3(32 * wpc), 0, stream, x, gamma, beta, out, M, d, eps);
-  else launch_pdl(ln_fwd_kernel<NV, false>, dim3(grid), dim3(32 * wpc), 0, stream, x, gamma, beta, out, M, d, eps);
+  if (out_bf16)
+    launch_pdl(ln_fwd_kernel<NV, true>, dim3(grid), dim3(32 * wpc), 0, stream, x, x, gamma, beta, out, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n);
+  else
+    launch_pdl(ln_fwd_kernel<NV, false>, dim3(grid), dim3(32 * wpc), 0, stream, x, x, gamma, beta, out, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n);
+}
+
+static const char* ln_fwd_dispatch(float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d, float eps,
+                                   const float* sp_prompt, int sp_L, int sp_row0, int sp_n, cudaStream_t stream) {
+  if (M <= 0) return nullptr;
+  if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
+  switch (pick_nv(d)) {
+    case 1: launch_ln_fwd<1>(x, gamma, beta, out, out_bf16, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n, stream); break;
+    case 2: launch_ln_fwd<2>(x, gamma, beta, out, out_bf16, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n, stream); break;
+    case 4: launch_ln_fwd<4>(x, gamma, beta, out, out_bf16, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n, stream); break;
+    case 6: launch_ln_fwd<6>(x, gamma, beta, out, out_bf16, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n, stream); break;
+    default: launch_ln_fwd<8>(x, gamma, beta, out, out_bf16, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n, stream); break;
+  }
+  count_launch(1);
+  return launch_status("layernorm fwd launch failed");
 }
 
 const char* layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
                           float eps, cudaStream_t stream) {
-  if (M <= 0) return nullptr;
-  if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
-  switch (pick_nv(d)) {
-    case 1: launch_ln_fwd<1>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
-    case 2: launch_ln_fwd<2>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
-    case 4: launch_ln_fwd<4>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
-    case 6: launch_ln_fwd<6>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
-    default: launch_ln_fwd<8>(x, gamma, beta, out, out_bf16, M, d, eps, stream); break;
-  }
-  count_launch(1);
-  return launch_status("layernorm fwd launch failed");
+  // (x is only written for spliced rows: none here)
+  return ln_fwd_dispatch(const_cast<float*>(x), gamma, beta, out, out_bf16, M, d, eps, nullptr, 1, 0, 0, stream);
+}
+
+const char* layernorm_fwd_splice(float* x, const float* prompt, int L, int row0, int n, const float* gamma, const float* beta,
+                                 void* out, bool out_bf16, int M, int d, float eps, cudaStream_t stream) {
+  if (n <= 0 || prompt == nullptr) return ln_fwd_dispatch(x, gamma, beta, out, out_bf16, M, d, eps, nullptr, 1, 0, 0, stream);
+  if (L <= 0 || row0 < 0 || row0 + n > L || M % L != 0) return "layernorm + splice: bad geometry";
+  return ln_fwd_dispatch(x, gamma, beta, out, out_bf16, M, d, eps, prompt, L, row0, n, stream);
 }
 
 // ------------------------------------------------------------------ LayerNorm backward (dgrad only)
@@ -312,6 +341,61 @@ __global__ void __launch_bounds__(256) splice_bwd_partial_kernel(float* __restri
   }
 }
 
+// The same two stages in ONE launch: every block writes its slice's partial, then the LAST block to finish (atomic ticket)
+// adds the slices in slice order -- the result does not depend on which block that is, so it stays deterministic.
+__global__ void __launch_bounds__(256) splice_bwd_fused_kernel(float* __restrict__ dx, bf16* __restrict__ dx_bf16,
+                                                               float* __restrict__ partial, float* __restrict__ dprompt,
+                                                               unsigned* __restrict__ ticket, int S, int L, int row0, int n, int d,
+                                                               int per_slice, int zero_rows) {
+  __shared__ float4 part[8][32];
+  __shared__ unsigned s_last;
+  const int r = blockIdx.x, slice = blockIdx.z, nslices = gridDim.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  const int s_end = min(S, (slice + 1) * per_slice);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();
+  pdl_trigger();
+  if (c < d) {
+    for (int s = slice * per_slice + warp; s < s_end; s += 8) {
+      const size_t off = (static_cast<size_t>(s) * L + row0 + r) * d + c;
+      const float4 v = *reinterpret_cast<const float4*>(dx + off);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      if (zero_rows) {
+        *reinterpret_cast<float4*>(dx + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dx_bf16 != nullptr) *reinterpret_cast<uint2*>(dx_bf16 + off) = make_uint2(0u, 0u);
+      }
+    }
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < d) {
+    float4 t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      t.x += part[w][lane].x; t.y += part[w][lane].y; t.z += part[w][lane].z; t.w += part[w][lane].w;
+    }
+    *reinterpret_cast<float4*>(partial + (static_cast<size_t>(slice) * n + r) * d + c) = t;
+  }
+  // ticket per (prompt row, column block): the last of its nslices blocks reduces them
+  __threadfence();
+  __syncthreads();
+  unsigned* tk = ticket + blockIdx.x * gridDim.y + blockIdx.y;
+  if (threadIdx.x == 0) s_last = atomicAdd(tk, 1u) == static_cast<unsigned>(nslices - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last == 0u) return;
+  __threadfence();
+  if (warp == 0 && c < d) {
+    float4 t = __ldcg(reinterpret_cast<const float4*>(partial + static_cast<size_t>(r) * d + c));
+    for (int sl = 1; sl < nslices; ++sl) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (static_cast<size_t>(sl) * n + r) * d + c));
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dprompt + static_cast<size_t>(r) * d + c) = t;
+  }
+  if (threadIdx.x == 0) *tk = 0u;  // leave the ticket clear for the next launch
+}
+
 __global__ void splice_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__ dprompt, int nslices, int nd) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   pdl_wait();
@@ -325,7 +409,9 @@ __global__ void splice_bwd_final_kernel(const float* __restrict__ partial, float
   *reinterpret_cast<float4*>(dprompt + i) = t;
 }
 
-size_t splice_bwd_workspace_floats(int n, int d) { return static_cast<size_t>(SPLICE_MAX_SLICES) * n * d; }
+// partials [SPLICE_MAX_SLICES][n][d] + (as the tail of the same allocation) one ticket per (row, 128-column block), zeroed once
+static size_t splice_ticket_slots(int n, int d) { return static_cast<size_t>(n) * ((d + 127) / 128); }
+size_t splice_bwd_workspace_floats(int n, int d) { return static_cast<size_t>(SPLICE_MAX_SLICES) * n * d + splice_ticket_slots(n, d); }
 
 const char* splice_bwd(float* dx, bf16* dx_bf16, float* dprompt, float* workspace, int S, int L, int row0, int n, int d,
                        bool zero_rows, cudaStream_t stream) {
@@ -335,10 +421,11 @@ const char* splice_bwd(float* dx, bf16* dx_bf16, float* dprompt, float* workspac
   if (nslices > SPLICE_MAX_SLICES) nslices = SPLICE_MAX_SLICES;
   if (nslices < 1) nslices = 1;
   const int per_slice = (S + nslices - 1) / nslices;
-  launch_pdl(splice_bwd_partial_kernel, dim3(n, (d + 127) / 128, nslices), dim3(256), 0, stream, dx, dx_bf16, workspace, S, L,
-             row0, n, d, per_slice, zero_rows ? 1 : 0);
-  launch_pdl(splice_bwd_final_kernel, dim3((n * d / 4 + 127) / 128), dim3(128), 0, stream, workspace, dprompt, nslices, n * d);
-  count_launch(2);
+  // the tickets live behind the partials and must be zero before the first launch (the owner of the workspace zeroes it once)
+  unsigned* ticket = reinterpret_cast<unsigned*>(workspace + static_cast<size_t>(SPLICE_MAX_SLICES) * n * d);
+  launch_pdl(splice_bwd_fused_kernel, dim3(n, (d + 127) / 128, nslices), dim3(256), 0, stream, dx, dx_bf16, workspace, dprompt, ticket,
+             S, L, row0, n, d, per_slice, zero_rows ? 1 : 0);
+  count_launch(1);
   return launch_status("splice bwd launch failed");
 }
 

@@ -7,11 +7,15 @@
 namespace mudpt {
 const char* layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d,
                           float eps, cudaStream_t stream);
+// LayerNorm with the deep-prompt splice of the block done in the same pass: rows (row % L) in [row0, row0 + n) are first
+// overwritten with prompt[row % L - row0] (verbatim)
+const char* layernorm_fwd_splice(float* x, const float* prompt, int L, int row0, int n, const float* gamma, const float* beta,
+                                 void* out, bool out_bf16, int M, int d, float eps, cudaStream_t stream);
 // x: fp32 rows, or (stats != nullptr) their bf16 copy + per-64-column partial statistics (fused-LayerNorm towers)
 const char* layernorm_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
                           float* dx, __nv_bfloat16* dx_bf16, int M, int d, float eps, cudaStream_t stream);
 const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, int n, int d, cudaStream_t stream);
-size_t splice_bwd_workspace_floats(int n, int d);
+size_t splice_bwd_workspace_floats(int n, int d);  // must be zero-initialised once (it ends with the kernel's tickets)
 const char* splice_bwd(float* dx, __nv_bfloat16* dx_bf16, float* dprompt, float* workspace, int S, int L, int row0, int n,
                        int d, bool zero_rows, cudaStream_t stream);
 // fused-LayerNorm plumbing (see rowops.cu): bf16 copy + per-64-column partial statistics of fp32 rows
