@@ -50,8 +50,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
       v[i] = *reinterpret_cast<const float4*>(src + c);
-      if (spliced) *reinterpret_cast<float4*>(xr + c) = v[i];
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  if (spliced) {  // (warp-uniform; after every load of the row has been issued)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) *reinterpret_cast<float4*>(xr + c) = v[i];
     }
   }
   const float mean = warp_sum(sum) / d;
