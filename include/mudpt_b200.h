@@ -70,7 +70,11 @@ void mudpt_destroy(mudpt_handle* h);
  *   "ln_bwd_fused" 0 (default; env MUDPT_LN_BWD_FUSED) 1 = LayerNorm dgrad in the dgrad GEMMs' epilogues (needs
  *               ln_fused; measured slower than the stand-alone kernel at the cfg-2 shapes, kept for narrow towers)
  *   "prune"     1 (default; env MUDPT_PRUNE) exact work skipping: the last block's out-proj / MLP (forward and
- *               dgrad) run on the CLS / EOT rows only (clip/model.py:548, trainers/mudpt.py:154), 0 = every row */
+ *               dgrad) run on the CLS / EOT rows only (clip/model.py:548, trainers/mudpt.py:154), 0 = every row
+ *   "grad_stream_bf16"  1 (default; env MUDPT_GRAD_BF16) the gradient of the residual stream travels between the
+ *               LayerNorm backward kernels as bf16 -- the copy the dgrad GEMMs read as their A operand anyway; fp32 rows
+ *               are kept for the deep-prompt window (what the splice backward sums); 0 = fp32 stream + bf16 copy.
+ *               Ignored (fp32) when the dense input gradient d_x0 is requested or with ln_bwd_fused. */
 int mudpt_set_option(mudpt_handle* h, const char* name, int32_t value);
 const char* mudpt_last_error(mudpt_handle* h);
 
@@ -126,6 +130,13 @@ int mudpt_layernorm_forward(const float* x, const float* gamma, const float* bet
                             int32_t rows, int32_t width, void* stream);                     /* clip/model.py:164-170 */
 int mudpt_layernorm_backward(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
                              uint16_t* dx_bf16, int32_t rows, int32_t width, void* stream);
+/* The form the towers use when the gradient of the residual stream is kept in bf16 (option "grad_stream_bf16"):
+ * dy bf16; x = fp32 rows (x_stats NULL) or their bf16 copy + per-64-column partial statistics (mudpt_rowstats);
+ * resid = fp32 rows, or (resid_bf16 != 0) bf16 rows that may alias dx_bf16, or NULL; dx (fp32) / dx_bf16 may each be
+ * NULL (not both); win_n >= 0: fp32 rows are written only where (row % win_L) is in [win_row0, win_row0 + win_n). */
+int mudpt_layernorm_backward_stream(const uint16_t* dy, const void* x, const float* x_stats, const float* gamma,
+                                    const void* resid, int32_t resid_bf16, float* dx, uint16_t* dx_bf16, int32_t rows,
+                                    int32_t width, int32_t win_L, int32_t win_row0, int32_t win_n, void* stream);
 int mudpt_splice_forward(float* x, const float* prompt, int32_t S, int32_t L, int32_t row0, int32_t n, int32_t width,
                          void* stream);                                                       /* clip/model.py:281-297 */
 int mudpt_splice_backward(float* dx, uint16_t* dx_bf16, float* d_prompt, int32_t S, int32_t L, int32_t row0, int32_t n,

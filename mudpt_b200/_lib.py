@@ -37,6 +37,8 @@ SIGNATURES = {
     "mudpt_logits_backward": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
     "mudpt_layernorm_forward": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_layernorm_backward": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "mudpt_layernorm_backward_stream": (C.c_int, [C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int32, c_f32p, C.c_void_p,
+                                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_splice_forward": (C.c_int, [c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mudpt_splice_backward": (C.c_int, [c_f32p, C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_void_p]),

@@ -144,6 +144,12 @@ struct mudpt_handle {
   bool ln_bwd_bf16x = true;  // env MUDPT_LN_BWD_BF16X
   // exact work skipping: the last block's out-proj / MLP on the CLS / EOT rows only
   bool prune = true;
+  // Gradient of the residual stream kept in bf16 between the LayerNorm backward kernels (the dgrad GEMMs read that copy
+  // as their A operand anyway); fp32 rows are written for the deep-prompt window only, which is all the splice backward
+  // reads.  8 instead of 14 B per element on the HBM-bound LayerNorm backward; each of the 2 x layers updates rounds the
+  // stream to bf16 (2^-9 relative): measured effect on the prompt gradients in profiles/r02_grad_stream_bf16.txt.
+  // Not used when the dense input gradient is requested (CoCoOp's d_x0) or with ln_bwd_fused.  env MUDPT_GRAD_BF16
+  bool grad_bf16 = true;
 };
 
 namespace {
@@ -532,6 +538,21 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
   const bool xstats = t.fwd_fused && !fused && h->ln_bwd_bf16x;
   const int parts = d / 64;
   const int dots_mlp = (4 * d + gemm_dots_span(4 * d) - 1) / gemm_dots_span(4 * d);
+  // bf16 gradient stream (see mudpt_handle::grad_bf16): the stand-alone LayerNorm backward reads the residual gradient
+  // from t.dx_bf16 and writes it back there; t.dx (fp32) gets the rows of the deep-prompt window only.
+  const bool gb = h->grad_bf16 && !fused && !need_dx0;
+  const double ln_bwd_bytes = (gb ? 6.0 : 12.0) + (xstats ? 2.0 : 4.0);  // dy 2, x, residual in, gradient out (+ its bf16 copy)
+  bool f32_whole = true;  // t.dx holds the whole stream in fp32 (head_backward / the pruned last block write both copies)
+  auto ln_bwd_main = [&](const void* xrow, const float2* stats, const float* gamma, bool has_resid, bool whole_f32_out) -> const char* {
+    if (!gb)
+      return layernorm_bwd(t.a_buf, true, xrow, stats, gamma, has_resid ? t.dx : nullptr, t.dx, t.dx_bf16, M, d, kLnEps, st);
+    const bool rb = has_resid && !f32_whole;
+    const void* resid = !has_resid ? nullptr : (rb ? static_cast<const void*>(t.dx_bf16) : static_cast<const void*>(t.dx));
+    const char* e = layernorm_bwd_stream(t.a_buf, true, xrow, stats, gamma, resid, rb, t.dx, t.dx_bf16, M, d, kLnEps, t.L, t.row0,
+                                         whole_f32_out ? -1 : t.n_ctx, st);
+    f32_whole = whole_f32_out;
+    return e;
+  };
   for (int i = t.layers - 1; i >= 0; --i) {
     const Layer& w = t.lw[i];
     const bool tail_pruned = t.fwd_pruned && i == t.layers - 1;
@@ -580,8 +601,8 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
       e2.mode = EPI_BF16; e2.out0 = t.a_buf;  // a_buf: forward transient, free during the backward
       CKP(h, st, PC_GEMM_DFC, 2.0 * Md * 4 * dd * dd, 2 * (Md * 4 * dd + 4 * dd * dd) + 2 * Md * dd,
           gemm_bf16_tn(t.dh_buf, 4 * d, w.w_fc_t, 4 * d, e2, M, d, 4 * d, st, &t.gws));
-      CKP(h, st, PC_LN_BWD, 0, Md * dd * 16, layernorm_bwd(t.a_buf, true, xstats ? static_cast<const void*>(t.xb_mid[i]) : t.x_mid[i], xstats ? t.st_mid[i] : nullptr, w.ln2_g, t.dx,
-                                                            t.dx, t.dx_bf16, M, d, kLnEps, st));
+      CKP(h, st, PC_LN_BWD, 0, Md * dd * ln_bwd_bytes,
+          ln_bwd_main(xstats ? static_cast<const void*>(t.xb_mid[i]) : t.x_mid[i], xstats ? t.st_mid[i] : nullptr, w.ln2_g, true, false));
     }
     // attention branch: dO = dx W_out ; (dQ,dK,dV) ; da = dQKV W_in ; dx += LN1_bwd(da)
     GemmEpilogue e3;
@@ -620,9 +641,10 @@ int tower_backward(mudpt_handle* h, Tower& t, float* d_prompts, int first_splice
       e4.mode = EPI_BF16; e4.out0 = t.a_buf;
       CKP(h, st, PC_GEMM_DQKV, 2.0 * Md * 3 * dd * dd, 2 * (Md * 3 * dd + 3 * dd * dd) + 2 * Md * dd,
           gemm_bf16_tn(t.dqkv_buf, 3 * d, w.w_in_t, 3 * d, e4, M, d, 3 * d, st, &t.gws));
-      CKP(h, st, PC_LN_BWD, 0, Md * dd * 16,
-          layernorm_bwd(t.a_buf, true, xstats ? static_cast<const void*>(t.xb_in[i]) : t.x_in[i], xstats ? t.st_in[i] : nullptr, w.ln1_g,
-                        tail_pruned ? nullptr : t.dx, t.dx, t.dx_bf16, M, d, kLnEps, st));
+      // (the pruned last block adds its S consumed rows into the fp32 stream right below: every fp32 row is written there)
+      CKP(h, st, PC_LN_BWD, 0, Md * dd * (tail_pruned ? 8.0 + (xstats ? 2.0 : 4.0) : ln_bwd_bytes),
+          ln_bwd_main(xstats ? static_cast<const void*>(t.xb_in[i]) : t.x_in[i], xstats ? t.st_in[i] : nullptr, w.ln1_g, !tail_pruned,
+                      tail_pruned));
     }
     if (tail_pruned)  // the residual path of the S consumed rows (everything else of it is zero)
       CKP(h, st, PC_SPLICE, 0, t.S * dd * 14, scatter_rows(t.pr_dx, t.sel_rows, t.S, t.L, t.dx, t.dx_bf16, d, true, st));
@@ -698,6 +720,7 @@ int mudpt_create(const mudpt_config* cfg, mudpt_handle** out) {
   h->ln_bwd_fused = env_flag("MUDPT_LN_BWD_FUSED", false);
   h->ln_bwd_bf16x = env_flag("MUDPT_LN_BWD_BF16X", true);
   h->prune = env_flag("MUDPT_PRUNE", true);
+  h->grad_bf16 = env_flag("MUDPT_GRAD_BF16", true);
   *out = h;
   return 0;
 }
@@ -722,6 +745,7 @@ int mudpt_set_option(mudpt_handle* h, const char* name, int32_t value) {
   if (!strcmp(name, "ln_fused")) h->ln_fused = value < 0 ? -1 : (value != 0 ? 1 : 0);
   else if (!strcmp(name, "ln_bwd_fused")) h->ln_bwd_fused = value != 0;
   else if (!strcmp(name, "prune")) h->prune = value != 0;
+  else if (!strcmp(name, "grad_stream_bf16")) h->grad_bf16 = value != 0;
   else return fail(h, "mudpt_set_option: unknown option %s", name);
   h->vis.fwd_done = h->txt.fwd_done = false;  // saved activations belong to the previous formulation
   return 0;
@@ -928,6 +952,13 @@ int mudpt_layernorm_forward(const float* x, const float* gamma, const float* bet
 int mudpt_layernorm_backward(const float* dy, const float* x, const float* gamma, const float* resid, float* dx,
                              uint16_t* dx_bf16, int32_t rows, int32_t width, void* stream) {
   CKG(layernorm_bwd(dy, false, x, nullptr, gamma, resid, dx, reinterpret_cast<bf16*>(dx_bf16), rows, width, kLnEps, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int mudpt_layernorm_backward_stream(const uint16_t* dy, const void* x, const float* x_stats, const float* gamma, const void* resid,
+                                    int32_t resid_bf16, float* dx, uint16_t* dx_bf16, int32_t rows, int32_t width, int32_t win_L,
+                                    int32_t win_row0, int32_t win_n, void* stream) {
+  CKG(layernorm_bwd_stream(dy, true, x, reinterpret_cast<const float2*>(x_stats), gamma, resid, resid_bf16 != 0, dx,
+                           reinterpret_cast<bf16*>(dx_bf16), rows, width, kLnEps, win_L, win_row0, win_n, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 int mudpt_splice_forward(float* x, const float* prompt, int32_t S, int32_t L, int32_t row0, int32_t n, int32_t width, void* stream) {

@@ -144,6 +144,22 @@ const char* layernorm_fwd_splice(float* x, const float* prompt, int L, int row0,
   return ln_fwd_dispatch(x, gamma, beta, out, out_bf16, M, d, eps, prompt, L, row0, n, stream);
 }
 
+// Registers holding the residual-gradient piece of a lane: fp32 (float4) or the packed bf16 form (uint2)
+template <bool BF16> struct ResidRegs;
+template <> struct ResidRegs<false> {
+  typedef float4 type;
+  __device__ __forceinline__ static float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ static float4 f32(const float4& r) { return r; }
+};
+template <> struct ResidRegs<true> {
+  typedef uint2 type;
+  __device__ __forceinline__ static uint2 zero() { return make_uint2(0u, 0u); }
+  __device__ __forceinline__ static float4 f32(const uint2& r) {
+    const float2 a = unpack_bf16(r.x), b = unpack_bf16(r.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+
 // ------------------------------------------------------------------ LayerNorm backward (dgrad only)
 // dx = resid + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.
 // gamma/beta are frozen (trainers/mudpt.py:205-212): no dgamma/dbeta. Statistics are
@@ -151,11 +167,15 @@ const char* layernorm_fwd_splice(float* x, const float* prompt, int L, int row0,
 // that feeds the next dgrad GEMM.  DY_BF16: dy comes from a bf16 GEMM epilogue.
 // X_STATS: the row comes as its bf16 copy + per-64-column partial statistics (the form the fused-LayerNorm forward
 // keeps, rowops.cu "fused-LayerNorm plumbing"): 2 B instead of 4 B per element read, exact fp32 mean / rstd.
-template <int NV, bool DY_BF16, bool X_STATS>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ xv,
+// RESID_BF16: the residual gradient is read from the bf16 copy of the stream (it may alias dx_bf16: every lane reads its
+// own elements before it writes them).  win_n >= 0 restricts the fp32 output to the rows of the deep-prompt window,
+// (row % win_L) in [win_row0, win_row0 + win_n) -- the only fp32 rows anyone reads when the gradient stream is kept in
+// bf16 (the splice backward sums them); win_n < 0: every row.  8 instead of 14 B per element on an HBM-bound kernel.
+template <int NV, bool DY_BF16, bool X_STATS, bool RESID_BF16>
+__global__ void __launch_bounds__(256, NV == 4 ? 4 : 1) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ xv,
                                                      const float2* __restrict__ stats, const float* __restrict__ gamma,
-                                                     const float* resid, float* dx, bf16* __restrict__ dx_bf16, int M, int d,
-                                                     float eps) {
+                                                     const void* resid, float* dx, bf16* dx_bf16, int M, int d,
+                                                     float eps, int win_L, int win_row0, int win_n) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_wait();
@@ -163,7 +183,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   if (row >= M) return;
   const size_t off = static_cast<size_t>(row) * d;
   const float* x = reinterpret_cast<const float*>(xv);
-  float4 v[NV], g[NV], rs[NV];
+  bool write_f32 = dx != nullptr;  // (warp-uniform)
+  if (win_n >= 0) {
+    const int pos = row % win_L - win_row0;
+    write_f32 = write_f32 && pos >= 0 && pos < win_n;
+  }
+  float4 v[NV], g[NV];
+  typename ResidRegs<RESID_BF16>::type rs[NV];
   float sum = 0.f;
   // issue every load of the row up front (x, dy, residual gradient): 3 streams in flight per lane.  The residual must be
   // in registers before the first store: dx may alias it, so a load placed after a store of the row is ordered behind it
@@ -171,9 +197,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
-    rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rs[i] = ResidRegs<RESID_BF16>::zero();
     if (c < d) {
-      if (resid != nullptr) rs[i] = *reinterpret_cast<const float4*>(resid + off + c);
+      if (resid != nullptr) {
+        if constexpr (RESID_BF16) rs[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(resid) + off + c);
+        else rs[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(resid) + off + c);
+      }
       if constexpr (X_STATS) {
         const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(xv) + off + c);
         const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
@@ -238,13 +267,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
-      const float4 r = rs[i];
+      const float4 r = ResidRegs<RESID_BF16>::f32(rs[i]);
       float4 o;
       o.x = r.x + rstd * (g[i].x - s1 - v[i].x * s2);
       o.y = r.y + rstd * (g[i].y - s1 - v[i].y * s2);
       o.z = r.z + rstd * (g[i].z - s1 - v[i].z * s2);
       o.w = r.w + rstd * (g[i].w - s1 - v[i].w * s2);
-      *reinterpret_cast<float4*>(dx + off + c) = o;
+      if (write_f32) *reinterpret_cast<float4*>(dx + off + c) = o;
       if (dx_bf16 != nullptr) {
         uint2 u;
         u.x = pack_bf16(o.x, o.y);
@@ -255,36 +284,62 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   }
 }
 
-template <int NV>
-static void launch_ln_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
-                          float* dx, bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
+template <int NV, bool RB>
+static void launch_ln_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const void* resid,
+                          float* dx, bf16* dx_bf16, int M, int d, float eps, int win_L, int win_row0, int win_n,
+                          cudaStream_t stream) {
   const int wpc = ln_warps();
   const int grid = (M + wpc - 1) / wpc;
   const dim3 blk(32 * wpc);
   if (stats != nullptr) {  // (bf16 dy only: the dgrad GEMM's output)
-    launch_pdl(ln_bwd_kernel<NV, true, true>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+    launch_pdl(ln_bwd_kernel<NV, true, true, RB>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps,
+               win_L, win_row0, win_n);
   } else if (dy_bf16) {
-    launch_pdl(ln_bwd_kernel<NV, true, false>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+    launch_pdl(ln_bwd_kernel<NV, true, false, RB>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps,
+               win_L, win_row0, win_n);
   } else {
-    launch_pdl(ln_bwd_kernel<NV, false, false>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps);
+    launch_pdl(ln_bwd_kernel<NV, false, false, RB>, dim3(grid), blk, 0, stream, dy, x, stats, gamma, resid, dx, dx_bf16, M, d, eps,
+               win_L, win_row0, win_n);
   }
 }
 
-// x: fp32 rows, or (stats != nullptr) their bf16 copy with the per-64-column partial statistics
-const char* layernorm_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
-                          float* dx, bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
+template <bool RB>
+static void dispatch_ln_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const void* resid,
+                            float* dx, bf16* dx_bf16, int M, int d, float eps, int win_L, int win_row0, int win_n,
+                            cudaStream_t stream) {
+  switch (pick_nv(d)) {
+    case 1: launch_ln_bwd<1, RB>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream); break;
+    case 2: launch_ln_bwd<2, RB>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream); break;
+    case 4: launch_ln_bwd<4, RB>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream); break;
+    case 6: launch_ln_bwd<6, RB>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream); break;
+    default: launch_ln_bwd<8, RB>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream); break;
+  }
+}
+
+// x: fp32 rows, or (stats != nullptr) their bf16 copy with the per-64-column partial statistics.
+// resid: fp32 rows, or (resid_bf16) the bf16 copy of the gradient stream; dx (fp32) and dx_bf16 may each be null (not both);
+// win_n >= 0: fp32 rows are written inside the deep-prompt window only (see the kernel).
+const char* layernorm_bwd_stream(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma,
+                                 const void* resid, bool resid_bf16, float* dx, bf16* dx_bf16, int M, int d, float eps,
+                                 int win_L, int win_row0, int win_n, cudaStream_t stream) {
   if (M <= 0) return nullptr;
   if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
   if (stats != nullptr && (!dy_bf16 || d % 64 != 0)) return "layernorm: the bf16-input form needs bf16 dy and width % 64 == 0";
-  switch (pick_nv(d)) {
-    case 1: launch_ln_bwd<1>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-    case 2: launch_ln_bwd<2>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-    case 4: launch_ln_bwd<4>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-    case 6: launch_ln_bwd<6>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-    default: launch_ln_bwd<8>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, stream); break;
-  }
+  if (dx == nullptr && dx_bf16 == nullptr) return "layernorm bwd: no output";
+  if (win_n > 0 && (win_L <= 0 || win_row0 < 0 || win_row0 + win_n > win_L)) return "layernorm bwd: bad window";
+  if (win_n >= 0 && win_L <= 0) win_L = 1;
+  if (resid_bf16 && resid != nullptr)
+    dispatch_ln_bwd<true>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream);
+  else
+    dispatch_ln_bwd<false>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream);
   count_launch(1);
   return launch_status("layernorm bwd launch failed");
+}
+
+const char* layernorm_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
+                          float* dx, bf16* dx_bf16, int M, int d, float eps, cudaStream_t stream) {
+  if (dx == nullptr) return "layernorm bwd: no fp32 output";
+  return layernorm_bwd_stream(dy, dy_bf16, x, stats, gamma, resid, false, dx, dx_bf16, M, d, eps, 1, 0, -1, stream);
 }
 
 // ------------------------------------------------------------------ deep-prompt splice

@@ -14,6 +14,12 @@ const char* layernorm_fwd_splice(float* x, const float* prompt, int L, int row0,
 // x: fp32 rows, or (stats != nullptr) their bf16 copy + per-64-column partial statistics (fused-LayerNorm towers)
 const char* layernorm_bwd(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma, const float* resid,
                           float* dx, __nv_bfloat16* dx_bf16, int M, int d, float eps, cudaStream_t stream);
+// The same with the gradient stream kept in bf16: resid is the fp32 stream or (resid_bf16) its bf16 copy, which may alias
+// dx_bf16; dx (fp32) may be null; win_n >= 0 writes fp32 rows only where (row % win_L) is in [win_row0, win_row0 + win_n)
+// (the deep-prompt rows the splice backward sums), win_n < 0 writes every row.
+const char* layernorm_bwd_stream(const void* dy, bool dy_bf16, const void* x, const float2* stats, const float* gamma,
+                                 const void* resid, bool resid_bf16, float* dx, __nv_bfloat16* dx_bf16, int M, int d, float eps,
+                                 int win_L, int win_row0, int win_n, cudaStream_t stream);
 const char* splice_fwd(float* x, const float* prompt, int S, int L, int row0, int n, int d, cudaStream_t stream);
 size_t splice_bwd_workspace_floats(int n, int d);  // must be zero-initialised once (it ends with the kernel's tickets)
 const char* splice_bwd(float* dx, __nv_bfloat16* dx_bf16, float* dprompt, float* workspace, int S, int L, int row0, int n,

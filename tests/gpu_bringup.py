@@ -404,6 +404,58 @@ def group_rowops(res):
         torch.cuda.synchronize()
         res[f"ln_bwd_{M}x{d}"] = {"f32": _metrics(dx, exp), "bf16": _metrics(dx16.float(), exp)}
         print(f"ln_{M}x{d}", res[f"ln_fwd_{M}x{d}"], res[f"ln_bwd_{M}x{d}"], flush=True)
+    # LayerNorm backward on the bf16 gradient stream (option grad_stream_bf16): bf16 dy, x as fp32 rows or bf16 + statistics,
+    # residual gradient fp32 or bf16 IN PLACE (aliasing the bf16 output), fp32 rows written in the prompt window only
+    def ln_bwd_ref(dy16, x_used, mean, rstd, gam, resid):
+        xh = (x_used - mean) * rstd
+        gg = dy16.float() * gam
+        return resid + rstd * (gg - gg.mean(1, keepdim=True) - xh * (gg * xh).mean(1, keepdim=True))
+    for (S_, L_, row0_, n_, d) in [(13, 77, 1, 2, 512), (32, 199, 197, 2, 768), (5, 9, 1, 4, 64), (3, 259, 257, 2, 1024)]:
+        M = S_ * L_
+        x = torch.randn(M, d, device=dev) * 2 + 0.5
+        gam = torch.randn(d, device=dev)
+        dy16 = torch.randn(M, d, device=dev).bfloat16()
+        mean = x.mean(1, keepdim=True)
+        rstd = torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-5)
+        xb = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+        stats = torch.empty(M, d // 64, 2, device=dev)
+        _lib.check(lib.mudpt_rowstats(x.data_ptr(), xb.data_ptr(), stats.data_ptr(), M, d, st))
+        resid32 = torch.randn(M, d, device=dev)
+        resid16 = resid32.bfloat16()
+        tok = torch.arange(M, device=dev) % L_
+        inwin = (tok >= row0_) & (tok < row0_ + n_)
+        out = {}
+        for xform in ("f32", "bf16"):
+            x_used = x if xform == "f32" else xb.float()
+            xp, sp = (x.data_ptr(), None) if xform == "f32" else (xb.data_ptr(), stats.data_ptr())
+            for rform in ("f32", "bf16", "none"):
+                resid = {"f32": resid32, "bf16": resid16.float(), "none": torch.zeros_like(resid32)}[rform]
+                exp = ln_bwd_ref(dy16, x_used, mean, rstd, gam, resid)
+                for win in (-1, n_, 0):
+                    dx = torch.full((M, d), 7.0, device=dev)
+                    dxb = resid16.clone()  # the bf16 residual is updated in place
+                    rp = {"f32": resid32.data_ptr(), "bf16": dxb.data_ptr(), "none": None}[rform]
+                    _lib.check(lib.mudpt_layernorm_backward_stream(dy16.data_ptr(), xp, sp, gam.data_ptr(), rp, 1 if rform == "bf16" else 0,
+                                                                   dx.data_ptr(), dxb.data_ptr(), M, d, L_, row0_, win, st))
+                    torch.cuda.synchronize()
+                    wr = torch.ones_like(inwin) if win < 0 else (inwin if win > 0 else torch.zeros_like(inwin))
+                    m = {"bf16": _metrics(dxb.float(), exp),
+                         "bf16_is_rounded_f32": bool(torch.equal(dxb[wr], dx[wr].bfloat16())),
+                         "untouched": bool((dx[~wr] == 7.0).all())}
+                    if bool(wr.any()):
+                        m["f32"] = _metrics(dx[wr], exp[wr])
+                    out[f"{xform}_{rform}_{win}"] = m
+        # fp32 output not requested at all
+        dxb = resid16.clone()
+        _lib.check(lib.mudpt_layernorm_backward_stream(dy16.data_ptr(), xb.data_ptr(), stats.data_ptr(), gam.data_ptr(), dxb.data_ptr(), 1,
+                                                       None, dxb.data_ptr(), M, d, L_, row0_, n_, st))
+        torch.cuda.synchronize()
+        out["no_f32"] = {"bf16": _metrics(dxb.float(), ln_bwd_ref(dy16, xb.float(), mean, rstd, gam, resid16.float()))}
+        res[f"ln_bwd_stream_{M}x{d}"] = out
+        worst32 = max(v["f32"]["rel"] for v in out.values() if "f32" in v)
+        worst16 = max(v["bf16"]["rel"] for v in out.values())
+        print(f"ln_bwd_stream_{M}x{d}: worst fp32 rel {worst32:.2e}, worst bf16 rel {worst16:.2e}, "
+              f"untouched {all(v.get('untouched', True) for v in out.values())}", flush=True)
     # splice
     S, L, row0, n, d = 33, 21, 19, 2, 768
     x = torch.randn(S, L, d, device=dev); p = torch.randn(n, d, device=dev)

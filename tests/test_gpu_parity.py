@@ -78,7 +78,15 @@ def test_layernorm_splice_im2col(bring):
     res = {}
     bring.group_rowops(res)
     for k, v in res.items():
-        if k.startswith("ln_"):
+        if k.startswith("ln_bwd_stream_"):
+            # the bf16-gradient-stream form: every combination of x form, residual form (fp32 / bf16 in place / none) and
+            # fp32 window; the bf16 output is the rounded fp32 result, fp32 rows outside the window are not touched
+            for case, m in v.items():
+                assert not m["bf16"]["nan"] and m["bf16"]["rel"] <= BF16_REL, (k, case, m)
+                if "f32" in m:
+                    assert m["f32"]["rel"] <= F32_REL and m["bf16_is_rounded_f32"], (k, case, m)
+                assert m.get("untouched", True), (k, case)
+        elif k.startswith("ln_"):
             assert v["f32"]["rel"] <= F32_REL and v["bf16"]["rel"] <= BF16_REL, (k, v)
         if k.startswith("im2col"):
             assert v is True, k
@@ -278,13 +286,19 @@ def test_headline_full_shape_vs_oracle():
 def test_unfused_layernorm_fallback_matches_reference(bring):
     """Every combination of the formulation options stays parity-green: ln_fused = 0 (stand-alone LayerNorm kernels,
     bf16(LN(x)) operands: the path for checkpoints whose residual rows have a mean far above their spread),
-    ln_bwd_fused = 1 (LayerNorm dgrad in the dgrad GEMM epilogues), prune = 0 (every row of the last block)."""
+    ln_bwd_fused = 1 (LayerNorm dgrad in the dgrad GEMM epilogues), prune = 0 (every row of the last block),
+    grad_stream_bf16 = 0 / 1 (gradient of the residual stream between the LayerNorm backward kernels in fp32 / bf16)."""
     c = gu.load("tiny_a")
     model, _ = gu.build_model(c, "cuda")
     eng = model._clip_ref[0].engine()
     from mudpt_b200 import _lib
     for opts in ({"ln_fused": 0, "prune": 0}, {"ln_fused": 1, "prune": 0}, {"ln_fused": 0, "prune": 1},
-                 {"ln_fused": 1, "ln_bwd_fused": 1, "prune": 1}, {"ln_fused": 1, "ln_bwd_fused": 1, "prune": 0}):
+                 {"ln_fused": 1, "ln_bwd_fused": 1, "prune": 1}, {"ln_fused": 1, "ln_bwd_fused": 1, "prune": 0},
+                 # gradient stream in fp32 (0) / bf16 (1, the default) under both LayerNorm formulations and prunings
+                 {"ln_fused": 0, "ln_bwd_fused": 0, "prune": 1, "grad_stream_bf16": 0},
+                 {"ln_fused": 1, "ln_bwd_fused": 0, "prune": 0, "grad_stream_bf16": 0},
+                 {"ln_fused": 1, "ln_bwd_fused": 0, "prune": 1, "grad_stream_bf16": 1},
+                 {"ln_fused": 0, "ln_bwd_fused": 0, "prune": 0, "grad_stream_bf16": 1}):
         for k, v in opts.items():
             _lib.check(eng.lib.mudpt_set_option(eng.h, k.encode(), v), eng.h)
         model.zero_grad(set_to_none=True)
