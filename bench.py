@@ -430,7 +430,8 @@ def run_ours(args):
                    "global_batch": gB, "classes_per_gpu": -(-N_CLASSES // world), "text_seq_len": full["text_len"],
                    "parallelism": f"dp{world} images x class-sharded text",
                    "l2": f"{NBUF} rotating input batches (154 MB > 126 MB L2); per-step activation working set is several GB",
-                   "operands": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LN / softmax / loss"},
+                   "operands": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LN / softmax / loss; the residual "
+                               "stream's GRADIENT travels between the LayerNorm backward kernels as bf16 (option grad_stream_bf16)"},
         "e2e": {"value": gB / (full["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": full["ms_e2e"],
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "api": "mudpt_b200.trainers.mudpt.MuDPT.prefetch(next batch) + forward_backward(batch): pinned host batches, each uploaded under the previous step; loss read back every step"},

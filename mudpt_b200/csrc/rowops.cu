@@ -316,6 +316,297 @@ static void dispatch_ln_bwd(const void* dy, bool dy_bf16, const void* x, const f
   }
 }
 
+// ------------------------------------------------------------------ LayerNorm backward, shared-memory pipeline
+// The register kernel above has one row per warp in flight: measured on the bf16 gradient stream it moves 3.5 TB/s where
+// 6.5 are available (ncu: every warp waits a full DRAM round trip per row, 45 % of the warp slots, no byte in flight while
+// a row is being reduced).  Here the loads are taken off the warps: a persistent CTA walks blocks of 8 * RPW consecutive
+// rows; ONE thread issues the block's rows -- contiguous in memory, so one 1-D bulk copy (cp.async.bulk, the TMA engine)
+// per operand: dy, x, residual gradient, statistics -- into a ring of `stages` shared-memory slots that complete on
+// mbarriers, `stages - 1` blocks ahead of the math; the 8 warps take a row each from the slot into registers, the slot is
+// refilled at once (the bytes in flight per SM no longer depend on occupancy), and the row is reduced and stored from
+// registers.  The residual gradient may alias the bf16 output: a row is read (bulk copy completed) before the same CTA
+// writes it, and no other CTA touches it.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = e.x; f[7] = e.y;
+}
+
+struct LnPipeArgs {
+  const bf16* dy;
+  const void* x;        // bf16 rows (X_STATS) or fp32 rows
+  const float2* stats;  // X_STATS: [M, d / 64] partial (sum, M2)
+  const float* gamma;
+  const void* resid;    // RESID 1: bf16 rows (may alias dx_bf16), 2: fp32 rows
+  float* dx;            // fp32 output (window rows only when win_n >= 0) or null
+  bf16* dx_bf16;        // bf16 output or null
+  int M, d;
+  float eps;
+  int win_L, win_row0, win_n;
+  int stages;
+  unsigned stage_bytes;
+};
+
+static constexpr int kPipeBarBytes = 128;
+__host__ __device__ constexpr unsigned align128(unsigned v) { return (v + 127u) & ~127u; }
+
+// NP = ceil(d / 256): 8-column pieces per lane.  RESID: 0 none, 1 bf16, 2 fp32.  RPW: rows per warp and block.
+template <int NP, bool X_STATS, int RESID, int RPW>
+__global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
+  extern __shared__ __align__(128) uint8_t ln_pipe_smem[];
+  constexpr int ROWS = 8 * RPW;
+  constexpr unsigned XB = X_STATS ? 2u : 4u;
+  constexpr unsigned RB = RESID == 1 ? 2u : (RESID == 2 ? 4u : 0u);
+  const int d = a.d, parts = d >> 6;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned dy_off = 0, x_off = ROWS * d * 2u, r_off = x_off + ROWS * d * XB, st_off = r_off + ROWS * d * RB;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ln_pipe_smem);
+  float* gam = reinterpret_cast<float*>(ln_pipe_smem + kPipeBarBytes);
+  uint8_t* stage0 = ln_pipe_smem + kPipeBarBytes + align128(d * 4u);
+  const int nblk = (a.M + ROWS - 1) / ROWS;
+  const int stages = a.stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  auto issue = [&](int blk, int s) {  // one thread: the rows of block `blk` into slot `s`
+    const int r0 = blk * ROWS;
+    const unsigned nr = static_cast<unsigned>(a.M - r0 < ROWS ? a.M - r0 : ROWS);
+    uint8_t* st = stage0 + static_cast<size_t>(s) * a.stage_bytes;
+    const unsigned rowsz = static_cast<unsigned>(d);
+    mbar_expect_tx(&full[s], nr * rowsz * (2u + XB + RB) + (X_STATS ? nr * parts * 8u : 0u));
+    bulk_load_1d(st + dy_off, a.dy + static_cast<size_t>(r0) * d, nr * rowsz * 2u, &full[s]);
+    bulk_load_1d(st + x_off, reinterpret_cast<const uint8_t*>(a.x) + static_cast<size_t>(r0) * d * XB, nr * rowsz * XB, &full[s]);
+    if constexpr (RESID != 0)
+      bulk_load_1d(st + r_off, reinterpret_cast<const uint8_t*>(a.resid) + static_cast<size_t>(r0) * d * RB, nr * rowsz * RB, &full[s]);
+    if constexpr (X_STATS) bulk_load_1d(st + st_off, a.stats + static_cast<size_t>(r0) * parts, nr * parts * 8u, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const int blk = blockIdx.x + s * gridDim.x;
+      if (blk < nblk) issue(blk, s);
+    }
+  }
+  for (int c = threadIdx.x * 4; c < d; c += 256 * 4) *reinterpret_cast<float4*>(gam + c) = *reinterpret_cast<const float4*>(a.gamma + c);
+  pdl_trigger();
+  __syncthreads();  // gamma staged
+  const float inv_d = 1.f / static_cast<float>(d);
+  int it = 0;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it) {
+    const int s = it % stages;
+    mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
+    const uint8_t* st = stage0 + static_cast<size_t>(s) * a.stage_bytes;
+#pragma unroll
+    for (int rw = 0; rw < RPW; ++rw) {
+      const int lr = warp * RPW + rw;  // row of the block
+      const int row = blk * ROWS + lr;
+      // ---- the row: shared memory -> registers
+      float gg[NP][8], xc[NP][8];
+      uint4 rq[NP];
+      float2 rf[RESID == 2 ? NP : 1][4];
+      float2 stp = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        rq[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (c < d) {
+          const uint4 q = *reinterpret_cast<const uint4*>(st + dy_off + (static_cast<size_t>(lr) * d + c) * 2u);
+          unpack8_bf16(q, gg[i]);
+          if constexpr (X_STATS) {
+            const uint4 u = *reinterpret_cast<const uint4*>(st + x_off + (static_cast<size_t>(lr) * d + c) * 2u);
+            unpack8_bf16(u, xc[i]);
+          } else {
+            const float4 u0 = *reinterpret_cast<const float4*>(st + x_off + (static_cast<size_t>(lr) * d + c) * 4u);
+            const float4 u1 = *reinterpret_cast<const float4*>(st + x_off + (static_cast<size_t>(lr) * d + c) * 4u + 16u);
+            xc[i][0] = u0.x; xc[i][1] = u0.y; xc[i][2] = u0.z; xc[i][3] = u0.w;
+            xc[i][4] = u1.x; xc[i][5] = u1.y; xc[i][6] = u1.z; xc[i][7] = u1.w;
+          }
+          if constexpr (RESID == 1) rq[i] = *reinterpret_cast<const uint4*>(st + r_off + (static_cast<size_t>(lr) * d + c) * 2u);
+          if constexpr (RESID == 2) {
+            const float4 u0 = *reinterpret_cast<const float4*>(st + r_off + (static_cast<size_t>(lr) * d + c) * 4u);
+            const float4 u1 = *reinterpret_cast<const float4*>(st + r_off + (static_cast<size_t>(lr) * d + c) * 4u + 16u);
+            rf[i][0] = make_float2(u0.x, u0.y); rf[i][1] = make_float2(u0.z, u0.w);
+            rf[i][2] = make_float2(u1.x, u1.y); rf[i][3] = make_float2(u1.z, u1.w);
+          }
+        }
+      }
+      float np = 0.f;
+      if constexpr (X_STATS) {
+        if (lane < parts) {
+          stp = *reinterpret_cast<const float2*>(st + st_off + (static_cast<size_t>(lr) * parts + lane) * 8u);
+          const int rem = d - lane * 64;
+          np = static_cast<float>(rem < 64 ? rem : 64);
+        }
+      }
+      if (rw == RPW - 1) {
+        __syncthreads();  // every warp holds its rows: the slot is free
+        if (threadIdx.x == 0) {
+          const int nb = blk + stages * gridDim.x;
+          fence_proxy_async_smem();  // the warps' reads of the slot (ordered by the barrier) before the async-proxy refill
+          if (nb < nblk) issue(nb, s);
+        }
+      }
+      if (row >= a.M) continue;  // (warp-uniform)
+      // ---- g = dy * gamma, s1 = mean(g); mean of x
+      float s1 = 0.f, sx = 0.f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < d) {
+          const float4 g0 = *reinterpret_cast<const float4*>(gam + c), g1 = *reinterpret_cast<const float4*>(gam + c + 4);
+          gg[i][0] *= g0.x; gg[i][1] *= g0.y; gg[i][2] *= g0.z; gg[i][3] *= g0.w;
+          gg[i][4] *= g1.x; gg[i][5] *= g1.y; gg[i][6] *= g1.z; gg[i][7] *= g1.w;
+          s1 += ((gg[i][0] + gg[i][1]) + (gg[i][2] + gg[i][3])) + ((gg[i][4] + gg[i][5]) + (gg[i][6] + gg[i][7]));
+          if constexpr (!X_STATS)
+            sx += ((xc[i][0] + xc[i][1]) + (xc[i][2] + xc[i][3])) + ((xc[i][4] + xc[i][5]) + (xc[i][6] + xc[i][7]));
+        }
+      }
+      if constexpr (X_STATS) sx = stp.x;
+      warp_sum2(s1, sx);
+      s1 *= inv_d;
+      const float mean = sx * inv_d;
+      // ---- centred row, its second moment (exact: partial M2 + shift, or recomputed) and C = sum g (x - mean)
+      float m2 = 0.f, cc = 0.f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < d) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            xc[i][j] -= mean;
+            cc += gg[i][j] * xc[i][j];
+            if constexpr (!X_STATS) m2 += xc[i][j] * xc[i][j];
+          }
+        }
+      }
+      if constexpr (X_STATS) {
+        const float dm = np > 0.f ? stp.x / np - mean : 0.f;
+        m2 = stp.y + np * dm * dm;
+      }
+      warp_sum2(m2, cc);
+      const float rstd = rsqrtf(m2 * inv_d + a.eps);
+      const float k2 = rstd * rstd * rstd * (cc * inv_d);  // rstd^2 * s2 with s2 = mean(g * xhat) = rstd * mean(g (x - mean))
+      // ---- dx = resid + rstd * (g - s1 - xhat * s2) = resid + rstd * (g - s1) - (x - mean) * rstd^3 * mean(g (x - mean))
+      bool write_f32 = a.dx != nullptr;
+      if (a.win_n >= 0) {
+        const int pos = row % a.win_L - a.win_row0;
+        write_f32 = write_f32 && pos >= 0 && pos < a.win_n;
+      }
+      const size_t off = static_cast<size_t>(row) * d;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < d) {
+          float r[8];
+          if constexpr (RESID == 1) unpack8_bf16(rq[i], r);
+          else if constexpr (RESID == 2) {
+            r[0] = rf[i][0].x; r[1] = rf[i][0].y; r[2] = rf[i][1].x; r[3] = rf[i][1].y;
+            r[4] = rf[i][2].x; r[5] = rf[i][2].y; r[6] = rf[i][3].x; r[7] = rf[i][3].y;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = 0.f;
+          }
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = r[j] + rstd * (gg[i][j] - s1) - xc[i][j] * k2;
+          if (write_f32) {
+            *reinterpret_cast<float4*>(a.dx + off + c) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(a.dx + off + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          if (a.dx_bf16 != nullptr) {
+            uint4 u;
+            u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+            *reinterpret_cast<uint4*>(a.dx_bf16 + off + c) = u;
+          }
+        }
+      }
+    }
+  }
+}
+
+static int ln_pipe_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+template <int NP, bool X_STATS, int RESID, int RPW>
+static const char* launch_ln_pipe(LnPipeArgs a, cudaStream_t stream) {
+  constexpr int ROWS = 8 * RPW;
+  auto kern = ln_bwd_pipe_kernel<NP, X_STATS, RESID, RPW>;
+  static int sms = 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+      return "layernorm bwd (pipeline): cudaFuncSetAttribute failed";
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    attr_done = true;
+  }
+  const unsigned row_bytes = static_cast<unsigned>(a.d) * (2u + (X_STATS ? 2u : 4u) + (RESID == 1 ? 2u : RESID == 2 ? 4u : 0u)) +
+                             (X_STATS ? static_cast<unsigned>(a.d >> 6) * 8u : 0u);
+  a.stage_bytes = align128(ROWS * row_bytes);
+  const unsigned fixed = kPipeBarBytes + align128(a.d * 4u);
+  // two CTAs per SM with up to 4 slots each when they fit (<= 110 KB per CTA), else one CTA with up to 4 slots
+  static const int want_ctas = ln_pipe_env("MUDPT_LN_PIPE_CTAS", 2);
+  static const int want_stages = ln_pipe_env("MUDPT_LN_PIPE_STAGES", 4);
+  int ctas = want_ctas < 1 ? 1 : want_ctas;
+  int stages = 0;
+  for (; ctas >= 1; --ctas) {
+    const unsigned budget = (227u * 1024u - 1024u * ctas) / ctas;  // 1 KB per CTA is reserved by the driver
+    stages = budget > fixed ? static_cast<int>((budget - fixed) / a.stage_bytes) : 0;
+    if (stages >= 2) break;
+  }
+  if (ctas < 1 || stages < 2) return "layernorm bwd (pipeline): row too wide for the shared-memory ring";
+  if (stages > want_stages) stages = want_stages < 2 ? 2 : want_stages;
+  if (stages > 8) stages = 8;
+  a.stages = stages;
+  const int nblk = (a.M + ROWS - 1) / ROWS;
+  const int grid = nblk < ctas * sms ? nblk : ctas * sms;
+  launch_pdl(kern, dim3(grid), dim3(256), fixed + static_cast<size_t>(stages) * a.stage_bytes, stream, a);
+  return nullptr;
+}
+
+template <bool X_STATS, int RESID, int RPW>
+static const char* dispatch_ln_pipe_np(const LnPipeArgs& a, cudaStream_t stream) {
+  switch ((a.d + 255) / 256) {
+    case 1: return launch_ln_pipe<1, X_STATS, RESID, RPW>(a, stream);
+    case 2: return launch_ln_pipe<2, X_STATS, RESID, RPW>(a, stream);
+    case 3: return launch_ln_pipe<3, X_STATS, RESID, RPW>(a, stream);
+    default: return launch_ln_pipe<4, X_STATS, RESID, RPW>(a, stream);
+  }
+}
+
+template <int RPW>
+static const char* dispatch_ln_pipe(const LnPipeArgs& a, bool x_stats, int resid, cudaStream_t stream) {
+  if (x_stats) {
+    return resid == 0 ? dispatch_ln_pipe_np<true, 0, RPW>(a, stream)
+                      : resid == 1 ? dispatch_ln_pipe_np<true, 1, RPW>(a, stream) : dispatch_ln_pipe_np<true, 2, RPW>(a, stream);
+  }
+  return resid == 0 ? dispatch_ln_pipe_np<false, 0, RPW>(a, stream)
+                    : resid == 1 ? dispatch_ln_pipe_np<false, 1, RPW>(a, stream) : dispatch_ln_pipe_np<false, 2, RPW>(a, stream);
+}
+
+// MUDPT_LN_BWD_PIPE: 0 = register kernel only, 1 (default) = pipeline kernel with one row per warp and block, 2 = two rows
+static int ln_bwd_pipe_mode() {
+  static const int m = ln_pipe_env("MUDPT_LN_BWD_PIPE", 1);
+  return m;
+}
+
 // x: fp32 rows, or (stats != nullptr) their bf16 copy with the per-64-column partial statistics.
 // resid: fp32 rows, or (resid_bf16) the bf16 copy of the gradient stream; dx (fp32) and dx_bf16 may each be null (not both);
 // win_n >= 0: fp32 rows are written inside the deep-prompt window only (see the kernel).
@@ -328,6 +619,18 @@ const char* layernorm_bwd_stream(const void* dy, bool dy_bf16, const void* x, co
   if (dx == nullptr && dx_bf16 == nullptr) return "layernorm bwd: no output";
   if (win_n > 0 && (win_L <= 0 || win_row0 < 0 || win_row0 + win_n > win_L)) return "layernorm bwd: bad window";
   if (win_n >= 0 && win_L <= 0) win_L = 1;
+  // bf16 dy, width a multiple of 128 (16-byte granules for every bulk copy, statistics included), >= 1 block per warp slot
+  if (ln_bwd_pipe_mode() > 0 && dy_bf16 && d % 128 == 0 && M >= 64) {
+    LnPipeArgs a;
+    a.dy = reinterpret_cast<const bf16*>(dy); a.x = x; a.stats = stats; a.gamma = gamma; a.resid = resid; a.dx = dx; a.dx_bf16 = dx_bf16;
+    a.M = M; a.d = d; a.eps = eps; a.win_L = win_L; a.win_row0 = win_row0; a.win_n = win_n; a.stages = 0; a.stage_bytes = 0;
+    const int rk = resid == nullptr ? 0 : (resid_bf16 ? 1 : 2);
+    const char* e = ln_bwd_pipe_mode() >= 2 ? dispatch_ln_pipe<2>(a, stats != nullptr, rk, stream)
+                                            : dispatch_ln_pipe<1>(a, stats != nullptr, rk, stream);
+    if (e) return e;
+    count_launch(1);
+    return launch_status("layernorm bwd (pipeline) launch failed");
+  }
   if (resid_bf16 && resid != nullptr)
     dispatch_ln_bwd<true>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream);
   else
