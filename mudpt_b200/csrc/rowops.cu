@@ -319,7 +319,7 @@ static void dispatch_ln_bwd(const void* dy, bool dy_bf16, const void* x, const f
 // ------------------------------------------------------------------ LayerNorm backward, shared-memory pipeline
 // The register kernel above has one row per warp in flight: measured on the bf16 gradient stream it moves 3.5 TB/s where
 // 6.5 are available (ncu: every warp waits a full DRAM round trip per row, 45 % of the warp slots, no byte in flight while
-// a row is being reduced).  Here the loads are taken off the warps: a persistent CTA walks blocks of 8 * RPW consecutive
+// a row is being reduced).  Here the loads are taken off the warps: a persistent CTA walks blocks of 8 consecutive
 // rows; ONE thread issues the block's rows -- contiguous in memory, so one 1-D bulk copy (cp.async.bulk, the TMA engine)
 // per operand: dy, x, residual gradient, statistics -- into a ring of `stages` shared-memory slots that complete on
 // mbarriers, `stages - 1` blocks ahead of the math; the 8 warps take a row each from the slot into registers, the slot is
@@ -361,11 +361,12 @@ struct LnPipeArgs {
 static constexpr int kPipeBarBytes = 128;
 __host__ __device__ constexpr unsigned align128(unsigned v) { return (v + 127u) & ~127u; }
 
-// NP = ceil(d / 256): 8-column pieces per lane.  RESID: 0 none, 1 bf16, 2 fp32.  RPW: rows per warp and block.
-template <int NP, bool X_STATS, int RESID, int RPW>
+// NP = ceil(d / 256): 8-column pieces per lane.  RESID: 0 none, 1 bf16, 2 fp32.  One row per warp and block (two rows per
+// warp -- 16 KB bulk copies, half the barriers -- measured no faster and need twice the ring).
+template <int NP, bool X_STATS, int RESID>
 __global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
   extern __shared__ __align__(128) uint8_t ln_pipe_smem[];
-  constexpr int ROWS = 8 * RPW;
+  constexpr int ROWS = 8;  // one row per warp
   constexpr unsigned XB = X_STATS ? 2u : 4u;
   constexpr unsigned RB = RESID == 1 ? 2u : (RESID == 2 ? 4u : 0u);
   const int d = a.d, parts = d >> 6;
@@ -409,9 +410,8 @@ __global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
     const int s = it % stages;
     mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
     const uint8_t* st = stage0 + static_cast<size_t>(s) * a.stage_bytes;
-#pragma unroll
-    for (int rw = 0; rw < RPW; ++rw) {
-      const int lr = warp * RPW + rw;  // row of the block
+    {
+      const int lr = warp;  // row of the block
       const int row = blk * ROWS + lr;
       // ---- the row: shared memory -> registers
       float gg[NP][8], xc[NP][8];
@@ -451,8 +451,8 @@ __global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
           np = static_cast<float>(rem < 64 ? rem : 64);
         }
       }
-      if (rw == RPW - 1) {
-        __syncthreads();  // every warp holds its rows: the slot is free
+      {
+        __syncthreads();  // every warp holds its row: the slot is free
         if (threadIdx.x == 0) {
           const int nb = blk + stages * gridDim.x;
           fence_proxy_async_smem();  // the warps' reads of the slot (ordered by the barrier) before the async-proxy refill
@@ -542,10 +542,12 @@ static int ln_pipe_env(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int NP, bool X_STATS, int RESID, int RPW>
+static const char kLnPipeNoFit[] = "layernorm bwd (pipeline): row too wide for the shared-memory ring";
+
+template <int NP, bool X_STATS, int RESID>
 static const char* launch_ln_pipe(LnPipeArgs a, cudaStream_t stream) {
-  constexpr int ROWS = 8 * RPW;
-  auto kern = ln_bwd_pipe_kernel<NP, X_STATS, RESID, RPW>;
+  constexpr int ROWS = 8;
+  auto kern = ln_bwd_pipe_kernel<NP, X_STATS, RESID>;
   static int sms = 0;
   static bool attr_done = false;
   if (!attr_done) {
@@ -561,17 +563,25 @@ static const char* launch_ln_pipe(LnPipeArgs a, cudaStream_t stream) {
                              (X_STATS ? static_cast<unsigned>(a.d >> 6) * 8u : 0u);
   a.stage_bytes = align128(ROWS * row_bytes);
   const unsigned fixed = kPipeBarBytes + align128(a.d * 4u);
-  // two CTAs per SM with up to 4 slots each when they fit (<= 110 KB per CTA), else one CTA with up to 4 slots
-  static const int want_ctas = ln_pipe_env("MUDPT_LN_PIPE_CTAS", 2);
+  // As many CTAs per SM as fit with at least 2 slots each, at most 3 (registers), at most 4 slots.  Measured on the text
+  // tower (77,000 x 512, 315 MB): 3 CTAs x 2 slots 52 us (0.92 of HBM), 2 x 4 slots 61 us, 1 x 4 slots 94 us, register kernel
+  // 87 us -- the warps' row math is what has to be covered, not the depth of the ring (profiles/r02_ln_bwd_pipe.txt)
+  static const int want_ctas = ln_pipe_env("MUDPT_LN_PIPE_CTAS", 3);
   static const int want_stages = ln_pipe_env("MUDPT_LN_PIPE_STAGES", 4);
-  int ctas = want_ctas < 1 ? 1 : want_ctas;
+  // registers bound the co-resident CTAs too (the persistent grid must not be larger than what runs at once: a CTA that
+  // waits for a free SM starts its share when the others are done)
+  static int reg_ctas = 0;
+  if (reg_ctas == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, kern, 256, 0) != cudaSuccess || reg_ctas < 1) reg_ctas = 1;
+  }
+  int ctas = want_ctas < 1 ? 1 : (want_ctas < reg_ctas ? want_ctas : reg_ctas);
   int stages = 0;
   for (; ctas >= 1; --ctas) {
     const unsigned budget = (227u * 1024u - 1024u * ctas) / ctas;  // 1 KB per CTA is reserved by the driver
     stages = budget > fixed ? static_cast<int>((budget - fixed) / a.stage_bytes) : 0;
     if (stages >= 2) break;
   }
-  if (ctas < 1 || stages < 2) return "layernorm bwd (pipeline): row too wide for the shared-memory ring";
+  if (ctas < 1 || stages < 2) return kLnPipeNoFit;  // (the caller falls back to the register kernel)
   if (stages > want_stages) stages = want_stages < 2 ? 2 : want_stages;
   if (stages > 8) stages = 8;
   a.stages = stages;
@@ -581,27 +591,26 @@ static const char* launch_ln_pipe(LnPipeArgs a, cudaStream_t stream) {
   return nullptr;
 }
 
-template <bool X_STATS, int RESID, int RPW>
+template <bool X_STATS, int RESID>
 static const char* dispatch_ln_pipe_np(const LnPipeArgs& a, cudaStream_t stream) {
   switch ((a.d + 255) / 256) {
-    case 1: return launch_ln_pipe<1, X_STATS, RESID, RPW>(a, stream);
-    case 2: return launch_ln_pipe<2, X_STATS, RESID, RPW>(a, stream);
-    case 3: return launch_ln_pipe<3, X_STATS, RESID, RPW>(a, stream);
-    default: return launch_ln_pipe<4, X_STATS, RESID, RPW>(a, stream);
+    case 1: return launch_ln_pipe<1, X_STATS, RESID>(a, stream);
+    case 2: return launch_ln_pipe<2, X_STATS, RESID>(a, stream);
+    case 3: return launch_ln_pipe<3, X_STATS, RESID>(a, stream);
+    default: return launch_ln_pipe<4, X_STATS, RESID>(a, stream);
   }
 }
 
-template <int RPW>
 static const char* dispatch_ln_pipe(const LnPipeArgs& a, bool x_stats, int resid, cudaStream_t stream) {
   if (x_stats) {
-    return resid == 0 ? dispatch_ln_pipe_np<true, 0, RPW>(a, stream)
-                      : resid == 1 ? dispatch_ln_pipe_np<true, 1, RPW>(a, stream) : dispatch_ln_pipe_np<true, 2, RPW>(a, stream);
+    return resid == 0 ? dispatch_ln_pipe_np<true, 0>(a, stream)
+                      : resid == 1 ? dispatch_ln_pipe_np<true, 1>(a, stream) : dispatch_ln_pipe_np<true, 2>(a, stream);
   }
-  return resid == 0 ? dispatch_ln_pipe_np<false, 0, RPW>(a, stream)
-                    : resid == 1 ? dispatch_ln_pipe_np<false, 1, RPW>(a, stream) : dispatch_ln_pipe_np<false, 2, RPW>(a, stream);
+  return resid == 0 ? dispatch_ln_pipe_np<false, 0>(a, stream)
+                    : resid == 1 ? dispatch_ln_pipe_np<false, 1>(a, stream) : dispatch_ln_pipe_np<false, 2>(a, stream);
 }
 
-// MUDPT_LN_BWD_PIPE: 0 = register kernel only, 1 (default) = pipeline kernel with one row per warp and block, 2 = two rows
+// MUDPT_LN_BWD_PIPE: 0 = register kernel only, 1 (default) = shared-memory pipeline where it applies
 static int ln_bwd_pipe_mode() {
   static const int m = ln_pipe_env("MUDPT_LN_BWD_PIPE", 1);
   return m;
@@ -625,11 +634,12 @@ const char* layernorm_bwd_stream(const void* dy, bool dy_bf16, const void* x, co
     a.dy = reinterpret_cast<const bf16*>(dy); a.x = x; a.stats = stats; a.gamma = gamma; a.resid = resid; a.dx = dx; a.dx_bf16 = dx_bf16;
     a.M = M; a.d = d; a.eps = eps; a.win_L = win_L; a.win_row0 = win_row0; a.win_n = win_n; a.stages = 0; a.stage_bytes = 0;
     const int rk = resid == nullptr ? 0 : (resid_bf16 ? 1 : 2);
-    const char* e = ln_bwd_pipe_mode() >= 2 ? dispatch_ln_pipe<2>(a, stats != nullptr, rk, stream)
-                                            : dispatch_ln_pipe<1>(a, stats != nullptr, rk, stream);
-    if (e) return e;
-    count_launch(1);
-    return launch_status("layernorm bwd (pipeline) launch failed");
+    const char* e = dispatch_ln_pipe(a, stats != nullptr, rk, stream);
+    if (e == nullptr) {
+      count_launch(1);
+      return launch_status("layernorm bwd (pipeline) launch failed");
+    }
+    if (e != kLnPipeNoFit) return e;
   }
   if (resid_bf16 && resid != nullptr)
     dispatch_ln_bwd<true>(dy, dy_bf16, x, stats, gamma, resid, dx, dx_bf16, M, d, eps, win_L, win_row0, win_n, stream);
