@@ -43,7 +43,7 @@ def main():
                 counts[cur][p] += 1
     names = demangle(list(counts))
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)}: instruction counts per kernel (sm_100a)")
-    print("# UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA loads/stores, HMMA = mma.sync (legacy path),")
+    print("# UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA loads/stores, UBLKCP = 1-D bulk copies (cp.async.bulk), HMMA = mma.sync (legacy path),")
     print("# LDL/STL = local-memory (spill) accesses")
     for fn, c in counts.items():
         short = re.sub(r"\(.*", "", names.get(fn, fn)).replace("void mudpt::", "")
