@@ -432,8 +432,12 @@ def group_rowops(res):
                 resid = {"f32": resid32, "bf16": resid16.float(), "none": torch.zeros_like(resid32)}[rform]
                 exp = ln_bwd_ref(dy16, x_used, mean, rstd, gam, resid)
                 for win in (-1, n_, 0):
-                    dx = torch.full((M, d), 7.0, device=dev)
-                    dxb = resid16.clone()  # the bf16 residual is updated in place
+                    # outputs sit between guard bands of 8 rows (compute-sanitizer is closed on the GPU pool: a write outside
+                    # the M rows -- e.g. from the last, partial 8-row block of the pipeline kernel -- shows up here)
+                    big32 = torch.full((M + 16, d), 7.0, device=dev)
+                    big16 = torch.full((M + 16, d), 3.0, device=dev, dtype=torch.bfloat16)
+                    dx, dxb = big32[8:8 + M], big16[8:8 + M]
+                    dxb.copy_(resid16)  # the bf16 residual is updated in place
                     rp = {"f32": resid32.data_ptr(), "bf16": dxb.data_ptr(), "none": None}[rform]
                     _lib.check(lib.mudpt_layernorm_backward_stream(dy16.data_ptr(), xp, sp, gam.data_ptr(), rp, 1 if rform == "bf16" else 0,
                                                                    dx.data_ptr(), dxb.data_ptr(), M, d, L_, row0_, win, st))
@@ -441,16 +445,21 @@ def group_rowops(res):
                     wr = torch.ones_like(inwin) if win < 0 else (inwin if win > 0 else torch.zeros_like(inwin))
                     m = {"bf16": _metrics(dxb.float(), exp),
                          "bf16_is_rounded_f32": bool(torch.equal(dxb[wr], dx[wr].bfloat16())),
-                         "untouched": bool((dx[~wr] == 7.0).all())}
+                         "untouched": bool((dx[~wr] == 7.0).all()),
+                         "guards_intact": bool((big32[:8] == 7.0).all() and (big32[8 + M:] == 7.0).all() and
+                                               (big16[:8] == 3.0).all() and (big16[8 + M:] == 3.0).all())}
                     if bool(wr.any()):
                         m["f32"] = _metrics(dx[wr], exp[wr])
                     out[f"{xform}_{rform}_{win}"] = m
         # fp32 output not requested at all
-        dxb = resid16.clone()
+        big16 = torch.full((M + 16, d), 3.0, device=dev, dtype=torch.bfloat16)
+        dxb = big16[8:8 + M]
+        dxb.copy_(resid16)
         _lib.check(lib.mudpt_layernorm_backward_stream(dy16.data_ptr(), xb.data_ptr(), stats.data_ptr(), gam.data_ptr(), dxb.data_ptr(), 1,
                                                        None, dxb.data_ptr(), M, d, L_, row0_, n_, st))
         torch.cuda.synchronize()
-        out["no_f32"] = {"bf16": _metrics(dxb.float(), ln_bwd_ref(dy16, xb.float(), mean, rstd, gam, resid16.float()))}
+        out["no_f32"] = {"bf16": _metrics(dxb.float(), ln_bwd_ref(dy16, xb.float(), mean, rstd, gam, resid16.float())),
+                         "guards_intact": bool((big16[:8] == 3.0).all() and (big16[8 + M:] == 3.0).all())}
         res[f"ln_bwd_stream_{M}x{d}"] = out
         worst32 = max(v["f32"]["rel"] for v in out.values() if "f32" in v)
         worst16 = max(v["bf16"]["rel"] for v in out.values())

@@ -85,7 +85,7 @@ def test_layernorm_splice_im2col(bring):
                 assert not m["bf16"]["nan"] and m["bf16"]["rel"] <= BF16_REL, (k, case, m)
                 if "f32" in m:
                     assert m["f32"]["rel"] <= F32_REL and m["bf16_is_rounded_f32"], (k, case, m)
-                assert m.get("untouched", True), (k, case)
+                assert m.get("untouched", True) and m["guards_intact"], (k, case)
         elif k.startswith("ln_"):
             assert v["f32"]["rel"] <= F32_REL and v["bf16"]["rel"] <= BF16_REL, (k, v)
         if k.startswith("im2col"):
