@@ -116,10 +116,22 @@ static void launch_ln_fwd(float* x, const float* gamma, const float* beta, void*
     launch_pdl(ln_fwd_kernel<NV, false>, dim3(grid), dim3(32 * wpc), 0, stream, x, x, gamma, beta, out, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n);
 }
 
+// (defined with the pipeline kernels below) true when the shared-memory pipeline took the launch; *err is set if it failed
+static bool ln_fwd_pipe_try(float* x, const float* gamma, const float* beta, bf16* out, int M, int d, float eps, const float* sp_prompt,
+                            int sp_L, int sp_row0, int sp_n, cudaStream_t stream, const char** err);
+
 static const char* ln_fwd_dispatch(float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int M, int d, float eps,
                                    const float* sp_prompt, int sp_L, int sp_row0, int sp_n, cudaStream_t stream) {
   if (M <= 0) return nullptr;
   if (d % 4 != 0 || d > LN_MAXV * 128) return "layernorm: width must be a multiple of 4 and <= 1024";
+  if (out_bf16) {
+    const char* e = nullptr;
+    if (ln_fwd_pipe_try(x, gamma, beta, reinterpret_cast<bf16*>(out), M, d, eps, sp_prompt, sp_L, sp_row0, sp_n, stream, &e)) {
+      if (e) return e;
+      count_launch(1);
+      return launch_status("layernorm fwd (pipeline) launch failed");
+    }
+  }
   switch (pick_nv(d)) {
     case 1: launch_ln_fwd<1>(x, gamma, beta, out, out_bf16, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n, stream); break;
     case 2: launch_ln_fwd<2>(x, gamma, beta, out, out_bf16, M, d, eps, sp_prompt, sp_L, sp_row0, sp_n, stream); break;
@@ -361,17 +373,21 @@ struct LnPipeArgs {
 static constexpr int kPipeBarBytes = 128;
 __host__ __device__ constexpr unsigned align128(unsigned v) { return (v + 127u) & ~127u; }
 
-// NP = ceil(d / 256): 8-column pieces per lane.  RESID: 0 none, 1 bf16, 2 fp32.  One row per warp and block (two rows per
-// warp -- 16 KB bulk copies, half the barriers -- measured no faster and need twice the ring).
+// d = NP * 256 exactly: lane l owns the 8 columns [(i * 32 + l) * 8, +8) of piece i < NP, no width predicates (other widths
+// take the register kernel).  RESID: 0 none, 1 bf16, 2 fp32.  One row per warp and block (two rows per warp -- 16 KB bulk
+// copies, half the barriers -- measured no faster and need twice the ring).  Addresses, ring slot / phase and the position in
+// the deep-prompt window advance incrementally: the first version spent 40 % of its 480 instructions per row on 64-bit index
+// arithmetic, width predicates and divisions (ncu source page), and the kernel is issue-bound once the loads are off the warps.
 template <int NP, bool X_STATS, int RESID>
 __global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
   extern __shared__ __align__(128) uint8_t ln_pipe_smem[];
   constexpr int ROWS = 8;  // one row per warp
+  constexpr unsigned d = NP * 256u;
   constexpr unsigned XB = X_STATS ? 2u : 4u;
   constexpr unsigned RB = RESID == 1 ? 2u : (RESID == 2 ? 4u : 0u);
-  const int d = a.d, parts = d >> 6;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned dy_off = 0, x_off = ROWS * d * 2u, r_off = x_off + ROWS * d * XB, st_off = r_off + ROWS * d * RB;
+  constexpr unsigned parts = d >> 6;
+  constexpr unsigned dy_off = 0, x_off = ROWS * d * 2u, r_off = x_off + ROWS * d * XB, st_off = r_off + ROWS * d * RB;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* full = reinterpret_cast<uint64_t*>(ln_pipe_smem);
   float* gam = reinterpret_cast<float*>(ln_pipe_smem + kPipeBarBytes);
   uint8_t* stage0 = ln_pipe_smem + kPipeBarBytes + align128(d * 4u);
@@ -387,12 +403,11 @@ __global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
     const int r0 = blk * ROWS;
     const unsigned nr = static_cast<unsigned>(a.M - r0 < ROWS ? a.M - r0 : ROWS);
     uint8_t* st = stage0 + static_cast<size_t>(s) * a.stage_bytes;
-    const unsigned rowsz = static_cast<unsigned>(d);
-    mbar_expect_tx(&full[s], nr * rowsz * (2u + XB + RB) + (X_STATS ? nr * parts * 8u : 0u));
-    bulk_load_1d(st + dy_off, a.dy + static_cast<size_t>(r0) * d, nr * rowsz * 2u, &full[s]);
-    bulk_load_1d(st + x_off, reinterpret_cast<const uint8_t*>(a.x) + static_cast<size_t>(r0) * d * XB, nr * rowsz * XB, &full[s]);
+    mbar_expect_tx(&full[s], nr * d * (2u + XB + RB) + (X_STATS ? nr * parts * 8u : 0u));
+    bulk_load_1d(st + dy_off, a.dy + static_cast<size_t>(r0) * d, nr * d * 2u, &full[s]);
+    bulk_load_1d(st + x_off, reinterpret_cast<const uint8_t*>(a.x) + static_cast<size_t>(r0) * d * XB, nr * d * XB, &full[s]);
     if constexpr (RESID != 0)
-      bulk_load_1d(st + r_off, reinterpret_cast<const uint8_t*>(a.resid) + static_cast<size_t>(r0) * d * RB, nr * rowsz * RB, &full[s]);
+      bulk_load_1d(st + r_off, reinterpret_cast<const uint8_t*>(a.resid) + static_cast<size_t>(r0) * d * RB, nr * d * RB, &full[s]);
     if constexpr (X_STATS) bulk_load_1d(st + st_off, a.stats + static_cast<size_t>(r0) * parts, nr * parts * 8u, &full[s]);
   };
   if (threadIdx.x == 0) {
@@ -401,78 +416,73 @@ __global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
       if (blk < nblk) issue(blk, s);
     }
   }
-  for (int c = threadIdx.x * 4; c < d; c += 256 * 4) *reinterpret_cast<float4*>(gam + c) = *reinterpret_cast<const float4*>(a.gamma + c);
+  for (unsigned c = threadIdx.x * 4; c < d; c += 256 * 4) *reinterpret_cast<float4*>(gam + c) = *reinterpret_cast<const float4*>(a.gamma + c);
   pdl_trigger();
   __syncthreads();  // gamma staged
-  const float inv_d = 1.f / static_cast<float>(d);
-  int it = 0;
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it) {
-    const int s = it % stages;
-    mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
-    const uint8_t* st = stage0 + static_cast<size_t>(s) * a.stage_bytes;
-    {
-      const int lr = warp;  // row of the block
-      const int row = blk * ROWS + lr;
-      // ---- the row: shared memory -> registers
-      float gg[NP][8], xc[NP][8];
-      uint4 rq[NP];
-      float2 rf[RESID == 2 ? NP : 1][4];
-      float2 stp = make_float2(0.f, 0.f);
+  constexpr float inv_d = 1.f / static_cast<float>(d);
+  // this warp's row inside a slot, this lane's 8 columns inside a piece
+  const unsigned o_dy = dy_off + warp * d * 2u + lane * 16u;
+  const unsigned o_x = x_off + warp * d * XB + lane * 8u * XB;
+  const unsigned o_r = r_off + warp * d * RB + lane * 8u * RB;
+  const unsigned o_st = st_off + (warp * parts + lane) * 8u;
+  const float* gl = gam + lane * 8u;
+  const float np = lane < parts ? 64.f : 0.f;  // (d is a multiple of 64: every partial statistic covers 64 columns)
+  const bool windowed = a.win_n >= 0;
+  const int row_step = ROWS * static_cast<int>(gridDim.x);
+  int row = static_cast<int>(blockIdx.x) * ROWS + static_cast<int>(warp);
+  int pos = 0, pos_step = 0;  // row % win_L, advanced without a division per row
+  if (windowed) {
+    pos = row % a.win_L;
+    pos_step = row_step % a.win_L;
+  }
+  int s = 0;
+  uint32_t phase = 0;
+  const uint8_t* st = stage0;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    mbar_wait(&full[s], phase);
+    // ---- the row: shared memory -> registers
+    float gg[NP][8], xc[NP][8];
+    uint4 rq[RESID == 1 ? NP : 1];
+    float4 rf[RESID == 2 ? NP : 1][2];
+    float2 stp = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        rq[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (c < d) {
-          const uint4 q = *reinterpret_cast<const uint4*>(st + dy_off + (static_cast<size_t>(lr) * d + c) * 2u);
-          unpack8_bf16(q, gg[i]);
-          if constexpr (X_STATS) {
-            const uint4 u = *reinterpret_cast<const uint4*>(st + x_off + (static_cast<size_t>(lr) * d + c) * 2u);
-            unpack8_bf16(u, xc[i]);
-          } else {
-            const float4 u0 = *reinterpret_cast<const float4*>(st + x_off + (static_cast<size_t>(lr) * d + c) * 4u);
-            const float4 u1 = *reinterpret_cast<const float4*>(st + x_off + (static_cast<size_t>(lr) * d + c) * 4u + 16u);
-            xc[i][0] = u0.x; xc[i][1] = u0.y; xc[i][2] = u0.z; xc[i][3] = u0.w;
-            xc[i][4] = u1.x; xc[i][5] = u1.y; xc[i][6] = u1.z; xc[i][7] = u1.w;
-          }
-          if constexpr (RESID == 1) rq[i] = *reinterpret_cast<const uint4*>(st + r_off + (static_cast<size_t>(lr) * d + c) * 2u);
-          if constexpr (RESID == 2) {
-            const float4 u0 = *reinterpret_cast<const float4*>(st + r_off + (static_cast<size_t>(lr) * d + c) * 4u);
-            const float4 u1 = *reinterpret_cast<const float4*>(st + r_off + (static_cast<size_t>(lr) * d + c) * 4u + 16u);
-            rf[i][0] = make_float2(u0.x, u0.y); rf[i][1] = make_float2(u0.z, u0.w);
-            rf[i][2] = make_float2(u1.x, u1.y); rf[i][3] = make_float2(u1.z, u1.w);
-          }
-        }
-      }
-      float np = 0.f;
+    for (int i = 0; i < NP; ++i) {
+      unpack8_bf16(*reinterpret_cast<const uint4*>(st + o_dy + i * 512u), gg[i]);
       if constexpr (X_STATS) {
-        if (lane < parts) {
-          stp = *reinterpret_cast<const float2*>(st + st_off + (static_cast<size_t>(lr) * parts + lane) * 8u);
-          const int rem = d - lane * 64;
-          np = static_cast<float>(rem < 64 ? rem : 64);
-        }
+        unpack8_bf16(*reinterpret_cast<const uint4*>(st + o_x + i * 512u), xc[i]);
+      } else {
+        const float4 u0 = *reinterpret_cast<const float4*>(st + o_x + i * 1024u);
+        const float4 u1 = *reinterpret_cast<const float4*>(st + o_x + i * 1024u + 16u);
+        xc[i][0] = u0.x; xc[i][1] = u0.y; xc[i][2] = u0.z; xc[i][3] = u0.w;
+        xc[i][4] = u1.x; xc[i][5] = u1.y; xc[i][6] = u1.z; xc[i][7] = u1.w;
       }
-      {
-        __syncthreads();  // every warp holds its row: the slot is free
-        if (threadIdx.x == 0) {
-          const int nb = blk + stages * gridDim.x;
-          fence_proxy_async_smem();  // the warps' reads of the slot (ordered by the barrier) before the async-proxy refill
-          if (nb < nblk) issue(nb, s);
-        }
+      if constexpr (RESID == 1) rq[i] = *reinterpret_cast<const uint4*>(st + o_r + i * 512u);
+      if constexpr (RESID == 2) {
+        rf[i][0] = *reinterpret_cast<const float4*>(st + o_r + i * 1024u);
+        rf[i][1] = *reinterpret_cast<const float4*>(st + o_r + i * 1024u + 16u);
       }
-      if (row >= a.M) continue;  // (warp-uniform)
+    }
+    if constexpr (X_STATS) {
+      if (lane < parts) stp = *reinterpret_cast<const float2*>(st + o_st);
+    }
+    __syncthreads();  // every warp holds its row: the slot is free
+    if (threadIdx.x == 0) {
+      const int nb = blk + stages * static_cast<int>(gridDim.x);
+      fence_proxy_async_smem();  // the warps' reads of the slot (ordered by the barrier) before the async-proxy refill
+      if (nb < nblk) issue(nb, s);
+    }
+    if (++s == stages) { s = 0; phase ^= 1u; st = stage0; } else { st += a.stage_bytes; }
+    if (row < a.M) {  // (warp-uniform)
       // ---- g = dy * gamma, s1 = mean(g); mean of x
       float s1 = 0.f, sx = 0.f;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < d) {
-          const float4 g0 = *reinterpret_cast<const float4*>(gam + c), g1 = *reinterpret_cast<const float4*>(gam + c + 4);
-          gg[i][0] *= g0.x; gg[i][1] *= g0.y; gg[i][2] *= g0.z; gg[i][3] *= g0.w;
-          gg[i][4] *= g1.x; gg[i][5] *= g1.y; gg[i][6] *= g1.z; gg[i][7] *= g1.w;
-          s1 += ((gg[i][0] + gg[i][1]) + (gg[i][2] + gg[i][3])) + ((gg[i][4] + gg[i][5]) + (gg[i][6] + gg[i][7]));
-          if constexpr (!X_STATS)
-            sx += ((xc[i][0] + xc[i][1]) + (xc[i][2] + xc[i][3])) + ((xc[i][4] + xc[i][5]) + (xc[i][6] + xc[i][7]));
-        }
+        const float4 g0 = *reinterpret_cast<const float4*>(gl + i * 256), g1 = *reinterpret_cast<const float4*>(gl + i * 256 + 4);
+        gg[i][0] *= g0.x; gg[i][1] *= g0.y; gg[i][2] *= g0.z; gg[i][3] *= g0.w;
+        gg[i][4] *= g1.x; gg[i][5] *= g1.y; gg[i][6] *= g1.z; gg[i][7] *= g1.w;
+        s1 += ((gg[i][0] + gg[i][1]) + (gg[i][2] + gg[i][3])) + ((gg[i][4] + gg[i][5]) + (gg[i][6] + gg[i][7]));
+        if constexpr (!X_STATS)
+          sx += ((xc[i][0] + xc[i][1]) + (xc[i][2] + xc[i][3])) + ((xc[i][4] + xc[i][5]) + (xc[i][6] + xc[i][7]));
       }
       if constexpr (X_STATS) sx = stp.x;
       warp_sum2(s1, sx);
@@ -482,57 +492,188 @@ __global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
       float m2 = 0.f, cc = 0.f;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < d) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            xc[i][j] -= mean;
-            cc += gg[i][j] * xc[i][j];
-            if constexpr (!X_STATS) m2 += xc[i][j] * xc[i][j];
-          }
+        for (int j = 0; j < 8; ++j) {
+          xc[i][j] -= mean;
+          cc = fmaf(gg[i][j], xc[i][j], cc);
+          if constexpr (!X_STATS) m2 = fmaf(xc[i][j], xc[i][j], m2);
         }
       }
       if constexpr (X_STATS) {
-        const float dm = np > 0.f ? stp.x / np - mean : 0.f;
+        const float dm = np > 0.f ? stp.x * (1.f / 64.f) - mean : 0.f;
         m2 = stp.y + np * dm * dm;
       }
       warp_sum2(m2, cc);
       const float rstd = rsqrtf(m2 * inv_d + a.eps);
-      const float k2 = rstd * rstd * rstd * (cc * inv_d);  // rstd^2 * s2 with s2 = mean(g * xhat) = rstd * mean(g (x - mean))
-      // ---- dx = resid + rstd * (g - s1 - xhat * s2) = resid + rstd * (g - s1) - (x - mean) * rstd^3 * mean(g (x - mean))
-      bool write_f32 = a.dx != nullptr;
-      if (a.win_n >= 0) {
-        const int pos = row % a.win_L - a.win_row0;
-        write_f32 = write_f32 && pos >= 0 && pos < a.win_n;
-      }
-      const size_t off = static_cast<size_t>(row) * d;
+      const float k2 = -(rstd * rstd * rstd * (cc * inv_d));  // -rstd^2 * s2 with s2 = mean(g * xhat) = rstd * mean(g (x - mean))
+      const float c0 = -rstd * s1;
+      // ---- dx = resid + rstd * (g - s1 - xhat * s2) = (resid - rstd * s1) + rstd * g - (x - mean) * rstd^3 * mean(g (x - mean))
+      const bool write_f32 = a.dx != nullptr && (!windowed || (pos >= a.win_row0 && pos < a.win_row0 + a.win_n));
+      const size_t off = static_cast<size_t>(row) * d + lane * 8u;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < d) {
-          float r[8];
-          if constexpr (RESID == 1) unpack8_bf16(rq[i], r);
-          else if constexpr (RESID == 2) {
-            r[0] = rf[i][0].x; r[1] = rf[i][0].y; r[2] = rf[i][1].x; r[3] = rf[i][1].y;
-            r[4] = rf[i][2].x; r[5] = rf[i][2].y; r[6] = rf[i][3].x; r[7] = rf[i][3].y;
-          } else {
+        float r[8];
+        if constexpr (RESID == 1) {
+          unpack8_bf16(rq[i], r);
+        } else if constexpr (RESID == 2) {
+          r[0] = rf[i][0].x; r[1] = rf[i][0].y; r[2] = rf[i][0].z; r[3] = rf[i][0].w;
+          r[4] = rf[i][1].x; r[5] = rf[i][1].y; r[6] = rf[i][1].z; r[7] = rf[i][1].w;
+        } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = 0.f;
-          }
-          float o[8];
+          for (int j = 0; j < 8; ++j) r[j] = 0.f;
+        }
+        float o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = r[j] + rstd * (gg[i][j] - s1) - xc[i][j] * k2;
-          if (write_f32) {
-            *reinterpret_cast<float4*>(a.dx + off + c) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(a.dx + off + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
-          }
-          if (a.dx_bf16 != nullptr) {
-            uint4 u;
-            u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
-            *reinterpret_cast<uint4*>(a.dx_bf16 + off + c) = u;
-          }
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(k2, xc[i][j], fmaf(rstd, gg[i][j], r[j] + c0));
+        if (write_f32) {
+          *reinterpret_cast<float4*>(a.dx + off + i * 256) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(a.dx + off + i * 256 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (a.dx_bf16 != nullptr) {
+          uint4 u;
+          u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+          *reinterpret_cast<uint4*>(a.dx_bf16 + off + i * 256) = u;
         }
       }
+    }
+    row += row_step;
+    if (windowed) {
+      pos += pos_step;
+      if (pos >= a.win_L) pos -= a.win_L;
+    }
+  }
+}
+
+// LayerNorm forward (bf16 output, optional deep-prompt splice) on the same pipeline: the stand-alone LayerNorms of the towers
+// (clip/model.py:299-300) at 6-10 thousand rows ran at 0.36 of the HBM rate on the one-row-per-warp kernel.
+struct LnFwdPipeArgs {
+  const float* x;   // fp32 rows (read by the bulk copies)
+  float* x_w;       // the same buffer: spliced rows are written back (rows no bulk copy of another CTA reads)
+  const float* gamma;
+  const float* beta;
+  bf16* out;
+  int M;
+  float eps;
+  const float* sp_prompt;  // or null
+  int sp_L, sp_row0, sp_n;
+  int stages;
+  unsigned stage_bytes;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(256) ln_fwd_pipe_kernel(const LnFwdPipeArgs a) {
+  extern __shared__ __align__(128) uint8_t ln_pipe_smem[];
+  constexpr int ROWS = 8;
+  constexpr unsigned d = NP * 256u;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ln_pipe_smem);
+  float* gam = reinterpret_cast<float*>(ln_pipe_smem + kPipeBarBytes);
+  float* bet = gam + d;
+  uint8_t* stage0 = ln_pipe_smem + kPipeBarBytes + align128(d * 8u);
+  const int nblk = (a.M + ROWS - 1) / ROWS;
+  const int stages = a.stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  auto issue = [&](int blk, int s) {
+    const int r0 = blk * ROWS;
+    const unsigned nr = static_cast<unsigned>(a.M - r0 < ROWS ? a.M - r0 : ROWS);
+    mbar_expect_tx(&full[s], nr * d * 4u);
+    bulk_load_1d(stage0 + static_cast<size_t>(s) * a.stage_bytes, a.x + static_cast<size_t>(r0) * d, nr * d * 4u, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const int blk = blockIdx.x + s * gridDim.x;
+      if (blk < nblk) issue(blk, s);
+    }
+  }
+  for (unsigned c = threadIdx.x * 4; c < d; c += 256 * 4) {
+    *reinterpret_cast<float4*>(gam + c) = *reinterpret_cast<const float4*>(a.gamma + c);
+    *reinterpret_cast<float4*>(bet + c) = *reinterpret_cast<const float4*>(a.beta + c);
+  }
+  pdl_trigger();
+  __syncthreads();
+  constexpr float inv_d = 1.f / static_cast<float>(d);
+  const unsigned o_x = warp * d * 4u + lane * 32u;
+  const float* gl = gam + lane * 8u;
+  const float* bl = bet + lane * 8u;
+  const bool splicing = a.sp_prompt != nullptr;
+  const int row_step = ROWS * static_cast<int>(gridDim.x);
+  int row = static_cast<int>(blockIdx.x) * ROWS + static_cast<int>(warp);
+  int pos = 0, pos_step = 0;
+  if (splicing) {
+    pos = row % a.sp_L;
+    pos_step = row_step % a.sp_L;
+  }
+  int s = 0;
+  uint32_t phase = 0;
+  const uint8_t* st = stage0;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    mbar_wait(&full[s], phase);
+    float xv[NP][8];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float4 u0 = *reinterpret_cast<const float4*>(st + o_x + i * 1024u);
+      const float4 u1 = *reinterpret_cast<const float4*>(st + o_x + i * 1024u + 16u);
+      xv[i][0] = u0.x; xv[i][1] = u0.y; xv[i][2] = u0.z; xv[i][3] = u0.w;
+      xv[i][4] = u1.x; xv[i][5] = u1.y; xv[i][6] = u1.z; xv[i][7] = u1.w;
+    }
+    __syncthreads();  // every warp holds its row: the slot is free
+    if (threadIdx.x == 0) {
+      const int nb = blk + stages * static_cast<int>(gridDim.x);
+      fence_proxy_async_smem();
+      if (nb < nblk) issue(nb, s);
+    }
+    if (++s == stages) { s = 0; phase ^= 1u; st = stage0; } else { st += a.stage_bytes; }
+    if (row < a.M) {  // (warp-uniform)
+      const size_t off = static_cast<size_t>(row) * d + lane * 8u;
+      if (splicing && pos >= a.sp_row0 && pos < a.sp_row0 + a.sp_n) {
+        // the deep-prompt splice of the block (clip/model.py:281-297): the row takes the prompt's values, copied verbatim
+        // into the residual stream (bit-exact), and is normalised like any other
+        const float* src = a.sp_prompt + static_cast<size_t>(pos - a.sp_row0) * d + lane * 8u;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const float4 u0 = *reinterpret_cast<const float4*>(src + i * 256), u1 = *reinterpret_cast<const float4*>(src + i * 256 + 4);
+          xv[i][0] = u0.x; xv[i][1] = u0.y; xv[i][2] = u0.z; xv[i][3] = u0.w;
+          xv[i][4] = u1.x; xv[i][5] = u1.y; xv[i][6] = u1.z; xv[i][7] = u1.w;
+          *reinterpret_cast<float4*>(a.x_w + off + i * 256) = u0;
+          *reinterpret_cast<float4*>(a.x_w + off + i * 256 + 4) = u1;
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i)
+        sum += ((xv[i][0] + xv[i][1]) + (xv[i][2] + xv[i][3])) + ((xv[i][4] + xv[i][5]) + (xv[i][6] + xv[i][7]));
+      const float mean = warp_sum(sum) * inv_d;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xv[i][j] -= mean;
+          sq = fmaf(xv[i][j], xv[i][j], sq);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(sq) * inv_d + a.eps);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gl + i * 256), g1 = *reinterpret_cast<const float4*>(gl + i * 256 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bl + i * 256), b1 = *reinterpret_cast<const float4*>(bl + i * 256 + 4);
+        uint4 u;
+        u.x = pack_bf16(fmaf(xv[i][0] * rstd, g0.x, b0.x), fmaf(xv[i][1] * rstd, g0.y, b0.y));
+        u.y = pack_bf16(fmaf(xv[i][2] * rstd, g0.z, b0.z), fmaf(xv[i][3] * rstd, g0.w, b0.w));
+        u.z = pack_bf16(fmaf(xv[i][4] * rstd, g1.x, b1.x), fmaf(xv[i][5] * rstd, g1.y, b1.y));
+        u.w = pack_bf16(fmaf(xv[i][6] * rstd, g1.z, b1.z), fmaf(xv[i][7] * rstd, g1.w, b1.w));
+        *reinterpret_cast<uint4*>(a.out + off + i * 256) = u;
+      }
+    }
+    row += row_step;
+    if (splicing) {
+      pos += pos_step;
+      if (pos >= a.sp_L) pos -= a.sp_L;
     }
   }
 }
@@ -616,6 +757,64 @@ static int ln_bwd_pipe_mode() {
   return m;
 }
 
+// MUDPT_LN_FWD_PIPE: 1 (default) = the pipeline for bf16-output LayerNorm forward of 512 / 768 / 1024-wide rows, 0 = register kernel
+static int ln_fwd_pipe_mode() {
+  static const int m = ln_pipe_env("MUDPT_LN_FWD_PIPE", 1);
+  return m;
+}
+
+template <int NP>
+static const char* launch_ln_fwd_pipe(LnFwdPipeArgs a, cudaStream_t stream) {
+  constexpr int ROWS = 8;
+  constexpr unsigned d = NP * 256u;
+  auto kern = ln_fwd_pipe_kernel<NP>;
+  static int sms = 0, reg_ctas = 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+      return "layernorm fwd (pipeline): cudaFuncSetAttribute failed";
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, kern, 256, 0) != cudaSuccess || reg_ctas < 1) reg_ctas = 1;
+    attr_done = true;
+  }
+  a.stage_bytes = ROWS * d * 4u;
+  const unsigned fixed = kPipeBarBytes + align128(d * 8u);
+  static const int want_ctas = ln_pipe_env("MUDPT_LN_PIPE_CTAS", 3);
+  static const int want_stages = ln_pipe_env("MUDPT_LN_PIPE_STAGES", 4);
+  int ctas = want_ctas < 1 ? 1 : (want_ctas < reg_ctas ? want_ctas : reg_ctas);
+  int stages = 0;
+  for (; ctas >= 1; --ctas) {
+    const unsigned budget = (227u * 1024u - 1024u * ctas) / ctas;
+    stages = budget > fixed ? static_cast<int>((budget - fixed) / a.stage_bytes) : 0;
+    if (stages >= 2) break;
+  }
+  if (ctas < 1 || stages < 2) return kLnPipeNoFit;
+  if (stages > want_stages) stages = want_stages < 2 ? 2 : want_stages;
+  if (stages > 8) stages = 8;
+  a.stages = stages;
+  const int nblk = (a.M + ROWS - 1) / ROWS;
+  const int grid = nblk < ctas * sms ? nblk : ctas * sms;
+  launch_pdl(kern, dim3(grid), dim3(256), fixed + static_cast<size_t>(stages) * a.stage_bytes, stream, a);
+  return nullptr;
+}
+
+static bool ln_fwd_pipe_try(float* x, const float* gamma, const float* beta, bf16* out, int M, int d, float eps, const float* sp_prompt,
+                            int sp_L, int sp_row0, int sp_n, cudaStream_t stream, const char** err) {
+  *err = nullptr;
+  if (ln_fwd_pipe_mode() <= 0 || d % 256 != 0 || d > 1024 || M < 64) return false;
+  LnFwdPipeArgs a;
+  a.x = x; a.x_w = x; a.gamma = gamma; a.beta = beta; a.out = out; a.M = M; a.eps = eps;
+  a.sp_prompt = sp_prompt; a.sp_L = sp_L > 0 ? sp_L : 1; a.sp_row0 = sp_row0; a.sp_n = sp_n; a.stages = 0; a.stage_bytes = 0;
+  const char* e = d == 256 ? launch_ln_fwd_pipe<1>(a, stream)
+                           : d == 512 ? launch_ln_fwd_pipe<2>(a, stream) : d == 768 ? launch_ln_fwd_pipe<3>(a, stream) : launch_ln_fwd_pipe<4>(a, stream);
+  if (e == kLnPipeNoFit) return false;
+  *err = e;
+  return true;
+}
+
 // x: fp32 rows, or (stats != nullptr) their bf16 copy with the per-64-column partial statistics.
 // resid: fp32 rows, or (resid_bf16) the bf16 copy of the gradient stream; dx (fp32) and dx_bf16 may each be null (not both);
 // win_n >= 0: fp32 rows are written inside the deep-prompt window only (see the kernel).
@@ -628,8 +827,8 @@ const char* layernorm_bwd_stream(const void* dy, bool dy_bf16, const void* x, co
   if (dx == nullptr && dx_bf16 == nullptr) return "layernorm bwd: no output";
   if (win_n > 0 && (win_L <= 0 || win_row0 < 0 || win_row0 + win_n > win_L)) return "layernorm bwd: bad window";
   if (win_n >= 0 && win_L <= 0) win_L = 1;
-  // bf16 dy, width a multiple of 128 (16-byte granules for every bulk copy, statistics included), >= 1 block per warp slot
-  if (ln_bwd_pipe_mode() > 0 && dy_bf16 && d % 128 == 0 && M >= 64) {
+  // bf16 dy, width a multiple of 256 (one 8-column piece per lane and 256 columns: 512 / 768 / 1024, the widths of the CLIP towers)
+  if (ln_bwd_pipe_mode() > 0 && dy_bf16 && d % 256 == 0 && M >= 64) {
     LnPipeArgs a;
     a.dy = reinterpret_cast<const bf16*>(dy); a.x = x; a.stats = stats; a.gamma = gamma; a.resid = resid; a.dx = dx; a.dx_bf16 = dx_bf16;
     a.M = M; a.d = d; a.eps = eps; a.win_L = win_L; a.win_row0 = win_row0; a.win_n = win_n; a.stages = 0; a.stage_bytes = 0;
