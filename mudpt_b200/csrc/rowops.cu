@@ -544,8 +544,9 @@ __global__ void __launch_bounds__(256) ln_bwd_pipe_kernel(const LnPipeArgs a) {
   }
 }
 
-// LayerNorm forward (bf16 output, optional deep-prompt splice) on the same pipeline: the stand-alone LayerNorms of the towers
-// (clip/model.py:299-300) at 6-10 thousand rows ran at 0.36 of the HBM rate on the one-row-per-warp kernel.
+// LayerNorm forward (bf16 output, optional deep-prompt splice) on the same pipeline (clip/model.py:299-300).  An experiment that
+// did not pay at the shapes where the forward LayerNorm is a stand-alone kernel (see ln_fwd_pipe_mode()): kept behind
+// MUDPT_LN_FWD_PIPE=1 for towers whose forward LayerNorm is not folded into the GEMMs at tens of thousands of rows.
 struct LnFwdPipeArgs {
   const float* x;   // fp32 rows (read by the bulk copies)
   float* x_w;       // the same buffer: spliced rows are written back (rows no bulk copy of another CTA reads)
@@ -757,9 +758,12 @@ static int ln_bwd_pipe_mode() {
   return m;
 }
 
-// MUDPT_LN_FWD_PIPE: 1 (default) = the pipeline for bf16-output LayerNorm forward of 512 / 768 / 1024-wide rows, 0 = register kernel
+// MUDPT_LN_FWD_PIPE: 1 = the pipeline for bf16-output LayerNorm forward of 512 / 768 / 1024-wide rows, 0 (default) = register
+// kernel.  Measured (profiles/r02_ln_bwd_pipe.txt): at the 6-10 thousand rows of the stand-alone forward LayerNorms the
+// pipeline is SLOWER (12.5 against 10.9 us per launch; N = 1 vision tower 13.3 against 12.0): with one operand and 2.7 rounds
+// of row blocks its prologue (barriers, gamma / beta staging, the first bulk copy) is not amortised.  Parity-tested, off.
 static int ln_fwd_pipe_mode() {
-  static const int m = ln_pipe_env("MUDPT_LN_FWD_PIPE", 1);
+  static const int m = ln_pipe_env("MUDPT_LN_FWD_PIPE", 0);
   return m;
 }
 
