@@ -527,6 +527,36 @@ class CustomCLIP(nn.Module):
 
 
 @TRAINER_REGISTRY.register()
+def apply_freeze_rule(model, keep):
+    """The reference trainers' freeze rule (trainers/mudpt.py:205-212, trainers/cocoop.py:221-225): a parameter stays
+    trainable iff its name contains one of the substrings `keep`; everything else (the whole CLIP) is frozen.
+    Returns the set of trainable names."""
+    for pname, p in model.named_parameters():
+        p.requires_grad_(any(k in pname for k in keep))
+    return {pname for pname, p in model.named_parameters() if p.requires_grad}
+
+
+def restore_checkpoints(trainer, directory, epoch, is_class_bound, after_load=None):
+    """Body of the reference trainers' load_model (trainers/mudpt.py:270-302, trainers/cocoop.py:285-320): for every
+    registered model read Dassl's `<directory>/<name>/model-best.pth.tar` (or `model.pth.tar-<epoch>`), drop the entries
+    that depend on the class names (`is_class_bound(key)`: the fixed token vectors, recomputed from the current names)
+    and load the rest non-strictly.  FileNotFoundError as in the reference."""
+    if not directory:
+        print("Note that load_model() is skipped as no pretrained model is given")
+        return
+    fname = "model-best.pth.tar" if epoch is None else "model.pth.tar-" + str(epoch)
+    for name in trainer.get_model_names():
+        path = osp.join(directory, name, fname)
+        if not osp.exists(path):
+            raise FileNotFoundError('Model not found at "{}"'.format(path))
+        ckpt = load_checkpoint(path)
+        weights = {k: v for k, v in ckpt["state_dict"].items() if not is_class_bound(k)}
+        print('Loading weights to {} from "{}" (epoch = {})'.format(name, path, ckpt["epoch"]))
+        trainer._models[name].load_state_dict(weights, strict=False)
+        if after_load is not None:
+            after_load(trainer._models[name])
+
+
 class MuDPT(TrainerX):
     def check_cfg(self, cfg):
         assert cfg.TRAINER.MUDPT.PREC in ["fp16", "fp32", "amp"]
@@ -542,11 +572,7 @@ class MuDPT(TrainerX):
         self.model = CustomCLIP(cfg, classnames, clip_model)
 
         print("Turning off gradients in both the image and the text encoder")
-        name_to_optimize = "prompt_learner"
-        for name, param in self.model.named_parameters():
-            if name_to_optimize not in name:
-                param.requires_grad_("visual_ctx" in name)
-        enabled = {name for name, p in self.model.named_parameters() if p.requires_grad}
+        enabled = apply_freeze_rule(self.model, ("prompt_learner", "visual_ctx"))
         print(f"Parameters to be updated: {enabled}")
 
         if getattr(cfg.MODEL, "INIT_WEIGHTS", ""):
@@ -681,26 +707,13 @@ class MuDPT(TrainerX):
         return cache[is_train]
 
     def load_model(self, directory, epoch=None):
-        if not directory:
-            print("Note that load_model() is skipped as no pretrained model is given")
-            return
-        names = self.get_model_names()
-        model_file = "model-best.pth.tar"
-        if epoch is not None:
-            model_file = "model.pth.tar-" + str(epoch)
-        for name in names:
-            model_path = osp.join(directory, name, model_file)
-            if not osp.exists(model_path):
-                raise FileNotFoundError('Model not found at "{}"'.format(model_path))
-            checkpoint = load_checkpoint(model_path)
-            state_dict = checkpoint["state_dict"]
-            epoch = checkpoint["epoch"]
-            # class names may differ (base -> new): ignore the fixed token vectors, whatever the learner is called
-            # (mudpt_ / umudpt_ / uumudpt_prompt_learner: trainers/mudpt.py:294-298, umudpt.py:337-341, uumudpt.py:343-347)
-            for key in [k for k in state_dict
-                        if k.endswith("prompt_learner.token_prefix") or k.endswith("prompt_learner.token_suffix")]:
-                del state_dict[key]
-            print('Loading weights to {} from "{}" (epoch = {})'.format(name, model_path, epoch))
-            self._models[name].load_state_dict(state_dict, strict=False)
-            self._models[name]._clip_ref[0].refresh_engine_weights()
-            self._models[name].invalidate_cache()  # cached text features / resident class set belong to the old weights
+        # class names may differ (base -> new): ignore the fixed token vectors, whatever the learner is called
+        # (mudpt_ / umudpt_ / uumudpt_prompt_learner: trainers/mudpt.py:294-298, umudpt.py:337-341, uumudpt.py:343-347)
+        def token_vector(key):
+            return key.endswith(("prompt_learner.token_prefix", "prompt_learner.token_suffix"))
+
+        def refresh(model):
+            model._clip_ref[0].refresh_engine_weights()
+            model.invalidate_cache()  # cached text features / resident class set belong to the old weights
+
+        restore_checkpoints(self, directory, epoch, token_vector, refresh)
