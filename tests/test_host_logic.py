@@ -294,3 +294,46 @@ def test_variant_checkpoint_reload_with_other_class_names(tmp_path, variant, new
     for (n, p), (_, q) in zip(a.model.named_parameters(), b.model.named_parameters()):
         if p.requires_grad:
             assert torch.equal(p, q), n
+
+
+def test_cocoop_checkpoint_round_trip_and_freeze_rule(tmp_path):
+    """BASELINE config 4 host logic: the CoCoOp trainer registers only the prompt learner (trainers/cocoop.py:232-236), saves it in
+    Dassl's layout and reloads it for OTHER class names -- trained tensors restored, the checkpoint's token vectors ignored
+    (:309-317), FileNotFoundError for a missing epoch (:300-301); the freeze rule leaves exactly the learner's 5 tensors trainable."""
+    import pytest
+    import torch
+    from mudpt_b200 import clip
+    from mudpt_b200 import synthetic as syn
+    from mudpt_b200.trainers import cocoop as CO
+    from mudpt_b200.trainers import mudpt as M
+    from tests import golden_util as gu
+    c = gu.load_cocoop("cocoop_tiny_b")
+
+    def make(classnames):
+        cfg = gu.make_cocoop_cfg(c["n_ctx"], "", c["arch"].image_resolution)
+        t = CO.CoCoOp.__new__(CO.CoCoOp)
+        M.TrainerX.__init__(t, None, None, "cpu")
+        t.cfg = cfg
+        t.model = CO.CustomCLIP(cfg, classnames, clip.CLIP(*c["arch"].astuple(), None).float(), tokenizer=syn.synthetic_tokenize)
+        enabled = M.apply_freeze_rule(t.model, ("prompt_learner",))
+        assert enabled == {"prompt_learner.ctx", "prompt_learner.meta_net.linear1.weight", "prompt_learner.meta_net.linear1.bias",
+                           "prompt_learner.meta_net.linear2.weight", "prompt_learner.meta_net.linear2.bias"}
+        t.optim = torch.optim.SGD(t.model.prompt_learner.parameters(), lr=0.1)
+        t.register_model("prompt_learner", t.model.prompt_learner, t.optim, None)
+        return t
+
+    a = make(["class 0", "class 1", "class 2"])
+    with torch.no_grad():
+        for p in a.model.prompt_learner.parameters():
+            p.add_(torch.randn_like(p))
+    a.save_model(1, str(tmp_path))
+    b = make(["dog", "cat", "bird", "fish"])
+    prefix_before, suffix_before = b.model.prompt_learner.token_prefix.clone(), b.model.prompt_learner.token_suffix.clone()
+    b.load_model(str(tmp_path), epoch=2)
+    for (n, p), (_, q) in zip(a.model.prompt_learner.named_parameters(), b.model.prompt_learner.named_parameters()):
+        assert torch.equal(p, q), n
+    assert torch.equal(b.model.prompt_learner.token_prefix, prefix_before)
+    assert torch.equal(b.model.prompt_learner.token_suffix, suffix_before)
+    with pytest.raises(FileNotFoundError):
+        b.load_model(str(tmp_path), epoch=99)
+    b.load_model("")  # no directory: skipped, as in the reference
