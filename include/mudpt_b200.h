@@ -133,7 +133,8 @@ int mudpt_layernorm_backward(const float* dy, const float* x, const float* gamma
 /* The form the towers use when the gradient of the residual stream is kept in bf16 (option "grad_stream_bf16"):
  * dy bf16; x = fp32 rows (x_stats NULL) or their bf16 copy + per-64-column partial statistics (mudpt_rowstats);
  * resid = fp32 rows, or (resid_bf16 != 0) bf16 rows that may alias dx_bf16, or NULL; dx (fp32) / dx_bf16 may each be
- * NULL (not both); win_n >= 0: fp32 rows are written only where (row % win_L) is in [win_row0, win_row0 + win_n). */
+ * NULL (not both); win_n >= 0: fp32 rows are written only where (row % win_L) is in [win_row0, win_row0 + win_n).
+ * Every pointer must be 16-byte aligned (rows are moved with 16-byte vector accesses / bulk copies). */
 int mudpt_layernorm_backward_stream(const uint16_t* dy, const void* x, const float* x_stats, const float* gamma,
                                     const void* resid, int32_t resid_bf16, float* dx, uint16_t* dx_bf16, int32_t rows,
                                     int32_t width, int32_t win_L, int32_t win_row0, int32_t win_n, void* stream);
