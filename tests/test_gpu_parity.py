@@ -4,7 +4,9 @@ REFERENCE (oracle/make_golden.py).
 
 Tolerances (stated once, used below).  The reference computes in fp32; the native path stores the
 residual stream, LayerNorm statistics, softmax and all accumulators in fp32 and rounds GEMM /
-attention operands to bf16 (8 significant bits, relative rounding error 2^-9 = 0.2 %):
+attention operands to bf16 (8 significant bits, relative rounding error 2^-9 = 0.2 %); the GRADIENT of the residual stream
+travels between the LayerNorm backward kernels as bf16 as well (option grad_stream_bf16, measured effect on the prompt gradients:
+profiles/r02_grad_stream_bf16.txt; the fp32 stream is one of the option combinations tested below):
   * fp32-output kernels (LN, splice, fp32 GEMM epilogues, heads) ....... rel-L2 <= 1e-5; splice bit-exact
   * bf16-output kernels (GEMM, attention) .............................. rel-L2 <= 5e-3
   * whole model vs reference: feature cosine >= 0.999 (north_star), logit max-abs error <= 0.05,
